@@ -1,0 +1,814 @@
+// ce_api.cu -- the C ABI of libce_gpu (include/ce_gpu.h): context management, validation in
+// the reference's order, sub-batch scheduling over the workspace, host-side score
+// finalisation in fp64.  No CPU fallback: every compute entry needs a CUDA device.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <new>
+
+#include "ce_internal.h"
+
+using namespace ce;
+
+struct ce_ctx {
+    Context c;
+};
+
+struct ce_ref {
+    ce_ctx* owner;
+    uint8_t* d_ref;  // device RGB8 (already XYB-round-tripped if the config asked for it)
+    size_t width, height;
+    ce_metric_config cfg;
+};
+
+static thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------ context helpers
+void Context::ensure_input(size_t bytes) {
+    if (bytes <= d_in_bytes) return;
+    if (d_in) CE_CUDA(cudaFree(d_in));
+    d_in = nullptr;
+    d_in_bytes = 0;
+    CE_CUDA(cudaMalloc(&d_in, bytes));
+    d_in_bytes = bytes;
+}
+void Context::ensure_results(size_t bytes) {
+    if (bytes <= h_pinned_bytes) return;
+    if (h_pinned) CE_CUDA(cudaFreeHost(h_pinned));
+    if (d_results) CE_CUDA(cudaFree(d_results));
+    h_pinned = nullptr;
+    d_results = nullptr;
+    h_pinned_bytes = d_results_bytes = 0;
+    size_t cap = std::max<size_t>(bytes, 1 << 20);
+    CE_CUDA(cudaMallocHost(&h_pinned, cap));
+    CE_CUDA(cudaMalloc(&d_results, cap));
+    h_pinned_bytes = d_results_bytes = cap;
+}
+
+// recursive Gaussian sigma 1.5 (libjxl CreateRecursiveGaussian), evaluated in double, stored as fp32
+static void make_rgauss(RGaussCoef& rg) {
+    const double sigma = 1.5;
+    const double radius = round(3.2795 * sigma + 0.2546);
+    const double pi_div_2r = M_PI / (2.0 * radius);
+    const double omega[3] = {pi_div_2r, 3.0 * pi_div_2r, 5.0 * pi_div_2r};
+    const double p_1 = 1.0 / tan(0.5 * omega[0]);
+    const double p_3 = -1.0 / tan(0.5 * omega[1]);
+    const double p_5 = 1.0 / tan(0.5 * omega[2]);
+    const double r_1 = p_1 * p_1 / sin(omega[0]);
+    const double r_3 = -p_3 * p_3 / sin(omega[1]);
+    const double r_5 = p_5 * p_5 / sin(omega[2]);
+    const double neg_half_sigma2 = -0.5 * sigma * sigma;
+    const double recip_radius = 1.0 / radius;
+    double rho[3];
+    for (int i = 0; i < 3; i++) rho[i] = exp(neg_half_sigma2 * omega[i] * omega[i]) * recip_radius;
+    const double D_13 = p_1 * r_3 - r_1 * p_3;
+    const double D_35 = p_3 * r_5 - r_3 * p_5;
+    const double D_51 = p_5 * r_1 - r_5 * p_1;
+    const double recip_d13 = 1.0 / D_13;
+    const double zeta_15 = D_35 * recip_d13;
+    const double zeta_35 = D_51 * recip_d13;
+    double A[3][3] = {{p_1, p_3, p_5}, {r_1, r_3, r_5}, {zeta_15, zeta_35, 1.0}};
+    double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                 A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+    double inv[3][3];
+    inv[0][0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) / det;
+    inv[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) / det;
+    inv[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / det;
+    inv[1][0] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) / det;
+    inv[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / det;
+    inv[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) / det;
+    inv[2][0] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / det;
+    inv[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / det;
+    inv[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / det;
+    const double gamma[3] = {1.0, radius * radius - sigma * sigma, zeta_15 * rho[0] + zeta_35 * rho[1] + rho[2]};
+    for (int i = 0; i < 3; i++) {
+        double beta = inv[i][0] * gamma[0] + inv[i][1] * gamma[1] + inv[i][2] * gamma[2];
+        rg.mul_in[i] = (float)(-beta * cos(omega[i] * (radius + 1.0)));
+        rg.mul_prev[i] = (float)(2.0 * cos(omega[i]));
+        rg.mul_prev2[i] = -1.0f;
+    }
+}
+
+// sRGB8 -> linear, the reference's expression (src/metrics/dssim.rs:77-85) evaluated once per code value
+static void make_srgb_lut(float* lut) {
+    for (int i = 0; i < 256; i++) {
+        float s = (float)i / 255.0f;
+        lut[i] = s <= 0.04045f ? s / 12.92f : powf((s + 0.055f) / 1.055f, 2.4f);
+    }
+}
+
+// ------------------------------------------------------------------ host-side finalisation
+static const double S2_WEIGHT[108] = {
+    0.0, 0.0007376606707406586, 0.0, 0.0, 0.0007793481682867309, 0.0, 0.0, 0.0004371155730107379, 0.0,
+    1.1041726426657346, 0.00066284834129271, 0.00015231632783718752, 0.0, 0.0016406437456599754, 0.0,
+    1.8422455520539298, 11.441172603757666, 0.0, 0.0007989109436015163, 0.000176816438078653, 0.0,
+    1.8787594979546387, 10.94906990605142, 0.0, 0.0007289346991508072, 0.9677937080626833, 0.0,
+    0.00014003424285435884, 0.9981766977854967, 0.00031949755934435053, 0.0004550992113792063, 0.0, 0.0,
+    0.0013648766163243398, 0.0, 0.0, 0.0, 0.0, 0.0, 7.466890328078848, 0.0, 17.445833984131262,
+    0.0006235601634041466, 0.0, 0.0, 6.683678146179332, 0.00037724407979611296, 1.027889937768264,
+    225.20515300849274, 0.0, 0.0, 19.213238186143016, 0.0011401524586618361, 0.001237755635509985,
+    176.39317598450694, 0.0, 0.0, 24.43300999870476, 0.28520802612117757, 0.0004485436923833408, 0.0, 0.0, 0.0,
+    34.77906344483772, 44.835625328877896, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0008680556573291698, 0.0, 0.0,
+    0.0, 0.0, 0.0, 0.0005313191874358747, 0.0, 0.00016533814161379112, 0.0, 0.0, 0.0, 0.0, 0.0,
+    0.0004179171803251336, 0.0017290828234722833, 0.0, 0.0020827005846636437, 0.0, 0.0, 8.826982764996862,
+    23.19243343998926, 0.0, 95.1080498811086, 0.9863978034400682, 0.9834382792465353, 0.0012286405048278493,
+    171.2667255897307, 0.9807858872435379, 0.0, 0.0, 0.0, 0.0005130064588990679, 0.0, 0.00010854057858411537};
+
+// sums: [nscales][18] raw sums, layout c*6 + {d, d^4, art, art^4, det, det^4}
+static double finalize_ssim2(const double* sums, int ns, size_t w, size_t h) {
+    double avg_ssim[6][6], avg_edge[6][12];
+    size_t cw = w, ch = h;
+    for (int s = 0; s < ns; s++) {
+        if (s > 0) { cw = (cw + 1) / 2; ch = (ch + 1) / 2; }
+        const double opp = 1.0 / (double)(cw * ch);
+        const double* S = sums + (size_t)s * 18;
+        for (int c = 0; c < 3; c++) {
+            avg_ssim[s][c * 2 + 0] = opp * S[c * 6 + 0];
+            avg_ssim[s][c * 2 + 1] = sqrt(sqrt(opp * S[c * 6 + 1]));
+            avg_edge[s][c * 4 + 0] = opp * S[c * 6 + 2];
+            avg_edge[s][c * 4 + 1] = sqrt(sqrt(opp * S[c * 6 + 3]));
+            avg_edge[s][c * 4 + 2] = opp * S[c * 6 + 4];
+            avg_edge[s][c * 4 + 3] = sqrt(sqrt(opp * S[c * 6 + 5]));
+        }
+    }
+    double ssim = 0.0;
+    size_t i = 0;
+    for (int c = 0; c < 3; c++)
+        for (int s = 0; s < ns; s++)
+            for (int n = 0; n < 2; n++) {
+                ssim = fma(S2_WEIGHT[i++], fabs(avg_ssim[s][c * 2 + n]), ssim);
+                ssim = fma(S2_WEIGHT[i++], fabs(avg_edge[s][c * 4 + n]), ssim);
+                ssim = fma(S2_WEIGHT[i++], fabs(avg_edge[s][c * 4 + n + 2]), ssim);
+            }
+    ssim *= 0.9562382616834844;
+    ssim = fma(6.248496625763138e-5 * ssim * ssim, ssim, fma(2.326765642916932, ssim, -0.020884521182843837 * ssim * ssim));
+    if (ssim > 0.0) ssim = fma(pow(ssim, 0.6276336467831387), -10.0, 100.0);
+    else ssim = 100.0;
+    return ssim;
+}
+
+static double finalize_dssim(const double* ds /* [5][2] */, int ns, size_t w, size_t h, double* scale_scores) {
+    static const double W[5] = {0.028, 0.197, 0.322, 0.298, 0.155};
+    size_t ws[5], hs[5];
+    dssim_num_scales(w, h, ws, hs);
+    double ssim_sum = 0.0, weight_sum = 0.0;
+    for (int s = 0; s < ns; s++) {
+        double len = (double)(ws[s] * hs[s]);
+        double score = 1.0 - ds[s * 2 + 1] / len;
+        if (scale_scores) scale_scores[s] = score;
+        ssim_sum += score * W[s];
+        weight_sum += W[s];
+    }
+    double ssim = ssim_sum / weight_sum;
+    if (ssim < 2.220446049250313e-16) ssim = 2.220446049250313e-16;
+    return 1.0 / ssim - 1.0;
+}
+
+static void finalize_butteraugli(const double* ba /* max, s3, s6, s12 */, size_t w, size_t h, double* mx, double* pn) {
+    double opp = 1.0 / (double)(w * h);
+    *mx = ba[0];
+    *pn = (pow(opp * ba[1], 1.0 / 3.0) + pow(opp * ba[2], 1.0 / 6.0) + pow(opp * ba[3], 1.0 / 12.0)) / 3.0;
+}
+
+static double finalize_psnr(uint64_t sse, size_t w, size_t h) {
+    // src/metrics/mod.rs:324-330
+    double mse = (double)sse / (double)(w * h * 3);
+    if (mse == 0.0) return INFINITY;
+    return 10.0 * log10(255.0 * 255.0 / mse);
+}
+
+// ------------------------------------------------------------------ the device batch
+struct DebugOut {
+    double* s2_sums = nullptr;   // [6*18]
+    int* s2_nscales = nullptr;
+    float* s2_planes = nullptr;  // device pointer
+    double* ds_scores = nullptr; // [5]
+    int* ds_nscales = nullptr;
+    float* ds_map0 = nullptr;    // device pointer
+    float* ba_diffmap = nullptr; // device pointer
+};
+
+static size_t per_pair_bytes(const ce_metric_config& cfg, size_t w, size_t h) {
+    size_t n = w * h;
+    size_t bytes = 1024;
+    if (cfg.xyb_roundtrip) bytes += n * 3 + 256;
+    bool perceptual = cfg.dssim || cfg.ssimulacra2 || cfg.butteraugli;
+    if (perceptual) bytes += 2 * 3 * n * 4 + 512;
+    size_t m = 0;
+    if (cfg.dssim) m = std::max(m, dssim_workspace_per_pair(w, h));
+    if (cfg.ssimulacra2) m = std::max(m, ssim2_workspace_per_pair(w, h));
+    if (cfg.butteraugli) m = std::max(m, butteraugli_workspace_per_pair(w, h));
+    return bytes + m;
+}
+
+// d_ref / d_dist: n device images; optional alpha/float inputs are handled by the callers.
+static void run_device_batch(Context& c, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, size_t w, size_t h,
+                             const ce_metric_config& cfg, float intensity, ce_result* out, const DebugOut* dbg) {
+    const size_t npix = w * h, img_bytes = npix * 3;
+    const bool small = (w < 8 || h < 8);
+    const bool perceptual = cfg.dssim || cfg.ssimulacra2 || cfg.butteraugli;
+    const size_t ppb = per_pair_bytes(cfg, w, h);
+    const size_t fixed = 1 << 20;
+    if (c.arena.cap < ppb + fixed) throw OomError("workspace too small for one pair of this size");
+    size_t Bmax = (c.arena.cap - fixed) / ppb;
+    Bmax = std::min<size_t>(Bmax, 16384);
+    // raw per-pair device results: sse(1 u64) + s2 sums(108) + ds(10) + ba(4) doubles
+    const size_t raw_doubles = 1 + 108 + 10 + 4;
+    for (size_t p0 = 0; p0 < n; p0 += Bmax) {
+        const size_t B = std::min(Bmax, n - p0);
+        c.arena.reset();
+        c.ensure_results(B * raw_doubles * 8);
+        double* d_raw = reinterpret_cast<double*>(c.d_results);
+        unsigned long long* d_sse = reinterpret_cast<unsigned long long*>(d_raw);
+        double* d_s2 = d_raw + B;
+        double* d_ds = d_s2 + B * 108;
+        double* d_ba = d_ds + B * 10;
+        const uint8_t* ref = d_ref + p0 * img_bytes;
+        const uint8_t* dist = d_dist + p0 * img_bytes;
+        if (cfg.xyb_roundtrip) {  // reference only, before every metric (src/eval/session.rs:447-456)
+            uint8_t* rt = c.arena.alloc<uint8_t>(B * img_bytes);
+            launch_xyb_roundtrip(c, ref, B * npix, rt);
+            ref = rt;
+        }
+        if (cfg.psnr) launch_sse(c, ref, dist, B, img_bytes, d_sse);
+        int s2_ns = 0, ds_ns = 0;
+        if (perceptual) {
+            float* lin = c.arena.alloc<float>(2 * B * 3 * npix);
+            float* lin2 = lin + B * 3 * npix;
+            launch_srgb8_to_linear(c, ref, B, npix, lin);
+            launch_srgb8_to_linear(c, dist, B, npix, lin2);
+            if (cfg.dssim) ds_ns = dssim_run(c, lin, lin2, nullptr, nullptr, B, w, h, d_ds, dbg ? dbg->ds_map0 : nullptr);
+            if (cfg.ssimulacra2 && !small) s2_ns = ssim2_run(c, lin, lin2, B, w, h, d_s2, dbg ? dbg->s2_planes : nullptr);
+            if (cfg.butteraugli && !small) butteraugli_run(c, lin, lin2, B, w, h, intensity, d_ba, dbg ? dbg->ba_diffmap : nullptr);
+        }
+        CE_CUDA(cudaMemcpyAsync(c.h_pinned, d_raw, B * raw_doubles * 8, cudaMemcpyDeviceToHost, c.stream));
+        CE_CUDA(cudaStreamSynchronize(c.stream));
+        const double* h_raw = reinterpret_cast<const double*>(c.h_pinned);
+        const uint64_t* h_sse = reinterpret_cast<const uint64_t*>(h_raw);
+        const double* h_s2 = h_raw + B;
+        const double* h_ds = h_s2 + B * 108;
+        const double* h_ba = h_ds + B * 10;
+        for (size_t i = 0; i < B; i++) {
+            ce_result& r = out[p0 + i];
+            memset(&r, 0, sizeof(r));
+            // reference order: psnr, dssim, ssimulacra2, butteraugli; first failure ends the pair
+            if (cfg.psnr) {
+                r.sse = h_sse[i];
+                r.psnr = finalize_psnr(r.sse, w, h);
+                r.valid |= CE_VALID_PSNR;
+            }
+            if (cfg.dssim) {
+                r.dssim = finalize_dssim(h_ds + i * 10, ds_ns, w, h, (dbg && i == 0) ? dbg->ds_scores : nullptr);
+                if (dbg && dbg->ds_nscales) *dbg->ds_nscales = ds_ns;
+                r.valid |= CE_VALID_DSSIM;
+            }
+            if (cfg.ssimulacra2) {
+                if (small) { r.status = CE_ERR_METRIC_CALCULATION; continue; }
+                r.ssimulacra2 = finalize_ssim2(h_s2 + i * 108, s2_ns, w, h);
+                if (dbg && i == 0 && dbg->s2_sums) memcpy(dbg->s2_sums, h_s2, sizeof(double) * 18 * (size_t)s2_ns);
+                if (dbg && dbg->s2_nscales) *dbg->s2_nscales = s2_ns;
+                r.valid |= CE_VALID_SSIMULACRA2;
+            }
+            if (cfg.butteraugli) {
+                if (small) { r.status = CE_ERR_METRIC_CALCULATION; continue; }
+                finalize_butteraugli(h_ba + i * 4, w, h, &r.butteraugli, &r.butteraugli_pnorm3);
+                r.valid |= CE_VALID_BUTTERAUGLI;
+            }
+        }
+    }
+    if (small && (cfg.ssimulacra2 || cfg.butteraugli))
+        c.last_error = cfg.ssimulacra2 ? "SSIMULACRA2: images must be at least 8x8 pixels" : "Butteraugli: images must be at least 8x8 pixels";
+}
+
+// ------------------------------------------------------------------ C ABI
+#define CE_TRY(ctx_expr, body)                                   \
+    try {                                                        \
+        body                                                     \
+    } catch (const OomError& e) {                                \
+        (ctx_expr).last_error = e.what();                        \
+        return CE_ERR_OUT_OF_MEMORY;                             \
+    } catch (const CudaError& e) {                               \
+        (ctx_expr).last_error = e.what();                        \
+        return CE_ERR_CUDA;                                      \
+    } catch (const std::exception& e) {                          \
+        (ctx_expr).last_error = e.what();                        \
+        return CE_ERR_CUDA;                                      \
+    }
+
+extern "C" {
+
+CE_API const char* ce_version(void) { return "ce_gpu 0.1.0 (sm_100a)"; }
+
+CE_API int ce_ctx_create(ce_ctx** out, int device, size_t workspace_bytes) {
+    if (!out) return CE_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    ce_ctx* ctx = nullptr;
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libce_gpu has no CPU fallback)";
+            return CE_ERR_CUDA;
+        }
+        if (device < 0 || device >= ndev) {
+            g_create_error = "device index out of range";
+            return CE_ERR_INVALID_ARGUMENT;
+        }
+        CE_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CE_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) {
+            g_create_error = "libce_gpu is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+            return CE_ERR_CUDA;
+        }
+        ctx = new ce_ctx();
+        Context& c = ctx->c;
+        c.device = device;
+        c.sm_count = prop.multiProcessorCount;
+        CE_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+        c.stream = c.own_stream;
+        if (workspace_bytes == 0) {
+            size_t free_b = 0, total_b = 0;
+            CE_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            workspace_bytes = std::min<size_t>(free_b / 2, (size_t)24 << 30);
+        }
+        CE_CUDA(cudaMalloc(&c.arena.base, workspace_bytes));
+        c.arena.cap = workspace_bytes;
+        float lut[256];
+        make_srgb_lut(lut);
+        CE_CUDA(cudaMalloc(&c.d_lut, sizeof(lut)));
+        CE_CUDA(cudaMemcpy(c.d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        make_rgauss(c.rg);
+        ssim2_init(c);
+        butteraugli_init(c);
+        c.ensure_results(1 << 20);
+        *out = ctx;
+        return CE_OK;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        if (ctx) ce_ctx_destroy(ctx);
+        return CE_ERR_CUDA;
+    }
+}
+
+CE_API void ce_ctx_destroy(ce_ctx* ctx) {
+    if (!ctx) return;
+    Context& c = ctx->c;
+    cudaSetDevice(c.device);
+    if (c.own_stream) cudaStreamSynchronize(c.own_stream);
+    if (c.arena.base) cudaFree(c.arena.base);
+    if (c.d_lut) cudaFree(c.d_lut);
+    if (c.h_pinned) cudaFreeHost(c.h_pinned);
+    if (c.d_results) cudaFree(c.d_results);
+    if (c.d_in) cudaFree(c.d_in);
+    for (auto& kv : c.ba_inv_cache) cudaFree(kv.second);
+    if (c.own_stream) cudaStreamDestroy(c.own_stream);
+    delete ctx;
+}
+
+CE_API int ce_ctx_set_stream(ce_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return CE_ERR_INVALID_ARGUMENT;
+    ctx->c.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->c.own_stream;
+    return CE_OK;
+}
+
+CE_API const char* ce_last_error(const ce_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : g_create_error.c_str(); }
+CE_API uint64_t ce_launch_count(const ce_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+CE_API int ce_evaluate_batch_device(ce_ctx* ctx, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, uint32_t width,
+                                    uint32_t height, const ce_metric_config* cfg, float intensity_target, ce_result* out) {
+    if (!ctx || !cfg || (!out && n) || ((!d_ref || !d_dist) && n)) return CE_ERR_INVALID_ARGUMENT;
+    if (n == 0) return CE_OK;
+    if (width == 0 || height == 0) {
+        ctx->c.last_error = "zero-sized image";
+        return CE_ERR_INVALID_ARGUMENT;
+    }
+    Context& c = ctx->c;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        run_device_batch(c, d_ref, d_dist, n, width, height, *cfg, intensity_target, out, nullptr);
+    })
+    return CE_OK;
+}
+
+// validation in the order of src/metrics/ssimulacra2.rs:65-82 / butteraugli.rs:51-68
+static int validate_pair(const ce_pair& p, std::string* why) {
+    if (!p.ref || !p.dist) return CE_ERR_INVALID_ARGUMENT;
+    if (p.ref_len != p.dist_len) {
+        if (why) *why = "reference and test buffers differ in length";
+        return CE_ERR_DIMENSION_MISMATCH;
+    }
+    size_t expected = (size_t)p.width * p.height * 3;
+    if (p.ref_len != expected || expected == 0) {
+        if (why) *why = "Invalid image size: expected " + std::to_string(expected) + " bytes, got " + std::to_string(p.ref_len);
+        return CE_ERR_METRIC_CALCULATION;
+    }
+    return CE_OK;
+}
+
+static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, const ce_metric_config& cfg, float intensity,
+                                ce_result* out, const DebugOut* dbg) {
+    // group valid pairs by size, keeping submission order inside a group
+    std::map<std::pair<uint32_t, uint32_t>, std::vector<size_t>> groups;
+    for (size_t i = 0; i < n; i++) {
+        memset(&out[i], 0, sizeof(ce_result));
+        std::string why;
+        int st = validate_pair(pairs[i], &why);
+        if (st != CE_OK) {
+            out[i].status = st;
+            if (!why.empty()) c.last_error = why;
+            continue;
+        }
+        groups[{pairs[i].width, pairs[i].height}].push_back(i);
+    }
+    std::vector<ce_result> tmp;
+    for (auto& g : groups) {
+        const size_t w = g.first.first, h = g.first.second, img_bytes = w * h * 3;
+        const std::vector<size_t>& idx = g.second;
+        // staging: at most 4 GiB of input per chunk
+        size_t chunk = std::max<size_t>(1, std::min<size_t>(idx.size(), ((size_t)2 << 30) / std::max<size_t>(img_bytes, 1)));
+        for (size_t k0 = 0; k0 < idx.size(); k0 += chunk) {
+            const size_t B = std::min(chunk, idx.size() - k0);
+            c.ensure_input(2 * B * img_bytes);
+            uint8_t* d_ref = c.d_in;
+            uint8_t* d_dist = c.d_in + B * img_bytes;
+            for (size_t k = 0; k < B; k++) {
+                const ce_pair& p = pairs[idx[k0 + k]];
+                CE_CUDA(cudaMemcpyAsync(d_ref + k * img_bytes, p.ref, img_bytes, cudaMemcpyHostToDevice, c.stream));
+                CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, p.dist, img_bytes, cudaMemcpyHostToDevice, c.stream));
+            }
+            tmp.resize(B);
+            run_device_batch(c, d_ref, d_dist, B, w, h, cfg, intensity, tmp.data(), dbg);
+            for (size_t k = 0; k < B; k++) out[idx[k0 + k]] = tmp[k];
+        }
+    }
+}
+
+CE_API int ce_evaluate_batch(ce_ctx* ctx, const ce_pair* pairs, size_t n, const ce_metric_config* cfg, float intensity_target,
+                             ce_result* out) {
+    if (!ctx || !cfg || (n && (!pairs || !out))) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        evaluate_host_pairs(c, pairs, n, *cfg, intensity_target, out, nullptr);
+    })
+    return CE_OK;
+}
+
+static int single_pair(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, const uint8_t* test, size_t test_len, size_t w, size_t h,
+                       const ce_metric_config& cfg, float intensity, ce_result* r, const DebugOut* dbg = nullptr) {
+    if (!ctx || !ref || !test) return CE_ERR_INVALID_ARGUMENT;
+    if (w > 0xffffffffull || h > 0xffffffffull) return CE_ERR_INVALID_ARGUMENT;
+    ce_pair p;
+    memset(&p, 0, sizeof(p));
+    p.ref = ref; p.dist = test; p.ref_len = ref_len; p.dist_len = test_len;
+    p.width = (uint32_t)w; p.height = (uint32_t)h;
+    Context& c = ctx->c;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        evaluate_host_pairs(c, &p, 1, cfg, intensity, r, dbg);
+    })
+    return r->status;
+}
+
+CE_API int ce_psnr(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, const uint8_t* test, size_t test_len, size_t width,
+                   size_t height, double* psnr, uint64_t* sse) {
+    // the reference asserts (panics) on both length checks, src/metrics/mod.rs:313-314
+    if (!ctx || !ref || !test) return CE_ERR_INVALID_ARGUMENT;
+    if (ref_len != test_len || ref_len != width * height * 3 || ref_len == 0) {
+        ctx->c.last_error = "calculate_psnr: buffer length does not match width*height*3";
+        return CE_ERR_INVALID_ARGUMENT;
+    }
+    ce_metric_config cfg = {0, 0, 0, 1, 0};
+    ce_result r;
+    int st = single_pair(ctx, ref, ref_len, test, test_len, width, height, cfg, 80.0f, &r);
+    if (st != CE_OK) return st;
+    if (psnr) *psnr = r.psnr;
+    if (sse) *sse = r.sse;
+    return CE_OK;
+}
+
+CE_API int ce_ssimulacra2(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, const uint8_t* test, size_t test_len, size_t width,
+                          size_t height, double* score) {
+    ce_metric_config cfg = {0, 1, 0, 0, 0};
+    ce_result r;
+    int st = single_pair(ctx, ref, ref_len, test, test_len, width, height, cfg, 80.0f, &r);
+    if (st != CE_OK) return st;
+    if (score) *score = r.ssimulacra2;
+    return CE_OK;
+}
+
+CE_API int ce_butteraugli(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, const uint8_t* test, size_t test_len, size_t width,
+                          size_t height, float intensity_target, double* score, double* pnorm3) {
+    ce_metric_config cfg = {0, 0, 1, 0, 0};
+    ce_result r;
+    int st = single_pair(ctx, ref, ref_len, test, test_len, width, height, cfg, intensity_target, &r);
+    if (st != CE_OK) return st;
+    if (score) *score = r.butteraugli;
+    if (pnorm3) *pnorm3 = r.butteraugli_pnorm3;
+    return CE_OK;
+}
+
+CE_API int ce_dssim_rgb8(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, const uint8_t* test, size_t test_len, size_t width,
+                         size_t height, double* dssim) {
+    ce_metric_config cfg = {1, 0, 0, 0, 0};
+    ce_result r;
+    int st = single_pair(ctx, ref, ref_len, test, test_len, width, height, cfg, 80.0f, &r);
+    if (st != CE_OK) return st;
+    if (dssim) *dssim = r.dssim;
+    return CE_OK;
+}
+
+CE_API int ce_dssim_rgbaf32(ce_ctx* ctx, const float* ref, size_t ref_w, size_t ref_h, size_t ref_stride, const float* test,
+                            size_t test_w, size_t test_h, size_t test_stride, double* dssim) {
+    if (!ctx || !ref || !test) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    if (ref_w != test_w || ref_h != test_h) {  // src/metrics/dssim.rs:45-50
+        c.last_error = "DSSIM: dimension mismatch";
+        return CE_ERR_DIMENSION_MISMATCH;
+    }
+    if (ref_w == 0 || ref_h == 0 || ref_stride < ref_w || test_stride < test_w) {
+        c.last_error = "DSSIM: Failed to create reference image";
+        return CE_ERR_METRIC_CALCULATION;
+    }
+    const size_t w = ref_w, h = ref_h, n = w * h;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        c.arena.reset();
+        const size_t need = (ref_stride + test_stride) * h * 16 + 8 * n * 4 + dssim_workspace_per_pair(w, h) + (1 << 20);
+        if (c.arena.cap < need) throw OomError("workspace too small for one pair of this size");
+        float* d_r = c.arena.alloc<float>(ref_stride * h * 4);
+        float* d_t = c.arena.alloc<float>(test_stride * h * 4);
+        CE_CUDA(cudaMemcpyAsync(d_r, ref, ref_stride * (h - 1) * 16 + w * 16, cudaMemcpyHostToDevice, c.stream));
+        CE_CUDA(cudaMemcpyAsync(d_t, test, test_stride * (h - 1) * 16 + w * 16, cudaMemcpyHostToDevice, c.stream));
+        float* p1 = c.arena.alloc<float>(4 * n);
+        float* p2 = c.arena.alloc<float>(4 * n);
+        launch_rgba_to_planar(c, d_r, w, h, ref_stride, p1);
+        launch_rgba_to_planar(c, d_t, w, h, test_stride, p2);
+        c.ensure_results(10 * 8);
+        double* d_ds = reinterpret_cast<double*>(c.d_results);
+        int ns = dssim_run(c, p1, p2, p1 + 3 * n, p2 + 3 * n, 1, w, h, d_ds, nullptr);
+        CE_CUDA(cudaMemcpyAsync(c.h_pinned, d_ds, 10 * 8, cudaMemcpyDeviceToHost, c.stream));
+        CE_CUDA(cudaStreamSynchronize(c.stream));
+        if (dssim) *dssim = finalize_dssim(reinterpret_cast<const double*>(c.h_pinned), ns, w, h, nullptr);
+    })
+    return CE_OK;
+}
+
+static int to_dssim_image(ce_ctx* ctx, const uint8_t* data, size_t len, size_t width, size_t height, int ch, float* out) {
+    if (!ctx || !data || !out) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    const size_t n = width * height;
+    if (len != n * ch) {
+        c.last_error = "buffer length does not match width*height*channels";
+        return CE_ERR_INVALID_ARGUMENT;
+    }
+    if (n == 0) return CE_OK;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        c.arena.reset();
+        uint8_t* d_in = c.arena.alloc<uint8_t>(len);
+        float* d_out = c.arena.alloc<float>(n * 4);
+        CE_CUDA(cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, c.stream));
+        launch_rgb8_to_rgba_linear(c, d_in, n, ch, d_out);
+        CE_CUDA(cudaMemcpyAsync(out, d_out, n * 16, cudaMemcpyDeviceToHost, c.stream));
+        CE_CUDA(cudaStreamSynchronize(c.stream));
+    })
+    return CE_OK;
+}
+CE_API int ce_rgb8_to_dssim_image(ce_ctx* ctx, const uint8_t* data, size_t len, size_t width, size_t height, float* out) {
+    return to_dssim_image(ctx, data, len, width, height, 3, out);
+}
+CE_API int ce_rgba8_to_dssim_image(ce_ctx* ctx, const uint8_t* data, size_t len, size_t width, size_t height, float* out) {
+    return to_dssim_image(ctx, data, len, width, height, 4, out);
+}
+
+CE_API int ce_xyb_roundtrip(ce_ctx* ctx, const uint8_t* rgb, size_t len, size_t width, size_t height, uint8_t* out) {
+    if (!ctx || !rgb || !out) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    const size_t n = width * height;
+    if (len != n * 3) {  // assert_eq! in src/metrics/xyb.rs:227
+        c.last_error = "Buffer size mismatch";
+        return CE_ERR_INVALID_ARGUMENT;
+    }
+    if (n == 0) return CE_OK;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        c.arena.reset();
+        uint8_t* d_in = c.arena.alloc<uint8_t>(len);
+        uint8_t* d_out = c.arena.alloc<uint8_t>(len);
+        CE_CUDA(cudaMemcpyAsync(d_in, rgb, len, cudaMemcpyHostToDevice, c.stream));
+        launch_xyb_roundtrip(c, d_in, n, d_out);
+        CE_CUDA(cudaMemcpyAsync(out, d_out, len, cudaMemcpyDeviceToHost, c.stream));
+        CE_CUDA(cudaStreamSynchronize(c.stream));
+    })
+    return CE_OK;
+}
+
+// ---- reference reuse ------------------------------------------------------
+CE_API int ce_reference_create(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, size_t width, size_t height,
+                               const ce_metric_config* cfg, ce_ref** out) {
+    if (!ctx || !ref || !cfg || !out) return CE_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    Context& c = ctx->c;
+    if (ref_len != width * height * 3 || ref_len == 0) {
+        c.last_error = "Invalid image size: expected " + std::to_string(width * height * 3) + " bytes, got " + std::to_string(ref_len);
+        return CE_ERR_METRIC_CALCULATION;
+    }
+    ce_ref* r = nullptr;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        r = new ce_ref();
+        r->owner = ctx; r->width = width; r->height = height; r->cfg = *cfg; r->d_ref = nullptr;
+        CE_CUDA(cudaMalloc(&r->d_ref, ref_len));
+        if (cfg->xyb_roundtrip) {
+            c.arena.reset();
+            uint8_t* d_in = c.arena.alloc<uint8_t>(ref_len);
+            CE_CUDA(cudaMemcpyAsync(d_in, ref, ref_len, cudaMemcpyHostToDevice, c.stream));
+            launch_xyb_roundtrip(c, d_in, width * height, r->d_ref);
+        } else {
+            CE_CUDA(cudaMemcpyAsync(r->d_ref, ref, ref_len, cudaMemcpyHostToDevice, c.stream));
+        }
+        CE_CUDA(cudaStreamSynchronize(c.stream));
+        r->cfg.xyb_roundtrip = 0;  // already applied
+        *out = r;
+    })
+    return CE_OK;
+}
+
+CE_API int ce_reference_compare_many(ce_ctx* ctx, ce_ref* ref, const uint8_t* const* dists, const size_t* dist_lens, size_t n_dist,
+                                     float intensity_target, ce_result* out) {
+    if (!ctx || !ref || ref->owner != ctx || (n_dist && (!dists || !dist_lens || !out))) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    const size_t img_bytes = ref->width * ref->height * 3;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        std::vector<size_t> ok;
+        for (size_t i = 0; i < n_dist; i++) {
+            memset(&out[i], 0, sizeof(ce_result));
+            if (!dists[i]) { out[i].status = CE_ERR_INVALID_ARGUMENT; continue; }
+            if (dist_lens[i] != img_bytes) {  // src/metrics/ssimulacra2.rs:65-70
+                out[i].status = CE_ERR_DIMENSION_MISMATCH;
+                c.last_error = "reference and test buffers differ in length";
+                continue;
+            }
+            ok.push_back(i);
+        }
+        const size_t B = ok.size();
+        if (B) {
+            c.ensure_input(2 * B * img_bytes);
+            uint8_t* d_ref = c.d_in;
+            uint8_t* d_dist = c.d_in + B * img_bytes;
+            for (size_t k = 0; k < B; k++) {
+                CE_CUDA(cudaMemcpyAsync(d_ref + k * img_bytes, ref->d_ref, img_bytes, cudaMemcpyDeviceToDevice, c.stream));
+                CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, dists[ok[k]], img_bytes, cudaMemcpyHostToDevice, c.stream));
+            }
+            std::vector<ce_result> tmp(B);
+            run_device_batch(c, d_ref, d_dist, B, ref->width, ref->height, ref->cfg, intensity_target, tmp.data(), nullptr);
+            for (size_t k = 0; k < B; k++) out[ok[k]] = tmp[k];
+        }
+    })
+    return CE_OK;
+}
+
+CE_API int ce_reference_compare(ce_ctx* ctx, ce_ref* ref, const uint8_t* dist, size_t dist_len, float intensity_target,
+                                ce_result* out) {
+    if (!out) return CE_ERR_INVALID_ARGUMENT;
+    int st = ce_reference_compare_many(ctx, ref, &dist, &dist_len, 1, intensity_target, out);
+    return st != CE_OK ? st : out->status;
+}
+
+CE_API void ce_reference_destroy(ce_ref* ref) {
+    if (!ref) return;
+    if (ref->d_ref) {
+        cudaSetDevice(ref->owner->c.device);
+        cudaFree(ref->d_ref);
+    }
+    delete ref;
+}
+
+// ---- stage-level entry points ----------------------------------------------
+CE_API int ce_debug_ssim2_sums(ce_ctx* ctx, const uint8_t* ref, const uint8_t* dist, size_t width, size_t height, double* sums,
+                               int* nscales) {
+    ce_metric_config cfg = {0, 1, 0, 0, 0};
+    ce_result r;
+    DebugOut d;
+    d.s2_sums = sums;
+    d.s2_nscales = nscales;
+    return single_pair(ctx, ref, width * height * 3, dist, width * height * 3, width, height, cfg, 80.0f, &r, &d);
+}
+
+CE_API int ce_debug_ssim2_scale0_planes(ce_ctx* ctx, const uint8_t* ref, const uint8_t* dist, size_t width, size_t height,
+                                        float* planes) {
+    if (!ctx || !planes) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    const size_t n = width * height;
+    float* d_planes = nullptr;
+    int st;
+    try {
+        CE_CUDA(cudaSetDevice(c.device));
+        CE_CUDA(cudaMalloc(&d_planes, 21 * n * 4));
+    } catch (const std::exception& e) { c.last_error = e.what(); return CE_ERR_CUDA; }
+    ce_metric_config cfg = {0, 1, 0, 0, 0};
+    ce_result r;
+    DebugOut d;
+    d.s2_planes = d_planes;
+    st = single_pair(ctx, ref, n * 3, dist, n * 3, width, height, cfg, 80.0f, &r, &d);
+    if (st == CE_OK) cudaMemcpy(planes, d_planes, 21 * n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_planes);
+    return st;
+}
+
+CE_API int ce_debug_dssim_scales(ce_ctx* ctx, const uint8_t* ref, const uint8_t* dist, size_t width, size_t height,
+                                 double* scale_scores, int* nscales, float* map0) {
+    if (!ctx) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    const size_t n = width * height;
+    float* d_map = nullptr;
+    if (map0) {
+        try {
+            CE_CUDA(cudaSetDevice(c.device));
+            CE_CUDA(cudaMalloc(&d_map, n * 4));
+        } catch (const std::exception& e) { c.last_error = e.what(); return CE_ERR_CUDA; }
+    }
+    ce_metric_config cfg = {1, 0, 0, 0, 0};
+    ce_result r;
+    DebugOut d;
+    d.ds_scores = scale_scores;
+    d.ds_nscales = nscales;
+    d.ds_map0 = d_map;
+    int st = single_pair(ctx, ref, n * 3, dist, n * 3, width, height, cfg, 80.0f, &r, &d);
+    if (st == CE_OK && map0) cudaMemcpy(map0, d_map, n * 4, cudaMemcpyDeviceToHost);
+    if (d_map) cudaFree(d_map);
+    return st;
+}
+
+CE_API int ce_debug_butteraugli_diffmap(ce_ctx* ctx, const uint8_t* ref, const uint8_t* dist, size_t width, size_t height,
+                                        float intensity_target, float* diffmap) {
+    if (!ctx || !diffmap) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    const size_t n = width * height;
+    float* d_map = nullptr;
+    try {
+        CE_CUDA(cudaSetDevice(c.device));
+        CE_CUDA(cudaMalloc(&d_map, n * 4));
+    } catch (const std::exception& e) { c.last_error = e.what(); return CE_ERR_CUDA; }
+    ce_metric_config cfg = {0, 0, 1, 0, 0};
+    ce_result r;
+    DebugOut d;
+    d.ba_diffmap = d_map;
+    int st = single_pair(ctx, ref, n * 3, dist, n * 3, width, height, cfg, intensity_target, &r, &d);
+    if (st == CE_OK) cudaMemcpy(diffmap, d_map, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_map);
+    return st;
+}
+
+static int debug_ba_image(ce_ctx* ctx, const uint8_t* rgb, size_t width, size_t height, float intensity, float* planes, int nplanes,
+                          bool opsin) {
+    if (!ctx || !rgb || !planes) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    const size_t n = width * height;
+    if (width < 8 || height < 8) return CE_ERR_METRIC_CALCULATION;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        c.arena.reset();
+        uint8_t* d_in = c.arena.alloc<uint8_t>(n * 3);
+        float* lin = c.arena.alloc<float>(3 * n);
+        float* d_out = c.arena.alloc<float>((size_t)nplanes * n);
+        CE_CUDA(cudaMemcpyAsync(d_in, rgb, n * 3, cudaMemcpyHostToDevice, c.stream));
+        launch_srgb8_to_linear(c, d_in, 1, n, lin);
+        if (opsin) butteraugli_debug_opsin(c, lin, width, height, intensity, d_out);
+        else butteraugli_debug_psycho(c, lin, width, height, intensity, d_out);
+        CE_CUDA(cudaMemcpyAsync(planes, d_out, (size_t)nplanes * n * 4, cudaMemcpyDeviceToHost, c.stream));
+        CE_CUDA(cudaStreamSynchronize(c.stream));
+    })
+    return CE_OK;
+}
+CE_API int ce_debug_butteraugli_psycho(ce_ctx* ctx, const uint8_t* rgb, size_t width, size_t height, float intensity_target,
+                                       float* planes) {
+    return debug_ba_image(ctx, rgb, width, height, intensity_target, planes, 10, false);
+}
+CE_API int ce_debug_butteraugli_opsin(ce_ctx* ctx, const uint8_t* rgb, size_t width, size_t height, float intensity_target,
+                                      float* planes) {
+    return debug_ba_image(ctx, rgb, width, height, intensity_target, planes, 3, true);
+}
+CE_API int ce_debug_ba_blur(ce_ctx* ctx, const float* plane, size_t width, size_t height, float sigma, float* out) {
+    if (!ctx || !plane || !out) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    const size_t n = width * height;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        c.arena.reset();
+        float* d_in = c.arena.alloc<float>(n);
+        float* d_out = c.arena.alloc<float>(n);
+        CE_CUDA(cudaMemcpyAsync(d_in, plane, n * 4, cudaMemcpyHostToDevice, c.stream));
+        butteraugli_debug_blur(c, d_in, width, height, sigma, d_out);
+        CE_CUDA(cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, c.stream));
+        CE_CUDA(cudaStreamSynchronize(c.stream));
+    })
+    return CE_OK;
+}
+
+}  // extern "C"

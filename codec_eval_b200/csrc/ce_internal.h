@@ -1,0 +1,123 @@
+// ce_internal.h -- host-side internals of libce_gpu: context, workspace arena,
+// and the launchers each kernel file exports.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ce_gpu.h"
+
+namespace ce {
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+struct OomError : std::runtime_error {
+    explicit OomError(const std::string& s) : std::runtime_error(s) {}
+};
+
+#define CE_CUDA(expr)                                                                            \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            char _b[512];                                                                        \
+            snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            throw ::ce::CudaError(_b);                                                           \
+        }                                                                                        \
+    } while (0)
+
+// bump allocator over one cudaMalloc'd workspace
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0, high = 0;
+    template <class T>
+    T* alloc(size_t n) {
+        size_t o = (off + 255) & ~size_t(255);
+        size_t bytes = n * sizeof(T);
+        if (o + bytes > cap) throw OomError("workspace exhausted");
+        off = o + bytes;
+        if (off > high) high = off;
+        return reinterpret_cast<T*>(base + o);
+    }
+    size_t mark() const { return off; }
+    void release(size_t m) { off = m; }
+    void reset() { off = 0; }
+};
+
+// recursive-Gaussian coefficients (sigma 1.5), fp32
+struct RGaussCoef {
+    float mul_in[3], mul_prev[3], mul_prev2[3];
+};
+
+// truncated-Gaussian kernel for Butteraugli blurs
+struct BaKernel {
+    int radius;
+    float w[33];
+};
+
+struct Context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    Arena arena;
+    float* d_lut = nullptr;       // 256-entry sRGB->linear table
+    void* h_pinned = nullptr;     // pinned result staging
+    size_t h_pinned_bytes = 0;
+    void* d_results = nullptr;    // device result staging
+    size_t d_results_bytes = 0;
+    uint8_t* d_in = nullptr;      // device input staging for host-pointer entries
+    size_t d_in_bytes = 0;
+    RGaussCoef rg;
+    std::string last_error;
+    uint64_t launches = 0;
+    std::map<uint64_t, float*> ba_inv_cache;  // Butteraugli border-renormalisation tables
+    int sm_count = 148;
+
+    void ensure_input(size_t bytes);
+    void ensure_results(size_t bytes);
+};
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---------------- k_color.cu ----------------
+// RGB8 interleaved [n_img][h*w][3] -> planar fp32 [n_img][3][h*w] through the LUT
+void launch_srgb8_to_linear(Context& c, const uint8_t* d_rgb, size_t n_img, size_t npix, float* d_planes);
+// exact integer SSE per pair: d_sse[n] (zeroed inside)
+void launch_sse(Context& c, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, size_t bytes_per_img,
+                unsigned long long* d_sse);
+void launch_xyb_roundtrip(Context& c, const uint8_t* d_rgb, size_t npix_total, uint8_t* d_out);
+void launch_rgb8_to_rgba_linear(Context& c, const uint8_t* d_in, size_t npix, int in_channels, float* d_out);
+void launch_rgba_to_planar(Context& c, const float* d_rgba, size_t w, size_t h, size_t stride, float* d_planes4);
+
+// ---------------- k_ssim2.cu ----------------
+// lin1/lin2: [B][3][h*w] linear planes (consumed: downsampled in place into scratch);
+// d_sums: [B][6][18] doubles.  Returns number of scales.
+int ssim2_run(Context& c, const float* lin1, const float* lin2, size_t B, size_t w, size_t h, double* d_sums,
+              float* dbg_planes /* nullable, B==1: 3*7*h*w */);
+size_t ssim2_workspace_per_pair(size_t w, size_t h);
+void ssim2_init(Context& c);  // uploads the recursive-Gaussian coefficients
+
+// ---------------- k_dssim.cu ----------------
+// lin1/lin2: [B][3][h*w]; alpha1/alpha2 nullable [B][h*w]; d_out: [B][5][2] doubles (sum_map, sum_absdev)
+int dssim_run(Context& c, const float* lin1, const float* lin2, const float* alpha1, const float* alpha2, size_t B,
+              size_t w, size_t h, double* d_out, float* dbg_map0 /* nullable */);
+size_t dssim_workspace_per_pair(size_t w, size_t h);
+int dssim_num_scales(size_t w, size_t h, size_t* ws, size_t* hs);
+
+// ---------------- k_butteraugli.cu ----------------
+// lin1: [2B][3][h*w] with the B distorted images following the B references (lin2 == lin1 + B*3*h*w);
+// d_out: [B][4] doubles (max, sum d^3, sum d^6, sum d^12)
+void butteraugli_run(Context& c, const float* lin1, const float* lin2, size_t B, size_t w, size_t h, float intensity,
+                     double* d_out, float* dbg_diffmap /* nullable, B==1 */);
+size_t butteraugli_workspace_per_pair(size_t w, size_t h);
+void butteraugli_init(Context& c);  // uploads the blur kernels
+void butteraugli_debug_psycho(Context& c, const float* lin, size_t w, size_t h, float intensity, float* d_planes10);
+void butteraugli_debug_opsin(Context& c, const float* lin, size_t w, size_t h, float intensity, float* d_planes3);
+void butteraugli_debug_blur(Context& c, const float* in, size_t w, size_t h, float sigma, float* out);
+
+}  // namespace ce

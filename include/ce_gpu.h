@@ -1,0 +1,170 @@
+/*
+ * ce_gpu.h -- C ABI of libce_gpu.so: codec-eval's metric hot path
+ * (SSIMULACRA2, DSSIM, Butteraugli, PSNR, XYB round-trip) as sm_100a CUDA
+ * kernels.  Plain pointers and sizes only; no exceptions cross the boundary.
+ *
+ * Each entry point names the reference interface it replaces (paths relative
+ * to the imazen/codec-eval tree).  A Rust `-sys` crate binds these 1:1, see
+ * INTEGRATION.md and rust/ce-gpu-sys.
+ *
+ * There is no CPU fallback: every compute entry returns CE_ERR_CUDA if no
+ * sm_100 device is usable.
+ */
+#ifndef CE_GPU_H
+#define CE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CE_API __attribute__((visibility("default")))
+#else
+#define CE_API
+#endif
+
+/* status codes.  1 and 2 map onto codec_eval::Error variants (src/error.rs:33,42). */
+enum {
+    CE_OK = 0,
+    CE_ERR_DIMENSION_MISMATCH = 1, /* Error::DimensionMismatch  */
+    CE_ERR_METRIC_CALCULATION = 2, /* Error::MetricCalculation  */
+    CE_ERR_INVALID_ARGUMENT = 3,   /* null pointer / bad context (a Rust panic / assert in the reference) */
+    CE_ERR_CUDA = 4,               /* CUDA runtime failure; text in ce_last_error() */
+    CE_ERR_OUT_OF_MEMORY = 5       /* workspace too small even for one pair */
+};
+
+/* one CUDA device + stream + workspace; single owner (!Sync), like
+ * GpuSsim2 (crates/codec-iter/src/gpu.rs:21-38). */
+typedef struct ce_ctx ce_ctx;
+
+/* = MetricConfig, src/metrics/mod.rs:45-63 (five bools, same order) */
+typedef struct {
+    uint8_t dssim, ssimulacra2, butteraugli, psnr, xyb_roundtrip;
+} ce_metric_config;
+
+/* one reference/distorted pair in HOST memory: RGB8, row-major, tight stride
+ * (src/metrics/ssimulacra2.rs:41-44).  ref_len/dist_len are the slice lengths
+ * the Rust caller holds (they drive the same validation, in the same order,
+ * as ssimulacra2.rs:65-82).  ref_id groups pairs that share a reference
+ * (evaluate_image's codecs x quality_levels, src/eval/session.rs:375-431). */
+typedef struct {
+    const uint8_t* ref;
+    const uint8_t* dist;
+    size_t ref_len, dist_len;
+    uint32_t width, height;
+    uint32_t ref_id;
+    uint32_t reserved;
+} ce_pair;
+
+/* = MetricResult (4 x Option<f64>, src/metrics/mod.rs:139-149) + raw SSE and
+ * the libjxl 3-norm.  valid bit0 dssim, bit1 ssimulacra2, bit2 butteraugli,
+ * bit3 psnr  <->  Some(..). */
+typedef struct {
+    int32_t status;
+    uint32_t valid;
+    uint64_t sse; /* exact sum of squared byte differences (PSNR bit-exactness) */
+    double dssim, ssimulacra2, butteraugli, psnr, butteraugli_pnorm3;
+} ce_result;
+
+#define CE_VALID_DSSIM 1u
+#define CE_VALID_SSIMULACRA2 2u
+#define CE_VALID_BUTTERAUGLI 4u
+#define CE_VALID_PSNR 8u
+
+/* ---- context ------------------------------------------------------- */
+
+/* replaces GpuSsim2::new (crates/codec-iter/src/gpu.rs:40-77).  workspace_bytes
+ * = device scratch for intermediates (0 = default: half of free memory, at most
+ * 24 GiB); batches larger than the workspace are processed in sub-batches. */
+CE_API int ce_ctx_create(ce_ctx** out, int device, size_t workspace_bytes);
+CE_API void ce_ctx_destroy(ce_ctx* ctx);
+/* run all work on the caller's CUDA stream (cudaStream_t); NULL = the context's own stream */
+CE_API int ce_ctx_set_stream(ce_ctx* ctx, void* cuda_stream);
+/* text for Error::MetricCalculation.reason / CUDA failures; valid until the next call on ctx.
+ * ctx == NULL returns the message of the last failed ce_ctx_create on this thread. */
+CE_API const char* ce_last_error(const ce_ctx* ctx);
+/* number of this library's kernels launched on ctx since creation */
+CE_API uint64_t ce_launch_count(const ce_ctx* ctx);
+CE_API const char* ce_version(void);
+
+/* ---- batched entry points ------------------------------------------ */
+
+/* The batched GPU entry point that EvalSession::calculate_metrics
+ * (src/eval/session.rs:437-497) and evaluate_single (src/eval/helpers.rs:105-173)
+ * dispatch into: n host pairs -> n results, same metric order and the same
+ * "reference only" XYB round-trip rule (session.rs:447-456).  Host->device copies
+ * happen inside.  A failing pair sets out[i].status and does not poison the batch;
+ * the return value is CE_OK unless the call itself could not run. */
+CE_API int ce_evaluate_batch(ce_ctx* ctx, const ce_pair* pairs, size_t n, const ce_metric_config* cfg,
+                             float intensity_target, ce_result* out);
+
+/* Same computation for a uniform-size batch already resident in device memory:
+ * d_ref / d_dist hold n tightly packed RGB8 images of width x height (the
+ * benchmark's timed entry; also what an on-device decoder would call). */
+CE_API int ce_evaluate_batch_device(ce_ctx* ctx, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, uint32_t width,
+                                    uint32_t height, const ce_metric_config* cfg, float intensity_target,
+                                    ce_result* out);
+
+/* ---- single-pair mirrors of src/metrics ----------------------------- */
+
+/* calculate_psnr, src/metrics/mod.rs:312-331 (length asserts become CE_ERR_INVALID_ARGUMENT) */
+CE_API int ce_psnr(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, const uint8_t* test, size_t test_len, size_t width,
+                   size_t height, double* psnr, uint64_t* sse);
+/* calculate_ssimulacra2, src/metrics/ssimulacra2.rs:59-100 */
+CE_API int ce_ssimulacra2(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, const uint8_t* test, size_t test_len,
+                          size_t width, size_t height, double* score);
+/* calculate_butteraugli / calculate_butteraugli_with_intensity, src/metrics/butteraugli.rs:45-81,99-136
+ * (default intensity_target 80.0); pnorm3 may be NULL */
+CE_API int ce_butteraugli(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, const uint8_t* test, size_t test_len,
+                          size_t width, size_t height, float intensity_target, double* score, double* pnorm3);
+/* rgb8_to_dssim_image x2 + calculate_dssim fused, src/metrics/dssim.rs:102-114,40-71 / session.rs:467-476 */
+CE_API int ce_dssim_rgb8(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, const uint8_t* test, size_t test_len,
+                         size_t width, size_t height, double* dssim);
+/* calculate_dssim on linear RGBA f32 (ImgVec<RGBA<f32>>), src/metrics/dssim.rs:40-71; strides in pixels */
+CE_API int ce_dssim_rgbaf32(ce_ctx* ctx, const float* ref, size_t ref_w, size_t ref_h, size_t ref_stride,
+                            const float* test, size_t test_w, size_t test_h, size_t test_stride, double* dssim);
+/* rgb8_to_dssim_image / rgba8_to_dssim_image, src/metrics/dssim.rs:102-114,131-143: out = width*height*4 floats */
+CE_API int ce_rgb8_to_dssim_image(ce_ctx* ctx, const uint8_t* data, size_t len, size_t width, size_t height, float* out);
+CE_API int ce_rgba8_to_dssim_image(ce_ctx* ctx, const uint8_t* data, size_t len, size_t width, size_t height, float* out);
+/* xyb_roundtrip, src/metrics/xyb.rs:225-253: out = width*height*3 bytes */
+CE_API int ce_xyb_roundtrip(ce_ctx* ctx, const uint8_t* rgb, size_t len, size_t width, size_t height, uint8_t* out);
+
+/* ---- reference reuse ------------------------------------------------ */
+/* mirrors fast_ssim2::Ssimulacra2Reference::new / .compare as used by
+ * crates/codec-iter/src/eval.rs:138-149,84-88: the reference image stays on the
+ * device; each compare uploads only the distorted image. */
+typedef struct ce_ref ce_ref;
+CE_API int ce_reference_create(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, size_t width, size_t height,
+                               const ce_metric_config* cfg, ce_ref** out);
+CE_API int ce_reference_compare(ce_ctx* ctx, ce_ref* ref, const uint8_t* dist, size_t dist_len, float intensity_target,
+                                ce_result* out);
+/* all distortions of one reference in one launch set (dists: n_dist host pointers) */
+CE_API int ce_reference_compare_many(ce_ctx* ctx, ce_ref* ref, const uint8_t* const* dists, const size_t* dist_lens,
+                                     size_t n_dist, float intensity_target, ce_result* out);
+CE_API void ce_reference_destroy(ce_ref* ref);
+
+/* ---- stage-level entry points (parity tests; device does the work) -- */
+/* Each runs ONE pipeline stage on the device for a single host image / pair
+ * and returns the intermediate, so tests can localise a mismatch against the
+ * oracle's same stage.  Not part of the reference's API. */
+CE_API int ce_debug_ssim2_sums(ce_ctx* ctx, const uint8_t* ref, const uint8_t* dist, size_t width, size_t height,
+                               double* sums /* 6*18 */, int* nscales);
+CE_API int ce_debug_ssim2_scale0_planes(ce_ctx* ctx, const uint8_t* ref, const uint8_t* dist, size_t width,
+                                        size_t height, float* planes /* 3*7*h*w: i1,i2,mu1,mu2,s11,s22,s12 */);
+CE_API int ce_debug_dssim_scales(ce_ctx* ctx, const uint8_t* ref, const uint8_t* dist, size_t width, size_t height,
+                                 double* scale_scores /* 5 */, int* nscales, float* map0 /* h*w or NULL */);
+CE_API int ce_debug_butteraugli_diffmap(ce_ctx* ctx, const uint8_t* ref, const uint8_t* dist, size_t width,
+                                        size_t height, float intensity_target, float* diffmap /* h*w */);
+CE_API int ce_debug_butteraugli_psycho(ce_ctx* ctx, const uint8_t* rgb, size_t width, size_t height,
+                                       float intensity_target, float* planes /* 10*h*w */);
+CE_API int ce_debug_butteraugli_opsin(ce_ctx* ctx, const uint8_t* rgb, size_t width, size_t height,
+                                      float intensity_target, float* planes /* 3*h*w */);
+CE_API int ce_debug_ba_blur(ce_ctx* ctx, const float* plane, size_t width, size_t height, float sigma, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CE_GPU_H */

@@ -1,0 +1,395 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the
+CPU oracle on the same seeded inputs and against the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): PSNR SSE bit-exact; SSIMULACRA2 0.01 absolute; DSSIM 1e-4 relative;
+Butteraugli max / 3-norm 1e-3 relative.  The kernels execute the oracle's fp32 operation sequence, so the
+observed differences are far smaller; tests assert the contract tolerance AND report the observed gap.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from codec_eval_b200.synth import G, cheap_distort
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "pairs.npz")
+
+S2_TOL = 0.01
+DS_RTOL = 1e-4
+BA_RTOL = 1e-3
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _cases(gold):
+    for k, row in enumerate(gold["table"]):
+        yield k, int(row[1]), int(row[2]), gold[f"ref{k}"], gold[f"dist{k}"], row
+
+
+# ------------------------------------------------------------------ PSNR
+def test_psnr_sse_bit_exact_golden(gpu, O, gold):
+    for k, w, h, ref, dist, row in _cases(gold):
+        assert gpu.calculate_sse(ref, dist, w, h) == int(row[5]) == O.sse(ref, dist)
+        assert gpu.calculate_psnr(ref, dist, w, h) == row[6]
+
+
+def test_psnr_reference_rows(gpu):
+    data = np.full(100 * 100 * 3, 128, np.uint8)
+    assert np.isinf(gpu.calculate_psnr(data, data, 100, 100))
+    a = np.full(100 * 100 * 3, 100, np.uint8)
+    b = np.full(100 * 100 * 3, 110, np.uint8)
+    assert 28.0 < gpu.calculate_psnr(a, b, 100, 100) < 29.0
+    with pytest.raises(AssertionError):
+        gpu.calculate_psnr(a, b[:-3], 100, 100)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (3, 5), (17, 9), (333, 77), (1024, 1024), (3840, 2160)])
+def test_psnr_sse_random_sizes(gpu, O, w, h):
+    rng = np.random.default_rng(w * 7 + h)
+    a = rng.integers(0, 256, w * h * 3, dtype=np.uint8)
+    b = rng.integers(0, 256, w * h * 3, dtype=np.uint8)
+    assert gpu.calculate_sse(a, b, w, h) == O.sse(a, b)
+    # extremes: max difference everywhere
+    z = np.zeros(w * h * 3, np.uint8)
+    f = np.full(w * h * 3, 255, np.uint8)
+    assert gpu.calculate_sse(z, f, w, h) == w * h * 3 * 65025
+
+
+# ------------------------------------------------------------------ XYB round trip
+def test_xyb_roundtrip_exact(gpu, O, gold):
+    g = np.arange(0, 256, 16, dtype=np.uint8)
+    cube = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    out = gpu.xyb_roundtrip(cube, cube.shape[0], 1)
+    exp = O.xyb_roundtrip(cube, cube.shape[0], 1)
+    assert np.array_equal(out, exp)
+    md = np.abs(out.reshape(-1, 3).astype(int) - cube.astype(int)).max()
+    assert 0 < md <= 30
+    rng = np.random.default_rng(5)
+    rnd = rng.integers(0, 256, 200 * 100 * 3, dtype=np.uint8)
+    out = gpu.xyb_roundtrip(rnd, 200, 100)
+    exp = O.xyb_roundtrip(rnd, 200, 100)
+    nbad = int((out != exp).sum())
+    assert nbad == 0, f"{nbad} of {rnd.size} bytes differ, max {np.abs(out.astype(int) - exp.astype(int)).max()}"
+    assert np.array_equal(gpu.xyb_roundtrip(gold["ref0"], 64, 64).reshape(64, 64, 3), gold["xyb_rt0"])
+
+
+# ------------------------------------------------------------------ sRGB -> linear
+def test_rgb8_to_dssim_image(gpu, O):
+    img = gpu.rgb8_to_dssim_image(np.array([255, 255, 255, 0, 0, 0], np.uint8), 2, 1)
+    assert abs(img[0, 0, 0] - 1.0) < 1e-3 and img[0, 0, 3] == 1.0 and abs(img[0, 1, 0]) < 1e-3
+    img = gpu.rgba8_to_dssim_image(np.array([255, 255, 255, 255, 0, 0, 0, 128], np.uint8), 2, 1)
+    assert abs(img[0, 0, 3] - 1.0) < 1e-3 and abs(img[0, 1, 3] - 0.502) < 0.01
+    ramp = np.repeat(np.arange(256, dtype=np.uint8), 3)
+    assert np.array_equal(gpu.rgb8_to_dssim_image(ramp, 256, 1), O.rgb8_to_dssim_image(ramp, 256, 1))
+
+
+# ------------------------------------------------------------------ SSIMULACRA2
+def test_ssim2_stage_planes(gpu, O, gold):
+    """scale-0 planes: positive XYB, mu1, mu2, s11, s22, s12 -- localises a mismatch to the colour kernel,
+    the row pass or the column pass."""
+    import ctypes as C
+
+    for k in (0, 2):
+        w, h = int(gold["table"][k][1]), int(gold["table"][k][2])
+        ref, dist = np.ascontiguousarray(gold[f"ref{k}"]), np.ascontiguousarray(gold[f"dist{k}"])
+        exp = O.ssimulacra2_scale0_planes(ref, dist, w, h)
+        got = np.empty((3, 7, h, w), np.float32)
+        st = gpu._L.ce_debug_ssim2_scale0_planes(gpu._h, ref.ctypes.data, dist.ctypes.data, w, h, got.ctypes.data)
+        assert st == 0, gpu.last_error()
+        names = ["i1", "i2", "mu1", "mu2", "s11", "s22", "s12"]
+        for c in range(3):
+            for p in range(7):
+                d = np.abs(got[c, p] - exp[c, p]).max()
+                assert d <= 1e-6, f"case {k} channel {c} plane {names[p]} max abs diff {d}"
+
+
+def test_ssim2_scale_sums(gpu, O, gold):
+    import ctypes as C
+
+    for k, w, h, ref, dist, row in _cases(gold):
+        ref, dist = np.ascontiguousarray(ref), np.ascontiguousarray(dist)
+        _, exp = O.ssimulacra2_ex(ref, dist, w, h)
+        got = np.zeros(6 * 18, np.float64)
+        ns = C.c_int()
+        st = gpu._L.ce_debug_ssim2_sums(gpu._h, ref.ctypes.data, dist.ctypes.data, w, h,
+                                        got.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ns))
+        assert st == 0, gpu.last_error()
+        assert ns.value == exp.shape[0]
+        got = got.reshape(6, 18)[: ns.value]
+        err = np.abs(got - exp) / np.maximum(np.abs(exp), 1e-12)
+        assert err.max() < 1e-6, f"case {k}: worst scale/feature {np.unravel_index(err.argmax(), err.shape)} rel {err.max()}"
+
+
+def test_ssim2_scores_golden(gpu, O, gold):
+    worst = 0.0
+    for k, w, h, ref, dist, row in _cases(gold):
+        got = gpu.calculate_ssimulacra2(ref, dist, w, h)
+        worst = max(worst, abs(got - row[7]))
+        assert abs(got - row[7]) < S2_TOL, (k, got, row[7])
+    print("ssimulacra2 worst |gpu-oracle| =", worst)
+    assert worst < 1e-4
+
+
+def test_ssim2_reference_rows(gpu):
+    ref = (np.arange(100 * 100 * 3) % 256).astype(np.uint8)
+    assert gpu.calculate_ssimulacra2(ref, ref, 100, 100) > 99.0
+    a = np.full(100 * 100 * 3, 100, np.uint8)
+    b = np.full(100 * 100 * 3, 200, np.uint8)
+    assert gpu.calculate_ssimulacra2(a, b, 100, 100) < 80.0
+    from codec_eval_b200.metrics import DimensionMismatch, MetricCalculation
+
+    with pytest.raises(DimensionMismatch):   # ssimulacra2.rs:177-182
+        gpu.calculate_ssimulacra2(np.zeros(50 * 50 * 3, np.uint8), np.zeros(100 * 100 * 3, np.uint8), 50, 50)
+    with pytest.raises(MetricCalculation):   # len != w*h*3
+        gpu.calculate_ssimulacra2(np.zeros(50 * 50 * 3, np.uint8), np.zeros(50 * 50 * 3, np.uint8), 60, 50)
+    with pytest.raises(MetricCalculation):   # below 8x8
+        gpu.calculate_ssimulacra2(np.zeros(7 * 9 * 3, np.uint8), np.zeros(7 * 9 * 3, np.uint8), 7, 9)
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (9, 33), (100, 100), (513, 255), (768, 512)])
+def test_ssim2_shapes_vs_oracle(gpu, O, w, h):
+    ref = G(w + h, w, h)
+    dist = cheap_distort(ref, 70, seed=w)
+    got, exp = gpu.calculate_ssimulacra2(ref, dist, w, h), O.ssimulacra2(ref, dist, w, h)
+    assert abs(got - exp) < S2_TOL, (got, exp)
+    assert gpu.calculate_ssimulacra2(ref, ref, w, h) == 100.0
+
+
+# ------------------------------------------------------------------ DSSIM
+def test_dssim_scales_and_map(gpu, O, gold):
+    import ctypes as C
+
+    for k in (0, 2, 3):
+        w, h = int(gold["table"][k][1]), int(gold["table"][k][2])
+        ref, dist = np.ascontiguousarray(gold[f"ref{k}"]), np.ascontiguousarray(gold[f"dist{k}"])
+        exp, exp_sc, exp_map = O.dssim_ex(ref, dist, w, h)
+        sc = np.zeros(5, np.float64)
+        ns = C.c_int()
+        m = np.empty((h, w), np.float32)
+        st = gpu._L.ce_debug_dssim_scales(gpu._h, ref.ctypes.data, dist.ctypes.data, w, h,
+                                          sc.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ns), m.ctypes.data)
+        assert st == 0, gpu.last_error()
+        assert ns.value == len(exp_sc)
+        assert np.abs(m - exp_map).max() <= 1e-6, f"case {k}: ssim map max abs diff {np.abs(m - exp_map).max()}"
+        assert np.abs(sc[: ns.value] - exp_sc).max() < 1e-9, (sc, exp_sc)
+
+
+def test_dssim_golden(gpu, gold):
+    worst = 0.0
+    for k, w, h, ref, dist, row in _cases(gold):
+        got = gpu.calculate_dssim_rgb8(ref, dist, w, h)
+        worst = max(worst, rel(got, row[8]))
+        assert rel(got, row[8]) < DS_RTOL, (k, got, row[8])
+    print("dssim worst rel =", worst)
+    assert worst < 1e-6
+
+
+def test_dssim_reference_rows(gpu, O):
+    from codec_eval_b200.metrics import DimensionMismatch
+
+    a = np.full((100, 100, 4), 0.5, np.float32)
+    a[..., 3] = 1.0
+    assert gpu.calculate_dssim(a, a) < 1e-4
+    b = np.full((100, 100, 4), 0.3, np.float32)
+    c = np.full((100, 100, 4), 0.7, np.float32)
+    b[..., 3] = c[..., 3] = 1.0
+    got = gpu.calculate_dssim(b, c)
+    assert got > 0.0 and rel(got, O.dssim_rgbaf32(b, c, 100, 100)) < DS_RTOL
+    with pytest.raises(DimensionMismatch):  # dssim.rs:226-249
+        gpu.calculate_dssim(np.zeros((100, 100, 4), np.float32), np.zeros((50, 50, 4), np.float32))
+
+
+def test_dssim_alpha_path(gpu, O):
+    rng = np.random.default_rng(3)
+    a = rng.random((40, 56, 4), dtype=np.float32)
+    b = np.clip(a + rng.normal(0, 0.03, a.shape).astype(np.float32), 0, 1).astype(np.float32)
+    got, exp = gpu.calculate_dssim(a, b), O.dssim_rgbaf32(a, b, 56, 40)
+    assert rel(got, exp) < DS_RTOL, (got, exp)
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (9, 33), (100, 100), (513, 255), (768, 512)])
+def test_dssim_shapes_vs_oracle(gpu, O, w, h):
+    ref = G(w + h, w, h)
+    dist = cheap_distort(ref, 70, seed=w)
+    got, exp = gpu.calculate_dssim_rgb8(ref, dist, w, h), O.dssim(ref, dist, w, h)
+    assert rel(got, exp) < DS_RTOL, (got, exp)
+    assert gpu.calculate_dssim_rgb8(ref, ref, w, h) == 0.0
+
+
+# ------------------------------------------------------------------ Butteraugli
+@pytest.mark.parametrize("sigma", [1.2, 1.56416327805, 2.7, 3.22489901262, 7.15593339443])
+def test_ba_blur_stage(gpu, O, sigma):
+    rng = np.random.default_rng(11)
+    for (w, h) in [(40, 24), (200, 130), (13, 70)]:
+        p = (rng.random((h, w), dtype=np.float32) * 100).astype(np.float32)
+        out = np.empty_like(p)
+        st = gpu._L.ce_debug_ba_blur(gpu._h, p.ctypes.data, w, h, sigma, out.ctypes.data)
+        assert st == 0, gpu.last_error()
+        exp = O.ba_blur(p, sigma)
+        d = np.abs(out - exp).max()
+        assert d <= 1e-5, f"sigma {sigma} {w}x{h}: max abs diff {d} at {np.unravel_index(np.abs(out - exp).argmax(), p.shape)}"
+
+
+def test_ba_opsin_and_psycho_stages(gpu, O, gold):
+    for k in (0, 2):
+        w, h = int(gold["table"][k][1]), int(gold["table"][k][2])
+        ref = np.ascontiguousarray(gold[f"dist{k}"])
+        exp = O.butteraugli_opsin(ref, w, h)
+        got = np.empty((3, h, w), np.float32)
+        st = gpu._L.ce_debug_butteraugli_opsin(gpu._h, ref.ctypes.data, w, h, 80.0, got.ctypes.data)
+        assert st == 0, gpu.last_error()
+        for c in range(3):
+            d = np.abs(got[c] - exp[c]).max()
+            assert d <= 1e-4 * max(1.0, np.abs(exp[c]).max()), f"opsin plane {c}: {d}"
+        exp = O.butteraugli_psycho(ref, w, h)
+        got = np.empty((10, h, w), np.float32)
+        st = gpu._L.ce_debug_butteraugli_psycho(gpu._h, ref.ctypes.data, w, h, 80.0, got.ctypes.data)
+        assert st == 0, gpu.last_error()
+        names = ["lf_x", "lf_y", "lf_b", "mf_x", "mf_y", "mf_b", "hf_x", "hf_y", "uhf_x", "uhf_y"]
+        for p in range(10):
+            d = np.abs(got[p] - exp[p]).max()
+            assert d <= 1e-4 * max(1.0, np.abs(exp[p]).max()), f"case {k} psycho plane {names[p]}: max abs diff {d}"
+
+
+def test_ba_diffmap(gpu, O, gold):
+    for k in (0, 2, 4):
+        w, h = int(gold["table"][k][1]), int(gold["table"][k][2])
+        ref, dist = np.ascontiguousarray(gold[f"ref{k}"]), np.ascontiguousarray(gold[f"dist{k}"])
+        _, _, exp = O.butteraugli_ex(ref, dist, w, h)
+        got = np.empty((h, w), np.float32)
+        st = gpu._L.ce_debug_butteraugli_diffmap(gpu._h, ref.ctypes.data, dist.ctypes.data, w, h, 80.0, got.ctypes.data)
+        assert st == 0, gpu.last_error()
+        d = np.abs(got - exp)
+        assert d.max() <= 1e-4 * exp.max(), f"case {k}: diffmap max abs diff {d.max()} at {np.unravel_index(d.argmax(), d.shape)} (max value {exp.max()})"
+
+
+def test_butteraugli_golden(gpu, gold):
+    worst = 0.0
+    for k, w, h, ref, dist, row in _cases(gold):
+        mx, pn = gpu.calculate_butteraugli(ref, dist, w, h, return_pnorm=True)
+        worst = max(worst, rel(mx, row[9]), rel(pn, row[10]))
+        assert rel(mx, row[9]) < BA_RTOL and rel(pn, row[10]) < BA_RTOL, (k, mx, row[9], pn, row[10])
+    print("butteraugli worst rel =", worst)
+    assert worst < 1e-5
+
+
+def test_butteraugli_reference_rows(gpu, O):
+    from codec_eval_b200.metrics import DimensionMismatch, MetricCalculation
+
+    ref = (np.arange(100 * 100 * 3) % 256).astype(np.uint8)
+    assert gpu.calculate_butteraugli(ref, ref, 100, 100) < 0.01
+    a = np.full(100 * 100 * 3, 100, np.uint8)
+    b = np.full(100 * 100 * 3, 200, np.uint8)
+    assert gpu.calculate_butteraugli(a, b, 100, 100) > 1.0
+    assert gpu.calculate_butteraugli_with_intensity(ref, ref, 100, 100, 250.0) < 0.01
+    with pytest.raises(DimensionMismatch):
+        gpu.calculate_butteraugli(np.zeros(50 * 50 * 3, np.uint8), np.zeros(100 * 100 * 3, np.uint8), 50, 50)
+    with pytest.raises(MetricCalculation):
+        gpu.calculate_butteraugli(np.zeros(4 * 4 * 3, np.uint8), np.zeros(4 * 4 * 3, np.uint8), 4, 4)
+    d = cheap_distort(G(1, 100, 100), 60)
+    got = gpu.calculate_butteraugli_with_intensity(G(1, 100, 100), d, 100, 100, 250.0)
+    assert rel(got, O.butteraugli(G(1, 100, 100), d, 100, 100, 250.0)[0]) < BA_RTOL
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (15, 17), (100, 100), (513, 255), (768, 512)])
+def test_butteraugli_shapes_vs_oracle(gpu, O, w, h):
+    ref = G(w + h, w, h)
+    dist = cheap_distort(ref, 70, seed=w)
+    mx, pn = gpu.calculate_butteraugli(ref, dist, w, h, return_pnorm=True)
+    emx, epn = O.butteraugli(ref, dist, w, h)
+    assert rel(mx, emx) < BA_RTOL and rel(pn, epn) < BA_RTOL, (mx, emx, pn, epn)
+    assert gpu.calculate_butteraugli(ref, ref, w, h) == 0.0
+
+
+# ------------------------------------------------------------------ batched entry
+def test_evaluate_batch_mixed(gpu, O, gold):
+    from codec_eval_b200.metrics import MetricConfig
+
+    pairs = []
+    for k, w, h, ref, dist, row in _cases(gold):
+        pairs.append((ref, dist, w, h))
+    pairs.append((gold["ref0"], gold["ref0"], 64, 64))            # identical
+    pairs.append((gold["ref1"], gold["dist1"], 96, 80))           # duplicate size group
+    res = gpu.evaluate_batch(pairs, MetricConfig.all())
+    for k, row in enumerate(gold["table"]):
+        r = res[k]
+        assert r.sse == int(row[5]) and r.psnr == row[6]
+        assert abs(r.ssimulacra2 - row[7]) < S2_TOL
+        assert rel(r.dssim, row[8]) < DS_RTOL
+        assert rel(r.butteraugli, row[9]) < BA_RTOL and rel(r.butteraugli_pnorm3, row[10]) < BA_RTOL
+    ident = res[len(gold["table"])]
+    assert ident.sse == 0 and np.isinf(ident.psnr) and ident.ssimulacra2 == 100.0 and ident.dssim == 0.0 and ident.butteraugli == 0.0
+    assert res[-1].ssimulacra2 == res[1].ssimulacra2 and res[-1].dssim == res[1].dssim
+
+
+def test_evaluate_batch_status_isolated(gpu, gold):
+    from codec_eval_b200 import _lib
+    from codec_eval_b200.metrics import MetricConfig
+
+    good = (gold["ref0"], gold["dist0"], 64, 64)
+    bad_len = (gold["ref0"], gold["dist1"], 64, 64)
+    bad_size = (gold["ref0"], gold["dist0"], 65, 64)
+    out = gpu.evaluate_batch_raw([good, bad_len, bad_size, good], MetricConfig.all())
+    assert [out[i].status for i in range(4)] == [0, _lib.CE_ERR_DIMENSION_MISMATCH, _lib.CE_ERR_METRIC_CALCULATION, 0]
+    assert out[0].ssimulacra2 == out[3].ssimulacra2 and out[0].valid == 15 and out[1].valid == 0
+    assert len(gpu.evaluate_batch([], MetricConfig.all())) == 0
+
+
+def test_xyb_roundtrip_config_applies_to_reference_only(gpu, O, gold):
+    from codec_eval_b200.metrics import MetricConfig
+
+    ref, dist = gold["ref0"], gold["dist0"]
+    r = gpu.evaluate_batch([(ref, dist, 64, 64)], MetricConfig.all().with_xyb_roundtrip())[0]
+    rt = O.xyb_roundtrip(ref, 64, 64)
+    assert r.sse == O.sse(rt, dist)
+    assert abs(r.ssimulacra2 - O.ssimulacra2(rt, dist, 64, 64)) < S2_TOL
+    assert rel(r.dssim, O.dssim(rt, dist, 64, 64)) < DS_RTOL
+    assert rel(r.butteraugli, O.butteraugli(rt, dist, 64, 64)[0]) < BA_RTOL
+
+
+def test_reference_handle(gpu, gold):
+    from codec_eval_b200.metrics import GpuReference, MetricConfig
+
+    ref = GpuReference(gpu, gold["ref3"], 256, 256, MetricConfig.ssimulacra2_only())
+    a = ref.compare(gold["dist3"]).ssimulacra2
+    many = ref.compare_many([gold["dist3"], gold["ref3"]])
+    assert a == many[0].ssimulacra2 == gpu.calculate_ssimulacra2(gold["ref3"], gold["dist3"], 256, 256)
+    assert many[1].ssimulacra2 == 100.0
+    ref.close()
+
+
+def test_device_batch_sub_batching_and_determinism(gpu, O):
+    """A device-resident uniform batch larger than one sub-batch of a small workspace; two runs bit-identical."""
+    import torch
+
+    from codec_eval_b200.metrics import GpuMetrics, MetricConfig
+
+    w, h, n = 128, 96, 24
+    refs = np.stack([G(i, w, h) for i in range(n)])
+    dists = np.stack([cheap_distort(refs[i], 40 + 2 * i, seed=i) for i in range(n)])
+    d_ref = torch.from_numpy(refs).cuda()
+    d_dist = torch.from_numpy(dists).cuda()
+    small = GpuMetrics(0, workspace_bytes=64 << 20)   # forces several sub-batches for Butteraugli
+    try:
+        small.set_stream(torch.cuda.current_stream().cuda_stream)
+        a = small.evaluate_batch_device(d_ref.data_ptr(), d_dist.data_ptr(), n, w, h, MetricConfig.all())
+        b = small.evaluate_batch_device(d_ref.data_ptr(), d_dist.data_ptr(), n, w, h, MetricConfig.all())
+        assert small.launch_count() > 0
+    finally:
+        small.close()
+    for i in range(n):
+        assert (a[i].sse, a[i].ssimulacra2, a[i].dssim, a[i].butteraugli, a[i].butteraugli_pnorm3) == \
+               (b[i].sse, b[i].ssimulacra2, b[i].dssim, b[i].butteraugli, b[i].butteraugli_pnorm3)
+    for i in (0, 7, 23):
+        assert a[i].sse == O.sse(refs[i], dists[i])
+        assert abs(a[i].ssimulacra2 - O.ssimulacra2(refs[i], dists[i], w, h)) < S2_TOL
+        assert rel(a[i].dssim, O.dssim(refs[i], dists[i], w, h)) < DS_RTOL
+        assert rel(a[i].butteraugli, O.butteraugli(refs[i], dists[i], w, h)[0]) < BA_RTOL

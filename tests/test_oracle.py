@@ -1,0 +1,175 @@
+"""CPU tests of the oracle: the reference's own unit-test rows re-expressed
+against oracle/ce_oracle.c, plus the committed golden table and structural properties."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "pairs.npz")
+
+
+# ---- src/metrics/mod.rs:369-383
+def test_psnr_identical(O):
+    data = np.full(100 * 100 * 3, 128, np.uint8)
+    assert np.isinf(O.psnr(data, data, 100, 100))
+
+
+def test_psnr_different(O):
+    ref = np.full(100 * 100 * 3, 100, np.uint8)
+    test = np.full(100 * 100 * 3, 110, np.uint8)
+    p = O.psnr(ref, test, 100, 100)
+    assert 28.0 < p < 29.0
+    assert abs(p - 10 * np.log10(255.0 ** 2 / 100.0)) < 1e-12
+    assert O.sse(ref, test) == 100 * 100 * 3 * 100
+    assert O.psnr_from_sse(O.sse(ref, test), 100, 100) == p
+
+
+# ---- src/metrics/ssimulacra2.rs:154-182
+def test_ssim2_identical_images(O):
+    ref = (np.arange(100 * 100 * 3) % 256).astype(np.uint8)
+    assert O.ssimulacra2(ref, ref, 100, 100) > 99.0
+    assert O.ssimulacra2(ref, ref, 100, 100) == 100.0
+
+
+def test_ssim2_different_images(O):
+    ref = np.full(100 * 100 * 3, 100, np.uint8)
+    test = np.full(100 * 100 * 3, 200, np.uint8)
+    assert O.ssimulacra2(ref, test, 100, 100) < 80.0
+
+
+def test_ssim2_too_small(O):
+    a = np.zeros(7 * 7 * 3, np.uint8)
+    with pytest.raises(O.OracleError):
+        O.ssimulacra2(a, a, 7, 7)
+
+
+def test_ssim2_scale_count(O):
+    # upstream checks the size before halving: 64x64 and 100x100 run 5 scales, >= 256 min side runs 6
+    for (w, h, ns) in [(64, 64, 5), (100, 100, 5), (256, 256, 6), (8, 8, 2), (40, 24, 3)]:
+        a = (np.arange(w * h * 3) % 251).astype(np.uint8)
+        _, sums = O.ssimulacra2_ex(a, a, w, h)
+        assert sums.shape[0] == ns, (w, h, sums.shape)
+
+
+# ---- src/metrics/butteraugli.rs:169-207
+def test_butteraugli_identical_different_intensity(O):
+    ref = (np.arange(100 * 100 * 3) % 256).astype(np.uint8)
+    assert O.butteraugli(ref, ref, 100, 100)[0] < 0.01
+    a = np.full(100 * 100 * 3, 100, np.uint8)
+    b = np.full(100 * 100 * 3, 200, np.uint8)
+    assert O.butteraugli(a, b, 100, 100)[0] > 1.0
+    assert O.butteraugli(ref, ref, 100, 100, 250.0)[0] < 0.01
+
+
+# ---- src/metrics/dssim.rs:181-273
+def test_dssim_identical_and_different(O):
+    a = np.full((100, 100, 4), 0.5, np.float32)
+    a[..., 3] = 1.0
+    assert O.dssim_rgbaf32(a, a, 100, 100) < 1e-4
+    b = np.full((100, 100, 4), 0.3, np.float32)
+    c = np.full((100, 100, 4), 0.7, np.float32)
+    b[..., 3] = c[..., 3] = 1.0
+    assert O.dssim_rgbaf32(b, c, 100, 100) > 0.0
+
+
+def test_rgb8_rgba8_conversion(O):
+    img = O.rgb8_to_dssim_image(np.array([255, 255, 255, 0, 0, 0], np.uint8), 2, 1)
+    assert abs(img[0, 0, 0] - 1.0) < 1e-3 and abs(img[0, 0, 3] - 1.0) < 1e-3 and abs(img[0, 1, 0]) < 1e-3
+    img = O.rgba8_to_dssim_image(np.array([255, 255, 255, 255, 0, 0, 0, 128], np.uint8), 2, 1)
+    assert abs(img[0, 0, 3] - 1.0) < 1e-3 and abs(img[0, 1, 3] - 0.502) < 0.01
+
+
+def test_dssim_rgb8_equals_rgbaf32(O):
+    z = np.load(GOLD)
+    ref, dist = z["ref0"], z["dist0"]
+    a = O.dssim(ref, dist, 64, 64)
+    b = O.dssim_rgbaf32(O.rgb8_to_dssim_image(ref, 64, 64), O.rgb8_to_dssim_image(dist, 64, 64), 64, 64)
+    assert a == b
+
+
+# ---- src/metrics/xyb.rs:260-301
+def test_xyb_roundtrip(O):
+    rgb = (np.arange(64 * 64 * 3) % 256).astype(np.uint8)
+    assert O.xyb_roundtrip(rgb, 64, 64).size == rgb.size
+    rgb = ((np.arange(32 * 32 * 3) * 7) % 256).astype(np.uint8)
+    assert np.array_equal(O.xyb_roundtrip(rgb, 32, 32), O.xyb_roundtrip(rgb, 32, 32))
+    g = np.arange(0, 256, 16, dtype=np.uint8)
+    cube = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    out = O.xyb_roundtrip(cube, cube.shape[0], 1).reshape(-1, 3)
+    md = np.abs(out.astype(int) - cube.astype(int)).max()
+    assert 0 < md <= 30
+
+
+# ---- golden table (regression pin of the oracle) and structural checks
+def test_golden_table(O):
+    z = np.load(GOLD)
+    for k, row in enumerate(z["table"]):
+        seed, w, h, q, ss, sse, ps, s2, ds, ba, pn = row
+        w, h = int(w), int(h)
+        ref, dist = z[f"ref{k}"], z[f"dist{k}"]
+        assert O.sse(ref, dist) == int(sse)
+        assert O.psnr(ref, dist, w, h) == ps
+        assert abs(O.ssimulacra2(ref, dist, w, h) - s2) < 1e-9
+        assert abs(O.dssim(ref, dist, w, h) - ds) < 1e-12
+        m, p = O.butteraugli(ref, dist, w, h)
+        assert abs(m - ba) < 1e-6 and abs(p - pn) < 1e-9
+    assert np.array_equal(O.xyb_roundtrip(z["ref0"], 64, 64).reshape(64, 64, 3), z["xyb_rt0"])
+
+
+def test_probe_anchors(O):
+    """an independent numpy restatement produced these levels on G(0,256,256) + Pillow JPEG.
+    DSSIM / Butteraugli agree to the printed digits; SSIMULACRA2 within 0.06 (fp32 recurrence vs FIR)."""
+    from codec_eval_b200.synth import G, J
+
+    ref = G(0, 256, 256)
+    anchors = {30: (64.920, 0.003860, 2.9728, 1.4364), 80: (78.987, 0.001286, 1.6587, 0.9388), 95: (88.249, 0.000400, 1.1509, 0.5905)}
+    for q, (s2, ds, ba, pn) in anchors.items():
+        d = J(ref, q, 2)
+        assert abs(O.ssimulacra2(ref, d, 256, 256) - s2) < 0.06
+        assert abs(O.dssim(ref, d, 256, 256) - ds) < 2e-6
+        m, p = O.butteraugli(ref, d, 256, 256)
+        assert abs(m - ba) < 2e-4 and abs(p - pn) < 2e-4
+
+
+def test_monotone_in_quality(O):
+    from codec_eval_b200.synth import G, J
+
+    ref = G(7, 128, 96)
+    prev = None
+    for q in (30, 50, 70, 90):
+        d = J(ref, q, 2)
+        cur = (O.ssimulacra2(ref, d, 128, 96), -O.dssim(ref, d, 128, 96), -O.butteraugli(ref, d, 128, 96)[1])
+        if prev is not None:
+            assert all(c > p for c, p in zip(cur, prev)), (q, cur, prev)
+        prev = cur
+
+
+def test_rgauss_is_9tap_fir(O):
+    """The sigma-1.5 recursive Gaussian equals a 9-tap symmetric FIR in exact arithmetic."""
+    imp = np.zeros((1, 41), np.float32)
+    imp[0, 20] = 1.0
+    taps = np.array([0.00941436781, 0.03601111466, 0.1093353728, 0.212928592, 0.2646211055])
+    # the vertical pass over a 1-row image multiplies by the centre tap
+    hrow = O.rgauss_blur(imp)[0] / taps[4]
+    full = np.concatenate([taps, taps[-2::-1]])
+    assert np.allclose(hrow[16:25], full, atol=2e-6)
+    assert np.abs(hrow[:16]).max() < 2e-6 and np.abs(hrow[25:]).max() < 2e-6
+
+
+def test_fast_log2_and_cbrt_accuracy(O):
+    xs = np.linspace(0.004, 1.2, 20001, dtype=np.float32)
+    c = np.array([O.lib().ceo_cbrtf(float(x)) for x in xs[::20]])
+    assert np.abs(c / np.cbrt(xs[::20].astype(np.float64)) - 1).max() < 2e-7
+    ys = np.geomspace(1e-3, 1e4, 2000).astype(np.float32)
+    l2 = np.array([O.lib().ceo_ba_fast_log2f(float(y)) for y in ys])
+    assert np.abs(l2 - np.log2(ys.astype(np.float64))).max() < 2e-5
+
+
+def test_batch_matches_single(O):
+    z = np.load(GOLD)
+    refs = np.stack([z["ref0"], z["ref0"]])
+    dists = np.stack([z["dist0"], z["ref0"]])
+    res = O.evaluate_batch(refs, dists, 64, 64, 15, threads=2)
+    assert res[0].sse == int(z["table"][0][5]) and res[1].sse == 0
+    assert abs(res[0].ssimulacra2 - z["table"][0][7]) < 1e-9
+    assert res[1].ssimulacra2 == 100.0 and res[1].dssim == 0.0 and res[1].butteraugli == 0.0 and np.isinf(res[1].psnr)
