@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- megapixel-pairs/second of the metric hot path (BASELINE.json `metric`).
+
+A step = one pass of the hot path (PSNR + DSSIM + SSIMULACRA2 + Butteraugli) over one batch of synthetic
+reference/distorted pairs.  Default workload = BASELINE.json configs[1]: the Kodak-shaped batch, 24 synthetic
+768x512 references x 8 quality levels = 192 pairs, all four metrics, per GPU (weak scaling: every rank
+evaluates its own 192-pair batch; the only collective is the NCCL all_gather of the result table).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA kernels via the C ABI)
+  python bench.py --impl reference ...                           the CPU arm: the oracle (port of the
+        reference's CPU metric path; the Rust crates cannot be built here) on all host cores.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, n_refs, qualities, description)
+    "cfg2": (768, 512, 24, [50, 60, 70, 75, 80, 85, 90, 95],
+             "cfg2 Kodak-shaped batch: 24 synthetic 768x512 refs x 8 JPEG quality levels = 192 pairs, all four metrics"),
+    "cfg3": (512, 512, 15, [75, 85, 95] * 4,
+             "cfg3 codec-iter quick-eval shape: 15 refs 512x512 x 3 qualities x 4 sweep cells = 180 pairs"),
+    "cfg5s": (1024, 1024, 64, [50, 60, 70, 75, 80, 85, 90, 95],
+              "cfg5 slice: 512 synthetic 1024x1024 pairs (the 10,000-pair corpus sweep is this batch repeated)"),
+    "cfg4s": (3840, 2160, 16, [85], "cfg4 slice: 16 synthetic 3840x2160 pairs"),
+}
+STAGED_BYTES_PER_PX = {"psnr": 6.0, "ssimulacra2": 326.0, "dssim": 225.0, "butteraugli": 970.0}
+
+
+def make_pairs(name: str, rank: int):
+    from codec_eval_b200.synth import G, J, cheap_distort
+
+    w, h, nref, quals, _ = WORKLOADS[name]
+    cache = f"/tmp/ce_bench_{name}_r{rank}.npz"
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return z["refs"], z["dists"]
+    refs, dists = [], []
+    use_jpeg = w * h <= 1024 * 1024
+    for i in range(nref):
+        ref = G(rank * 1000 + i, w, h)
+        for k, q in enumerate(quals):
+            refs.append(ref)
+            ss = 2 if (k // 3) % 2 == 0 else 0
+            dists.append(J(ref, q, ss) if use_jpeg else cheap_distort(ref, q, seed=i))
+    refs, dists = np.stack(refs), np.stack(dists)
+    try:
+        np.savez(cache, refs=refs, dists=dists)
+    except Exception:
+        pass
+    return refs, dists
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline(refs, dists, w, h, flags, sample_pairs, threads=0):
+    """The oracle (port) on the host cores over a bounded sample of the same workload."""
+    from oracle import oracle as O
+
+    n = min(sample_pairs, refs.shape[0])
+    t0 = time.perf_counter()
+    O.evaluate_batch(refs[:n], dists[:n], w, h, flags, threads=threads)
+    dt = time.perf_counter() - t0
+    return n * w * h / 1e6 / dt, n, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU metric path = the oracle port, all host threads, bounded sample/step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    w, h, _, _, desc = WORKLOADS[args.workload]
+    refs, dists = make_pairs(args.workload, 0)
+    cores = O.max_threads()
+    sample = max(cores, min(refs.shape[0], int(16 * (768 * 512) / (w * h)) or 1))
+    sample = min(sample, refs.shape[0])
+    flags = 15
+    for _ in range(args.warmup):
+        O.evaluate_batch(refs[:sample], dists[:sample], w, h, flags)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.evaluate_batch(refs[:sample], dists[:sample], w, h, flags)
+    dt = time.perf_counter() - t0
+    val = sample * w * h / 1e6 * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "mpix_pairs_per_sec_all_metrics", "value": val, "unit": "MPix-pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "width": w, "height": h, "metrics": "psnr+dssim+ssimulacra2+butteraugli"},
+        "cpu_baseline": {"value": val, "unit": "MPix-pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {refs.shape[0]} pairs per step, all four metrics, OpenMP over pairs"},
+        "e2e": {"value": val, "unit": "MPix-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-per-metric", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel table (JSON) here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from codec_eval_b200 import _lib
+    from codec_eval_b200.metrics import GpuMetrics, MetricConfig
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: codec_eval_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w, h, _, _, desc = WORKLOADS[args.workload]
+    refs, dists = make_pairs(args.workload, rank)
+    n = refs.shape[0]
+    mpix = n * w * h / 1e6
+    d_ref = torch.from_numpy(refs).cuda()
+    d_dist = torch.from_numpy(dists).cuda()
+    ctx = GpuMetrics(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    L = ctx._L
+    res_bytes = C.sizeof(_lib.CeResult) * n
+    gather_in = torch.empty(res_bytes, dtype=torch.uint8, device="cuda")
+    gather_out = torch.empty(res_bytes * world, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def make_step(cfg: MetricConfig):
+        ccfg = cfg._c()
+        out = (_lib.CeResult * n)()
+
+        def step():
+            st = L.ce_evaluate_batch_device(ctx._h, C.c_void_p(d_ref.data_ptr()), C.c_void_p(d_dist.data_ptr()), n, w, h,
+                                            C.byref(ccfg), 80.0, out)
+            if st != 0:
+                raise RuntimeError(f"ce_evaluate_batch_device failed: {st} {ctx.last_error()}")
+            if world > 1:  # the final score gather (NCCL); 56 B per pair
+                gather_in.copy_(torch.frombuffer(out, dtype=torch.uint8), non_blocking=False)
+                dist.all_gather_into_tensor(gather_out, gather_in)
+            return out
+
+        return step
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- headline: all four metrics, inputs resident in HBM
+    all_cfg = MetricConfig.all()
+    step_all = make_step(all_cfg)
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        step_all()
+    ctx.profile(True, reset=True)
+    l0 = ctx.launch_count()
+    sampler.start()
+    ms = timed(step_all, args.steps, 0)
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    prof = ctx.profile_report()
+    ctx.profile(False, reset=False)
+    value = mpix * world * args.steps / (ms / 1e3)
+
+    out = step_all()
+    sanity = {"ssimulacra2_pair0": out[0].ssimulacra2, "dssim_pair0": out[0].dssim, "butteraugli_pair0": out[0].butteraugli,
+              "psnr_pair0": out[0].psnr, "status_ok": all(out[i].status == 0 and out[i].valid == 15 for i in range(n))}
+
+    # ---- roofline of the dominant kernel (CUDA events around every launch of the timed region)
+    peak, peak_src = measured_peak_gbs()
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
+    total_kernel_ms = sum(v["ms"] for v in prof.values())
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    roofline = None
+    if top:
+        name, v = top
+        ach = v["bytes"] / (v["ms"] / 1e3) / 1e9
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload, {}).get(name)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src, "launches": v["launches"],
+                    "avg_launch_ms": v["ms"] / v["launches"], "algorithmic_bytes_per_launch": v["bytes"] / v["launches"],
+                    "share_of_kernel_time": v["ms"] / total_kernel_ms if total_kernel_ms else None}
+    kernels = {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
+                   "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 else None,
+                   "frac_of_peak": (v["bytes"] / (v["ms"] / 1e3) / 1e9 / peak) if v["ms"] > 0 else None}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # ---- per-metric throughput (same batch, one metric at a time)
+    per_metric = {}
+    if not args.no_per_metric:
+        for mname, cfg in [("psnr", MetricConfig(psnr=True)), ("ssimulacra2", MetricConfig(ssimulacra2=True)),
+                           ("dssim", MetricConfig(dssim=True)), ("butteraugli", MetricConfig(butteraugli=True))]:
+            st = make_step(cfg)
+            k = args.steps if mname != "psnr" else args.steps * 5
+            m_ms = timed(st, k, 3)
+            v = mpix * world * k / (m_ms / 1e3)
+            gbs = v * 1e6 * STAGED_BYTES_PER_PX[mname] / 1e9 / world
+            per_metric[mname] = {"mpix_pairs_per_sec": v, "ms_per_step": m_ms / k,
+                                 "staged_model_gbs_per_gpu": gbs, "frac_of_hbm_staged_model": gbs / peak}
+
+    # ---- end to end through the host-pointer C-ABI entry (pinned host buffers; H2D + D2H inside the timed region)
+    h_ref = torch.from_numpy(refs).pin_memory()
+    h_dist = torch.from_numpy(dists).pin_memory()
+    img_bytes = w * h * 3
+    pairs = (_lib.CePair * n)()
+    for i in range(n):
+        pairs[i] = _lib.CePair(h_ref.data_ptr() + i * img_bytes, h_dist.data_ptr() + i * img_bytes, img_bytes, img_bytes,
+                               w, h, i // max(1, len(WORKLOADS[args.workload][3])), 0)
+    e2e_out = (_lib.CeResult * n)()
+    ccfg = all_cfg._c()
+
+    def step_e2e():
+        st = L.ce_evaluate_batch(ctx._h, pairs, n, C.byref(ccfg), 80.0, e2e_out)
+        if st != 0:
+            raise RuntimeError(f"ce_evaluate_batch failed: {st} {ctx.last_error()}")
+        if world > 1:
+            gather_in.copy_(torch.frombuffer(e2e_out, dtype=torch.uint8))
+            dist.all_gather_into_tensor(gather_out, gather_in)
+
+    e2e_ms = timed(step_e2e, args.steps, 2)
+    e2e_val = mpix * world * args.steps / (e2e_ms / 1e3)
+    e2e = {"value": e2e_val, "unit": "MPix-pairs/s", "h2d_bytes_per_step": 2 * n * img_bytes,
+           "d2h_bytes_per_step": n * (1 + 108 + 10 + 4) * 8, "ms_per_step": e2e_ms / args.steps}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+
+        cores = O.max_threads()
+        sample = max(cores, 16)
+        v, ns, dt = cpu_baseline(refs, dists, w, h, 15, sample)
+        cpu = {"value": v, "unit": "MPix-pairs/s", "cores": cores, "kind": "port",
+               "sample": f"{ns} of {n} pairs, all four metrics, OpenMP over pairs, {dt:.1f} s wall"}
+
+    if rank == 0:
+        line = {
+            "metric": "mpix_pairs_per_sec_all_metrics", "value": value, "unit": "MPix-pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "pairs_per_gpu": n, "width": w, "height": h,
+                       "metrics": "psnr+dssim+ssimulacra2+butteraugli (max + 3-norm)",
+                       "l2": f"no explicit flush: {2 * n * img_bytes / 1e6:.0f} MB of inputs and >1 GB of fp32 intermediates per step exceed the 126 MB L2",
+                       "parallelism": f"pairs sharded over {world} rank(s), NCCL all_gather of 56 B/pair results"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "per_metric": per_metric, "kernels": kernels, "sanity": sanity,
+        }
+        print(json.dumps(line), flush=True)
+        if args.profile_out:
+            with open(args.profile_out, "w") as f:
+                json.dump({"workload": desc, "steps": args.steps, "kernels": kernels, "roofline": roofline,
+                           "per_metric": per_metric}, f, indent=1)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

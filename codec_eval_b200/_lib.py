@@ -37,6 +37,7 @@ class CeResult(C.Structure):
 # every symbol include/ce_gpu.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "ce_ctx_create", "ce_ctx_destroy", "ce_ctx_set_stream", "ce_last_error", "ce_launch_count", "ce_version",
+    "ce_profile_enable", "ce_profile_reset", "ce_profile_report",
     "ce_evaluate_batch", "ce_evaluate_batch_device", "ce_psnr", "ce_ssimulacra2", "ce_butteraugli", "ce_dssim_rgb8",
     "ce_dssim_rgbaf32", "ce_rgb8_to_dssim_image", "ce_rgba8_to_dssim_image", "ce_xyb_roundtrip",
     "ce_reference_create", "ce_reference_compare", "ce_reference_compare_many", "ce_reference_destroy",
@@ -69,6 +70,10 @@ def load():
     L.ce_launch_count.argtypes = [vp]
     L.ce_launch_count.restype = C.c_uint64
     L.ce_version.restype = C.c_char_p
+    L.ce_profile_enable.argtypes = [vp, C.c_int]
+    L.ce_profile_reset.argtypes = [vp]
+    L.ce_profile_report.argtypes = [vp, C.c_char_p, sz]
+    L.ce_profile_report.restype = sz
     L.ce_evaluate_batch.argtypes = [vp, C.POINTER(CePair), sz, cfgp, C.c_float, resp]
     L.ce_evaluate_batch_device.argtypes = [vp, vp, vp, sz, C.c_uint32, C.c_uint32, cfgp, C.c_float, resp]
     L.ce_psnr.argtypes = [vp, u8p, sz, u8p, sz, sz, sz, f64p, C.POINTER(C.c_uint64)]

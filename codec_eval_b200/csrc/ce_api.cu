@@ -47,6 +47,49 @@ void Context::ensure_results(size_t bytes) {
     h_pinned_bytes = d_results_bytes = cap;
 }
 
+void Context::prof_begin(const char* name, double bytes) {
+    launches++;
+    if (!prof.enabled) return;
+    auto it = prof.index.find(name);
+    int idx;
+    if (it == prof.index.end()) {
+        idx = (int)prof.stats.size();
+        prof.index[name] = idx;
+        KernelStat ks;
+        ks.name = name;
+        prof.stats.push_back(ks);
+    } else idx = it->second;
+    prof.stats[idx].launches++;
+    prof.stats[idx].bytes += bytes;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!prof.pool.empty()) { e = prof.pool.back(); prof.pool.pop_back(); }
+        else CE_CUDA(cudaEventCreate(&e));
+        return e;
+    };
+    prof.cur = idx;
+    prof.cur_a = get();
+    CE_CUDA(cudaEventRecord(prof.cur_a, stream));
+}
+void Context::prof_end() {
+    if (!prof.enabled || prof.cur < 0) return;
+    cudaEvent_t b;
+    if (!prof.pool.empty()) { b = prof.pool.back(); prof.pool.pop_back(); }
+    else CE_CUDA(cudaEventCreate(&b));
+    CE_CUDA(cudaEventRecord(b, stream));
+    prof.pending.push_back({prof.cur, prof.cur_a, b});
+    prof.cur = -1;
+}
+void Context::prof_collect() {
+    for (auto& p : prof.pending) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) prof.stats[p.stat].ms += ms;
+        prof.pool.push_back(p.a);
+        prof.pool.push_back(p.b);
+    }
+    prof.pending.clear();
+}
+
 // recursive Gaussian sigma 1.5 (libjxl CreateRecursiveGaussian), evaluated in double, stored as fp32
 static void make_rgauss(RGaussCoef& rg) {
     const double sigma = 1.5;
@@ -245,6 +288,7 @@ static void run_device_batch(Context& c, const uint8_t* d_ref, const uint8_t* d_
         }
         CE_CUDA(cudaMemcpyAsync(c.h_pinned, d_raw, B * raw_doubles * 8, cudaMemcpyDeviceToHost, c.stream));
         CE_CUDA(cudaStreamSynchronize(c.stream));
+        c.prof_collect();
         const double* h_raw = reinterpret_cast<const double*>(c.h_pinned);
         const uint64_t* h_sse = reinterpret_cast<const uint64_t*>(h_raw);
         const double* h_s2 = h_raw + B;
@@ -364,6 +408,8 @@ CE_API void ce_ctx_destroy(ce_ctx* ctx) {
     if (c.d_results) cudaFree(c.d_results);
     if (c.d_in) cudaFree(c.d_in);
     for (auto& kv : c.ba_inv_cache) cudaFree(kv.second);
+    c.prof_collect();
+    for (auto e : c.prof.pool) cudaEventDestroy(e);
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     delete ctx;
 }
@@ -376,6 +422,33 @@ CE_API int ce_ctx_set_stream(ce_ctx* ctx, void* cuda_stream) {
 
 CE_API const char* ce_last_error(const ce_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : g_create_error.c_str(); }
 CE_API uint64_t ce_launch_count(const ce_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+CE_API int ce_profile_enable(ce_ctx* ctx, int enable) {
+    if (!ctx) return CE_ERR_INVALID_ARGUMENT;
+    ctx->c.prof.enabled = enable != 0;
+    return CE_OK;
+}
+CE_API int ce_profile_reset(ce_ctx* ctx) {
+    if (!ctx) return CE_ERR_INVALID_ARGUMENT;
+    for (auto& k : ctx->c.prof.stats) { k.launches = 0; k.ms = 0.0; k.bytes = 0.0; }
+    return CE_OK;
+}
+CE_API size_t ce_profile_report(ce_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx) return 0;
+    std::string out;
+    char line[512];
+    for (auto& k : ctx->c.prof.stats) {
+        if (!k.launches) continue;
+        snprintf(line, sizeof(line), "%s\t%llu\t%.6f\t%.0f\n", k.name.c_str(), (unsigned long long)k.launches, k.ms, k.bytes);
+        out += line;
+    }
+    if (buf && cap) {
+        size_t n = std::min(cap - 1, out.size());
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return out.size();
+}
 
 CE_API int ce_evaluate_batch_device(ce_ctx* ctx, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, uint32_t width,
                                     uint32_t height, const ce_metric_config* cfg, float intensity_target, ce_result* out) {

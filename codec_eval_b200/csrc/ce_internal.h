@@ -60,6 +60,24 @@ struct BaKernel {
     float w[33];
 };
 
+// per-kernel CUDA-event timing (opt-in; bench.py's roofline numbers come from here)
+struct KernelStat {
+    std::string name;
+    uint64_t launches = 0;
+    double ms = 0.0;      // summed device time of the timed launches
+    double bytes = 0.0;   // summed ALGORITHMIC bytes (distinct inputs read once + outputs written once)
+};
+struct Profiler {
+    bool enabled = false;
+    struct Pending { int stat; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+    std::map<std::string, int> index;
+    std::vector<KernelStat> stats;
+    int cur = -1;
+    cudaEvent_t cur_a = nullptr;
+};
+
 struct Context {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -78,9 +96,21 @@ struct Context {
     std::map<uint64_t, float*> ba_inv_cache;  // Butteraugli border-renormalisation tables
     int sm_count = 148;
 
+    Profiler prof;
+    void prof_begin(const char* name, double bytes);
+    void prof_end();
+    void prof_collect();   // call after the stream is synchronised
     void ensure_input(size_t bytes);
     void ensure_results(size_t bytes);
 };
+
+// every kernel launch of the library goes through this: counts it, and (when profiling) brackets it with events
+#define CE_LAUNCH(ctx, name, bytes, ...)            \
+    do {                                            \
+        (ctx).prof_begin(name, (double)(bytes));    \
+        __VA_ARGS__;                                \
+        (ctx).prof_end();                           \
+    } while (0)
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

@@ -202,10 +202,13 @@ static void blur_slot(Context& c, const float* in, float* tmp, float* out, size_
     for (size_t p0 = 0; p0 < np; p0 += 65535) {
         unsigned z = (unsigned)std::min<size_t>(65535, np - p0);
         dim3 gh(cdiv(w, 128), cdiv(h, 8), z);
-        k_ba_blur_h<SLOT, R><<<gh, 256, 0, c.stream>>>(in + p0 * n, (int)w, (int)h, n, t.inv_x[SLOT], tmp + p0 * n);
+        static const char* const hn[4] = {"k_ba_blur_h<R16>", "k_ba_blur_h<R7>", "k_ba_blur_h<R3>", "k_ba_blur_h<R6>"};
+        static const char* const vn[4] = {"k_ba_blur_v<R16>", "k_ba_blur_v<R7>", "k_ba_blur_v<R3>", "k_ba_blur_v<R6>"};
+        CE_LAUNCH(c, hn[SLOT], (double)z * n * 8,
+                  k_ba_blur_h<SLOT, R><<<gh, 256, 0, c.stream>>>(in + p0 * n, (int)w, (int)h, n, t.inv_x[SLOT], tmp + p0 * n));
         dim3 gv(cdiv(w, 32), cdiv(h, 64), z);
-        k_ba_blur_v<SLOT, R><<<gv, 256, 0, c.stream>>>(tmp + p0 * n, (int)w, (int)h, n, t.inv_y[SLOT], out + p0 * n);
-        c.launches += 2;
+        CE_LAUNCH(c, vn[SLOT], (double)z * n * 8,
+                  k_ba_blur_v<SLOT, R><<<gv, 256, 0, c.stream>>>(tmp + p0 * n, (int)w, (int)h, n, t.inv_y[SLOT], out + p0 * n));
     }
     CE_CUDA(cudaGetLastError());
 }
@@ -693,21 +696,17 @@ static void ba_psycho_level(Context& c, const float* lin, size_t NI, size_t w, s
                             float* dbg_opsin) {
     const size_t n = w * h;
     size_t t3 = NI * 3 * n, t1 = NI * n;
-    k_ba_blur5<<<ew_blocks(c, t3), 256, 0, c.stream>>>(lin, (int)w, (int)h, n, t3, 0, L.tmpA);
-    k_ba_blur5<<<ew_blocks(c, t3), 256, 0, c.stream>>>(L.tmpA, (int)w, (int)h, n, t3, 1, L.tmpB);
-    k_ba_opsin<<<ew_blocks(c, t1), 256, 0, c.stream>>>(lin, L.tmpB, n, t1, intensity, L.xyb);
-    c.launches += 3;
+    CE_LAUNCH(c, "k_ba_blur5", (double)t3 * 8, k_ba_blur5<<<ew_blocks(c, t3), 256, 0, c.stream>>>(lin, (int)w, (int)h, n, t3, 0, L.tmpA));
+    CE_LAUNCH(c, "k_ba_blur5", (double)t3 * 8, k_ba_blur5<<<ew_blocks(c, t3), 256, 0, c.stream>>>(L.tmpA, (int)w, (int)h, n, t3, 1, L.tmpB));
+    CE_LAUNCH(c, "k_ba_opsin", (double)t1 * 36, k_ba_opsin<<<ew_blocks(c, t1), 256, 0, c.stream>>>(lin, L.tmpB, n, t1, intensity, L.xyb));
     if (dbg_opsin) CE_CUDA(cudaMemcpyAsync(dbg_opsin, L.xyb, 3 * n * 4, cudaMemcpyDeviceToDevice, c.stream));
     blur_planes(c, 0, L.xyb, L.tmpA, L.lf, NI * 3, w, h, L.tables);
-    k_ba_sub<<<ew_blocks(c, t3), 256, 0, c.stream>>>(L.xyb, L.lf, t3, L.tmpB);
-    c.launches++;
+    CE_LAUNCH(c, "k_ba_sub", (double)t3 * 12, k_ba_sub<<<ew_blocks(c, t3), 256, 0, c.stream>>>(L.xyb, L.lf, t3, L.tmpB));
     blur_planes(c, 1, L.tmpB, L.tmpA, L.mf, NI * 3, w, h, L.tables);
-    k_ba_split_hf<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.tmpB, L.mf, n, t1, L.hf);
-    c.launches++;
+    CE_LAUNCH(c, "k_ba_split_hf", (double)t1 * 32, k_ba_split_hf<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.tmpB, L.mf, n, t1, L.hf));
     blur_planes(c, 2, L.hf, L.tmpA, L.tmpB, NI * 2, w, h, L.tables);
-    k_ba_split_uhf<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.hf, L.tmpB, n, t1, L.uhf);
-    k_ba_lf_vals<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.lf, n, t1);
-    c.launches += 2;
+    CE_LAUNCH(c, "k_ba_split_uhf", (double)t1 * 32, k_ba_split_uhf<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.hf, L.tmpB, n, t1, L.uhf));
+    CE_LAUNCH(c, "k_ba_lf_vals", (double)t1 * 24, k_ba_lf_vals<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.lf, n, t1));
     CE_CUDA(cudaGetLastError());
 }
 
@@ -724,16 +723,16 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t B, size_t w, s
     for (size_t b0 = 0; b0 < B; b0 += 32768) {
         if (b0 != 0) throw CudaError("butteraugli sub-batch too large");  // sub-batches are far smaller than 32768 pairs
         dim3 grid(tx, ty, (unsigned)B);
-        k_ba_malta<1><<<grid, 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, (int)w, (int)h, n, B, p1, L.ac);
-        k_ba_malta<0><<<grid, 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, (int)w, (int)h, n, B, p0, L.ac);
-        c.launches += 2;
+        CE_LAUNCH(c, "k_ba_malta", (double)B * n * 28,
+                  k_ba_malta<1><<<grid, 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, (int)w, (int)h, n, B, p1, L.ac));
+        CE_LAUNCH(c, "k_ba_malta", (double)B * n * 28,
+                  k_ba_malta<0><<<grid, 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, (int)w, (int)h, n, B, p0, L.ac));
     }
     size_t t1 = NI * n;
-    k_ba_mask_pre<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.hf, L.uhf, n, t1, L.m);
-    c.launches++;
+    CE_LAUNCH(c, "k_ba_mask_pre", (double)t1 * 20, k_ba_mask_pre<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.hf, L.uhf, n, t1, L.m));
     blur_planes(c, 3, L.m, L.tmpA, L.bl, NI, w, h, L.tables);
-    k_ba_combine<<<ew_blocks(c, B * n), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, xmul, diffmap);
-    c.launches++;
+    CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,
+              k_ba_combine<<<ew_blocks(c, B * n), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, xmul, diffmap));
     CE_CUDA(cudaGetLastError());
     c.arena.release(mark);
 }
@@ -759,19 +758,19 @@ void butteraugli_run(Context& c, const float* lin, const float* lin2, size_t B, 
         float* slin = c.arena.alloc<float>(2 * B * 3 * sn);
         sub = c.arena.alloc<float>(B * sn);
         size_t total = 2 * B * 3 * sn;
-        k_ba_subsample<<<ew_blocks(c, total), 256, 0, c.stream>>>(lin, (int)w, (int)h, n, (int)sw, (int)sh, sn, total, slin);
-        c.launches++;
+        CE_LAUNCH(c, "k_ba_subsample", (double)total * 20,
+                  k_ba_subsample<<<ew_blocks(c, total), 256, 0, c.stream>>>(lin, (int)w, (int)h, n, (int)sw, (int)sh, sn, total, slin));
         ba_diffmap_level(c, slin, B, sw, sh, intensity, sub);
     }
     for (size_t b0 = 0; b0 < B; b0 += 32768) {
         unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
         dim3 grid(BA_RED_BLOCKS, nb);
-        k_ba_finish<<<grid, 256, 0, c.stream>>>(diffmap + b0 * n, sub ? sub + b0 * sn : nullptr, (int)w, (int)sw, n, sn,
-                                                 partial + b0 * BA_RED_BLOCKS * 4);
-        c.launches++;
+        CE_LAUNCH(c, "k_ba_finish", (double)nb * (sub ? 8 * n + 4 * sn : 4 * n),
+                  k_ba_finish<<<grid, 256, 0, c.stream>>>(diffmap + b0 * n, sub ? sub + b0 * sn : nullptr, (int)w, (int)sw, n, sn,
+                                                           partial + b0 * BA_RED_BLOCKS * 4));
     }
-    k_ba_finish_reduce<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, BA_RED_BLOCKS, B, d_out);
-    c.launches++;
+    CE_LAUNCH(c, "k_ba_finish_reduce", (double)B * (BA_RED_BLOCKS + 1) * 32,
+              k_ba_finish_reduce<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, BA_RED_BLOCKS, B, d_out));
     if (dbg_diffmap) CE_CUDA(cudaMemcpyAsync(dbg_diffmap, diffmap, n * 4, cudaMemcpyDeviceToDevice, c.stream));
     CE_CUDA(cudaGetLastError());
     c.arena.release(mark);
@@ -804,9 +803,8 @@ void butteraugli_debug_blur(Context& c, const float* in, size_t w, size_t h, flo
     BaLevelBufs L;
     ba_alloc_level(c, 1, w, h, L);
     if (fabsf(sigma - 1.2f) < 1e-6f) {
-        k_ba_blur5<<<ew_blocks(c, n), 256, 0, c.stream>>>(in, (int)w, (int)h, n, n, 0, L.tmpA);
-        k_ba_blur5<<<ew_blocks(c, n), 256, 0, c.stream>>>(L.tmpA, (int)w, (int)h, n, n, 1, out);
-        c.launches += 2;
+        CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_blur5<<<ew_blocks(c, n), 256, 0, c.stream>>>(in, (int)w, (int)h, n, n, 0, L.tmpA));
+        CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_blur5<<<ew_blocks(c, n), 256, 0, c.stream>>>(L.tmpA, (int)w, (int)h, n, n, 1, out));
     } else {
         int slot = -1;
         for (int s = 0; s < 4; s++)

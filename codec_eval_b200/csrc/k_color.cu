@@ -64,13 +64,14 @@ void launch_srgb8_to_linear(Context& c, const uint8_t* d_rgb, size_t n_img, size
     if (npix % 16 == 0 && (reinterpret_cast<uintptr_t>(d_rgb) & 15) == 0) {
         size_t gpi = npix / 16, ng = gpi * n_img;
         unsigned blocks = (unsigned)std::min<size_t>(cdiv(ng, 256), (size_t)wave * 4);
-        k_srgb8_to_linear_v16<<<blocks, 256, 0, c.stream>>>(d_rgb, c.d_lut, ng, gpi, npix, d_planes);
+        CE_LAUNCH(c, "k_srgb8_to_linear_v16", n_img * npix * 15,
+                  k_srgb8_to_linear_v16<<<blocks, 256, 0, c.stream>>>(d_rgb, c.d_lut, ng, gpi, npix, d_planes));
     } else {
         size_t nt = npix * n_img;
         unsigned blocks = (unsigned)std::min<size_t>(cdiv(nt, 256), (size_t)wave * 4);
-        k_srgb8_to_linear_px<<<blocks, 256, 0, c.stream>>>(d_rgb, c.d_lut, nt, npix, d_planes);
+        CE_LAUNCH(c, "k_srgb8_to_linear_px", n_img * npix * 15,
+                  k_srgb8_to_linear_px<<<blocks, 256, 0, c.stream>>>(d_rgb, c.d_lut, nt, npix, d_planes));
     }
-    c.launches++;
     CE_CUDA(cudaGetLastError());
 }
 
@@ -176,10 +177,10 @@ void launch_sse(Context& c, const uint8_t* d_ref, const uint8_t* d_dist, size_t 
         const uint8_t* d = d_dist + p0 * bytes_per_img;
         bool same_align = ((reinterpret_cast<uintptr_t>(r) ^ reinterpret_cast<uintptr_t>(d)) & 15) == 0;
         if (same_align)
-            k_sse<<<grid, 256, 0, c.stream>>>(r, d, bytes_per_img, d_sse + p0);
+            CE_LAUNCH(c, "k_sse", (double)np * (2 * bytes_per_img + 8), k_sse<<<grid, 256, 0, c.stream>>>(r, d, bytes_per_img, d_sse + p0));
         else
-            k_sse_scalar<<<grid, 256, 0, c.stream>>>(r, d, bytes_per_img, d_sse + p0);
-        c.launches++;
+            CE_LAUNCH(c, "k_sse_scalar", (double)np * (2 * bytes_per_img + 8),
+                      k_sse_scalar<<<grid, 256, 0, c.stream>>>(r, d, bytes_per_img, d_sse + p0));
     }
     CE_CUDA(cudaGetLastError());
 }
@@ -247,8 +248,7 @@ __global__ void __launch_bounds__(256) k_xyb_roundtrip(const uint8_t* __restrict
 void launch_xyb_roundtrip(Context& c, const uint8_t* d_rgb, size_t npix_total, uint8_t* d_out) {
     if (npix_total == 0) return;
     unsigned blocks = (unsigned)std::min<size_t>(cdiv(npix_total, 256), (size_t)c.sm_count * 32);
-    k_xyb_roundtrip<<<blocks, 256, 0, c.stream>>>(d_rgb, npix_total, d_out);
-    c.launches++;
+    CE_LAUNCH(c, "k_xyb_roundtrip", npix_total * 6, k_xyb_roundtrip<<<blocks, 256, 0, c.stream>>>(d_rgb, npix_total, d_out));
     CE_CUDA(cudaGetLastError());
 }
 
@@ -271,8 +271,8 @@ __global__ void __launch_bounds__(256) k_rgb8_to_rgba_linear(const uint8_t* __re
 void launch_rgb8_to_rgba_linear(Context& c, const uint8_t* d_in, size_t npix, int in_channels, float* d_out) {
     if (npix == 0) return;
     unsigned blocks = (unsigned)std::min<size_t>(cdiv(npix, 256), (size_t)c.sm_count * 32);
-    k_rgb8_to_rgba_linear<<<blocks, 256, 0, c.stream>>>(d_in, c.d_lut, npix, in_channels, reinterpret_cast<float4*>(d_out));
-    c.launches++;
+    CE_LAUNCH(c, "k_rgb8_to_rgba_linear", npix * (in_channels + 16),
+              k_rgb8_to_rgba_linear<<<blocks, 256, 0, c.stream>>>(d_in, c.d_lut, npix, in_channels, reinterpret_cast<float4*>(d_out)));
     CE_CUDA(cudaGetLastError());
 }
 
@@ -292,8 +292,8 @@ __global__ void __launch_bounds__(256) k_rgba_to_planar(const float4* __restrict
 void launch_rgba_to_planar(Context& c, const float* d_rgba, size_t w, size_t h, size_t stride, float* d_planes4) {
     if (w * h == 0) return;
     unsigned blocks = (unsigned)std::min<size_t>(cdiv(w * h, 256), (size_t)c.sm_count * 32);
-    k_rgba_to_planar<<<blocks, 256, 0, c.stream>>>(reinterpret_cast<const float4*>(d_rgba), w, h, stride, d_planes4);
-    c.launches++;
+    CE_LAUNCH(c, "k_rgba_to_planar", w * h * 32,
+              k_rgba_to_planar<<<blocks, 256, 0, c.stream>>>(reinterpret_cast<const float4*>(d_rgba), w, h, stride, d_planes4));
     CE_CUDA(cudaGetLastError());
 }
 

@@ -298,15 +298,15 @@ int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const floa
             for (int im = 0; im < 2; im++) {
                 float* dst = nl[s & 1][im];
                 size_t total = B * 3 * n;
-                k_ds_down<<<std::min<unsigned>(cdiv(total, 256), wave * 4), 256, 0, c.stream>>>(l[im], (int)pw, pn, (int)cw, (int)ch,
-                                                                                              n, total, dst);
-                c.launches++;
+                CE_LAUNCH(c, "k_ds_down", (double)total * 20,
+                          k_ds_down<<<std::min<unsigned>(cdiv(total, 256), wave * 4), 256, 0, c.stream>>>(l[im], (int)pw, pn, (int)cw,
+                                                                                                        (int)ch, n, total, dst));
                 if (has_alpha) {
                     float* adst = nal[s & 1][im];
                     size_t atotal = B * n;
-                    k_ds_down<<<std::min<unsigned>(cdiv(atotal, 256), wave * 4), 256, 0, c.stream>>>(al[im], (int)pw, pn, (int)cw,
-                                                                                                   (int)ch, n, atotal, adst);
-                    c.launches++;
+                    CE_LAUNCH(c, "k_ds_down", (double)atotal * 20,
+                              k_ds_down<<<std::min<unsigned>(cdiv(atotal, 256), wave * 4), 256, 0, c.stream>>>(
+                                  al[im], (int)pw, pn, (int)cw, (int)ch, n, atotal, adst));
                     al[im] = adst;
                 }
                 l[im] = dst;
@@ -314,35 +314,35 @@ int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const floa
         }
         for (int im = 0; im < 2; im++) {
             size_t total = B * n;
-            k_ds_lab<<<std::min<unsigned>(cdiv(total, 256), wave * 4), 256, 0, c.stream>>>(l[im], has_alpha ? al[im] : nullptr,
-                                                                                         (int)cw, n, total, im, img, chroma);
-            c.launches++;
+            CE_LAUNCH(c, "k_ds_lab", (double)total * (has_alpha ? 28 : 24),
+                      k_ds_lab<<<std::min<unsigned>(cdiv(total, 256), wave * 4), 256, 0, c.stream>>>(
+                          l[im], has_alpha ? al[im] : nullptr, (int)cw, n, total, im, img, chroma));
         }
         const unsigned tx = cdiv(cw, DS_TW), ty = cdiv(ch, DS_TH);
         for (size_t p0 = 0; p0 < B * 4; p0 += 32768) {  // gridDim.z <= 65535; keep pairs whole (4 planes per pair)
             unsigned np = (unsigned)std::min<size_t>(32768, B * 4 - p0);
             dim3 grid(tx, ty, np);
-            k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma + p0 * n, (int)cw, (int)ch, n, img + (p0 / 2) * 3 * n);
-            c.launches++;
+            CE_LAUNCH(c, "k_ds_blur2", (double)np * n * 8,
+                      k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma + p0 * n, (int)cw, (int)ch, n, img + (p0 / 2) * 3 * n));
         }
         const int ntiles = (int)(tx * ty);
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
             dim3 grid(tx, ty, nb);
-            k_ds_stats<<<grid, 256, 0, c.stream>>>(img + b0 * 6 * n, (int)cw, (int)ch, n, map + b0 * n, partial + b0 * ntiles);
-            c.launches++;
+            CE_LAUNCH(c, "k_ds_stats", (double)nb * n * 28,
+                      k_ds_stats<<<grid, 256, 0, c.stream>>>(img + b0 * 6 * n, (int)cw, (int)ch, n, map + b0 * n, partial + b0 * ntiles));
         }
-        k_ds_mean<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, ntiles, B, n, s, d_out, avg);
-        c.launches++;
+        CE_LAUNCH(c, "k_ds_mean", (double)B * (ntiles + 2) * 8,
+                  k_ds_mean<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, ntiles, B, n, s, d_out, avg));
         if (dbg_map0 && s == 0) CE_CUDA(cudaMemcpyAsync(dbg_map0, map, n * 4, cudaMemcpyDeviceToDevice, c.stream));
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
             dim3 grid(DS_MAD_BLOCKS, nb);
-            k_ds_mad<<<grid, 256, 0, c.stream>>>(map + b0 * n, n, avg + b0, partial + b0 * DS_MAD_BLOCKS);
-            c.launches++;
+            CE_LAUNCH(c, "k_ds_mad", (double)nb * n * 4,
+                      k_ds_mad<<<grid, 256, 0, c.stream>>>(map + b0 * n, n, avg + b0, partial + b0 * DS_MAD_BLOCKS));
         }
-        k_ds_mad_reduce<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, DS_MAD_BLOCKS, B, s, d_out);
-        c.launches++;
+        CE_LAUNCH(c, "k_ds_mad_reduce", (double)B * (DS_MAD_BLOCKS + 1) * 8,
+                  k_ds_mad_reduce<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, DS_MAD_BLOCKS, B, s, d_out));
         CE_CUDA(cudaGetLastError());
     }
     c.arena.release(mark);

@@ -293,26 +293,25 @@ int ssim2_run(Context& c, const float* lin1_in, const float* lin2_in, size_t B, 
         float* d2 = nl[scale & 1][1];
         {
             dim3 grid(cdiv(ow, 64), cdiv(oh, 4), (unsigned)(B * 2));
-            k_s2_xyb_down<<<grid, 256, 0, c.stream>>>(l1, l2, (int)cw, (int)ch, (int)ow, (int)oh, n, ow * oh, xyb, d1, d2,
-                                                       has_next ? 1 : 0);
-            c.launches++;
+            CE_LAUNCH(c, "k_s2_xyb_down", (double)B * 4 * (12 * n + (has_next ? 6 * ow * oh : 0)),
+                      k_s2_xyb_down<<<grid, 256, 0, c.stream>>>(l1, l2, (int)cw, (int)ch, (int)ow, (int)oh, n, ow * oh, xyb, d1,
+                                                                 d2, has_next ? 1 : 0));
         }
         {
             dim3 grid(cdiv(ch, HP_ROWS), (unsigned)(B * 3));
-            k_s2_hpass<<<grid, 160, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n);
-            c.launches++;
+            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4, k_s2_hpass<<<grid, 160, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n));
         }
         const int nblk = cdiv(cw, VP_THREADS);
         float* dbg = (dbg_planes && scale == 0) ? dbg_planes : nullptr;
         {
             dim3 grid(nblk, (unsigned)(B * 3));
-            k_s2_vpass<<<grid, VP_THREADS, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, partials, dbg);
-            c.launches++;
+            CE_LAUNCH(c, "k_s2_vpass", (double)B * 3 * 7 * n * 4,
+                      k_s2_vpass<<<grid, VP_THREADS, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, partials, dbg));
         }
         {
             size_t total = B * 3 * 6;
-            k_s2_reduce<<<cdiv(total, 128), 128, 0, c.stream>>>(partials, nblk, total, scale, d_sums);
-            c.launches++;
+            CE_LAUNCH(c, "k_s2_reduce", (double)total * (nblk + 1) * 8,
+                      k_s2_reduce<<<cdiv(total, 128), 128, 0, c.stream>>>(partials, nblk, total, scale, d_sums));
         }
         if (dbg) {
             for (int cc = 0; cc < 3; cc++) {

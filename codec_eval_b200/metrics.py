@@ -220,6 +220,22 @@ class GpuMetrics:
     def launch_count(self) -> int:
         return int(self._L.ce_launch_count(self._h))
 
+    def profile(self, enable: bool = True, reset: bool = True):
+        """Per-kernel CUDA-event timing (name -> launches, ms, algorithmic bytes)."""
+        self._L.ce_profile_enable(self._h, int(enable))
+        if reset:
+            self._L.ce_profile_reset(self._h)
+
+    def profile_report(self):
+        n = self._L.ce_profile_report(self._h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self._L.ce_profile_report(self._h, buf, n + 1)
+        rows = {}
+        for line in buf.value.decode().splitlines():
+            name, launches, ms, nbytes = line.split("\t")
+            rows[name] = {"launches": int(launches), "ms": float(ms), "bytes": float(nbytes)}
+        return rows
+
     def _raise(self, st: int, metric: str, expected=None, actual=None):
         if st == _lib.CE_OK:
             return

@@ -89,6 +89,12 @@ CE_API const char* ce_last_error(const ce_ctx* ctx);
 /* number of this library's kernels launched on ctx since creation */
 CE_API uint64_t ce_launch_count(const ce_ctx* ctx);
 CE_API const char* ce_version(void);
+/* opt-in per-kernel CUDA-event timing on the context's stream (bench.py's roofline evidence).
+ * report: one line per kernel "name\tlaunches\tmilliseconds\talgorithmic_bytes\n"; returns the
+ * length needed.  Durations are collected when a batch call synchronises. */
+CE_API int ce_profile_enable(ce_ctx* ctx, int enable);
+CE_API int ce_profile_reset(ce_ctx* ctx);
+CE_API size_t ce_profile_report(ce_ctx* ctx, char* buf, size_t cap);
 
 /* ---- batched entry points ------------------------------------------ */
 
