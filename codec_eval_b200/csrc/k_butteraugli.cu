@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) k_ba_blur5(const float* __restrict__ in, 
             c = p[i]; l1 = p[(size_t)mirror(y - 1, h) * w + x]; r1 = p[(size_t)mirror(y + 1, h) * w + x];
             l2 = p[(size_t)mirror(y - 2, h) * w + x]; r2 = p[(size_t)mirror(y + 2, h) * w + x];
         }
-        out[t] = (c * w0 + (l1 + r1) * w1) + (l2 + r2) * w2;
+        out[t] = __fmaf_rn(l2 + r2, w2, __fmaf_rn(l1 + r1, w1, c * w0));  // libjxl Separable5 MulAdd chain
     }
 }
 
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) k_ba_blur_h(const float* __restrict__ in,
             if (x < w) {
                 float sum = 0.0f;
 #pragma unroll
-                for (int t = 0; t <= 2 * R; t++) sum += v[k + (RUP - R) + t] * c_ba.w[SLOT][t];
+                for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], c_ba.w[SLOT][t], sum);
                 o[(size_t)y * w + x] = sum * inv[x];
             }
         }
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in,
             if (y < h) {
                 float sum = 0.0f;
 #pragma unroll
-                for (int t = 0; t <= 2 * R; t++) sum += v[k + t] * c_ba.w[SLOT][t];
+                for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], c_ba.w[SLOT][t], sum);
                 o[(size_t)y * w + x] = sum * inv[y];
             }
         }

@@ -843,7 +843,7 @@ static void ba_conv_line(const float* in, size_t istride, float* out, size_t ost
         ptrdiff_t lo = x - R < 0 ? 0 : x - R;
         ptrdiff_t hi = x + R > len - 1 ? len - 1 : x + R;
         float sum = 0.0f;
-        for (ptrdiff_t j = lo; j <= hi; j++) sum += in[(size_t)j * istride] * k->w[j - x + R];
+        for (ptrdiff_t j = lo; j <= hi; j++) sum = fmaf(in[(size_t)j * istride], k->w[j - x + R], sum); /* libjxl MulAdd */
         out[(size_t)x * ostride] = sum * inv_weight[x];
     }
 }
@@ -867,7 +867,7 @@ static void ba_conv5_line(const float* in, size_t istride, float* out, size_t os
         float c = in[(size_t)x * istride];
         float l1 = in[(size_t)ba_mirror(x - 1, len) * istride], r1 = in[(size_t)ba_mirror(x + 1, len) * istride];
         float l2 = in[(size_t)ba_mirror(x - 2, len) * istride], r2 = in[(size_t)ba_mirror(x + 2, len) * istride];
-        out[(size_t)x * ostride] = (c * w0 + (l1 + r1) * w1) + (l2 + r2) * w2;
+        out[(size_t)x * ostride] = fmaf(l2 + r2, w2, fmaf(l1 + r1, w1, c * w0)); /* libjxl Separable5 MulAdd chain */
     }
 }
 
@@ -897,7 +897,7 @@ static void ba_blur(const float* in, size_t w, size_t h, float sigma, float* out
             for (ptrdiff_t j = lo; j <= hi; j++) {
                 float wt = k.w[j - (ptrdiff_t)y + R];
                 const float* r = tmp + (size_t)j * w;
-                for (size_t x = 0; x < w; x++) o[x] += r[x] * wt;
+                for (size_t x = 0; x < w; x++) o[x] = fmaf(r[x], wt, o[x]);
             }
             for (size_t x = 0; x < w; x++) o[x] *= invy[y];
         }
