@@ -3,14 +3,20 @@
 // two-resolution diffmap.
 //
 // Image index convention: NI = 2B images, image i = which*B + b (which 0 = reference).
-// Stages per resolution:
-//   blur sigma 1.2 (5-tap mirror) -> opsin dynamics -> blur 7.16 (LF) -> blur 3.22 (MF)
-//   -> blur 1.56 (UHF) with the range/clamp epilogues -> fused Malta (3 bands, 16 oriented line
-//   sums over a 9x9 window in shared memory) + L2 diffs -> mask (DiffPrecompute, blur 2.7,
-//   fuzzy erosion) -> combine -> diffmap; half-resolution diffmap supersample-added, then
-//   max / sum d^3,d^6,d^12 reduced in fp64 (warp shuffles -> block partials -> fixed order).
-// All separable blurs: shared-memory tiles, zero padding + per-coordinate 1/sum(in-range taps)
-// tables (the renormalised borders of libjxl's ConvolveBorderColumn).
+// Kernels per resolution (each stage's pointwise epilogue is fused into the blur that feeds it):
+//   k_ba_opsin   : sigma-1.2 blur (5-tap mirror, H+V through a smem tile) + opsin dynamics      lin -> xyb
+//   k_ba_blur_h  : sigma-7.16 (33 taps) along x                                               xyb -> tmp
+//   k_ba_blur_v  : sigma-7.16 along y + LF epilogue (mf_pre = xyb - lf, LF scaling)            tmp -> lf, mf_pre
+//   k_ba_blur2d<MF> : sigma-3.22 H+V through a smem tile + HF split epilogue                   mf_pre -> mf, hf_pre
+//   k_ba_blur2d<HF> : sigma-1.56 H+V + UHF split + mask precompute                             hf_pre -> hf, uhf, m
+//   k_ba_blur2d<NONE>: sigma-2.7 H+V of the mask input                                         m -> bl
+//   k_ba_malta   : Malta filters, 3 bands x {X,Y}: diffs staged in smem, 9x12 register window per
+//                  thread (4 pixels), 16 oriented line sums each, + L2 diffs                    -> ac
+//   k_ba_combine : fuzzy erosion, mask, DC/AC combine                                          -> diffmap
+// then the half-resolution diffmap is supersample-added and max / sum d^3,d^6,d^12 reduced in
+// fp64 (warp shuffles -> block partials -> fixed order).
+// Blurs use zero padding + per-coordinate 1/sum(in-range taps) tables (the renormalised
+// borders of libjxl's ConvolveBorderColumn); tile loads are 128-bit where the row pitch allows.
 #include "ce_common.cuh"
 #include "ce_internal.h"
 
@@ -93,100 +99,337 @@ static float* ba_inv_table(Context& c, int slot, size_t len) {
     return d;
 }
 
-// ---------------------------------------------------------------- 5-tap mirror blur (sigma 1.2)
+
+// ---------------------------------------------------------------- tile loader
 CE_DEVINL int mirror(int x, int n) {
     while (x < 0 || x >= n) { if (x < 0) x = -x - 1; else x = 2 * n - 1 - x; }
     return x;
 }
-// dir 0: along x, 1: along y.  planes [np][n]
-__global__ void __launch_bounds__(256) k_ba_blur5(const float* __restrict__ in, int w, int h, size_t n, size_t total, int dir,
-                                                   float* __restrict__ out) {
-    const float w0 = c_ba.w5[0], w1 = c_ba.w5[1], w2 = c_ba.w5[2];
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        size_t pl = t / n, i = t - pl * n;
-        int y = (int)(i / w), x = (int)(i - (size_t)y * w);
-        const float* p = in + pl * n;
-        float c, l1, r1, l2, r2;
-        if (dir == 0) {
-            const float* row = p + (size_t)y * w;
-            c = row[x]; l1 = row[mirror(x - 1, w)]; r1 = row[mirror(x + 1, w)]; l2 = row[mirror(x - 2, w)]; r2 = row[mirror(x + 2, w)];
+
+// s[r][4*c4 .. 4*c4+3] = plane[y0 + r][x0 + 4*c4 ..] for r < rows, c4 < COLS4; x0 % 4 == 0.
+// BORDER 0: zero outside the image, 1: mirror.  vec: w % 4 == 0 and the plane base is 16-B aligned.
+template <int BORDER, int COLS4>
+CE_DEVINL void load_tile(float* __restrict__ s, int pitch, const float* __restrict__ p, int w, int h, int x0, int y0,
+                         int rows, bool vec) {
+    for (int e = threadIdx.x; e < rows * COLS4; e += blockDim.x) {
+        const int r = e / COLS4, c4 = e - r * COLS4;
+        const int y = y0 + r, x = x0 + 4 * c4;
+        float4 v;
+        if (vec && y >= 0 && y < h && x >= 0 && x + 3 < w) {
+            v = *reinterpret_cast<const float4*>(p + (size_t)y * w + x);
         } else {
-            c = p[i]; l1 = p[(size_t)mirror(y - 1, h) * w + x]; r1 = p[(size_t)mirror(y + 1, h) * w + x];
-            l2 = p[(size_t)mirror(y - 2, h) * w + x]; r2 = p[(size_t)mirror(y + 2, h) * w + x];
+            float t[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int xx = x + k, yy = y;
+                if (BORDER == 1) {
+                    xx = mirror(xx, w); yy = mirror(yy, h);
+                    t[k] = p[(size_t)yy * w + xx];
+                } else {
+                    t[k] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? p[(size_t)yy * w + xx] : 0.0f;
+                }
+            }
+            v = make_float4(t[0], t[1], t[2], t[3]);
         }
-        out[t] = __fmaf_rn(l2 + r2, w2, __fmaf_rn(l1 + r1, w1, c * w0));  // libjxl Separable5 MulAdd chain
+        *reinterpret_cast<float4*>(s + r * pitch + 4 * c4) = v;
     }
 }
 
-// ---------------------------------------------------------------- generic separable blur
-// horizontal: tile 128 x 8, thread = 4 consecutive outputs of one row, LDS.128 staging
+// ---------------------------------------------------------------- sigma-1.2 blur (+ opsin dynamics)
+#define OP_TW 64
+#define OP_TH 16
+#define OP_P (OP_TW + 8)      // columns x0-4 .. x0+67
+#define OP_ROWS (OP_TH + 4)   // rows y0-2 .. y0+17
+
+CE_DEVINL float blur5(float l2, float l1, float c, float r1, float r2) {
+    return __fmaf_rn(l2 + r2, c_ba.w5[2], __fmaf_rn(l1 + r1, c_ba.w5[1], c * c_ba.w5[0]));  // libjxl Separable5 MulAdd chain
+}
+
+// OPSIN = true : lin [NI][3][n] -> xyb [NI][3][n] (blur + OpsinDynamicsImage), grid.z = image
+// OPSIN = false: one plane per grid.z, out = blurred plane (stage test entry)
+template <bool OPSIN>
+__global__ void __launch_bounds__(256) k_ba_opsin(const float* __restrict__ lin, int w, int h, size_t n, float intensity,
+                                                   float* __restrict__ out, int vec) {
+    constexpr int NPL = OPSIN ? 3 : 1;
+    __shared__ __align__(16) float s_in[NPL][OP_ROWS * OP_P];
+    __shared__ __align__(16) float s_h[NPL][OP_ROWS * OP_TW];
+    const int x0 = blockIdx.x * OP_TW, y0 = blockIdx.y * OP_TH;
+    const float* src = lin + (size_t)blockIdx.z * NPL * n;
+    float* dst = out + (size_t)blockIdx.z * NPL * n;
+#pragma unroll
+    for (int c = 0; c < NPL; c++) load_tile<1, OP_P / 4>(s_in[c], OP_P, src + (size_t)c * n, w, h, x0 - 4, y0 - 2, OP_ROWS, vec != 0);
+    __syncthreads();
+    // horizontal pass: (row, 4-column group) items
+    for (int e = threadIdx.x; e < OP_ROWS * (OP_TW / 4); e += 256) {
+        const int r = e >> 4, g = e & 15;
+#pragma unroll
+        for (int c = 0; c < NPL; c++) {
+            const float4* row = reinterpret_cast<const float4*>(s_in[c] + r * OP_P + 4 * g);
+            const float4 a = row[0], b = row[1], d = row[2];
+            const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+            float4 o;
+            o.x = blur5(v[2], v[3], v[4], v[5], v[6]);
+            o.y = blur5(v[3], v[4], v[5], v[6], v[7]);
+            o.z = blur5(v[4], v[5], v[6], v[7], v[8]);
+            o.w = blur5(v[5], v[6], v[7], v[8], v[9]);
+            *reinterpret_cast<float4*>(s_h[c] + r * OP_TW + 4 * g) = o;
+        }
+    }
+    __syncthreads();
+    const int g = threadIdx.x & 15, r = threadIdx.x >> 4;
+    const int x = x0 + 4 * g, y = y0 + r;
+    if (y >= h || x >= w) return;
+    float bl[NPL][4];
+#pragma unroll
+    for (int c = 0; c < NPL; c++) {
+        float4 q[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) q[j] = *reinterpret_cast<const float4*>(s_h[c] + (r + j) * OP_TW + 4 * g);
+        bl[c][0] = blur5(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x);
+        bl[c][1] = blur5(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y);
+        bl[c][2] = blur5(q[0].z, q[1].z, q[2].z, q[3].z, q[4].z);
+        bl[c][3] = blur5(q[0].w, q[1].w, q[2].w, q[3].w, q[4].w);
+    }
+    float res[NPL][4];
+    if (OPSIN) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float p0, p1, p2;
+            ba_opsin_absorbance(bl[0][k] * intensity, bl[NPL > 1 ? 1 : 0][k] * intensity, bl[NPL > 2 ? 2 : 0][k] * intensity, p0, p1, p2);
+            p0 = fmaxf(p0, 1e-4f); p1 = fmaxf(p1, 1e-4f); p2 = fmaxf(p2, 1e-4f);
+            const float s0 = fmaxf(ba_gamma(p0) / p0, 1e-4f);
+            const float s1 = fmaxf(ba_gamma(p1) / p1, 1e-4f);
+            const float s2 = fmaxf(ba_gamma(p2) / p2, 1e-4f);
+            const int ci = (r + 2) * OP_P + 4 * g + 4 + k;
+            float c0, c1, c2;
+            ba_opsin_absorbance(s_in[0][ci] * intensity, s_in[NPL > 1 ? 1 : 0][ci] * intensity, s_in[NPL > 2 ? 2 : 0][ci] * intensity, c0, c1, c2);
+            c0 *= s0; c1 *= s1; c2 *= s2;
+            c0 = fmaxf(c0, 1.7557483643287353f);
+            c1 = fmaxf(c1, 1.7557483643287353f);
+            c2 = fmaxf(c2, 12.226454707163354f);
+            res[0][k] = c0 - c1; res[NPL > 1 ? 1 : 0][k] = c0 + c1; res[NPL > 2 ? 2 : 0][k] = c2;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) res[0][k] = bl[0][k];
+    }
+    const size_t idx = (size_t)y * w + x;
+#pragma unroll
+    for (int c = 0; c < NPL; c++) {
+        float* o = dst + (size_t)c * n + idx;
+        if (vec) *reinterpret_cast<float4*>(o) = make_float4(res[c][0], res[c][1], res[c][2], res[c][3]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (x + k < w) o[k] = res[c][k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- wide separable blur (sigma 7.16)
+// horizontal: tile 128 x 8, thread = 4 consecutive outputs of one row
 template <int SLOT, int R>
 __global__ void __launch_bounds__(256) k_ba_blur_h(const float* __restrict__ in, int w, int h, size_t n,
-                                                    const float* __restrict__ inv, float* __restrict__ out) {
+                                                    const float* __restrict__ inv, float* __restrict__ out, int vec) {
     constexpr int RUP = (R + 3) & ~3;
     constexpr int PITCH = 128 + 2 * RUP;
-    __shared__ __align__(16) float s[8][PITCH];
+    __shared__ __align__(16) float s[8 * PITCH];
     const int x0 = blockIdx.x * 128, y0 = blockIdx.y * 8;
     const float* p = in + (size_t)blockIdx.z * n;
     float* o = out + (size_t)blockIdx.z * n;
-    for (int e = threadIdx.x; e < 8 * PITCH; e += 256) {
-        int ry = e / PITCH, i = e - ry * PITCH;
-        int x = x0 - RUP + i, y = y0 + ry;
-        s[ry][i] = (x >= 0 && x < w && y < h) ? p[(size_t)y * w + x] : 0.0f;
-    }
+    load_tile<0, PITCH / 4>(s, PITCH, p, w, h, x0 - RUP, y0, 8, vec != 0);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int y = y0 + ty;
+    const int y = y0 + ty, x = x0 + tx * 4;
+    if (y >= h || x >= w) return;
     float v[4 + 2 * RUP];
 #pragma unroll
     for (int q = 0; q < (4 + 2 * RUP) / 4; q++) {
-        float4 f = *reinterpret_cast<const float4*>(&s[ty][tx * 4 + q * 4]);
+        float4 f = *reinterpret_cast<const float4*>(&s[ty * PITCH + tx * 4 + q * 4]);
         v[q * 4] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
     }
-    if (y < h) {
+    float res[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int x = x0 + tx * 4 + k;
-            if (x < w) {
-                float sum = 0.0f;
+    for (int k = 0; k < 4; k++) {
+        float sum = 0.0f;
 #pragma unroll
-                for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], c_ba.w[SLOT][t], sum);
-                o[(size_t)y * w + x] = sum * inv[x];
-            }
+        for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], c_ba.w[SLOT][t], sum);
+        res[k] = sum * (x + k < w ? inv[x + k] : 0.0f);
+    }
+    float* d = o + (size_t)y * w + x;
+    if (vec) *reinterpret_cast<float4*>(d) = make_float4(res[0], res[1], res[2], res[3]);
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (x + k < w) d[k] = res[k];
+    }
+}
+
+// vertical: tile 32 x 64, thread = 8 consecutive outputs of one column, NPL planes per image in one block.
+// EPI 0: out[pl] = blurred plane (grid.z counts plane groups of NPL)
+// EPI 1 (NPL = 3): LF epilogue -- lf = blurred xyb; mf_pre = xyb - lf; lf scaled (XybLowFreqToVals)
+template <int SLOT, int R, int NPL, int EPI>
+__global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in, int w, int h, size_t n,
+                                                    const float* __restrict__ inv, float* __restrict__ out,
+                                                    const float* __restrict__ xyb, float* __restrict__ mf_pre) {
+    constexpr int ROWS = 64 + 2 * R;
+    __shared__ __align__(16) float s[ROWS * 32];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 64;
+    const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int x = x0 + cx;
+    const size_t base = (size_t)blockIdx.z * NPL * n;
+    const bool vec = (w & 3) == 0;
+    float res[NPL][8];
+#pragma unroll
+    for (int c = 0; c < NPL; c++) {
+        if (c) __syncthreads();
+        load_tile<0, 8>(s, 32, in + base + (size_t)c * n, w, h, x0, y0 - R, ROWS, vec);
+        __syncthreads();
+        float v[8 + 2 * R];
+#pragma unroll
+        for (int q = 0; q < 8 + 2 * R; q++) v[q] = s[(g * 8 + q) * 32 + cx];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int y = y0 + g * 8 + k;
+            float sum = 0.0f;
+#pragma unroll
+            for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], c_ba.w[SLOT][t], sum);
+            res[c][k] = sum * (y < h ? inv[y] : 0.0f);
+        }
+    }
+    if (x >= w) return;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int y = y0 + g * 8 + k;
+        if (y >= h) break;
+        const size_t idx = base + (size_t)y * w + x;
+        if (EPI == 0) {
+#pragma unroll
+            for (int c = 0; c < NPL; c++) out[idx + (size_t)c * n] = res[c][k];
+        } else {
+            const float lx = res[0][k], ly = res[NPL > 1 ? 1 : 0][k], lb = res[NPL > 2 ? 2 : 0][k];
+            mf_pre[idx] = xyb[idx] - lx;
+            mf_pre[idx + n] = xyb[idx + n] - ly;
+            mf_pre[idx + 2 * n] = xyb[idx + 2 * n] - lb;
+            const float bb = __fmaf_rn(-0.362267051518f, ly, lb);
+            out[idx + 2 * n] = bb * 49.87984651440f;
+            out[idx] = lx * 33.832837186260f;
+            out[idx + n] = ly * 14.458268100570f;
         }
     }
 }
 
-// vertical: tile 32 x 64, thread = 8 consecutive outputs of one column
-template <int SLOT, int R>
-__global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in, int w, int h, size_t n,
-                                                    const float* __restrict__ inv, float* __restrict__ out) {
-    constexpr int ROWS = 64 + 2 * R;
-    __shared__ float s[ROWS][32];
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 64;
-    const float* p = in + (size_t)blockIdx.z * n;
-    float* o = out + (size_t)blockIdx.z * n;
-    for (int e = threadIdx.x; e < ROWS * 32; e += 256) {
-        int ry = e >> 5, cx = e & 31;
-        int x = x0 + cx, y = y0 - R + ry;
-        s[ry][cx] = (x < w && y >= 0 && y < h) ? p[(size_t)y * w + x] : 0.0f;
-    }
-    __syncthreads();
-    const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+// ---------------------------------------------------------------- fused 2-D blur (H then V through smem) + epilogues
+// tile 64 x 32 outputs; the horizontal pass runs on the 32 + 2R rows the vertical pass needs.
+// EPI 0 (NPL 1)  : out = blurred plane
+// EPI 2 (NPL 3)  : MF -- in = mf_pre [img][3][n]; out_a = mf (range ops on X,Y; B as blurred) [img][3][n];
+//                   out_b = hf_pre [img][2][n] (X suppressed by Y)
+// EPI 3 (NPL 2)  : HF -- in = hf_pre [img][2][n]; out_a = hf [img][2][n]; out_b = uhf [img][2][n];
+//                   out_c = mask input m [img][n] = DiffPrecompute(combine(hf, uhf))
+#define B2_TW 64
+#define B2_TH 32
+template <int SLOT, int R, int NPL, int EPI>
+__global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in, int w, int h, size_t n,
+                                                    const float* __restrict__ inv_x, const float* __restrict__ inv_y,
+                                                    float* __restrict__ out_a, float* __restrict__ out_b,
+                                                    float* __restrict__ out_c) {
+    constexpr int RUP = (R + 3) & ~3;
+    constexpr int PITCH = B2_TW + 2 * RUP;
+    constexpr int ROWS = B2_TH + 2 * R;
+    __shared__ __align__(16) float s_in[ROWS * PITCH];
+    __shared__ __align__(16) float s_h[ROWS * B2_TW];
+    const int x0 = blockIdx.x * B2_TW, y0 = blockIdx.y * B2_TH;
+    const size_t img = blockIdx.z;
+    const bool vec = (w & 3) == 0;
+    const int cx = threadIdx.x & 63, g = threadIdx.x >> 6;   // vertical pass: column cx, rows g*8 .. g*8+7
     const int x = x0 + cx;
-    float v[8 + 2 * R];
+    float res[NPL][8], ctr[NPL][8];
 #pragma unroll
-    for (int q = 0; q < 8 + 2 * R; q++) v[q] = s[g * 8 + q][cx];
-    if (x < w) {
+    for (int c = 0; c < NPL; c++) {
+        if (c) __syncthreads();
+        load_tile<0, PITCH / 4>(s_in, PITCH, in + (img * NPL + c) * n, w, h, x0 - RUP, y0 - R, ROWS, vec);
+        __syncthreads();
+        for (int e = threadIdx.x; e < ROWS * (B2_TW / 4); e += 256) {
+            const int r = e >> 4, q4 = e & 15;
+            float v[4 + 2 * RUP];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            int y = y0 + g * 8 + k;
-            if (y < h) {
+            for (int q = 0; q < (4 + 2 * RUP) / 4; q++) {
+                float4 f = *reinterpret_cast<const float4*>(&s_in[r * PITCH + q4 * 4 + q * 4]);
+                v[q * 4] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
+            }
+            float o4[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int xx = x0 + q4 * 4 + k;
                 float sum = 0.0f;
 #pragma unroll
-                for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], c_ba.w[SLOT][t], sum);
-                o[(size_t)y * w + x] = sum * inv[y];
+                for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], c_ba.w[SLOT][t], sum);
+                o4[k] = sum * (xx < w ? inv_x[xx] : 0.0f);
             }
+            *reinterpret_cast<float4*>(&s_h[r * B2_TW + q4 * 4]) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+        if (EPI != 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) ctr[c][k] = s_in[(g * 8 + k + R) * PITCH + cx + RUP];
+        }
+        __syncthreads();
+        float v[8 + 2 * R];
+#pragma unroll
+        for (int q = 0; q < 8 + 2 * R; q++) v[q] = s_h[(g * 8 + q) * B2_TW + cx];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int y = y0 + g * 8 + k;
+            float sum = 0.0f;
+#pragma unroll
+            for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], c_ba.w[SLOT][t], sum);
+            res[c][k] = sum * (y < h ? inv_y[y] : 0.0f);
+        }
+    }
+    if (x >= w) return;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int y = y0 + g * 8 + k;
+        if (y >= h) break;
+        const size_t i = (size_t)y * w + x;
+        if (EPI == 0) {
+#pragma unroll
+            for (int c = 0; c < NPL; c++) out_a[(img * NPL + c) * n + i] = res[c][k];
+        } else if (EPI == 2) {
+            const float bx = res[0][k], by = res[NPL > 1 ? 1 : 0][k];
+            const float hfx = ctr[0][k] - bx, hfy = ctr[NPL > 1 ? 1 : 0][k] - by;
+            float* M = out_a + img * 3 * n + i;
+            M[0] = ba_remove_range(bx, 0.29f);
+            M[n] = ba_amplify_range(by, 0.1f);
+            M[2 * n] = res[NPL > 2 ? 2 : 0][k];
+            const float scaler = __fmaf_rn(46.0f / __fmaf_rn(hfy, hfy, 46.0f), (float)(1.0 - 0.653020556257), 0.653020556257f);
+            float* H = out_b + img * 2 * n + i;
+            H[0] = scaler * hfx;
+            H[n] = hfy;
+        } else {
+            float* H = out_a + img * 2 * n + i;
+            float* U = out_b + img * 2 * n + i;
+            float hx, ux, hy, uy;
+            {
+                const float hb = res[0][k];
+                ux = ba_remove_range(ctr[0][k] - hb, 0.04f);
+                hx = ba_remove_range(hb, 1.5f);
+            }
+            {
+                float hb = ba_max_clamp(res[NPL > 1 ? 1 : 0][k], 28.4691806922f);
+                float u = ctr[NPL > 1 ? 1 : 0][k] - hb;
+                u = ba_max_clamp(u, 5.19175294647f);
+                uy = u * 2.69313763794f;
+                hb = hb * 2.155f;
+                hy = ba_amplify_range(hb, 0.132f);
+            }
+            H[0] = hx; H[n] = hy; U[0] = ux; U[n] = uy;
+            // mask input: DiffPrecompute(sqrt(((uhf_x+hf_x)*2.5)^2 + (uhf_y*0.4+hf_y*0.4)^2))
+            const float kMul = 6.19424080439f, kBias = 12.61050594197f;
+            const float bias = kMul * kBias;
+            const float xd = (ux + hx) * 2.5f;
+            const float yd = uy * 0.4f + hy * 0.4f;
+            const float vv = sqrtf(xd * xd + yd * yd);
+            out_c[img * n + i] = sqrtf(kMul * fabsf(vv) + bias) - sqrtf(bias);
         }
     }
 }
@@ -196,146 +439,14 @@ struct BlurTables {
     float* inv_y[4];
 };
 
-template <int SLOT, int R>
-static void blur_slot(Context& c, const float* in, float* tmp, float* out, size_t np, size_t w, size_t h, const BlurTables& t) {
-    const size_t n = w * h;
-    for (size_t p0 = 0; p0 < np; p0 += 65535) {
-        unsigned z = (unsigned)std::min<size_t>(65535, np - p0);
-        dim3 gh(cdiv(w, 128), cdiv(h, 8), z);
-        static const char* const hn[4] = {"k_ba_blur_h<R16>", "k_ba_blur_h<R7>", "k_ba_blur_h<R3>", "k_ba_blur_h<R6>"};
-        static const char* const vn[4] = {"k_ba_blur_v<R16>", "k_ba_blur_v<R7>", "k_ba_blur_v<R3>", "k_ba_blur_v<R6>"};
-        CE_LAUNCH(c, hn[SLOT], (double)z * n * 8,
-                  k_ba_blur_h<SLOT, R><<<gh, 256, 0, c.stream>>>(in + p0 * n, (int)w, (int)h, n, t.inv_x[SLOT], tmp + p0 * n));
-        dim3 gv(cdiv(w, 32), cdiv(h, 64), z);
-        CE_LAUNCH(c, vn[SLOT], (double)z * n * 8,
-                  k_ba_blur_v<SLOT, R><<<gv, 256, 0, c.stream>>>(tmp + p0 * n, (int)w, (int)h, n, t.inv_y[SLOT], out + p0 * n));
-    }
-    CE_CUDA(cudaGetLastError());
-}
-static void blur_planes(Context& c, int slot, const float* in, float* tmp, float* out, size_t np, size_t w, size_t h,
-                        const BlurTables& t) {
-    switch (slot) {
-        case 0: blur_slot<0, 16>(c, in, tmp, out, np, w, h, t); break;
-        case 1: blur_slot<1, 7>(c, in, tmp, out, np, w, h, t); break;
-        case 2: blur_slot<2, 3>(c, in, tmp, out, np, w, h, t); break;
-        default: blur_slot<3, 6>(c, in, tmp, out, np, w, h, t); break;
-    }
-}
-
-// ---------------------------------------------------------------- pointwise stages
-// opsin dynamics: lin [NI][3][n], blurred [NI][3][n] -> xyb [NI][3][n]
-__global__ void __launch_bounds__(256) k_ba_opsin(const float* __restrict__ lin, const float* __restrict__ blurred, size_t n,
-                                                   size_t total, float intensity, float* __restrict__ xyb) {
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        size_t im = t / n, i = t - im * n;
-        const float* L = lin + im * 3 * n + i;
-        const float* Bl = blurred + im * 3 * n + i;
-        float p0, p1, p2;
-        ba_opsin_absorbance(Bl[0] * intensity, Bl[n] * intensity, Bl[2 * n] * intensity, p0, p1, p2);
-        p0 = fmaxf(p0, 1e-4f); p1 = fmaxf(p1, 1e-4f); p2 = fmaxf(p2, 1e-4f);
-        float s0 = fmaxf(ba_gamma(p0) / p0, 1e-4f);
-        float s1 = fmaxf(ba_gamma(p1) / p1, 1e-4f);
-        float s2 = fmaxf(ba_gamma(p2) / p2, 1e-4f);
-        float c0, c1, c2;
-        ba_opsin_absorbance(L[0] * intensity, L[n] * intensity, L[2 * n] * intensity, c0, c1, c2);
-        c0 *= s0; c1 *= s1; c2 *= s2;
-        c0 = fmaxf(c0, 1.7557483643287353f);
-        c1 = fmaxf(c1, 1.7557483643287353f);
-        c2 = fmaxf(c2, 12.226454707163354f);
-        float* o = xyb + im * 3 * n + i;
-        o[0] = c0 - c1; o[n] = c0 + c1; o[2 * n] = c2;
-    }
-}
-
-// out = a - b elementwise
-__global__ void __launch_bounds__(256) k_ba_sub(const float* __restrict__ a, const float* __restrict__ b, size_t total,
-                                                 float* __restrict__ out) {
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
-        out[t] = a[t] - b[t];
-}
-
-// t = unblurred mf [NI][3][n]; mf = blurred mf [NI][3][n] (in/out); hf [NI][2][n] out
-__global__ void __launch_bounds__(256) k_ba_split_hf(const float* __restrict__ t_, float* __restrict__ mf, size_t n,
-                                                      size_t total, float* __restrict__ hf) {
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        size_t im = t / n, i = t - im * n;
-        const float* T = t_ + im * 3 * n + i;
-        float* M = mf + im * 3 * n + i;
-        float bx = M[0], by = M[n];
-        float hfx = T[0] - bx, hfy = T[n] - by;
-        M[0] = ba_remove_range(bx, 0.29f);
-        M[n] = ba_amplify_range(by, 0.1f);
-        float scaler = __fmaf_rn(46.0f / __fmaf_rn(hfy, hfy, 46.0f), (float)(1.0 - 0.653020556257), 0.653020556257f);
-        float* H = hf + im * 2 * n + i;
-        H[0] = scaler * hfx;
-        H[n] = hfy;
-    }
-}
-
-// hf [NI][2][n] (orig in, final out), hfb blurred [NI][2][n], uhf out
-__global__ void __launch_bounds__(256) k_ba_split_uhf(float* __restrict__ hf, const float* __restrict__ hfb, size_t n,
-                                                       size_t total, float* __restrict__ uhf) {
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        size_t im = t / n, i = t - im * n;
-        float* H = hf + im * 2 * n + i;
-        const float* Bq = hfb + im * 2 * n + i;
-        float* U = uhf + im * 2 * n + i;
-        {
-            float h = Bq[0];
-            float u = H[0] - h;
-            H[0] = ba_remove_range(h, 1.5f);
-            U[0] = ba_remove_range(u, 0.04f);
-        }
-        {
-            float h = ba_max_clamp(Bq[n], 28.4691806922f);
-            float u = H[n] - h;
-            u = ba_max_clamp(u, 5.19175294647f);
-            u = u * 2.69313763794f;
-            h = h * 2.155f;
-            h = ba_amplify_range(h, 0.132f);
-            H[n] = h;
-            U[n] = u;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_ba_lf_vals(float* __restrict__ lf, size_t n, size_t total) {
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        size_t im = t / n, i = t - im * n;
-        float* Lp = lf + im * 3 * n + i;
-        float x = Lp[0], y = Lp[n], b = Lp[2 * n];
-        float bb = __fmaf_rn(-0.362267051518f, y, b);
-        Lp[2 * n] = bb * 49.87984651440f;
-        Lp[0] = x * 33.832837186260f;
-        Lp[n] = y * 14.458268100570f;
-    }
-}
-
-// mask input per image: m = DiffPrecompute(sqrt(((uhf_x+hf_x)*2.5)^2 + (uhf_y*0.4+hf_y*0.4)^2))
-__global__ void __launch_bounds__(256) k_ba_mask_pre(const float* __restrict__ hf, const float* __restrict__ uhf, size_t n,
-                                                      size_t total, float* __restrict__ m) {
-    const float kMul = 6.19424080439f, kBias = 12.61050594197f;
-    const float bias = kMul * kBias;
-    const float sqrt_bias = sqrtf(bias);
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        size_t im = t / n, i = t - im * n;
-        const float* H = hf + im * 2 * n + i;
-        const float* U = uhf + im * 2 * n + i;
-        float xd = (U[0] + H[0]) * 2.5f;
-        float yd = U[n] * 0.4f + H[n] * 0.4f;
-        float v = sqrtf(xd * xd + yd * yd);
-        m[t] = sqrtf(kMul * fabsf(v) + bias) - sqrt_bias;
-    }
-}
-
 // ---------------------------------------------------------------- Malta
-#define MT_TW 32
+#define MT_TW 64
 #define MT_TH 16
 #define MT_P (MT_TW + 8)
 #define MT_ROWS (MT_TH + 8)
-#define D(dy, dx) s[(dy) * MT_P + (dx)]
-
-CE_DEVINL float malta_hf(const float* s) {  // s -> centre of the window, pitch MT_P
+#define D(dy, dx) win[(dy) + 4][(dx) + 4 + K]
+template <int K>
+CE_DEVINL float malta_hf(const float (&win)[9][12]) {  // pixel K of the thread's 4; window rows -4..4, cols -4..7
     float acc = 0.0f, t;
     t = D(0,-4) + D(0,-3) + D(0,-2) + D(0,-1) + D(0,0) + D(0,1) + D(0,2) + D(0,3) + D(0,4);
     acc = __fmaf_rn(t, t, acc);
@@ -371,7 +482,8 @@ CE_DEVINL float malta_hf(const float* s) {  // s -> centre of the window, pitch 
     acc = __fmaf_rn(t, t, acc);
     return acc;
 }
-CE_DEVINL float malta_lf(const float* s) {  // s -> centre of the window, pitch MT_P
+template <int K>
+CE_DEVINL float malta_lf(const float (&win)[9][12]) {
     float acc = 0.0f, t;
     t = D(0,-4) + D(0,-2) + D(0,0) + D(0,2) + D(0,4);
     acc = __fmaf_rn(t, t, acc);
@@ -409,6 +521,7 @@ CE_DEVINL float malta_lf(const float* s) {  // s -> centre of the window, pitch 
 }
 #undef D
 
+
 struct MaltaBand {
     float norm2_0gt1, norm2_0lt1, norm1;
 };
@@ -437,63 +550,138 @@ CE_DEVINL float malta_diff(float v0, float v1, const MaltaBand& p) {
     return d;
 }
 
-// grid (tiles_x, tiles_y, B).  Planes of channel C for image 0 / image 1 of each pair:
-// uhf,hf: [NI][2][n]; mf: [NI][3][n].  ac out: [B][2][n] plane C.
-template <int C>
-__global__ void __launch_bounds__(256) k_ba_malta(const float* __restrict__ uhf, const float* __restrict__ hf,
-                                                   const float* __restrict__ mf, int w, int h, size_t n, size_t B,
-                                                   MaltaParams prm, float* __restrict__ ac) {
-    __shared__ float s_d[MT_ROWS * MT_P];
-    const size_t b = blockIdx.z;
-    const int tx0 = blockIdx.x * MT_TW, ty0 = blockIdx.y * MT_TH;
-    const int ox = threadIdx.x & 31, oy0 = threadIdx.x >> 5;
-    const float* band0[3] = {uhf + (b * 2 + C) * n, hf + (b * 2 + C) * n, mf + (b * 3 + C) * n};
-    const float* band1[3] = {uhf + ((B + b) * 2 + C) * n, hf + ((B + b) * 2 + C) * n, mf + ((B + b) * 3 + C) * n};
-    float acc[2] = {0.0f, 0.0f};
+
+struct MaltaParams2 {
+    MaltaParams ch[2];
+};
+
+// Pointwise: the asymmetric, masked difference the Malta filters sum over, for the 3 bands x {X,Y} of every
+// pair.  uhf,hf: [NI][2][n]; mf: [NI][3][n]  ->  diff [B][2 ch][3 bands][n].  One thread = 4 pixels (VEC) or 1.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_ba_malta_diff(const float* __restrict__ uhf, const float* __restrict__ hf,
+                                                        const float* __restrict__ mf, size_t n, size_t B,
+                                                        const __grid_constant__ MaltaParams2 prm2, float* __restrict__ diff) {
+    const size_t per = VEC ? n / 4 : n;
+    const size_t total = B * 2 * per;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t bc = t / per, q = t - bc * per;
+        const size_t b = bc >> 1;
+        const int C = (int)(bc & 1);
+        const size_t i = VEC ? q * 4 : q;
+        const float* p0[3] = {uhf + (b * 2 + C) * n + i, hf + (b * 2 + C) * n + i, mf + (b * 3 + C) * n + i};
+        const float* p1[3] = {uhf + ((B + b) * 2 + C) * n + i, hf + ((B + b) * 2 + C) * n + i, mf + ((B + b) * 3 + C) * n + i};
+        float* o = diff + bc * 3 * n + i;
+        if (VEC) {
+            float4 a[3], d[3];
 #pragma unroll
-    for (int bd = 0; bd < 3; bd++) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < MT_ROWS * MT_P; e += 256) {
-            int ry = e / MT_P, rx = e - ry * MT_P;
-            int x = tx0 - 4 + rx, y = ty0 - 4 + ry;
-            float d = 0.0f;
-            if (x >= 0 && x < w && y >= 0 && y < h) {
-                size_t idx = (size_t)y * w + x;
-                d = malta_diff(band0[bd][idx], band1[bd][idx], prm.band[bd]);
+            for (int bd = 0; bd < 3; bd++) {
+                a[bd] = *reinterpret_cast<const float4*>(p0[bd]);
+                d[bd] = *reinterpret_cast<const float4*>(p1[bd]);
             }
-            s_d[e] = d;
-        }
-        __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const float* ctr = s_d + (oy0 + k * 8 + 4) * MT_P + ox + 4;
-            float m = (bd == 0) ? malta_hf(ctr) : malta_lf(ctr);
-            acc[k] += m;
+            for (int bd = 0; bd < 3; bd++) {
+                const MaltaBand& mb = prm2.ch[C].band[bd];
+                *reinterpret_cast<float4*>(o + (size_t)bd * n) =
+                    make_float4(malta_diff(a[bd].x, d[bd].x, mb), malta_diff(a[bd].y, d[bd].y, mb),
+                                malta_diff(a[bd].z, d[bd].z, mb), malta_diff(a[bd].w, d[bd].w, mb));
+            }
+        } else {
+#pragma unroll
+            for (int bd = 0; bd < 3; bd++) o[(size_t)bd * n] = malta_diff(*p0[bd], *p1[bd], prm2.ch[C].band[bd]);
         }
     }
+}
+
+// grid (tiles_x, tiles_y, 2B): blockIdx.z = b*2 + C.  diff: [B][2][3][n]; hf: [NI][2][n]; mf: [NI][3][n];
+// ac out: [B][2][n] plane C.  The three band tiles (+ halo 4, zero outside the image) are staged with
+// cp.async; each thread then pulls the 9x12 window of its 4 pixels into registers (27 LDS.128 per band)
+// and evaluates the 16 oriented line sums per pixel from there.
+__global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ diff, const float* __restrict__ hf,
+                                                      const float* __restrict__ mf, int w, int h, size_t n, size_t B,
+                                                      const __grid_constant__ MaltaParams2 prm2, float* __restrict__ ac) {
+    __shared__ __align__(16) float s_d[3][MT_ROWS * MT_P];
+    const size_t b = blockIdx.z >> 1;
+    const int C = blockIdx.z & 1;
+    const MaltaParams& prm = prm2.ch[C];
+    const int tx0 = blockIdx.x * MT_TW, ty0 = blockIdx.y * MT_TH;
+    const int g = threadIdx.x & 15, oy = threadIdx.x >> 4;
+    const bool vec = (w & 3) == 0;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        int x = tx0 + ox, y = ty0 + oy0 + k * 8;
-        if (x < w && y < h) {
-            size_t idx = (size_t)y * w + x;
-            float total = acc[k];
-            {   // L2DiffAsymmetric on hf
-                float v0 = band0[1][idx], v1 = band1[1][idx];
-                float diff = v0 - v1;
-                total = __fmaf_rn(diff * diff, prm.l2_hf_gt, total);
-                float fabs0 = fabsf(v0);
-                float too_small = 0.4f * fabs0, too_big = fabs0;
-                float if_neg = v1 > -too_small ? v1 + too_small : (v1 < -too_big ? -v1 - too_big : 0.0f);
-                float if_pos = v1 < too_small ? too_small - v1 : (v1 > too_big ? v1 - too_big : 0.0f);
-                float v = v0 < 0.0f ? if_neg : if_pos;
-                total = __fmaf_rn(prm.l2_hf_lt, v * v, total);
+    for (int bd = 0; bd < 3; bd++)
+        load_tile_async<MT_P / 4>(s_d[bd], MT_P, diff + ((size_t)blockIdx.z * 3 + bd) * n, w, h, tx0 - 4, ty0 - 4, MT_ROWS, vec);
+    cp_async_commit();
+    const int x = tx0 + 4 * g, y = ty0 + oy;
+    const bool live = y < h && x < w;
+    cp_async_wait<0>();
+    __syncthreads();
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int bd = 0; bd < 3; bd++) {
+        float win[9][12];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const float4 f = *reinterpret_cast<const float4*>(&s_d[bd][(oy + r) * MT_P + 4 * g + 4 * q]);
+                win[r][4 * q] = f.x; win[r][4 * q + 1] = f.y; win[r][4 * q + 2] = f.z; win[r][4 * q + 3] = f.w;
             }
-            {   // L2Diff on mf
-                float dm = band0[2][idx] - band1[2][idx];
-                total = __fmaf_rn(dm * dm, prm.l2_mf, total);
-            }
-            ac[(b * 2 + C) * n + idx] = total;
         }
+        if (bd == 0) {
+            acc[0] += malta_hf<0>(win); acc[1] += malta_hf<1>(win); acc[2] += malta_hf<2>(win); acc[3] += malta_hf<3>(win);
+        } else {
+            acc[0] += malta_lf<0>(win); acc[1] += malta_lf<1>(win); acc[2] += malta_lf<2>(win); acc[3] += malta_lf<3>(win);
+        }
+    }
+    if (!live) return;
+    const size_t idx = (size_t)(live ? y : 0) * w + (live ? x : 0);
+    const float* h0 = hf + (b * 2 + C) * n + idx;
+    const float* h1 = hf + ((B + b) * 2 + C) * n + idx;
+    const float* m0 = mf + (b * 3 + C) * n + idx;
+    const float* m1 = mf + ((B + b) * 3 + C) * n + idx;
+    float hv0[4], hv1[4], mv0[4], mv1[4];
+    if (vec) {
+        const float4 a = *reinterpret_cast<const float4*>(h0), q = *reinterpret_cast<const float4*>(h1);
+        const float4 m = *reinterpret_cast<const float4*>(m0), o = *reinterpret_cast<const float4*>(m1);
+        hv0[0] = a.x; hv0[1] = a.y; hv0[2] = a.z; hv0[3] = a.w; hv1[0] = q.x; hv1[1] = q.y; hv1[2] = q.z; hv1[3] = q.w;
+        mv0[0] = m.x; mv0[1] = m.y; mv0[2] = m.z; mv0[3] = m.w; mv1[0] = o.x; mv1[1] = o.y; mv1[2] = o.z; mv1[3] = o.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool ok = live && x + k < w;
+            hv0[k] = ok ? h0[k] : 0.0f; hv1[k] = ok ? h1[k] : 0.0f;
+            mv0[k] = ok ? m0[k] : 0.0f; mv1[k] = ok ? m1[k] : 0.0f;
+        }
+    }
+    float l2a[4], l2b[4], l2c[4];   // the three L2 products, added after the Malta sums in the upstream order
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float v0 = hv0[k], v1 = hv1[k];
+        const float df = v0 - v1;
+        l2a[k] = df * df;
+        const float fabs0 = fabsf(v0);
+        const float too_small = 0.4f * fabs0, too_big = fabs0;
+        const float if_neg = v1 > -too_small ? v1 + too_small : (v1 < -too_big ? -v1 - too_big : 0.0f);
+        const float if_pos = v1 < too_small ? too_small - v1 : (v1 > too_big ? v1 - too_big : 0.0f);
+        const float v = v0 < 0.0f ? if_neg : if_pos;
+        l2b[k] = v * v;
+        const float dm = mv0[k] - mv1[k];
+        l2c[k] = dm * dm;
+    }
+    float tot[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float total = acc[k];
+        total = __fmaf_rn(l2a[k], prm.l2_hf_gt, total);   // L2DiffAsymmetric on hf
+        total = __fmaf_rn(prm.l2_hf_lt, l2b[k], total);
+        total = __fmaf_rn(l2c[k], prm.l2_mf, total);      // L2Diff on mf
+        tot[k] = total;
+    }
+    float* o = ac + (b * 2 + C) * n + idx;
+    if (vec) *reinterpret_cast<float4*>(o) = make_float4(tot[0], tot[1], tot[2], tot[3]);
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (x + k < w) o[k] = tot[k];
     }
 }
 
@@ -659,14 +847,21 @@ static MaltaParams make_malta_params(int c, float hf_asym) {
     return p;
 }
 
+
+// per-level planes.  Aliasing (a buffer is reused once its producer's consumers have all run):
+//   hf_pre = tmp[0..1]            (tmp is dead after the LF vertical pass)
+//   hf, m  = xyb[0..1], xyb[2]    (xyb is dead after the LF vertical pass)
+//   uhf, bl = mf_pre[0..1], [2]   (mf_pre is dead after the MF blur)
 struct BaLevelBufs {
-    float *tmpA, *tmpB, *xyb, *lf, *mf, *hf, *uhf, *ac, *m, *bl;
+    float *xyb, *tmp, *lf, *mf_pre, *mf, *ac;
+    float *hf_pre, *hf, *uhf, *m, *bl;   // views, strides below
+    float* mdiff;                        // [B][2][3][n] Malta difference planes = tmp (dead after the HF blur)
     BlurTables tables;
 };
 
 static size_t ba_level_floats_per_pair(size_t n) {
-    // per image: tmpA 3, tmpB 3, xyb 3, lf 3, mf 3, hf 2, uhf 2 = 19 ; x2 images = 38; pair: ac 2, m 2, bl 2 = 6
-    return 44 * n;
+    // per image: xyb 3, tmp 3, lf 3, mf_pre 3, mf 3 = 15; x2 images = 30; pair: ac 2
+    return 32 * n;
 }
 
 static unsigned ew_blocks(Context& c, size_t total) {
@@ -675,38 +870,55 @@ static unsigned ew_blocks(Context& c, size_t total) {
 
 static void ba_alloc_level(Context& c, size_t B, size_t w, size_t h, BaLevelBufs& L) {
     const size_t n = w * h, NI = 2 * B;
-    L.tmpA = c.arena.alloc<float>(NI * 3 * n);
-    L.tmpB = c.arena.alloc<float>(NI * 3 * n);
     L.xyb = c.arena.alloc<float>(NI * 3 * n);
+    L.tmp = c.arena.alloc<float>(NI * 3 * n);
     L.lf = c.arena.alloc<float>(NI * 3 * n);
+    L.mf_pre = c.arena.alloc<float>(NI * 3 * n);
     L.mf = c.arena.alloc<float>(NI * 3 * n);
-    L.hf = c.arena.alloc<float>(NI * 2 * n);
-    L.uhf = c.arena.alloc<float>(NI * 2 * n);
     L.ac = c.arena.alloc<float>(B * 2 * n);
-    L.m = c.arena.alloc<float>(NI * n);
-    L.bl = c.arena.alloc<float>(NI * n);
+    L.hf_pre = L.tmp;                  // [NI][2][n]
+    L.mdiff = L.tmp;                   // [B][2][3][n] == NI*3*n floats
+    L.hf = L.xyb;                      // [NI][2][n]
+    L.m = L.xyb + NI * 2 * n;          // [NI][n]
+    L.uhf = L.mf_pre;                  // [NI][2][n]
+    L.bl = L.mf_pre + NI * 2 * n;      // [NI][n]
     for (int s = 0; s < 4; s++) {
         L.tables.inv_x[s] = ba_inv_table(c, s, w);
         L.tables.inv_y[s] = ba_inv_table(c, s, h);
     }
 }
 
-// lin: [NI][3][n] -> psycho planes in L (lf, mf, hf, uhf)
+static void check_grid_z(size_t z) {
+    if (z > 65535) throw CudaError("butteraugli sub-batch too large for one launch");
+}
+
+// lin: [NI][3][n] -> psycho planes in L (lf, mf, hf, uhf) and the mask input m
 static void ba_psycho_level(Context& c, const float* lin, size_t NI, size_t w, size_t h, float intensity, BaLevelBufs& L,
                             float* dbg_opsin) {
     const size_t n = w * h;
-    size_t t3 = NI * 3 * n, t1 = NI * n;
-    CE_LAUNCH(c, "k_ba_blur5", (double)t3 * 8, k_ba_blur5<<<ew_blocks(c, t3), 256, 0, c.stream>>>(lin, (int)w, (int)h, n, t3, 0, L.tmpA));
-    CE_LAUNCH(c, "k_ba_blur5", (double)t3 * 8, k_ba_blur5<<<ew_blocks(c, t3), 256, 0, c.stream>>>(L.tmpA, (int)w, (int)h, n, t3, 1, L.tmpB));
-    CE_LAUNCH(c, "k_ba_opsin", (double)t1 * 36, k_ba_opsin<<<ew_blocks(c, t1), 256, 0, c.stream>>>(lin, L.tmpB, n, t1, intensity, L.xyb));
+    const int vec = (w % 4 == 0) ? 1 : 0;
+    check_grid_z(NI * 3);
+    {
+        dim3 grid(cdiv(w, OP_TW), cdiv(h, OP_TH), (unsigned)NI);
+        CE_LAUNCH(c, "k_ba_opsin", (double)NI * n * 24,
+                  k_ba_opsin<true><<<grid, 256, 0, c.stream>>>(lin, (int)w, (int)h, n, intensity, L.xyb, vec));
+    }
     if (dbg_opsin) CE_CUDA(cudaMemcpyAsync(dbg_opsin, L.xyb, 3 * n * 4, cudaMemcpyDeviceToDevice, c.stream));
-    blur_planes(c, 0, L.xyb, L.tmpA, L.lf, NI * 3, w, h, L.tables);
-    CE_LAUNCH(c, "k_ba_sub", (double)t3 * 12, k_ba_sub<<<ew_blocks(c, t3), 256, 0, c.stream>>>(L.xyb, L.lf, t3, L.tmpB));
-    blur_planes(c, 1, L.tmpB, L.tmpA, L.mf, NI * 3, w, h, L.tables);
-    CE_LAUNCH(c, "k_ba_split_hf", (double)t1 * 32, k_ba_split_hf<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.tmpB, L.mf, n, t1, L.hf));
-    blur_planes(c, 2, L.hf, L.tmpA, L.tmpB, NI * 2, w, h, L.tables);
-    CE_LAUNCH(c, "k_ba_split_uhf", (double)t1 * 32, k_ba_split_uhf<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.hf, L.tmpB, n, t1, L.uhf));
-    CE_LAUNCH(c, "k_ba_lf_vals", (double)t1 * 24, k_ba_lf_vals<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.lf, n, t1));
+    {
+        dim3 gh(cdiv(w, 128), cdiv(h, 8), (unsigned)(NI * 3));
+        CE_LAUNCH(c, "k_ba_blur_h<R16>", (double)NI * n * 24,
+                  k_ba_blur_h<0, 16><<<gh, 256, 0, c.stream>>>(L.xyb, (int)w, (int)h, n, L.tables.inv_x[0], L.tmp, vec));
+        dim3 gv(cdiv(w, 32), cdiv(h, 64), (unsigned)NI);
+        CE_LAUNCH(c, "k_ba_blur_v<R16>+lf", (double)NI * n * 48,
+                  k_ba_blur_v<0, 16, 3, 1><<<gv, 256, 0, c.stream>>>(L.tmp, (int)w, (int)h, n, L.tables.inv_y[0], L.lf, L.xyb, L.mf_pre));
+    }
+    dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), (unsigned)NI);
+    CE_LAUNCH(c, "k_ba_blur2d<R7>+hf_split", (double)NI * n * 32,
+              k_ba_blur2d<1, 7, 3, 2><<<g2, 256, 0, c.stream>>>(L.mf_pre, (int)w, (int)h, n, L.tables.inv_x[1], L.tables.inv_y[1], L.mf,
+                                                              L.hf_pre, nullptr));
+    CE_LAUNCH(c, "k_ba_blur2d<R3>+uhf_split", (double)NI * n * 28,
+              k_ba_blur2d<2, 3, 2, 3><<<g2, 256, 0, c.stream>>>(L.hf_pre, (int)w, (int)h, n, L.tables.inv_x[2], L.tables.inv_y[2], L.hf,
+                                                              L.uhf, L.m));
     CE_CUDA(cudaGetLastError());
 }
 
@@ -718,19 +930,26 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t B, size_t w, s
     BaLevelBufs L;
     ba_alloc_level(c, B, w, h, L);
     ba_psycho_level(c, lin, NI, w, h, intensity, L, nullptr);
-    const unsigned tx = cdiv(w, MT_TW), ty = cdiv(h, MT_TH);
-    MaltaParams p0 = make_malta_params(0, hf_asym), p1 = make_malta_params(1, hf_asym);
-    for (size_t b0 = 0; b0 < B; b0 += 32768) {
-        if (b0 != 0) throw CudaError("butteraugli sub-batch too large");  // sub-batches are far smaller than 32768 pairs
-        dim3 grid(tx, ty, (unsigned)B);
-        CE_LAUNCH(c, "k_ba_malta", (double)B * n * 28,
-                  k_ba_malta<1><<<grid, 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, (int)w, (int)h, n, B, p1, L.ac));
-        CE_LAUNCH(c, "k_ba_malta", (double)B * n * 28,
-                  k_ba_malta<0><<<grid, 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, (int)w, (int)h, n, B, p0, L.ac));
+    {
+        dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), (unsigned)NI);
+        CE_LAUNCH(c, "k_ba_blur2d<R6>", (double)NI * n * 8,
+                  k_ba_blur2d<3, 6, 1, 0><<<g2, 256, 0, c.stream>>>(L.m, (int)w, (int)h, n, L.tables.inv_x[3], L.tables.inv_y[3], L.bl,
+                                                                  nullptr, nullptr));
     }
-    size_t t1 = NI * n;
-    CE_LAUNCH(c, "k_ba_mask_pre", (double)t1 * 20, k_ba_mask_pre<<<ew_blocks(c, t1), 256, 0, c.stream>>>(L.hf, L.uhf, n, t1, L.m));
-    blur_planes(c, 3, L.m, L.tmpA, L.bl, NI, w, h, L.tables);
+    {
+        MaltaParams2 mp;
+        mp.ch[0] = make_malta_params(0, hf_asym);
+        mp.ch[1] = make_malta_params(1, hf_asym);
+        if (n % 4 == 0)
+            CE_LAUNCH(c, "k_ba_malta_diff", (double)B * n * 72,
+                      k_ba_malta_diff<true><<<ew_blocks(c, B * 2 * (n / 4)), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, mp, L.mdiff));
+        else
+            CE_LAUNCH(c, "k_ba_malta_diff", (double)B * n * 72,
+                      k_ba_malta_diff<false><<<ew_blocks(c, B * 2 * n), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, mp, L.mdiff));
+        dim3 grid(cdiv(w, MT_TW), cdiv(h, MT_TH), (unsigned)(2 * B));
+        CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
+                  k_ba_malta<<<grid, 256, 0, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, B, mp, L.ac));
+    }
     CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,
               k_ba_combine<<<ew_blocks(c, B * n), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, xmul, diffmap));
     CE_CUDA(cudaGetLastError());
@@ -748,6 +967,7 @@ void butteraugli_run(Context& c, const float* lin, const float* lin2, size_t B, 
                      double* d_out, float* dbg_diffmap) {
     const size_t n = w * h;
     if (lin2 != lin + B * 3 * n) throw CudaError("butteraugli_run expects lin2 == lin1 + B*3*n");
+    check_grid_z(B * 6);
     size_t mark = c.arena.mark();
     float* diffmap = c.arena.alloc<float>(B * n);
     double* partial = c.arena.alloc<double>(B * BA_RED_BLOCKS * 4);
@@ -783,6 +1003,9 @@ void butteraugli_debug_psycho(Context& c, const float* lin, size_t w, size_t h, 
     size_t mark = c.arena.mark();
     BaLevelBufs L;
     ba_alloc_level(c, 1, w, h, L);
+    // with NI = 1 the alias views must be re-based on one image
+    L.m = L.xyb + 2 * n;
+    L.bl = L.mf_pre + 2 * n;
     ba_psycho_level(c, lin, 1, w, h, intensity, L, nullptr);
     CE_CUDA(cudaMemcpyAsync(d_planes10, L.lf, 3 * n * 4, cudaMemcpyDeviceToDevice, c.stream));
     CE_CUDA(cudaMemcpyAsync(d_planes10 + 3 * n, L.mf, 3 * n * 4, cudaMemcpyDeviceToDevice, c.stream));
@@ -794,23 +1017,40 @@ void butteraugli_debug_opsin(Context& c, const float* lin, size_t w, size_t h, f
     size_t mark = c.arena.mark();
     BaLevelBufs L;
     ba_alloc_level(c, 1, w, h, L);
+    L.m = L.xyb + 2 * w * h;
+    L.bl = L.mf_pre + 2 * w * h;
     ba_psycho_level(c, lin, 1, w, h, intensity, L, d_planes3);
     c.arena.release(mark);
 }
+// one plane through the production blur of that sigma (identity epilogue)
 void butteraugli_debug_blur(Context& c, const float* in, size_t w, size_t h, float sigma, float* out) {
     const size_t n = w * h;
     size_t mark = c.arena.mark();
     BaLevelBufs L;
     ba_alloc_level(c, 1, w, h, L);
+    const int vec = (w % 4 == 0) ? 1 : 0;
+    dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), 1);
     if (fabsf(sigma - 1.2f) < 1e-6f) {
-        CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_blur5<<<ew_blocks(c, n), 256, 0, c.stream>>>(in, (int)w, (int)h, n, n, 0, L.tmpA));
-        CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_blur5<<<ew_blocks(c, n), 256, 0, c.stream>>>(L.tmpA, (int)w, (int)h, n, n, 1, out));
+        dim3 grid(cdiv(w, OP_TW), cdiv(h, OP_TH), 1);
+        CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_opsin<false><<<grid, 256, 0, c.stream>>>(in, (int)w, (int)h, n, 0.0f, out, vec));
+    } else if (fabsf(sigma - kSigmas[0]) < 1e-5f) {
+        dim3 gh(cdiv(w, 128), cdiv(h, 8), 1);
+        CE_LAUNCH(c, "k_ba_blur_h<R16>", (double)n * 8,
+                  k_ba_blur_h<0, 16><<<gh, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[0], L.tmp, vec));
+        dim3 gv(cdiv(w, 32), cdiv(h, 64), 1);
+        CE_LAUNCH(c, "k_ba_blur_v<R16>", (double)n * 8,
+                  k_ba_blur_v<0, 16, 1, 0><<<gv, 256, 0, c.stream>>>(L.tmp, (int)w, (int)h, n, L.tables.inv_y[0], out, nullptr, nullptr));
+    } else if (fabsf(sigma - kSigmas[1]) < 1e-5f) {
+        CE_LAUNCH(c, "k_ba_blur2d<R7>", (double)n * 8,
+                  k_ba_blur2d<1, 7, 1, 0><<<g2, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[1], L.tables.inv_y[1], out, nullptr, nullptr));
+    } else if (fabsf(sigma - kSigmas[2]) < 1e-5f) {
+        CE_LAUNCH(c, "k_ba_blur2d<R3>", (double)n * 8,
+                  k_ba_blur2d<2, 3, 1, 0><<<g2, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[2], L.tables.inv_y[2], out, nullptr, nullptr));
+    } else if (fabsf(sigma - kSigmas[3]) < 1e-5f) {
+        CE_LAUNCH(c, "k_ba_blur2d<R6>", (double)n * 8,
+                  k_ba_blur2d<3, 6, 1, 0><<<g2, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[3], L.tables.inv_y[3], out, nullptr, nullptr));
     } else {
-        int slot = -1;
-        for (int s = 0; s < 4; s++)
-            if (fabsf(sigma - kSigmas[s]) < 1e-5f) slot = s;
-        if (slot < 0) throw CudaError("unsupported sigma");
-        blur_planes(c, slot, in, L.tmpA, out, 1, w, h, L.tables);
+        throw CudaError("unsupported sigma");
     }
     CE_CUDA(cudaGetLastError());
     c.arena.release(mark);

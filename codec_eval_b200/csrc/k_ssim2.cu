@@ -3,11 +3,12 @@
 //
 // Per scale (6 scales, ceil-halving with clamp on LINEAR rgb):
 //   k_s2_xyb_down : linear(s) -> positive-XYB(s) planes + linear(s+1)        [HBM-bound, pointwise]
-//   k_s2_hpass    : recursive Gaussian along x of {i1,i2,i1^2,i2^2,i1*i2};   [HBM-bound, rows staged in smem]
-//                   lane = row, warp = product, 32x32 tiles staged through shared memory
-//   k_s2_vpass    : column-parallel recurrence along y (thread = column, 10-row register
-//                   delay line) fused with the SSIM / edge-artifact / detail-loss maps and
-//                   L1/L4 pooling in fp64 (warp shuffles -> per-block partials)
+//   k_s2_hpass    : recursive Gaussian along x of {i1,i2,i1^2,i2^2,i1*i2};   [rows staged in smem by cp.async]
+//                   lane = row, warp = product, 32x32 tiles double-buffered through shared memory,
+//                   128-bit shared / global accesses
+//   k_s2_vpass    : column-parallel recurrence along y (lane = column, warp = product, 10-row
+//                   register delay line) fused with the SSIM / edge-artifact / detail-loss maps
+//                   and L1/L4 pooling in fp64 (warp shuffles -> per-block partials)
 //   k_s2_reduce   : fixed-order sum of the block partials -> 18 sums per (pair, scale)
 // The recurrence is the exact operation sequence of the upstream code so the
 // result does not depend on the tiling.
@@ -88,22 +89,29 @@ CE_DEVINL float rg_step(RGState& s, float sum) {
 
 #define HP_ROWS 32
 #define HP_COLS 32
-#define HP_PITCH 33
+#define HP_PITCH 36   // 16-B aligned rows; lane = row reads LDS.128 at chunk 9*row + q: conflict-free per quarter warp
 
-CE_DEVINL float hp_product(int p, const float* s1, const float* s2, int idx) {
-    // p is warp-uniform: 0 i1, 1 i2, 2 i1*i1, 3 i2*i2, 4 i1*i2
-    if (p == 0) return s1[idx];
-    if (p == 1) return s2[idx];
-    if (p == 2) { float a = s1[idx]; return a * a; }
-    if (p == 3) { float b = s2[idx]; return b * b; }
-    return s1[idx] * s2[idx];
+// product p (warp-uniform) of 4 consecutive columns: 0 i1, 1 i2, 2 i1*i1, 3 i2*i2, 4 i1*i2
+CE_DEVINL float4 hp_product4(int p, const float* a, const float* b) {
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+    if (p != 1 && p != 3) u = *reinterpret_cast<const float4*>(a);
+    if (p != 0 && p != 2) v = *reinterpret_cast<const float4*>(b);
+    if (p == 0) return u;
+    if (p == 1) return v;
+    if (p == 2) return make_float4(u.x * u.x, u.y * u.y, u.z * u.z, u.w * u.w);
+    if (p == 3) return make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+    return make_float4(u.x * v.x, u.y * v.y, u.z * v.z, u.w * v.w);
 }
 
-// grid (ceil(h/32), 3*B); block 160 = 5 warps (product) x 32 lanes (row)
+// grid (ceil(h/32), 3*B); block 160 = 5 warps (product) x 32 lanes (row).
+// The row is walked in 32-column chunks staged by cp.async (double buffered, zero-filled past the image).
+// Output n needs in[n+4] and in[n-6], so the recurrence runs 4 columns behind the loads: chunk k
+// (input columns 32k .. 32k+31) produces output columns 32k-4 .. 32k+27; the first four steps are the
+// upstream warm-up (n = -4 .. -1), and ceil((w+4)/32) chunks reach the last column.
 __global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb, float* __restrict__ hb, int w, int h,
-                                                   size_t n) {
-    __shared__ float s_in[2][3][HP_ROWS * HP_PITCH];
-    __shared__ float s_out[5][HP_ROWS * HP_PITCH];
+                                                   size_t n, int vec) {
+    __shared__ __align__(16) float s_in[2][2][HP_ROWS * HP_PITCH];
+    __shared__ __align__(16) float s_out[5][HP_ROWS * HP_PITCH];
     const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
     const size_t b = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
@@ -111,125 +119,162 @@ __global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb,
     const float* i1 = xyb + ((b * 2 + 0) * 3 + c) * n;
     const float* i2 = xyb + ((b * 2 + 1) * 3 + c) * n;
     float* outp = hb + ((b * 3 + c) * 5) * n;
-    const int nchunks = (w + HP_COLS - 1) / HP_COLS;
+    const int nchunks = (w + 4 + HP_COLS - 1) / HP_COLS;
 
-    auto load_chunk = [&](int k, int slot) {
-        for (int e = threadIdx.x; e < 2 * HP_ROWS * HP_COLS; e += 160) {
-            int pl = e >> 10, rr = (e >> 5) & 31, cc = e & 31;
-            int y = row0 + rr, x = k * HP_COLS + cc;
-            float v = 0.0f;
-            if (y < h && x < w) v = (pl ? i2 : i1)[(size_t)y * w + x];
-            s_in[pl][slot][rr * HP_PITCH + cc] = v;
+    auto issue = [&](int k, int slot) {
+        for (int e = threadIdx.x; e < 2 * HP_ROWS * (HP_COLS / 4); e += 160) {
+            const int pl = e >> 8, rr = (e >> 3) & 31, c4 = e & 7;
+            const int y = row0 + rr, x = k * HP_COLS + 4 * c4;
+            const float* base = pl ? i2 : i1;
+            float* dst = &s_in[slot][pl][rr * HP_PITCH + 4 * c4];
+            if (vec) {
+                const bool ok = y < h && x < w;
+                cp_async16(dst, ok ? base + (size_t)y * w + x : base, ok);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool ok = y < h && x + j < w;
+                    cp_async4(dst + j, ok ? base + (size_t)y * w + x + j : base, ok);
+                }
+            }
         }
+        cp_async_commit();
     };
-    // slot 2 plays chunk -1 (zeros), slot 0 = chunk 0
-    for (int e = threadIdx.x; e < 2 * HP_ROWS * HP_PITCH; e += 160) {
-        int pl = e / (HP_ROWS * HP_PITCH), r = e % (HP_ROWS * HP_PITCH);
-        s_in[pl][2][r] = 0.0f;
-    }
-    load_chunk(0, 0);
-    __syncthreads();
+
+    issue(0, 0);
     RGState st = {0, 0, 0, 0, 0, 0};
-    const int rbase = lane * HP_PITCH;
-    // warm-up steps n = -4..-1: right = in[0..3], left = 0
-#pragma unroll
-    for (int cidx = 0; cidx < 4; cidx++) {
-        float r = hp_product(p, s_in[0][0], s_in[1][0], rbase + cidx);
-        rg_step(st, r);
-    }
+    float P0[4] = {0, 0, 0, 0}, P1[4] = {0, 0, 0, 0};   // products of columns c-12..c-9 and c-8..c-5 (c = current group)
+    float P2[4] = {0, 0, 0, 0};                         // c-4..c-1
     for (int k = 0; k < nchunks; k++) {
-        const int s_cur = k % 3, s_next = (k + 1) % 3, s_prev = (k + 2) % 3;
-        load_chunk(k + 1, s_next);
-        __syncthreads();
-        const float* c1 = s_in[0][s_cur];  const float* c2 = s_in[1][s_cur];
-        const float* n1 = s_in[0][s_next]; const float* n2 = s_in[1][s_next];
-        const float* p1 = s_in[0][s_prev]; const float* p2 = s_in[1][s_prev];
+        if (k + 1 < nchunks) {
+            issue(k + 1, (k + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();   // chunk k visible; everyone is done writing out chunk k-1 from s_out
+        const float* a = s_in[k & 1][0] + lane * HP_PITCH;
+        const float* bq = s_in[k & 1][1] + lane * HP_PITCH;
 #pragma unroll
-        for (int cc = 0; cc < HP_COLS; cc++) {
-            float r = (cc + 4 < HP_COLS) ? hp_product(p, c1, c2, rbase + cc + 4) : hp_product(p, n1, n2, rbase + cc + 4 - HP_COLS);
-            float l = (cc - 6 >= 0) ? hp_product(p, c1, c2, rbase + cc - 6) : hp_product(p, p1, p2, rbase + cc - 6 + HP_COLS);
-            float o = rg_step(st, l + r);
-            s_out[p][rbase + cc] = o;
+        for (int m = 0; m < HP_COLS / 4; m++) {
+            const float4 g4 = hp_product4(p, a + 4 * m, bq + 4 * m);
+            const float G[4] = {g4.x, g4.y, g4.z, g4.w};
+            // steps n = c-4+j: right = in[n+4] = G[j]; left = in[n-6] = column c-10+j
+            float4 o;
+            o.x = rg_step(st, P0[2] + G[0]);
+            o.y = rg_step(st, P0[3] + G[1]);
+            o.z = rg_step(st, P1[0] + G[2]);
+            o.w = rg_step(st, P1[1] + G[3]);
+            *reinterpret_cast<float4*>(&s_out[p][lane * HP_PITCH + 4 * m]) = o;
+#pragma unroll
+            for (int j = 0; j < 4; j++) { P0[j] = P1[j]; P1[j] = P2[j]; P2[j] = G[j]; }
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < 5 * HP_ROWS * HP_COLS; e += 160) {
-            int pp = e >> 10, rr = (e >> 5) & 31, cc = e & 31;
-            int y = row0 + rr, x = k * HP_COLS + cc;
-            if (y < h && x < w) outp[(size_t)pp * n + (size_t)y * w + x] = s_out[pp][rr * HP_PITCH + cc];
+        const int xb = k * HP_COLS - 4;
+        for (int e = threadIdx.x; e < 5 * HP_ROWS * (HP_COLS / 4); e += 160) {
+            const int pp = e >> 8, rr = (e >> 3) & 31, c4 = e & 7;
+            const int y = row0 + rr, x = xb + 4 * c4;
+            if (y < h && x >= 0 && x < w) {
+                const float4 v = *reinterpret_cast<const float4*>(&s_out[pp][rr * HP_PITCH + 4 * c4]);
+                float* d = outp + (size_t)pp * n + (size_t)y * w + x;
+                if (vec) *reinterpret_cast<float4*>(d) = v;
+                else {
+                    d[0] = v.x;
+                    if (x + 1 < w) d[1] = v.y;
+                    if (x + 2 < w) d[2] = v.z;
+                    if (x + 3 < w) d[3] = v.w;
+                }
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------ vertical pass + maps
-#define VP_THREADS 128
+#define VP_COLS 32
+#define VP_BATCH 5
 
-// grid (ceil(w/128), 3*B); thread = column.  partials: [(b*3+c)][gridDim.x][6]
-__global__ void __launch_bounds__(VP_THREADS) k_s2_vpass(const float* __restrict__ xyb, const float* __restrict__ hb,
-                                                          int w, int h, size_t n, double* __restrict__ partials,
-                                                          float* __restrict__ dbg) {
+// grid (ceil(w/32), 3*B); block 160 = 5 warps x 32 lanes.  lane = column.  Each warp runs the recurrence of
+// ONE product down the column strip (1 coalesced 128-B load per row, 10-row register delay line); every 5
+// rows the five blurred values of each pixel meet in shared memory and warp r evaluates the SSIM /
+// edge-artifact / detail-loss terms of row r of the batch.  partials: [(b*3+c)][gridDim.x][6]
+__global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb, const float* __restrict__ hb,
+                                                   int w, int h, size_t n, double* __restrict__ partials,
+                                                   float* __restrict__ dbg) {
+    __shared__ float s_v[2][VP_BATCH][5][VP_COLS];
     __shared__ double scratch[6 * 32];
-    const int x = blockIdx.x * VP_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
+    const int x = blockIdx.x * VP_COLS + lane;
     const size_t b = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
     const bool active = x < w;
-    const float* i1 = xyb + ((b * 2 + 0) * 3 + c) * n;
-    const float* i2 = xyb + ((b * 2 + 1) * 3 + c) * n;
-    const float* hp = hb + ((b * 3 + c) * 5) * n;
+    const int xs = active ? x : 0;
+    const float* i1 = xyb + ((b * 2 + 0) * 3 + c) * n + xs;
+    const float* i2 = xyb + ((b * 2 + 1) * 3 + c) * n + xs;
+    const float* hp = hb + ((b * 3 + c) * 5 + p) * n + xs;
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    if (active) {
-        RGState st[5];
-        float ring[5][10];
+    RGState st = {0, 0, 0, 0, 0, 0};
+    float ring[10];
 #pragma unroll
-        for (int p = 0; p < 5; p++) {
-            st[p] = {0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < 10; j++) ring[j] = 0.0f;
+    const int total = h + 4;  // input rows j = 0 .. h+3 (rows >= h are zero); output row y = j - 4
+    float cur[VP_BATCH], nxt[VP_BATCH];
 #pragma unroll
-            for (int j = 0; j < 10; j++) ring[p][j] = 0.0f;
-        }
-        const int total = h + 4;  // input rows j = 0 .. h+3 (rows >= h are zero); output row n = j - 4
-        for (int j0 = 0; j0 < total; j0 += 10) {
+    for (int r = 0; r < VP_BATCH; r++) cur[r] = (r < h) ? hp[(size_t)r * w] : 0.0f;
+    int buf = 0;
+    for (int j0 = 0; j0 < total; j0 += 2 * VP_BATCH) {
 #pragma unroll
-            for (int jj = 0; jj < 10; jj++) {
-                const int j = j0 + jj;
-                if (j < total) {
-                    float o[5];
+        for (int half = 0; half < 2; half++) {
+            const int jb = j0 + half * VP_BATCH;
+            if (jb < total) {   // block-uniform
+                // prefetch the next batch of this warp's plane, and the two image values of the pixel this warp maps
 #pragma unroll
-                    for (int p = 0; p < 5; p++) {
-                        float r = (j < h) ? hp[(size_t)p * n + (size_t)j * w + x] : 0.0f;
-                        float l = ring[p][jj];
-                        ring[p][jj] = r;
-                        o[p] = rg_step(st[p], l + r);
-                    }
-                    const int y = j - 4;
-                    if (y >= 0) {
-                        const size_t idx = (size_t)y * w + x;
-                        const float a1 = i1[idx], a2 = i2[idx];
-                        const float m1 = o[0], m2 = o[1], s11 = o[2], s22 = o[3], s12 = o[4];
-                        if (dbg) {
-                            float* d = dbg + (size_t)c * 7 * n + idx;
-                            d[2 * n] = m1; d[3 * n] = m2; d[4 * n] = s11; d[5 * n] = s22; d[6 * n] = s12;
-                        }
-                        // ssim_map
-                        float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
-                        float mdiff = m1 - m2;
-                        float num_m = __fmaf_rn(mdiff, -mdiff, 1.0f);
-                        float num_s = __fmaf_rn(2.0f, s12 - m12, 0.0009f);
-                        float denom_s = ((s11 - m11) + (s22 - m22)) + 0.0009f;
-                        double d = 1.0 - (double)((num_m * num_s) / denom_s);
-                        if (!(d > 0.0)) d = 0.0;
-                        double d2 = d * d;
-                        acc[0] += d;
-                        acc[1] += d2 * d2;
-                        // edge_diff_map
-                        double d1 = (1.0 + (double)fabsf(a2 - m2)) / (1.0 + (double)fabsf(a1 - m1)) - 1.0;
-                        double art = d1 > 0.0 ? d1 : 0.0;
-                        double det = d1 < 0.0 ? -d1 : 0.0;
-                        double a2_ = art * art, l2 = det * det;
-                        acc[2] += art;
-                        acc[3] += a2_ * a2_;
-                        acc[4] += det;
-                        acc[5] += l2 * l2;
-                    }
+                for (int r = 0; r < VP_BATCH; r++) {
+                    const int jn = jb + VP_BATCH + r;
+                    nxt[r] = (jn < h) ? hp[(size_t)jn * w] : 0.0f;
                 }
+                const int y = jb + p - 4;
+                const bool ylive = y >= 0 && y < h;
+                float a1 = 0.0f, a2 = 0.0f;
+                if (ylive) { a1 = i1[(size_t)y * w]; a2 = i2[(size_t)y * w]; }
+#pragma unroll
+                for (int r = 0; r < VP_BATCH; r++) {
+                    const float rv = cur[r];
+                    const float l = ring[half * VP_BATCH + r];
+                    ring[half * VP_BATCH + r] = rv;
+                    s_v[buf][r][p][lane] = rg_step(st, l + rv);
+                }
+                __syncthreads();
+                if (ylive && active) {
+                    const float m1 = s_v[buf][p][0][lane], m2 = s_v[buf][p][1][lane], s11 = s_v[buf][p][2][lane],
+                                s22 = s_v[buf][p][3][lane], s12 = s_v[buf][p][4][lane];
+                    if (dbg) {
+                        float* d = dbg + (size_t)c * 7 * n + (size_t)y * w + x;
+                        d[2 * n] = m1; d[3 * n] = m2; d[4 * n] = s11; d[5 * n] = s22; d[6 * n] = s12;
+                    }
+                    // ssim_map
+                    const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+                    const float mdiff = m1 - m2;
+                    const float num_m = __fmaf_rn(mdiff, -mdiff, 1.0f);
+                    const float num_s = __fmaf_rn(2.0f, s12 - m12, 0.0009f);
+                    const float denom_s = ((s11 - m11) + (s22 - m22)) + 0.0009f;
+                    double d = 1.0 - (double)((num_m * num_s) / denom_s);
+                    if (!(d > 0.0)) d = 0.0;
+                    const double d2 = d * d;
+                    acc[0] += d;
+                    acc[1] += d2 * d2;
+                    // edge_diff_map
+                    const double d1 = (1.0 + (double)fabsf(a2 - m2)) / (1.0 + (double)fabsf(a1 - m1)) - 1.0;
+                    const double art = d1 > 0.0 ? d1 : 0.0;
+                    const double det = d1 < 0.0 ? -d1 : 0.0;
+                    const double a2_ = art * art, l2 = det * det;
+                    acc[2] += art;
+                    acc[3] += a2_ * a2_;
+                    acc[4] += det;
+                    acc[5] += l2 * l2;
+                }
+                buf ^= 1;
+#pragma unroll
+                for (int r = 0; r < VP_BATCH; r++) cur[r] = nxt[r];
             }
         }
     }
@@ -263,7 +308,7 @@ void ssim2_init(Context& c) {
 size_t ssim2_workspace_per_pair(size_t w, size_t h) {
     size_t n = w * h;
     // next-scale linear (2*3*n/4 .. geometric), xyb 6n, hb 15n, partials
-    size_t bytes = (6 * n + 15 * n) * 4 + (2 * 3 * ((w + 1) / 2) * ((h + 1) / 2)) * 4 * 2 + 3 * cdiv(w, VP_THREADS) * 6 * 8 + 4096;
+    size_t bytes = (6 * n + 15 * n) * 4 + (2 * 3 * ((w + 1) / 2) * ((h + 1) / 2)) * 4 * 2 + 3 * cdiv(w, VP_COLS) * 6 * 8 + 4096;
     return bytes;
 }
 
@@ -277,7 +322,7 @@ int ssim2_run(Context& c, const float* lin1_in, const float* lin2_in, size_t B, 
     float* nl[2][2];  // ping-pong next-scale linear buffers [pingpong][img]
     for (int i = 0; i < 2; i++)
         for (int j = 0; j < 2; j++) nl[i][j] = c.arena.alloc<float>(B * 3 * ow0 * oh0);
-    const int nblk0 = cdiv(w, VP_THREADS);
+    const int nblk0 = cdiv(w, VP_COLS);
     double* partials = c.arena.alloc<double>(B * 3 * nblk0 * 6);
 
     const float* l1 = lin1_in;
@@ -299,14 +344,14 @@ int ssim2_run(Context& c, const float* lin1_in, const float* lin2_in, size_t B, 
         }
         {
             dim3 grid(cdiv(ch, HP_ROWS), (unsigned)(B * 3));
-            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4, k_s2_hpass<<<grid, 160, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n));
+            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4, k_s2_hpass<<<grid, 160, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, (cw % 4 == 0) ? 1 : 0));
         }
-        const int nblk = cdiv(cw, VP_THREADS);
+        const int nblk = cdiv(cw, VP_COLS);
         float* dbg = (dbg_planes && scale == 0) ? dbg_planes : nullptr;
         {
             dim3 grid(nblk, (unsigned)(B * 3));
             CE_LAUNCH(c, "k_s2_vpass", (double)B * 3 * 7 * n * 4,
-                      k_s2_vpass<<<grid, VP_THREADS, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, partials, dbg));
+                      k_s2_vpass<<<grid, 160, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, partials, dbg));
         }
         {
             size_t total = B * 3 * 6;
