@@ -88,196 +88,261 @@ CE_DEVINL float rg_step(RGState& s, float sum) {
 }
 
 #define HP_ROWS 32
-#define HP_COLS 32
-#define HP_PITCH 36   // 16-B aligned rows; lane = row reads LDS.128 at chunk 9*row + q: conflict-free per quarter warp
-
-// product p (warp-uniform) of 4 consecutive columns: 0 i1, 1 i2, 2 i1*i1, 3 i2*i2, 4 i1*i2
-CE_DEVINL float4 hp_product4(int p, const float* a, const float* b) {
-    float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
-    if (p != 1 && p != 3) u = *reinterpret_cast<const float4*>(a);
-    if (p != 0 && p != 2) v = *reinterpret_cast<const float4*>(b);
-    if (p == 0) return u;
-    if (p == 1) return v;
-    if (p == 2) return make_float4(u.x * u.x, u.y * u.y, u.z * u.z, u.w * u.w);
-    if (p == 3) return make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
-    return make_float4(u.x * v.x, u.y * v.y, u.z * v.z, u.w * v.w);
-}
+#ifndef HP_COLS
+#define HP_COLS 64
+#endif
+#define HP_C4 (HP_COLS / 4)
+#define HP_PITCH (HP_COLS + 4)   // 16-B aligned rows; lane = row reads LDS.128 at chunk (C4+1)*row + q: conflict-free per quarter warp
+#define HP_SLOTS 3
+#define HP_SMEM_BYTES ((HP_SLOTS * 2 + 5) * HP_ROWS * HP_PITCH * 4)
 
 // grid (ceil(h/32), 3*B); block 160 = 5 warps (product) x 32 lanes (row).
-// The row is walked in 32-column chunks staged by cp.async (double buffered, zero-filled past the image).
-// Output n needs in[n+4] and in[n-6], so the recurrence runs 4 columns behind the loads: chunk k
-// (input columns 32k .. 32k+31) produces output columns 32k-4 .. 32k+27; the first four steps are the
-// upstream warm-up (n = -4 .. -1), and ceil((w+4)/32) chunks reach the last column.
+// warp p blurs product p of the band's 32 rows: 0 i1, 1 i2, 2 i1*i1, 3 i2*i2, 4 i1*i2 (one code path for all
+// five so the loop body stays inside the instruction cache).
+// The row is walked in HP_COLS-column chunks staged by cp.async (three slots, two chunks in flight,
+// zero-filled past the image, one block barrier per chunk).  Output n needs in[n+4] and in[n-6], so the
+// recurrence runs 4 columns behind the loads: chunk k (input columns k*HP_COLS ..) produces output columns
+// k*HP_COLS-4 .. ; the first four steps are the upstream warm-up (n = -4 .. -1), and
+// ceil((w+4)/HP_COLS) chunks reach the last column.  Each warp writes out the plane it produced.
 __global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb, float* __restrict__ hb, int w, int h,
                                                    size_t n, int vec) {
-    __shared__ __align__(16) float s_in[2][2][HP_ROWS * HP_PITCH];
-    __shared__ __align__(16) float s_out[5][HP_ROWS * HP_PITCH];
+    extern __shared__ __align__(16) float s_dyn[];   // HP_SMEM_BYTES (> 48 KB: opt-in dynamic shared memory)
+    float* s_in = s_dyn;
     const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
+    float* so = s_dyn + HP_SLOTS * 2 * HP_ROWS * HP_PITCH + p * (HP_ROWS * HP_PITCH);
     const size_t b = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
     const int row0 = blockIdx.x * HP_ROWS;
     const float* i1 = xyb + ((b * 2 + 0) * 3 + c) * n;
     const float* i2 = xyb + ((b * 2 + 1) * 3 + c) * n;
-    float* outp = hb + ((b * 3 + c) * 5) * n;
+    float* op = hb + ((b * 3 + c) * 5 + p) * n;
     const int nchunks = (w + 4 + HP_COLS - 1) / HP_COLS;
+    // product roles
+    const int offA = (p == 1 || p == 3) ? HP_ROWS * HP_PITCH : 0;   // plane of the first factor
+    const int offB = (p >= 3) ? HP_ROWS * HP_PITCH : 0;             // plane of the second factor
+    const bool mul = p >= 2;
+    // loader role (threads 0..127): plane lpl, rows lr0 + (64/C4)*i, 16-B column group lc4
+    const int lpl = (threadIdx.x >> 6) & 1, lu = threadIdx.x & 63, lr0 = lu / HP_C4, lc4 = lu % HP_C4;
+    const float* lbase = lpl ? i2 : i1;
 
-    auto issue = [&](int k, int slot) {
-        for (int e = threadIdx.x; e < 2 * HP_ROWS * (HP_COLS / 4); e += 160) {
-            const int pl = e >> 8, rr = (e >> 3) & 31, c4 = e & 7;
-            const int y = row0 + rr, x = k * HP_COLS + 4 * c4;
-            const float* base = pl ? i2 : i1;
-            float* dst = &s_in[slot][pl][rr * HP_PITCH + 4 * c4];
-            if (vec) {
-                const bool ok = y < h && x < w;
-                cp_async16(dst, ok ? base + (size_t)y * w + x : base, ok);
-            } else {
+    auto issue = [&](int k) {
+        if (p < 4 && k < nchunks) {
+            const int x = k * HP_COLS + 4 * lc4;
+            float* dst = s_in + (((k % HP_SLOTS) * 2 + lpl) * HP_ROWS + lr0) * HP_PITCH + 4 * lc4;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const bool ok = y < h && x + j < w;
-                    cp_async4(dst + j, ok ? base + (size_t)y * w + x + j : base, ok);
+            for (int i = 0; i < HP_C4 / 2; i++) {
+                const int rr = (64 / HP_C4) * i;
+                const int y = row0 + lr0 + rr;
+                if (vec) {
+                    const bool ok = y < h && x < w;
+                    cp_async16(dst + rr * HP_PITCH, ok ? lbase + (size_t)y * w + x : lbase, ok);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const bool ok = y < h && x + j < w;
+                        cp_async4(dst + rr * HP_PITCH + j, ok ? lbase + (size_t)y * w + x + j : lbase, ok);
+                    }
                 }
             }
         }
         cp_async_commit();
     };
-
-    issue(0, 0);
+    issue(0);
+    issue(1);
     RGState st = {0, 0, 0, 0, 0, 0};
-    float P0[4] = {0, 0, 0, 0}, P1[4] = {0, 0, 0, 0};   // products of columns c-12..c-9 and c-8..c-5 (c = current group)
-    float P2[4] = {0, 0, 0, 0};                         // c-4..c-1
+    // products of the previous 16 columns: Q0 = c-16..c-13, Q1 = c-12..c-9, Q2 = c-8..c-5, Q3 = c-4..c-1
+    float Q0[4] = {0, 0, 0, 0}, Q1[4] = {0, 0, 0, 0}, Q2[4] = {0, 0, 0, 0}, Q3[4] = {0, 0, 0, 0};
     for (int k = 0; k < nchunks; k++) {
-        if (k + 1 < nchunks) {
-            issue(k + 1, (k + 1) & 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();   // chunk k visible; everyone is done writing out chunk k-1 from s_out
-        const float* a = s_in[k & 1][0] + lane * HP_PITCH;
-        const float* bq = s_in[k & 1][1] + lane * HP_PITCH;
+        cp_async_wait<1>();
+        __syncthreads();   // chunk k visible to all; every warp is past its reads of slot (k-1) % 3
+        issue(k + 2);      // -> slot (k-1) % 3
+        const float* a = s_in + ((k % HP_SLOTS) * 2 * HP_ROWS + lane) * HP_PITCH;
+#pragma unroll 1
+        for (int m0 = 0; m0 < HP_C4; m0 += 4) {
 #pragma unroll
-        for (int m = 0; m < HP_COLS / 4; m++) {
-            const float4 g4 = hp_product4(p, a + 4 * m, bq + 4 * m);
-            const float G[4] = {g4.x, g4.y, g4.z, g4.w};
-            // steps n = c-4+j: right = in[n+4] = G[j]; left = in[n-6] = column c-10+j
-            float4 o;
-            o.x = rg_step(st, P0[2] + G[0]);
-            o.y = rg_step(st, P0[3] + G[1]);
-            o.z = rg_step(st, P1[0] + G[2]);
-            o.w = rg_step(st, P1[1] + G[3]);
-            *reinterpret_cast<float4*>(&s_out[p][lane * HP_PITCH + 4 * m]) = o;
-#pragma unroll
-            for (int j = 0; j < 4; j++) { P0[j] = P1[j]; P1[j] = P2[j]; P2[j] = G[j]; }
+            for (int mm = 0; mm < 4; mm++) {
+                const int m = m0 + mm;
+                float4 g4 = *reinterpret_cast<const float4*>(a + offA + 4 * m);
+                if (mul) {
+                    const float4 v = *reinterpret_cast<const float4*>(a + offB + 4 * m);
+                    g4.x *= v.x; g4.y *= v.y; g4.z *= v.z; g4.w *= v.w;
+                }
+                // steps n = c-4+j: right = in[n+4] = g4[j]; left = in[n-6] = column c-10+j
+                float4 o;
+                float* L0 = (mm == 0) ? Q1 : (mm == 1) ? Q2 : (mm == 2) ? Q3 : Q0;   // group holding c-12..c-9
+                float* L1 = (mm == 0) ? Q2 : (mm == 1) ? Q3 : (mm == 2) ? Q0 : Q1;   // group holding c-8..c-5
+                float* NW = (mm == 0) ? Q0 : (mm == 1) ? Q1 : (mm == 2) ? Q2 : Q3;   // oldest group, replaced by the new one
+                o.x = rg_step(st, L0[2] + g4.x);
+                o.y = rg_step(st, L0[3] + g4.y);
+                o.z = rg_step(st, L1[0] + g4.z);
+                o.w = rg_step(st, L1[1] + g4.w);
+                *reinterpret_cast<float4*>(so + lane * HP_PITCH + 4 * m) = o;
+                NW[0] = g4.x; NW[1] = g4.y; NW[2] = g4.z; NW[3] = g4.w;
+            }
         }
-        __syncthreads();
-        const int xb = k * HP_COLS - 4;
-        for (int e = threadIdx.x; e < 5 * HP_ROWS * (HP_COLS / 4); e += 160) {
-            const int pp = e >> 8, rr = (e >> 3) & 31, c4 = e & 7;
-            const int y = row0 + rr, x = xb + 4 * c4;
-            if (y < h && x >= 0 && x < w) {
-                const float4 v = *reinterpret_cast<const float4*>(&s_out[pp][rr * HP_PITCH + 4 * c4]);
-                float* d = outp + (size_t)pp * n + (size_t)y * w + x;
-                if (vec) *reinterpret_cast<float4*>(d) = v;
-                else {
-                    d[0] = v.x;
-                    if (x + 1 < w) d[1] = v.y;
-                    if (x + 2 < w) d[2] = v.z;
-                    if (x + 3 < w) d[3] = v.w;
+        __syncwarp();
+        // this warp writes out the plane it produced: lane -> (row lane/C4 + (32/C4)*i, 16-B group lane%C4)
+        const int x = k * HP_COLS - 4 + 4 * (lane % HP_C4);
+        if (x >= 0 && x < w) {
+#pragma unroll
+            for (int i = 0; i < HP_C4; i++) {
+                const int rr = (32 / HP_C4) * i + lane / HP_C4;
+                const int y = row0 + rr;
+                if (y < h) {
+                    const float4 v = *reinterpret_cast<const float4*>(so + rr * HP_PITCH + 4 * (lane % HP_C4));
+                    float* d = op + (size_t)y * w + x;
+                    if (vec) *reinterpret_cast<float4*>(d) = v;
+                    else {
+                        d[0] = v.x;
+                        if (x + 1 < w) d[1] = v.y;
+                        if (x + 2 < w) d[2] = v.z;
+                        if (x + 3 < w) d[3] = v.w;
+                    }
                 }
             }
         }
+        __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------ vertical pass + maps
 #define VP_COLS 32
 #define VP_BATCH 5
+#define VP_SLOTS 4
+#define VP_PLANES 7   // 5 row-pass planes + i1 + i2
+#define VP_SLOT_FLOATS (VP_BATCH * VP_PLANES * VP_COLS)
 
 // grid (ceil(w/32), 3*B); block 160 = 5 warps x 32 lanes.  lane = column.  Each warp runs the recurrence of
-// ONE product down the column strip (1 coalesced 128-B load per row, 10-row register delay line); every 5
-// rows the five blurred values of each pixel meet in shared memory and warp r evaluates the SSIM /
-// edge-artifact / detail-loss terms of row r of the batch.  partials: [(b*3+c)][gridDim.x][6]
+// ONE product down the column strip (10-row register delay line).  Rows arrive in batches of 5 through a
+// 4-slot cp.async ring (two batches in flight; every thread owns fixed copy slots so there is no index
+// arithmetic in the loop); the five blurred values of each pixel meet in shared memory and, one batch
+// later, warp r evaluates the SSIM / edge-artifact / detail-loss terms of row r of that batch -- so there
+// is ONE block barrier per 5 rows.  partials: [(b*3+c)][gridDim.x][6]
 __global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb, const float* __restrict__ hb,
                                                    int w, int h, size_t n, double* __restrict__ partials,
-                                                   float* __restrict__ dbg) {
+                                                   float* __restrict__ dbg, int vec) {
+    __shared__ __align__(16) float s_ld[VP_SLOTS * VP_SLOT_FLOATS];   // [slot][row r][plane][col]
     __shared__ float s_v[2][VP_BATCH][5][VP_COLS];
     __shared__ double scratch[6 * 32];
     const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
-    const int x = blockIdx.x * VP_COLS + lane;
+    const int x0 = blockIdx.x * VP_COLS;
+    const int x = x0 + lane;
     const size_t b = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
     const bool active = x < w;
-    const int xs = active ? x : 0;
-    const float* i1 = xyb + ((b * 2 + 0) * 3 + c) * n + xs;
-    const float* i2 = xyb + ((b * 2 + 1) * 3 + c) * n + xs;
-    const float* hp = hb + ((b * 3 + c) * 5 + p) * n + xs;
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    RGState st = {0, 0, 0, 0, 0, 0};
-    float ring[10];
-#pragma unroll
-    for (int j = 0; j < 10; j++) ring[j] = 0.0f;
+    const float* i1 = xyb + ((b * 2 + 0) * 3 + c) * n;
+    const float* i2 = xyb + ((b * 2 + 1) * 3 + c) * n;
+    const float* hp = hb + ((b * 3 + c) * 5) * n;
     const int total = h + 4;  // input rows j = 0 .. h+3 (rows >= h are zero); output row y = j - 4
-    float cur[VP_BATCH], nxt[VP_BATCH];
+    const int nbatch = (total + VP_BATCH - 1) / VP_BATCH;
+
+    // copy roles.  vec: warp p brings plane p: lane -> (row lane/8, 16-B group lane%8) for rows 0..3, lanes 0..7 also row 4;
+    // threads 0..79 bring i1 / i2 (rows shifted by -4).
+    const int cr = lane >> 3, cc4 = lane & 7;
+    const bool cx_ok = x0 + 4 * cc4 < w;
+    const float* src_p = hp + (size_t)p * n + x0 + 4 * cc4;
+    const int e_pl = threadIdx.x / 40, e_r = (threadIdx.x % 40) >> 3;   // threads 0..79: plane 5 + e_pl, row e_r
+    const float* src_e = (e_pl ? i2 : i1) + x0 + 4 * cc4;
+
+    auto issue = [&](int t) {
+        if (t < nbatch) {
+            float* slot = s_ld + (t & (VP_SLOTS - 1)) * VP_SLOT_FLOATS;
+            const int j0 = t * VP_BATCH;
+            if (vec) {
+                {
+                    const int j = j0 + cr;
+                    const bool ok = cx_ok && j < h;
+                    cp_async16(slot + (cr * VP_PLANES + p) * VP_COLS + 4 * cc4, ok ? src_p + (size_t)j * w : hp, ok);
+                }
+                if (lane < 8) {
+                    const int j = j0 + 4;
+                    const bool ok = cx_ok && j < h;
+                    cp_async16(slot + (4 * VP_PLANES + p) * VP_COLS + 4 * cc4, ok ? src_p + (size_t)j * w : hp, ok);
+                }
+                if (threadIdx.x < 80) {
+                    const int y = j0 + e_r - 4;
+                    const bool ok = cx_ok && y >= 0 && y < h;
+                    cp_async16(slot + (e_r * VP_PLANES + 5 + e_pl) * VP_COLS + 4 * cc4, ok ? src_e + (size_t)y * w : hp, ok);
+                }
+            } else {
+                for (int e = threadIdx.x; e < VP_BATCH * VP_PLANES * VP_COLS; e += 160) {
+                    const int cx = e & 31, pl = (e >> 5) % VP_PLANES, r = e / (VP_PLANES * 32);
+                    const int xx = x0 + cx;
+                    const int row = (pl < 5) ? j0 + r : j0 + r - 4;
+                    const float* base = (pl < 5) ? hp + (size_t)pl * n : (pl == 5 ? i1 : i2);
+                    const bool ok = row >= 0 && row < h && xx < w;
+                    cp_async4(slot + (r * VP_PLANES + pl) * VP_COLS + cx, ok ? base + (size_t)row * w + xx : base, ok);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    // SSIM / edge terms of row r = p of batch t (values in s_v[t & 1], image rows in slot t % VP_SLOTS)
+    auto map_rows = [&](int t) {
+        const int y = t * VP_BATCH + p - 4;
+        if (y >= 0 && y < h && active) {
+            const int bf = t & 1;
+            const float m1 = s_v[bf][p][0][lane], m2 = s_v[bf][p][1][lane], s11 = s_v[bf][p][2][lane],
+                        s22 = s_v[bf][p][3][lane], s12 = s_v[bf][p][4][lane];
+            const float* slot = s_ld + (t & (VP_SLOTS - 1)) * VP_SLOT_FLOATS + (p * VP_PLANES) * VP_COLS + lane;
+            const float a1 = slot[5 * VP_COLS], a2 = slot[6 * VP_COLS];
+            if (dbg) {
+                float* d = dbg + (size_t)c * 7 * n + (size_t)y * w + x;
+                d[2 * n] = m1; d[3 * n] = m2; d[4 * n] = s11; d[5 * n] = s22; d[6 * n] = s12;
+            }
+            // ssim_map
+            const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+            const float mdiff = m1 - m2;
+            const float num_m = __fmaf_rn(mdiff, -mdiff, 1.0f);
+            const float num_s = __fmaf_rn(2.0f, s12 - m12, 0.0009f);
+            const float denom_s = ((s11 - m11) + (s22 - m22)) + 0.0009f;
+            double d = 1.0 - (double)((num_m * num_s) / denom_s);
+            if (!(d > 0.0)) d = 0.0;
+            const double d2 = d * d;
+            acc[0] += d;
+            acc[1] += d2 * d2;
+            // edge_diff_map
+            const double d1 = (1.0 + (double)fabsf(a2 - m2)) / (1.0 + (double)fabsf(a1 - m1)) - 1.0;
+            const double art = d1 > 0.0 ? d1 : 0.0;
+            const double det = d1 < 0.0 ? -d1 : 0.0;
+            const double a2_ = art * art, l2 = det * det;
+            acc[2] += art;
+            acc[3] += a2_ * a2_;
+            acc[4] += det;
+            acc[5] += l2 * l2;
+        }
+    };
+
+    issue(0);
+    issue(1);
+    RGState st = {0, 0, 0, 0, 0, 0};
+    float ring[2 * VP_BATCH];
 #pragma unroll
-    for (int r = 0; r < VP_BATCH; r++) cur[r] = (r < h) ? hp[(size_t)r * w] : 0.0f;
-    int buf = 0;
-    for (int j0 = 0; j0 < total; j0 += 2 * VP_BATCH) {
+    for (int j = 0; j < 2 * VP_BATCH; j++) ring[j] = 0.0f;
+    for (int t0 = 0; t0 < nbatch; t0 += 2) {
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            const int jb = j0 + half * VP_BATCH;
-            if (jb < total) {   // block-uniform
-                // prefetch the next batch of this warp's plane, and the two image values of the pixel this warp maps
+            const int t = t0 + half;
+            if (t < nbatch) {   // block-uniform
+                cp_async_wait<1>();
+                __syncthreads();   // batch t landed; s_v of batch t-1 complete; slot (t-2) % 4 free
+                issue(t + 2);
+                const float* in = s_ld + (t & (VP_SLOTS - 1)) * VP_SLOT_FLOATS + p * VP_COLS + lane;
 #pragma unroll
                 for (int r = 0; r < VP_BATCH; r++) {
-                    const int jn = jb + VP_BATCH + r;
-                    nxt[r] = (jn < h) ? hp[(size_t)jn * w] : 0.0f;
-                }
-                const int y = jb + p - 4;
-                const bool ylive = y >= 0 && y < h;
-                float a1 = 0.0f, a2 = 0.0f;
-                if (ylive) { a1 = i1[(size_t)y * w]; a2 = i2[(size_t)y * w]; }
-#pragma unroll
-                for (int r = 0; r < VP_BATCH; r++) {
-                    const float rv = cur[r];
+                    const float rv = in[r * VP_PLANES * VP_COLS];
                     const float l = ring[half * VP_BATCH + r];
                     ring[half * VP_BATCH + r] = rv;
-                    s_v[buf][r][p][lane] = rg_step(st, l + rv);
+                    s_v[half][r][p][lane] = rg_step(st, l + rv);
                 }
-                __syncthreads();
-                if (ylive && active) {
-                    const float m1 = s_v[buf][p][0][lane], m2 = s_v[buf][p][1][lane], s11 = s_v[buf][p][2][lane],
-                                s22 = s_v[buf][p][3][lane], s12 = s_v[buf][p][4][lane];
-                    if (dbg) {
-                        float* d = dbg + (size_t)c * 7 * n + (size_t)y * w + x;
-                        d[2 * n] = m1; d[3 * n] = m2; d[4 * n] = s11; d[5 * n] = s22; d[6 * n] = s12;
-                    }
-                    // ssim_map
-                    const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
-                    const float mdiff = m1 - m2;
-                    const float num_m = __fmaf_rn(mdiff, -mdiff, 1.0f);
-                    const float num_s = __fmaf_rn(2.0f, s12 - m12, 0.0009f);
-                    const float denom_s = ((s11 - m11) + (s22 - m22)) + 0.0009f;
-                    double d = 1.0 - (double)((num_m * num_s) / denom_s);
-                    if (!(d > 0.0)) d = 0.0;
-                    const double d2 = d * d;
-                    acc[0] += d;
-                    acc[1] += d2 * d2;
-                    // edge_diff_map
-                    const double d1 = (1.0 + (double)fabsf(a2 - m2)) / (1.0 + (double)fabsf(a1 - m1)) - 1.0;
-                    const double art = d1 > 0.0 ? d1 : 0.0;
-                    const double det = d1 < 0.0 ? -d1 : 0.0;
-                    const double a2_ = art * art, l2 = det * det;
-                    acc[2] += art;
-                    acc[3] += a2_ * a2_;
-                    acc[4] += det;
-                    acc[5] += l2 * l2;
-                }
-                buf ^= 1;
-#pragma unroll
-                for (int r = 0; r < VP_BATCH; r++) cur[r] = nxt[r];
+                if (t > 0) map_rows(t - 1);
             }
         }
     }
+    __syncthreads();
+    map_rows(nbatch - 1);
     block_sum<6>(acc, scratch);
     if (threadIdx.x == 0) {
         double* o = partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 6;
@@ -303,6 +368,7 @@ __global__ void k_s2_reduce(const double* __restrict__ partials, int nblk, size_
 
 void ssim2_init(Context& c) {
     CE_CUDA(cudaMemcpyToSymbol(c_rg, &c.rg, sizeof(RGaussCoef), 0, cudaMemcpyHostToDevice));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, HP_SMEM_BYTES));
 }
 
 size_t ssim2_workspace_per_pair(size_t w, size_t h) {
@@ -344,14 +410,14 @@ int ssim2_run(Context& c, const float* lin1_in, const float* lin2_in, size_t B, 
         }
         {
             dim3 grid(cdiv(ch, HP_ROWS), (unsigned)(B * 3));
-            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4, k_s2_hpass<<<grid, 160, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, (cw % 4 == 0) ? 1 : 0));
+            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4, k_s2_hpass<<<grid, 160, HP_SMEM_BYTES, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, (cw % 4 == 0) ? 1 : 0));
         }
         const int nblk = cdiv(cw, VP_COLS);
         float* dbg = (dbg_planes && scale == 0) ? dbg_planes : nullptr;
         {
             dim3 grid(nblk, (unsigned)(B * 3));
             CE_LAUNCH(c, "k_s2_vpass", (double)B * 3 * 7 * n * 4,
-                      k_s2_vpass<<<grid, 160, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, partials, dbg));
+                      k_s2_vpass<<<grid, 160, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, partials, dbg, (cw % 4 == 0) ? 1 : 0));
         }
         {
             size_t total = B * 3 * 6;
