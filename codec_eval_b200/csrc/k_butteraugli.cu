@@ -100,41 +100,6 @@ static float* ba_inv_table(Context& c, int slot, size_t len) {
 }
 
 
-// ---------------------------------------------------------------- tile loader
-CE_DEVINL int mirror(int x, int n) {
-    while (x < 0 || x >= n) { if (x < 0) x = -x - 1; else x = 2 * n - 1 - x; }
-    return x;
-}
-
-// s[r][4*c4 .. 4*c4+3] = plane[y0 + r][x0 + 4*c4 ..] for r < rows, c4 < COLS4; x0 % 4 == 0.
-// BORDER 0: zero outside the image, 1: mirror.  vec: w % 4 == 0 and the plane base is 16-B aligned.
-template <int BORDER, int COLS4>
-CE_DEVINL void load_tile(float* __restrict__ s, int pitch, const float* __restrict__ p, int w, int h, int x0, int y0,
-                         int rows, bool vec) {
-    for (int e = threadIdx.x; e < rows * COLS4; e += blockDim.x) {
-        const int r = e / COLS4, c4 = e - r * COLS4;
-        const int y = y0 + r, x = x0 + 4 * c4;
-        float4 v;
-        if (vec && y >= 0 && y < h && x >= 0 && x + 3 < w) {
-            v = *reinterpret_cast<const float4*>(p + (size_t)y * w + x);
-        } else {
-            float t[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int xx = x + k, yy = y;
-                if (BORDER == 1) {
-                    xx = mirror(xx, w); yy = mirror(yy, h);
-                    t[k] = p[(size_t)yy * w + xx];
-                } else {
-                    t[k] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? p[(size_t)yy * w + xx] : 0.0f;
-                }
-            }
-            v = make_float4(t[0], t[1], t[2], t[3]);
-        }
-        *reinterpret_cast<float4*>(s + r * pitch + 4 * c4) = v;
-    }
-}
-
 // ---------------------------------------------------------------- sigma-1.2 blur (+ opsin dynamics)
 #define OP_TW 64
 #define OP_TH 16

@@ -2,13 +2,12 @@
 // for a batch of B pairs.
 //
 // Per scale (<= 5 scales, floor-halving with crop on LINEAR rgb(a)):
-//   k_ds_down    : 2x2 average to the next scale                               [HBM-bound]
-//   k_ds_lab     : linear -> L (final) and a,b (to be pre-blurred)              [HBM-bound, pointwise]
-//   k_ds_blur2   : chroma pre-blur: the 3x3 kernel applied twice, fused through a
-//                  shared-memory tile (halo 2, clamp-replicate per pass)         [HBM-bound]
-//   k_ds_stats   : per channel the five double-3x3 blurs {ch1,ch2,ch1^2,ch2^2,ch1*ch2}
-//                  of a 32x16 tile fused in shared memory, channel-averaged SSIM map
-//                  written once + fp64 block partial of its sum                   [HBM<->ALU ridge]
+//   k_ds_prep    : per image: linear tile (+ halo 2) staged once -> Lab; L written, a/b blurred by the
+//                  3x3 kernel applied twice (clamp-replicate per pass) through shared memory; the 2x2
+//                  average for the next scale comes from the same staged tile          [HBM-bound target]
+//   k_ds_stats   : per channel the five double-3x3 blurs {ch1,ch2,ch1^2,ch2^2,ch1*ch2} of a 64x16 tile,
+//                  4 positions per thread from 128-bit shared loads; channel-averaged SSIM map
+//                  written once + fp64 block partial of its sum                        [FP32-issue bound]
 //   k_ds_mean    : fixed-order reduce -> sum(map), avg = max(mean,0)^(0.5^scale)
 //   k_ds_mad     : sum |avg - map_i| in fp64 -> block partials; k_ds_mad_reduce fixes the order
 #include "ce_common.cuh"
@@ -16,12 +15,13 @@
 
 namespace ce {
 
-#define DS_TW 32
+#define DS_TW 64
 #define DS_TH 16
-#define DS_IW (DS_TW + 4)
-#define DS_IH (DS_TH + 4)
-#define DS_FW (DS_TW + 2)
-#define DS_FH (DS_TH + 2)
+#define DS_IW (DS_TW + 8)   // staged columns x0-4 .. x0+67 (16-B aligned start; the blurs need x0-2 .. x0+65)
+#define DS_IH (DS_TH + 4)   // rows y0-2 .. y0+17
+#define DS_FW (DS_TW + 4)   // first-pass positions x0-2 .. x0+65 (column j <-> x = x0-2+j; j < 66 used)
+#define DS_FH (DS_TH + 2)   // first-pass rows y0-1 .. y0+16
+#define DS_FG (DS_FW / 4)   // 17 four-column groups per first-pass row
 
 __constant__ float c_dsk[9] = {0.095332f, 0.118095f, 0.095332f, 0.118095f, 0.146293f,
                                0.118095f, 0.095332f, 0.118095f, 0.095332f};
@@ -33,7 +33,38 @@ CE_DEVINL float ds_k9(float v00, float v01, float v02, float v10, float v11, flo
     return (a + b) + c;
 }
 
-// ------------------------------------------------------------------ downsample
+// 3 rows x 8 staged columns (i = 4q .. 4q+7) -> the 3x3 blur at the 4 positions j = 4q .. 4q+3 (centre column i = j+2)
+CE_DEVINL float4 ds_k9x4(const float (&r0)[8], const float (&r1)[8], const float (&r2)[8]) {
+    float4 o;
+    o.x = ds_k9(r0[1], r0[2], r0[3], r1[1], r1[2], r1[3], r2[1], r2[2], r2[3]);
+    o.y = ds_k9(r0[2], r0[3], r0[4], r1[2], r1[3], r1[4], r2[2], r2[3], r2[4]);
+    o.z = ds_k9(r0[3], r0[4], r0[5], r1[3], r1[4], r1[5], r2[3], r2[4], r2[5]);
+    o.w = ds_k9(r0[4], r0[5], r0[6], r1[4], r1[5], r1[6], r2[4], r2[5], r2[6]);
+    return o;
+}
+CE_DEVINL void ds_ld8(const float* s, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// The second 3x3 pass reads its input with clamped coordinates, so a first-pass value at a position outside
+// the image is the first-pass value at the nearest inside position.  Border tiles patch those entries.
+CE_DEVINL void ds_fix_border(float* __restrict__ s_f, int nplanes, int plane_stride, int w, int h, int x0, int y0) {
+    const bool border = x0 - 2 < 0 || x0 + DS_TW + 1 >= w || y0 - 1 < 0 || y0 + DS_TH >= h;
+    if (!border) return;   // block-uniform
+    for (int e = threadIdx.x; e < DS_FH * DS_FW; e += blockDim.x) {
+        const int ry = e / DS_FW, j = e - ry * DS_FW;
+        const int x = x0 - 2 + j, y = y0 - 1 + ry;
+        const int cx = min(max(x, 0), w - 1), cy = min(max(y, 0), h - 1);
+        if (cx != x || cy != y) {
+            const int cj = cx - (x0 - 2), cr = cy - (y0 - 1);
+            if (cj >= 0 && cj < DS_FW && cr >= 0 && cr < DS_FH)
+                for (int f = 0; f < nplanes; f++) s_f[f * plane_stride + e] = s_f[f * plane_stride + cr * DS_FW + cj];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ downsample (alpha plane / generic)
 // planes: [nplanes][n] -> [nplanes][on]; floor size, (a+b+c+d)*0.25
 __global__ void __launch_bounds__(256) k_ds_down(const float* __restrict__ in, int w, size_t n, int ow, int oh, size_t on,
                                                   size_t total, float* __restrict__ out) {
@@ -46,157 +77,189 @@ __global__ void __launch_bounds__(256) k_ds_down(const float* __restrict__ in, i
     }
 }
 
-// ------------------------------------------------------------------ Lab
-// lin: [B][3][n] per image, alpha nullable [B][n]; writes img[(b*2+which)*3 + 0] = L,
-// chroma[(b*2+which)*2 + {0,1}] = a,b (un-blurred)
-__global__ void __launch_bounds__(256) k_ds_lab(const float* __restrict__ lin, const float* __restrict__ alpha, int w,
-                                                 size_t n, size_t total, int which, float* __restrict__ img,
-                                                 float* __restrict__ chroma) {
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        size_t b = t / n, i = t - b * n;
-        const float* p = lin + b * 3 * n + i;
-        float r = p[0], g = p[n], bl = p[2 * n];
+// ------------------------------------------------------------------ per-image preparation of one scale
+// linear rgb [B][3][n] (+ alpha [B][n]) of image `which` ->
+//   img[(b*2+which)*3 + 0] = L, + 1,2 = a,b blurred by the 3x3 kernel applied twice (clamped borders per pass);
+//   nlin [B][3][on] = 2x2 average of the linear planes for the next scale (if has_next).
+// One 64x16 tile per block: the rgb tile (+ halo 2) is staged once; Lab is evaluated on the halo as well.
+__global__ void __launch_bounds__(256) k_ds_prep(const float* __restrict__ lin, const float* __restrict__ alpha, int w, int h,
+                                                  size_t n, int which, float* __restrict__ img, int has_next, int ow, int oh,
+                                                  size_t on, float* __restrict__ nlin) {
+    __shared__ __align__(16) float s_lin[3][DS_IH * DS_IW];
+    __shared__ __align__(16) float s_ab[2][DS_IH * DS_IW];
+    __shared__ __align__(16) float s_f[2][DS_FH * DS_FW];
+    const int x0 = blockIdx.x * DS_TW, y0 = blockIdx.y * DS_TH;
+    const size_t b = blockIdx.z;
+    const bool vec = (w & 3) == 0;
+    const float* src = lin + b * 3 * n;
+#pragma unroll
+    for (int c = 0; c < 3; c++) load_tile<2, DS_IW / 4>(s_lin[c], DS_IW, src + (size_t)c * n, w, h, x0 - 4, y0 - 2, DS_IH, vec);
+    __syncthreads();
+    float* L_out = img + ((b * 2 + which) * 3) * n;
+    for (int e = threadIdx.x; e < DS_IH * DS_IW; e += 256) {
+        const int r = e / DS_IW, i = e - r * DS_IW;
+        const int x = x0 - 4 + i, y = y0 - 2 + r;
+        float rr = s_lin[0][e], gg = s_lin[1][e], bb = s_lin[2][e];
         if (alpha) {
-            float a = alpha[b * n + i];
+            const int gx = min(max(x, 0), w - 1), gy = min(max(y, 0), h - 1);
+            const float a = alpha[b * n + (size_t)gy * w + gx];
             if (a < 255.0f / 256.0f) {
-                unsigned y = (unsigned)(i / w), x = (unsigned)(i - (size_t)y * w);
-                unsigned nn = (x + 11u) ^ (y + 11u);
-                if (nn & 16u) r += 1.0f - a;
-                if (nn & 8u) g += 1.0f - a;
-                if (nn & 32u) bl += 1.0f - a;
+                const unsigned nn = ((unsigned)gx + 11u) ^ ((unsigned)gy + 11u);
+                if (nn & 16u) rr += 1.0f - a;
+                if (nn & 8u) gg += 1.0f - a;
+                if (nn & 32u) bb += 1.0f - a;
             }
         }
         float L, A, Bv;
-        ds_to_lab(r, g, bl, L, A, Bv);
-        img[((b * 2 + which) * 3) * n + i] = L;
-        chroma[((b * 2 + which) * 2 + 0) * n + i] = A;
-        chroma[((b * 2 + which) * 2 + 1) * n + i] = Bv;
+        ds_to_lab(rr, gg, bb, L, A, Bv);
+        s_ab[0][e] = A;
+        s_ab[1][e] = Bv;
+        if (i >= 4 && i < 4 + DS_TW && r >= 2 && r < 2 + DS_TH && x < w && y < h) L_out[(size_t)y * w + x] = L;
     }
-}
-
-// ------------------------------------------------------------------ shared tile helpers
-// s_in[(iy,ix)] = plane[clamp(ty0-2+iy)][clamp(tx0-2+ix)]
-CE_DEVINL void ds_load_tile(const float* __restrict__ plane, int w, int h, int tx0, int ty0, float* s_in) {
-    for (int e = threadIdx.x; e < DS_IW * DS_IH; e += blockDim.x) {
-        int iy = e / DS_IW, ix = e - iy * DS_IW;
-        int gx = min(max(tx0 - 2 + ix, 0), w - 1), gy = min(max(ty0 - 2 + iy, 0), h - 1);
-        s_in[e] = plane[(size_t)gy * w + gx];
-    }
-}
-
-// ------------------------------------------------------------------ chroma pre-blur (two passes)
-// grid (tiles_x, tiles_y, nplanes); in: chroma[(b*2+img)*2 + k], out: img[(b*2+img)*3 + 1 + k]
-__global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chroma, int w, int h, size_t n,
-                                                   float* __restrict__ img) {
-    __shared__ float s_in[DS_IW * DS_IH];
-    __shared__ float s_f[DS_FW * DS_FH];
-    const int tx0 = blockIdx.x * DS_TW, ty0 = blockIdx.y * DS_TH;
-    const size_t pl = blockIdx.z;  // (b*2+img)*2 + k
-    const float* src = chroma + pl * n;
-    float* dst = img + ((pl >> 1) * 3 + 1 + (pl & 1)) * n;
-    ds_load_tile(src, w, h, tx0, ty0, s_in);
-    __syncthreads();
-    for (int e = threadIdx.x; e < DS_FW * DS_FH; e += blockDim.x) {
-        int ry = e / DS_FW, rx = e - ry * DS_FW;
-        int gx = min(max(tx0 - 1 + rx, 0), w - 1), gy = min(max(ty0 - 1 + ry, 0), h - 1);
-        int ix = gx - tx0 + 2, iy = gy - ty0 + 2;
-        const float* r0 = s_in + (iy - 1) * DS_IW + ix;
-        const float* r1 = r0 + DS_IW;
-        const float* r2 = r1 + DS_IW;
-        s_f[e] = ds_k9(r0[-1], r0[0], r0[1], r1[-1], r1[0], r1[1], r2[-1], r2[0], r2[1]);
+    if (has_next) {
+        // 32 x 8 outputs per plane; one thread per output
+        const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+        const int ox = (x0 >> 1) + lx, oy = (y0 >> 1) + ly;
+        if (ox < ow && oy < oh) {
+            const int e = (2 + 2 * ly) * DS_IW + 4 + 2 * lx;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float* t = s_lin[c] + e;
+                nlin[(b * 3 + c) * on + (size_t)oy * ow + ox] = (((t[0] + t[1]) + t[DS_IW]) + t[DS_IW + 1]) * 0.25f;
+            }
+        }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < DS_TW * DS_TH; e += blockDim.x) {
-        int oy = e / DS_TW, ox = e - oy * DS_TW;
-        int x = tx0 + ox, y = ty0 + oy;
-        if (x < w && y < h) {
-            const float* r0 = s_f + oy * DS_FW + ox + 1;
-            const float* r1 = r0 + DS_FW;
-            const float* r2 = r1 + DS_FW;
-            dst[(size_t)y * w + x] = ds_k9(r0[-1], r0[0], r0[1], r1[-1], r1[0], r1[1], r2[-1], r2[0], r2[1]);
+    // first 3x3 pass over the positions the second pass needs
+    for (int e = threadIdx.x; e < DS_FH * DS_FG; e += 256) {
+        const int ry = e / DS_FG, q = e - ry * DS_FG;
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            float r0[8], r1[8], r2[8];
+            const float* base = s_ab[pl] + ry * DS_IW + 4 * q;
+            ds_ld8(base, r0); ds_ld8(base + DS_IW, r1); ds_ld8(base + 2 * DS_IW, r2);
+            *reinterpret_cast<float4*>(&s_f[pl][ry * DS_FW + 4 * q]) = ds_k9x4(r0, r1, r2);
+        }
+    }
+    __syncthreads();
+    ds_fix_border(&s_f[0][0], 2, DS_FH * DS_FW, w, h, x0, y0);
+    __syncthreads();
+    // second pass -> the 4 pixels of this thread
+    const int g = threadIdx.x & 15, oy = threadIdx.x >> 4;
+    const int x = x0 + 4 * g, y = y0 + oy;
+    if (x >= w || y >= h) return;
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++) {
+        float r0[8], r1[8], r2[8];
+        const float* base = s_f[pl] + oy * DS_FW + 4 * g;
+        ds_ld8(base, r0); ds_ld8(base + DS_FW, r1); ds_ld8(base + 2 * DS_FW, r2);
+        const float4 o = ds_k9x4(r0, r1, r2);
+        float* d = img + ((b * 2 + which) * 3 + 1 + pl) * n + (size_t)y * w + x;
+        if (vec) *reinterpret_cast<float4*>(d) = o;
+        else {
+            d[0] = o.x;
+            if (x + 1 < w) d[1] = o.y;
+            if (x + 2 < w) d[2] = o.z;
+            if (x + 3 < w) d[3] = o.w;
         }
     }
 }
 
 // ------------------------------------------------------------------ statistics + SSIM map
-// grid (tiles_x, tiles_y, B); img: [B][2][3][n]; map: [B][n]; partial: [B][tiles] doubles
-__global__ void __launch_bounds__(256) k_ds_stats(const float* __restrict__ img, int w, int h, size_t n,
-                                                   float* __restrict__ map, double* __restrict__ partial) {
-    __shared__ float s_in1[DS_IW * DS_IH];
-    __shared__ float s_in2[DS_IW * DS_IH];
-    __shared__ float s_f[5][DS_FW * DS_FH];
+// grid (tiles_x, tiles_y, B), block 320; img: [B][2][3][n]; map: [B][n]; partial: [B][tiles] doubles.
+// Per channel: the two image tiles (+ halo 2, clamped) are staged; the first 3x3 pass of the five quantities
+// {ch1, ch2, ch1^2, ch2^2, ch1*ch2} is evaluated 4 positions per thread from 128-bit shared loads, the second
+// pass likewise for the thread's 4 pixels; channel sums are accumulated in the upstream order.
+#define DS_ST_THREADS 320
+__global__ void __launch_bounds__(DS_ST_THREADS) k_ds_stats(const float* __restrict__ img, int w, int h, size_t n,
+                                                             float* __restrict__ map, double* __restrict__ partial) {
+    __shared__ __align__(16) float s_in[2][DS_IH * DS_IW];
+    __shared__ __align__(16) float s_f[5][DS_FH * DS_FW];
     __shared__ double scratch[32];
-    const int tx0 = blockIdx.x * DS_TW, ty0 = blockIdx.y * DS_TH;
+    const int x0 = blockIdx.x * DS_TW, y0 = blockIdx.y * DS_TH;
     const size_t b = blockIdx.z;
-    // per-thread outputs: (ox, oy0) and (ox, oy0 + 8)
-    const int ox = threadIdx.x & 31, oy0 = threadIdx.x >> 5;
-    float ch_m11[2][3], ch_m12[2][3], ch_m22[2][3], ch_s1[2][3], ch_s2[2][3], ch_s12[2][3];
+    const bool vec = (w & 3) == 0;
+    const int g = threadIdx.x & 15, oy = threadIdx.x >> 4;   // second pass: threads 0..255
+    const bool p2 = threadIdx.x < 256;
+    float sm11[4], sm12[4], sm22[4], ss1[4], ss2[4], ss12[4];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const float* p1 = img + ((b * 2 + 0) * 3 + c) * n;
-        const float* p2 = img + ((b * 2 + 1) * 3 + c) * n;
+        const float* pq = img + ((b * 2 + 1) * 3 + c) * n;
         __syncthreads();  // previous channel's s_f / s_in no longer read
-        ds_load_tile(p1, w, h, tx0, ty0, s_in1);
-        ds_load_tile(p2, w, h, tx0, ty0, s_in2);
+        load_tile<2, DS_IW / 4>(s_in[0], DS_IW, p1, w, h, x0 - 4, y0 - 2, DS_IH, vec);
+        load_tile<2, DS_IW / 4>(s_in[1], DS_IW, pq, w, h, x0 - 4, y0 - 2, DS_IH, vec);
         __syncthreads();
-        for (int e = threadIdx.x; e < DS_FW * DS_FH; e += blockDim.x) {
-            int ry = e / DS_FW, rx = e - ry * DS_FW;
-            int gx = min(max(tx0 - 1 + rx, 0), w - 1), gy = min(max(ty0 - 1 + ry, 0), h - 1);
-            int ix = gx - tx0 + 2, iy = gy - ty0 + 2;
-            float u[9], v[9];
+        if (threadIdx.x < DS_FH * DS_FG) {
+            const int ry = threadIdx.x / DS_FG, q = threadIdx.x - ry * DS_FG;
+            float u[3][8], v[3][8], t[3][8];
 #pragma unroll
-            for (int dy = 0; dy < 3; dy++)
+            for (int r = 0; r < 3; r++) {
+                ds_ld8(s_in[0] + (ry + r) * DS_IW + 4 * q, u[r]);
+                ds_ld8(s_in[1] + (ry + r) * DS_IW + 4 * q, v[r]);
+            }
+            float* o = &s_f[0][ry * DS_FW + 4 * q];
+            *reinterpret_cast<float4*>(o) = ds_k9x4(u[0], u[1], u[2]);
+            *reinterpret_cast<float4*>(o + DS_FH * DS_FW) = ds_k9x4(v[0], v[1], v[2]);
 #pragma unroll
-                for (int dx = 0; dx < 3; dx++) {
-                    int o = (iy - 1 + dy) * DS_IW + ix - 1 + dx;
-                    u[dy * 3 + dx] = s_in1[o];
-                    v[dy * 3 + dx] = s_in2[o];
-                }
-            s_f[0][e] = ds_k9(u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7], u[8]);
-            s_f[1][e] = ds_k9(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
-            s_f[2][e] = ds_k9(u[0] * u[0], u[1] * u[1], u[2] * u[2], u[3] * u[3], u[4] * u[4], u[5] * u[5], u[6] * u[6],
-                              u[7] * u[7], u[8] * u[8]);
-            s_f[3][e] = ds_k9(v[0] * v[0], v[1] * v[1], v[2] * v[2], v[3] * v[3], v[4] * v[4], v[5] * v[5], v[6] * v[6],
-                              v[7] * v[7], v[8] * v[8]);
-            s_f[4][e] = ds_k9(u[0] * v[0], u[1] * v[1], u[2] * v[2], u[3] * v[3], u[4] * v[4], u[5] * v[5], u[6] * v[6],
-                              u[7] * v[7], u[8] * v[8]);
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int i = 1; i < 7; i++) t[r][i] = u[r][i] * u[r][i];
+            *reinterpret_cast<float4*>(o + 2 * DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int i = 1; i < 7; i++) t[r][i] = v[r][i] * v[r][i];
+            *reinterpret_cast<float4*>(o + 3 * DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int i = 1; i < 7; i++) t[r][i] = u[r][i] * v[r][i];
+            *reinterpret_cast<float4*>(o + 4 * DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            int oy = oy0 + k * 8;
-            float q[5];
+        ds_fix_border(&s_f[0][0], 5, DS_FH * DS_FW, w, h, x0, y0);
+        __syncthreads();
+        if (p2) {
+            float q[5][4];
 #pragma unroll
             for (int f = 0; f < 5; f++) {
-                const float* r0 = s_f[f] + oy * DS_FW + ox + 1;
-                const float* r1 = r0 + DS_FW;
-                const float* r2 = r1 + DS_FW;
-                q[f] = ds_k9(r0[-1], r0[0], r0[1], r1[-1], r1[0], r1[1], r2[-1], r2[0], r2[1]);
+                float r0[8], r1[8], r2[8];
+                const float* base = s_f[f] + oy * DS_FW + 4 * g;
+                ds_ld8(base, r0); ds_ld8(base + DS_FW, r1); ds_ld8(base + 2 * DS_FW, r2);
+                const float4 o = ds_k9x4(r0, r1, r2);
+                q[f][0] = o.x; q[f][1] = o.y; q[f][2] = o.z; q[f][3] = o.w;
             }
-            float mu1 = q[0], mu2 = q[1];
-            float m11 = mu1 * mu1, m12 = mu1 * mu2, m22 = mu2 * mu2;
-            ch_m11[k][c] = m11; ch_m12[k][c] = m12; ch_m22[k][c] = m22;
-            ch_s1[k][c] = q[2] - m11;
-            ch_s2[k][c] = q[3] - m22;
-            ch_s12[k][c] = q[4] - m12;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float mu1 = q[0][k], mu2 = q[1][k];
+                const float m11 = mu1 * mu1, m12 = mu1 * mu2, m22 = mu2 * mu2;
+                const float s1 = q[2][k] - m11, s2 = q[3][k] - m22, s12 = q[4][k] - m12;
+                if (c == 0) { sm11[k] = m11; sm12[k] = m12; sm22[k] = m22; ss1[k] = s1; ss2[k] = s2; ss12[k] = s12; }
+                else { sm11[k] += m11; sm12[k] += m12; sm22[k] += m22; ss1[k] += s1; ss2[k] += s2; ss12[k] += s12; }
+            }
         }
     }
     const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f, third = 1.0f / 3.0f;
     double acc = 0.0;
+    const int x = x0 + 4 * g, y = y0 + oy;
+    if (p2 && x < w && y < h) {
+        float vv[4];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        int x = tx0 + ox, y = ty0 + oy0 + k * 8;
-        if (x < w && y < h) {
-            float mu1_sq = ((ch_m11[k][0] + ch_m11[k][1]) + ch_m11[k][2]) * third;
-            float mu2_sq = ((ch_m22[k][0] + ch_m22[k][1]) + ch_m22[k][2]) * third;
-            float mu1_mu2 = ((ch_m12[k][0] + ch_m12[k][1]) + ch_m12[k][2]) * third;
-            float sigma1_sq = ((ch_s1[k][0] + ch_s1[k][1]) + ch_s1[k][2]) * third;
-            float sigma2_sq = ((ch_s2[k][0] + ch_s2[k][1]) + ch_s2[k][2]) * third;
-            float sigma12 = ((ch_s12[k][0] + ch_s12[k][1]) + ch_s12[k][2]) * third;
-            float v = (__fmaf_rn(2.0f, mu1_mu2, c1) * __fmaf_rn(2.0f, sigma12, c2)) /
-                      (((mu1_sq + mu2_sq) + c1) * ((sigma1_sq + sigma2_sq) + c2));
-            map[b * n + (size_t)y * w + x] = v;
-            acc += (double)v;
+        for (int k = 0; k < 4; k++) {
+            const float mu1_sq = sm11[k] * third, mu2_sq = sm22[k] * third, mu1_mu2 = sm12[k] * third;
+            const float sigma1_sq = ss1[k] * third, sigma2_sq = ss2[k] * third, sigma12 = ss12[k] * third;
+            vv[k] = (__fmaf_rn(2.0f, mu1_mu2, c1) * __fmaf_rn(2.0f, sigma12, c2)) /
+                    (((mu1_sq + mu2_sq) + c1) * ((sigma1_sq + sigma2_sq) + c2));
+        }
+        float* d = map + b * n + (size_t)y * w + x;
+        if (vec) {
+            *reinterpret_cast<float4*>(d) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            acc = (((double)vv[0] + (double)vv[1]) + (double)vv[2]) + (double)vv[3];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (x + k < w) { d[k] = vv[k]; acc += (double)vv[k]; }
         }
     }
     double a1[1] = {acc};
@@ -259,8 +322,8 @@ int dssim_num_scales(size_t w, size_t h, size_t* ws, size_t* hs) {
 size_t dssim_workspace_per_pair(size_t w, size_t h) {
     size_t n = w * h;
     size_t tiles = (size_t)cdiv(w, DS_TW) * cdiv(h, DS_TH);
-    // img 6n, chroma 4n, map n, next-scale rgba ping-pong 2*2*4*(n/4)
-    return (6 * n + 4 * n + n + 4 * n) * 4 + (tiles + DS_MAD_BLOCKS + 4) * 8 + 8192;
+    // img 6n, map n, next-scale rgb(a) ping-pong 2*2*4*(n/4)
+    return (6 * n + n + 4 * n) * 4 + (tiles + DS_MAD_BLOCKS + 4) * 8 + 8192;
 }
 
 int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const float* alpha1_in, const float* alpha2_in, size_t B,
@@ -270,7 +333,6 @@ int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const floa
     size_t mark = c.arena.mark();
     const size_t n0 = w * h;
     float* img = c.arena.alloc<float>(B * 6 * n0);
-    float* chroma = c.arena.alloc<float>(B * 4 * n0);
     float* map = c.arena.alloc<float>(B * n0);
     const size_t tiles0 = (size_t)cdiv(w, DS_TW) * cdiv(h, DS_TH);
     double* partial = c.arena.alloc<double>(B * std::max<size_t>(tiles0, DS_MAD_BLOCKS));
@@ -293,44 +355,32 @@ int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const floa
     const unsigned wave = (unsigned)c.sm_count * 8;
     for (int s = 0; s < ns; s++) {
         const size_t cw = ws[s], ch = hs[s], n = cw * ch;
-        if (s > 0) {
-            const size_t pw = ws[s - 1], pn = ws[s - 1] * hs[s - 1];
-            for (int im = 0; im < 2; im++) {
-                float* dst = nl[s & 1][im];
-                size_t total = B * 3 * n;
-                CE_LAUNCH(c, "k_ds_down", (double)total * 20,
-                          k_ds_down<<<std::min<unsigned>(cdiv(total, 256), wave * 4), 256, 0, c.stream>>>(l[im], (int)pw, pn, (int)cw,
-                                                                                                        (int)ch, n, total, dst));
-                if (has_alpha) {
-                    float* adst = nal[s & 1][im];
-                    size_t atotal = B * n;
-                    CE_LAUNCH(c, "k_ds_down", (double)atotal * 20,
-                              k_ds_down<<<std::min<unsigned>(cdiv(atotal, 256), wave * 4), 256, 0, c.stream>>>(
-                                  al[im], (int)pw, pn, (int)cw, (int)ch, n, atotal, adst));
-                    al[im] = adst;
-                }
-                l[im] = dst;
-            }
-        }
-        for (int im = 0; im < 2; im++) {
-            size_t total = B * n;
-            CE_LAUNCH(c, "k_ds_lab", (double)total * (has_alpha ? 28 : 24),
-                      k_ds_lab<<<std::min<unsigned>(cdiv(total, 256), wave * 4), 256, 0, c.stream>>>(
-                          l[im], has_alpha ? al[im] : nullptr, (int)cw, n, total, im, img, chroma));
-        }
+        const bool has_next = s + 1 < ns;
+        const size_t nw = has_next ? ws[s + 1] : 0, nh = has_next ? hs[s + 1] : 0, nn = nw * nh;
         const unsigned tx = cdiv(cw, DS_TW), ty = cdiv(ch, DS_TH);
-        for (size_t p0 = 0; p0 < B * 4; p0 += 32768) {  // gridDim.z <= 65535; keep pairs whole (4 planes per pair)
-            unsigned np = (unsigned)std::min<size_t>(32768, B * 4 - p0);
-            dim3 grid(tx, ty, np);
-            CE_LAUNCH(c, "k_ds_blur2", (double)np * n * 8,
-                      k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma + p0 * n, (int)cw, (int)ch, n, img + (p0 / 2) * 3 * n));
+        if (B > 65535) throw CudaError("dssim sub-batch too large for one launch");
+        for (int im = 0; im < 2; im++) {
+            float* dst = has_next ? nl[(s + 1) & 1][im] : nullptr;
+            dim3 grid(tx, ty, (unsigned)B);
+            CE_LAUNCH(c, "k_ds_prep", (double)B * (n * (has_alpha ? 28 : 24) + nn * 12),
+                      k_ds_prep<<<grid, 256, 0, c.stream>>>(l[im], has_alpha ? al[im] : nullptr, (int)cw, (int)ch, n, im, img,
+                                                           has_next ? 1 : 0, (int)nw, (int)nh, nn, dst));
+            if (has_next && has_alpha) {
+                float* adst = nal[(s + 1) & 1][im];
+                size_t atotal = B * nn;
+                CE_LAUNCH(c, "k_ds_down", (double)atotal * 20,
+                          k_ds_down<<<std::min<unsigned>(cdiv(atotal, 256), wave * 4), 256, 0, c.stream>>>(
+                              al[im], (int)cw, n, (int)nw, (int)nh, nn, atotal, adst));
+                al[im] = adst;
+            }
+            if (has_next) l[im] = dst;
         }
         const int ntiles = (int)(tx * ty);
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
             dim3 grid(tx, ty, nb);
             CE_LAUNCH(c, "k_ds_stats", (double)nb * n * 28,
-                      k_ds_stats<<<grid, 256, 0, c.stream>>>(img + b0 * 6 * n, (int)cw, (int)ch, n, map + b0 * n, partial + b0 * ntiles));
+                      k_ds_stats<<<grid, DS_ST_THREADS, 0, c.stream>>>(img + b0 * 6 * n, (int)cw, (int)ch, n, map + b0 * n, partial + b0 * ntiles));
         }
         CE_LAUNCH(c, "k_ds_mean", (double)B * (ntiles + 2) * 8,
                   k_ds_mean<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, ntiles, B, n, s, d_out, avg));
