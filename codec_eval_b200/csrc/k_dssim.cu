@@ -2,9 +2,10 @@
 // for a batch of B pairs.
 //
 // Per scale (<= 5 scales, floor-halving with crop on LINEAR rgb(a)):
-//   k_ds_prep    : per image: linear tile (+ halo 2) staged once -> Lab; L written, a/b blurred by the
-//                  3x3 kernel applied twice (clamp-replicate per pass) through shared memory; the 2x2
-//                  average for the next scale comes from the same staged tile          [HBM-bound target]
+//   k_ds_lab     : pointwise, thread = 2x2 block: linear -> L (final), a/b (to be pre-blurred), and the
+//                  2x2 average of the linear planes for the next scale                 [HBM-bound]
+//   k_ds_blur2   : chroma pre-blur: the 3x3 kernel applied twice (clamp-replicate per pass) through a
+//                  shared-memory tile, 4 positions per thread from 128-bit shared loads [HBM-bound]
 //   k_ds_stats   : per channel the five double-3x3 blurs {ch1,ch2,ch1^2,ch2^2,ch1*ch2} of a 64x16 tile,
 //                  4 positions per thread from 128-bit shared loads; channel-averaged SSIM map
 //                  written once + fp64 block partial of its sum                        [FP32-issue bound]
@@ -77,69 +78,80 @@ __global__ void __launch_bounds__(256) k_ds_down(const float* __restrict__ in, i
     }
 }
 
-// ------------------------------------------------------------------ per-image preparation of one scale
-// linear rgb [B][3][n] (+ alpha [B][n]) of image `which` ->
-//   img[(b*2+which)*3 + 0] = L, + 1,2 = a,b blurred by the 3x3 kernel applied twice (clamped borders per pass);
-//   nlin [B][3][on] = 2x2 average of the linear planes for the next scale (if has_next).
-// One 64x16 tile per block: the rgb tile (+ halo 2) is staged once; Lab is evaluated on the halo as well.
-__global__ void __launch_bounds__(256) k_ds_prep(const float* __restrict__ lin, const float* __restrict__ alpha, int w, int h,
-                                                  size_t n, int which, float* __restrict__ img, int has_next, int ow, int oh,
-                                                  size_t on, float* __restrict__ nlin) {
-    __shared__ __align__(16) float s_lin[3][DS_IH * DS_IW];
-    __shared__ __align__(16) float s_ab[2][DS_IH * DS_IW];
-    __shared__ __align__(16) float s_f[2][DS_FH * DS_FW];
-    const int x0 = blockIdx.x * DS_TW, y0 = blockIdx.y * DS_TH;
+// ------------------------------------------------------------------ Lab (+ next scale)
+// thread = one 2x2 block of the current scale.  linear rgb [B][3][n] (+ alpha [B][n]) of image `which` ->
+//   img[(b*2+which)*3 + 0] = L;  chroma[(b*2+which)*2 + {0,1}] = a, b (un-blurred);
+//   nlin [B][3][on] = 2x2 average of the linear planes (floor size: a trailing odd row / column is dropped).
+__global__ void __launch_bounds__(256) k_ds_lab(const float* __restrict__ lin, const float* __restrict__ alpha, int w, int h,
+                                                 size_t n, int which, float* __restrict__ img, float* __restrict__ chroma,
+                                                 int has_next, int ow, int oh, size_t on, float* __restrict__ nlin) {
+    const int ox = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
     const size_t b = blockIdx.z;
-    const bool vec = (w & 3) == 0;
+    const int x0 = 2 * ox, y0 = 2 * oy;
+    if (x0 >= w || y0 >= h) return;
+    const bool vx = x0 + 1 < w, vy = y0 + 1 < h;
     const float* src = lin + b * 3 * n;
+    const size_t i00 = (size_t)y0 * w + x0;
+    const size_t off[4] = {i00, i00 + (vx ? 1 : 0), i00 + (vy ? (size_t)w : 0), i00 + (vy ? (size_t)w : 0) + (vx ? 1 : 0)};
+    float p[3][4];
 #pragma unroll
-    for (int c = 0; c < 3; c++) load_tile<2, DS_IW / 4>(s_lin[c], DS_IW, src + (size_t)c * n, w, h, x0 - 4, y0 - 2, DS_IH, vec);
-    __syncthreads();
-    float* L_out = img + ((b * 2 + which) * 3) * n;
-    for (int e = threadIdx.x; e < DS_IH * DS_IW; e += 256) {
-        const int r = e / DS_IW, i = e - r * DS_IW;
-        const int x = x0 - 4 + i, y = y0 - 2 + r;
-        float rr = s_lin[0][e], gg = s_lin[1][e], bb = s_lin[2][e];
+    for (int c = 0; c < 3; c++) {
+        const float* pl = src + (size_t)c * n;
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[c][k] = pl[off[k]];
+    }
+    if (has_next && vx && vy && ox < ow && oy < oh) {
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            nlin[(b * 3 + c) * on + (size_t)oy * ow + ox] = (((p[c][0] + p[c][1]) + p[c][2]) + p[c][3]) * 0.25f;
+    }
+    float* Lp = img + ((b * 2 + which) * 3) * n;
+    float* Ap = chroma + ((b * 2 + which) * 2) * n;
+    float* Bp = Ap + n;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if ((k & 1) && !vx) continue;
+        if ((k & 2) && !vy) continue;
+        float r = p[0][k], g = p[1][k], bl = p[2][k];
         if (alpha) {
-            const int gx = min(max(x, 0), w - 1), gy = min(max(y, 0), h - 1);
-            const float a = alpha[b * n + (size_t)gy * w + gx];
+            const float a = alpha[b * n + off[k]];
             if (a < 255.0f / 256.0f) {
-                const unsigned nn = ((unsigned)gx + 11u) ^ ((unsigned)gy + 11u);
-                if (nn & 16u) rr += 1.0f - a;
-                if (nn & 8u) gg += 1.0f - a;
-                if (nn & 32u) bb += 1.0f - a;
+                const unsigned x = (unsigned)(x0 + (k & 1)), y = (unsigned)(y0 + (k >> 1));
+                const unsigned nn = (x + 11u) ^ (y + 11u);
+                if (nn & 16u) r += 1.0f - a;
+                if (nn & 8u) g += 1.0f - a;
+                if (nn & 32u) bl += 1.0f - a;
             }
         }
         float L, A, Bv;
-        ds_to_lab(rr, gg, bb, L, A, Bv);
-        s_ab[0][e] = A;
-        s_ab[1][e] = Bv;
-        if (i >= 4 && i < 4 + DS_TW && r >= 2 && r < 2 + DS_TH && x < w && y < h) L_out[(size_t)y * w + x] = L;
+        ds_to_lab(r, g, bl, L, A, Bv);
+        Lp[off[k]] = L; Ap[off[k]] = A; Bp[off[k]] = Bv;
     }
-    if (has_next) {
-        // 32 x 8 outputs per plane; one thread per output
-        const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-        const int ox = (x0 >> 1) + lx, oy = (y0 >> 1) + ly;
-        if (ox < ow && oy < oh) {
-            const int e = (2 + 2 * ly) * DS_IW + 4 + 2 * lx;
+}
+
+// ------------------------------------------------------------------ chroma pre-blur (3x3 kernel applied twice)
+// grid (tiles_x, tiles_y, 2B): blockIdx.z = b*2 + which; chroma [2B][2][n] -> img[(z*3) + 1 + {0,1}].
+// Both planes of a 64x16 tile (+ halo 2, clamped) are staged; each pass evaluates 4 positions per thread
+// from 128-bit shared loads.
+__global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chroma, int w, int h, size_t n,
+                                                   float* __restrict__ img) {
+    __shared__ __align__(16) float s_ab[2][DS_IH * DS_IW];
+    __shared__ __align__(16) float s_f[2][DS_FH * DS_FW];
+    const int x0 = blockIdx.x * DS_TW, y0 = blockIdx.y * DS_TH;
+    const size_t z = blockIdx.z;
+    const bool vec = (w & 3) == 0;
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const float* t = s_lin[c] + e;
-                nlin[(b * 3 + c) * on + (size_t)oy * ow + ox] = (((t[0] + t[1]) + t[DS_IW]) + t[DS_IW + 1]) * 0.25f;
-            }
-        }
-    }
+    for (int pl = 0; pl < 2; pl++) load_tile<2, DS_IW / 4>(s_ab[pl], DS_IW, chroma + (z * 2 + pl) * n, w, h, x0 - 4, y0 - 2, DS_IH, vec);
     __syncthreads();
     // first 3x3 pass over the positions the second pass needs
-    for (int e = threadIdx.x; e < DS_FH * DS_FG; e += 256) {
-        const int ry = e / DS_FG, q = e - ry * DS_FG;
-#pragma unroll
-        for (int pl = 0; pl < 2; pl++) {
-            float r0[8], r1[8], r2[8];
-            const float* base = s_ab[pl] + ry * DS_IW + 4 * q;
-            ds_ld8(base, r0); ds_ld8(base + DS_IW, r1); ds_ld8(base + 2 * DS_IW, r2);
-            *reinterpret_cast<float4*>(&s_f[pl][ry * DS_FW + 4 * q]) = ds_k9x4(r0, r1, r2);
-        }
+    for (int e = threadIdx.x; e < 2 * DS_FH * DS_FG; e += 256) {
+        const int pl = e / (DS_FH * DS_FG), r = e - pl * (DS_FH * DS_FG);
+        const int ry = r / DS_FG, q = r - ry * DS_FG;
+        float r0[8], r1[8], r2[8];
+        const float* base = s_ab[pl] + ry * DS_IW + 4 * q;
+        ds_ld8(base, r0); ds_ld8(base + DS_IW, r1); ds_ld8(base + 2 * DS_IW, r2);
+        *reinterpret_cast<float4*>(&s_f[pl][ry * DS_FW + 4 * q]) = ds_k9x4(r0, r1, r2);
     }
     __syncthreads();
     ds_fix_border(&s_f[0][0], 2, DS_FH * DS_FW, w, h, x0, y0);
@@ -154,7 +166,7 @@ __global__ void __launch_bounds__(256) k_ds_prep(const float* __restrict__ lin, 
         const float* base = s_f[pl] + oy * DS_FW + 4 * g;
         ds_ld8(base, r0); ds_ld8(base + DS_FW, r1); ds_ld8(base + 2 * DS_FW, r2);
         const float4 o = ds_k9x4(r0, r1, r2);
-        float* d = img + ((b * 2 + which) * 3 + 1 + pl) * n + (size_t)y * w + x;
+        float* d = img + (z * 3 + 1 + pl) * n + (size_t)y * w + x;
         if (vec) *reinterpret_cast<float4*>(d) = o;
         else {
             d[0] = o.x;
@@ -171,7 +183,7 @@ __global__ void __launch_bounds__(256) k_ds_prep(const float* __restrict__ lin, 
 // {ch1, ch2, ch1^2, ch2^2, ch1*ch2} is evaluated 4 positions per thread from 128-bit shared loads, the second
 // pass likewise for the thread's 4 pixels; channel sums are accumulated in the upstream order.
 #define DS_ST_THREADS 320
-__global__ void __launch_bounds__(DS_ST_THREADS) k_ds_stats(const float* __restrict__ img, int w, int h, size_t n,
+__global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __restrict__ img, int w, int h, size_t n,
                                                              float* __restrict__ map, double* __restrict__ partial) {
     __shared__ __align__(16) float s_in[2][DS_IH * DS_IW];
     __shared__ __align__(16) float s_f[5][DS_FH * DS_FW];
@@ -322,8 +334,8 @@ int dssim_num_scales(size_t w, size_t h, size_t* ws, size_t* hs) {
 size_t dssim_workspace_per_pair(size_t w, size_t h) {
     size_t n = w * h;
     size_t tiles = (size_t)cdiv(w, DS_TW) * cdiv(h, DS_TH);
-    // img 6n, map n, next-scale rgb(a) ping-pong 2*2*4*(n/4)
-    return (6 * n + n + 4 * n) * 4 + (tiles + DS_MAD_BLOCKS + 4) * 8 + 8192;
+    // img 6n, chroma 4n, map n, next-scale rgb(a) ping-pong 2*2*4*(n/4)
+    return (6 * n + 4 * n + n + 4 * n) * 4 + (tiles + DS_MAD_BLOCKS + 4) * 8 + 8192;
 }
 
 int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const float* alpha1_in, const float* alpha2_in, size_t B,
@@ -333,6 +345,7 @@ int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const floa
     size_t mark = c.arena.mark();
     const size_t n0 = w * h;
     float* img = c.arena.alloc<float>(B * 6 * n0);
+    float* chroma = c.arena.alloc<float>(B * 4 * n0);
     float* map = c.arena.alloc<float>(B * n0);
     const size_t tiles0 = (size_t)cdiv(w, DS_TW) * cdiv(h, DS_TH);
     double* partial = c.arena.alloc<double>(B * std::max<size_t>(tiles0, DS_MAD_BLOCKS));
@@ -361,10 +374,10 @@ int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const floa
         if (B > 65535) throw CudaError("dssim sub-batch too large for one launch");
         for (int im = 0; im < 2; im++) {
             float* dst = has_next ? nl[(s + 1) & 1][im] : nullptr;
-            dim3 grid(tx, ty, (unsigned)B);
-            CE_LAUNCH(c, "k_ds_prep", (double)B * (n * (has_alpha ? 28 : 24) + nn * 12),
-                      k_ds_prep<<<grid, 256, 0, c.stream>>>(l[im], has_alpha ? al[im] : nullptr, (int)cw, (int)ch, n, im, img,
-                                                           has_next ? 1 : 0, (int)nw, (int)nh, nn, dst));
+            dim3 grid(cdiv((cw + 1) / 2, 64), cdiv((ch + 1) / 2, 4), (unsigned)B);
+            CE_LAUNCH(c, "k_ds_lab", (double)B * (n * (has_alpha ? 28 : 24) + nn * 12),
+                      k_ds_lab<<<grid, 256, 0, c.stream>>>(l[im], has_alpha ? al[im] : nullptr, (int)cw, (int)ch, n, im, img, chroma,
+                                                          has_next ? 1 : 0, (int)nw, (int)nh, nn, dst));
             if (has_next && has_alpha) {
                 float* adst = nal[(s + 1) & 1][im];
                 size_t atotal = B * nn;
@@ -374,6 +387,11 @@ int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const floa
                 al[im] = adst;
             }
             if (has_next) l[im] = dst;
+        }
+        {
+            if (2 * B > 65535) throw CudaError("dssim sub-batch too large for one launch");
+            dim3 grid(tx, ty, (unsigned)(2 * B));
+            CE_LAUNCH(c, "k_ds_blur2", (double)B * n * 32, k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img));
         }
         const int ntiles = (int)(tx * ty);
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
