@@ -42,27 +42,29 @@ STAGED_BYTES_PER_PX = {"psnr": 6.0, "ssimulacra2": 326.0, "dssim": 225.0, "butte
 
 
 def make_pairs(name: str, rank: int):
+    """-> (urefs [nref,h,w,3], dists [n,h,w,3], ref_index [n]): every reference with its len(quals) distortions."""
     from codec_eval_b200.synth import G, J, cheap_distort
 
     w, h, nref, quals, _ = WORKLOADS[name]
-    cache = f"/tmp/ce_bench_{name}_r{rank}.npz"
+    cache = f"/tmp/ce_bench2_{name}_r{rank}.npz"
     if os.path.exists(cache):
         z = np.load(cache)
-        return z["refs"], z["dists"]
-    refs, dists = [], []
+        return z["urefs"], z["dists"], z["ref_index"]
+    urefs, dists, ref_index = [], [], []
     use_jpeg = w * h <= 1024 * 1024
     for i in range(nref):
         ref = G(rank * 1000 + i, w, h)
+        urefs.append(ref)
         for k, q in enumerate(quals):
-            refs.append(ref)
             ss = 2 if (k // 3) % 2 == 0 else 0
             dists.append(J(ref, q, ss) if use_jpeg else cheap_distort(ref, q, seed=i))
-    refs, dists = np.stack(refs), np.stack(dists)
+            ref_index.append(i)
+    urefs, dists, ref_index = np.stack(urefs), np.stack(dists), np.asarray(ref_index, np.uint32)
     try:
-        np.savez(cache, refs=refs, dists=dists)
+        np.savez(cache, urefs=urefs, dists=dists, ref_index=ref_index)
     except Exception:
         pass
-    return refs, dists
+    return urefs, dists, ref_index
 
 
 class ClockSampler:
@@ -141,7 +143,8 @@ def run_reference(args):
     from oracle import oracle as O
 
     w, h, _, _, desc = WORKLOADS[args.workload]
-    refs, dists = make_pairs(args.workload, 0)
+    urefs, dists, ref_index = make_pairs(args.workload, 0)
+    refs = urefs[ref_index]
     cores = O.max_threads()
     sample = max(cores, min(refs.shape[0], int(16 * (768 * 512) / (w * h)) or 1))
     sample = min(sample, refs.shape[0])
@@ -200,11 +203,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w, h, _, _, desc = WORKLOADS[args.workload]
-    refs, dists = make_pairs(args.workload, rank)
-    n = refs.shape[0]
+    urefs, dists, ref_index = make_pairs(args.workload, rank)
+    n, n_ref = dists.shape[0], urefs.shape[0]
     mpix = n * w * h / 1e6
-    d_ref = torch.from_numpy(refs).cuda()
+    d_ref = torch.from_numpy(urefs).cuda()
     d_dist = torch.from_numpy(dists).cuda()
+    ri_c = np.ascontiguousarray(ref_index, np.uint32)
+    ri_p = ri_c.ctypes.data_as(C.POINTER(C.c_uint32))
     ctx = GpuMetrics(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -218,10 +223,10 @@ def main():
         out = (_lib.CeResult * n)()
 
         def step():
-            st = L.ce_evaluate_batch_device(ctx._h, C.c_void_p(d_ref.data_ptr()), C.c_void_p(d_dist.data_ptr()), n, w, h,
-                                            C.byref(ccfg), 80.0, out)
+            st = L.ce_evaluate_batch_device_grouped(ctx._h, C.c_void_p(d_ref.data_ptr()), n_ref, C.c_void_p(d_dist.data_ptr()),
+                                                    n, ri_p, w, h, C.byref(ccfg), 80.0, out)
             if st != 0:
-                raise RuntimeError(f"ce_evaluate_batch_device failed: {st} {ctx.last_error()}")
+                raise RuntimeError(f"ce_evaluate_batch_device_grouped failed: {st} {ctx.last_error()}")
             if world > 1:  # the final score gather (NCCL); 56 B per pair
                 gather_in.copy_(torch.frombuffer(out, dtype=torch.uint8), non_blocking=False)
                 dist.all_gather_into_tensor(gather_out, gather_in)
@@ -250,21 +255,25 @@ def main():
             ms = float(t.item())
         return ms
 
-    # ---- headline: all four metrics, inputs resident in HBM
+    # ---- headline: all four metrics, inputs resident in HBM (profiler off: the three perceptual metrics of a
+    # sub-batch overlap on separate streams)
     all_cfg = MetricConfig.all()
     step_all = make_step(all_cfg)
     sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step_all()
-    ctx.profile(True, reset=True)
     l0 = ctx.launch_count()
     sampler.start()
     ms = timed(step_all, args.steps, 0)
     clocks = sampler.stop()
     launches = ctx.launch_count() - l0
+    value = mpix * world * args.steps / (ms / 1e3)
+
+    # ---- per-kernel CUDA-event pass (profiler on => metrics serialised so every event pair brackets one kernel)
+    ctx.profile(True, reset=True)
+    prof_ms = timed(step_all, args.steps, 0)
     prof = ctx.profile_report()
     ctx.profile(False, reset=False)
-    value = mpix * world * args.steps / (ms / 1e3)
 
     out = step_all()
     sanity = {"ssimulacra2_pair0": out[0].ssimulacra2, "dssim_pair0": out[0].dssim, "butteraugli_pair0": out[0].butteraugli,
@@ -308,13 +317,13 @@ def main():
                                  "staged_model_gbs_per_gpu": gbs, "frac_of_hbm_staged_model": gbs / peak}
 
     # ---- end to end through the host-pointer C-ABI entry (pinned host buffers; H2D + D2H inside the timed region)
-    h_ref = torch.from_numpy(refs).pin_memory()
+    h_ref = torch.from_numpy(urefs).pin_memory()     # every reference once; its pairs share the host pointer
     h_dist = torch.from_numpy(dists).pin_memory()
     img_bytes = w * h * 3
     pairs = (_lib.CePair * n)()
     for i in range(n):
-        pairs[i] = _lib.CePair(h_ref.data_ptr() + i * img_bytes, h_dist.data_ptr() + i * img_bytes, img_bytes, img_bytes,
-                               w, h, i // max(1, len(WORKLOADS[args.workload][3])), 0)
+        pairs[i] = _lib.CePair(h_ref.data_ptr() + int(ref_index[i]) * img_bytes, h_dist.data_ptr() + i * img_bytes, img_bytes,
+                               img_bytes, w, h, int(ref_index[i]), 0)
     e2e_out = (_lib.CeResult * n)()
     ccfg = all_cfg._c()
 
@@ -328,7 +337,7 @@ def main():
 
     e2e_ms = timed(step_e2e, args.steps, 2)
     e2e_val = mpix * world * args.steps / (e2e_ms / 1e3)
-    e2e = {"value": e2e_val, "unit": "MPix-pairs/s", "h2d_bytes_per_step": 2 * n * img_bytes,
+    e2e = {"value": e2e_val, "unit": "MPix-pairs/s", "h2d_bytes_per_step": (n + n_ref) * img_bytes,
            "d2h_bytes_per_step": n * (1 + 108 + 10 + 4) * 8, "ms_per_step": e2e_ms / args.steps}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample
@@ -338,7 +347,7 @@ def main():
 
         cores = O.max_threads()
         sample = max(cores, 16)
-        v, ns, dt = cpu_baseline(refs, dists, w, h, 15, sample)
+        v, ns, dt = cpu_baseline(urefs[ref_index[:sample]], dists, w, h, 15, sample)
         cpu = {"value": v, "unit": "MPix-pairs/s", "cores": cores, "kind": "port",
                "sample": f"{ns} of {n} pairs, all four metrics, OpenMP over pairs, {dt:.1f} s wall"}
 
@@ -349,7 +358,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "pairs_per_gpu": n, "width": w, "height": h,
                        "metrics": "psnr+dssim+ssimulacra2+butteraugli (max + 3-norm)",
-                       "l2": f"no explicit flush: {2 * n * img_bytes / 1e6:.0f} MB of inputs and >1 GB of fp32 intermediates per step exceed the 126 MB L2",
+                       "references": f"{n_ref} distinct references, {n // max(n_ref, 1)} distortions each; reference-side work is done once per distinct reference (the reference's Ssimulacra2Reference reuse, generalised)",
+                       "l2": f"no explicit flush: {(n + n_ref) * img_bytes / 1e6:.0f} MB of inputs and >1 GB of fp32 intermediates per step exceed the 126 MB L2",
                        "parallelism": f"pairs sharded over {world} rank(s), NCCL all_gather of 56 B/pair results"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "per_metric": per_metric, "kernels": kernels, "sanity": sanity,

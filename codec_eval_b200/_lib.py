@@ -38,7 +38,7 @@ class CeResult(C.Structure):
 EXPORTS = [
     "ce_ctx_create", "ce_ctx_destroy", "ce_ctx_set_stream", "ce_last_error", "ce_launch_count", "ce_version",
     "ce_profile_enable", "ce_profile_reset", "ce_profile_report",
-    "ce_evaluate_batch", "ce_evaluate_batch_device", "ce_psnr", "ce_ssimulacra2", "ce_butteraugli", "ce_dssim_rgb8",
+    "ce_evaluate_batch", "ce_evaluate_batch_device", "ce_evaluate_batch_device_grouped", "ce_psnr", "ce_ssimulacra2", "ce_butteraugli", "ce_dssim_rgb8",
     "ce_dssim_rgbaf32", "ce_rgb8_to_dssim_image", "ce_rgba8_to_dssim_image", "ce_xyb_roundtrip",
     "ce_reference_create", "ce_reference_compare", "ce_reference_compare_many", "ce_reference_destroy",
     "ce_debug_ssim2_sums", "ce_debug_ssim2_scale0_planes", "ce_debug_dssim_scales", "ce_debug_butteraugli_diffmap",
@@ -76,6 +76,8 @@ def load():
     L.ce_profile_report.restype = sz
     L.ce_evaluate_batch.argtypes = [vp, C.POINTER(CePair), sz, cfgp, C.c_float, resp]
     L.ce_evaluate_batch_device.argtypes = [vp, vp, vp, sz, C.c_uint32, C.c_uint32, cfgp, C.c_float, resp]
+    L.ce_evaluate_batch_device_grouped.argtypes = [vp, vp, sz, vp, sz, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, cfgp,
+                                                   C.c_float, resp]
     L.ce_psnr.argtypes = [vp, u8p, sz, u8p, sz, sz, sz, f64p, C.POINTER(C.c_uint64)]
     L.ce_ssimulacra2.argtypes = [vp, u8p, sz, u8p, sz, sz, sz, f64p]
     L.ce_butteraugli.argtypes = [vp, u8p, sz, u8p, sz, sz, sz, C.c_float, f64p, f64p]

@@ -47,6 +47,19 @@ void Context::ensure_results(size_t bytes) {
     h_pinned_bytes = d_results_bytes = cap;
 }
 
+void Context::ensure_idx(size_t count) {
+    if (count <= idx_cap) return;
+    if (h_idx) CE_CUDA(cudaFreeHost(h_idx));
+    if (d_idx) CE_CUDA(cudaFree(d_idx));
+    h_idx = nullptr;
+    d_idx = nullptr;
+    idx_cap = 0;
+    size_t cap = std::max<size_t>(count, 1 << 16);
+    CE_CUDA(cudaMallocHost(&h_idx, cap * sizeof(int)));
+    CE_CUDA(cudaMalloc(&d_idx, cap * sizeof(int)));
+    idx_cap = cap;
+}
+
 void Context::prof_begin(const char* name, double bytes) {
     launches++;
     if (!prof.enabled) return;
@@ -239,16 +252,21 @@ static size_t per_pair_bytes(const ce_metric_config& cfg, size_t w, size_t h) {
     if (cfg.xyb_roundtrip) bytes += n * 3 + 256;
     bool perceptual = cfg.dssim || cfg.ssimulacra2 || cfg.butteraugli;
     if (perceptual) bytes += 2 * 3 * n * 4 + 512;
+    // the metrics run concurrently on separate streams, so their workspaces coexist
     size_t m = 0;
-    if (cfg.dssim) m = std::max(m, dssim_workspace_per_pair(w, h));
-    if (cfg.ssimulacra2) m = std::max(m, ssim2_workspace_per_pair(w, h));
-    if (cfg.butteraugli) m = std::max(m, butteraugli_workspace_per_pair(w, h));
+    if (cfg.dssim) m += dssim_workspace_per_pair(w, h);
+    if (cfg.ssimulacra2) m += ssim2_workspace_per_pair(w, h);
+    if (cfg.butteraugli) m += butteraugli_workspace_per_pair(w, h);
     return bytes + m;
 }
 
-// d_ref / d_dist: n device images; optional alpha/float inputs are handled by the callers.
-static void run_device_batch(Context& c, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, size_t w, size_t h,
-                             const ce_metric_config& cfg, float intensity, ce_result* out, const DebugOut* dbg) {
+// d_ref: n_ref device images, d_dist: n device images (tight RGB8, w x h).  Pair i compares reference
+// ref_of[i] (host array; nullptr = identity, n_ref == n) with distorted image i.  Reference-side work of a
+// sub-batch is done once per distinct reference (fast_ssim2's Ssimulacra2Reference reuse,
+// crates/codec-iter/src/eval.rs:138-149, generalised to all metrics).
+static void run_device_batch(Context& c, const uint8_t* d_ref, size_t n_ref, const uint8_t* d_dist, size_t n,
+                             const uint32_t* ref_of, size_t w, size_t h, const ce_metric_config& cfg, float intensity,
+                             ce_result* out, const DebugOut* dbg) {
     const size_t npix = w * h, img_bytes = npix * 3;
     const bool small = (w < 8 || h < 8);
     const bool perceptual = cfg.dssim || cfg.ssimulacra2 || cfg.butteraugli;
@@ -259,32 +277,88 @@ static void run_device_batch(Context& c, const uint8_t* d_ref, const uint8_t* d_
     Bmax = std::min<size_t>(Bmax, 16384);
     // raw per-pair device results: sse(1 u64) + s2 sums(108) + ds(10) + ba(4) doubles
     const size_t raw_doubles = 1 + 108 + 10 + 4;
+    std::vector<int> local_of(ref_of ? n_ref : 0, -1);
     for (size_t p0 = 0; p0 < n; p0 += Bmax) {
         const size_t B = std::min(Bmax, n - p0);
         c.arena.reset();
         c.ensure_results(B * raw_doubles * 8);
+        // ---- index tables of the sub-batch: ridx[B] local reference of each pair, uniq[R] global reference
+        // image of each local one, gref[B] global reference image of each pair
+        c.ensure_idx(3 * B);
+        int* h_ridx = c.h_idx;
+        int* h_uniq = c.h_idx + B;
+        int* h_gref = c.h_idx + 2 * B;
+        size_t R = 0;
+        if (ref_of) {
+            for (size_t i = 0; i < B; i++) {
+                const uint32_t g = ref_of[p0 + i];
+                if (local_of[g] < 0) { local_of[g] = (int)R; h_uniq[R++] = (int)g; }
+                h_ridx[i] = local_of[g];
+                h_gref[i] = (int)g;
+            }
+            for (size_t r = 0; r < R; r++) local_of[h_uniq[r]] = -1;
+        } else {
+            R = B;
+            for (size_t i = 0; i < B; i++) { h_ridx[i] = (int)i; h_uniq[i] = (int)(p0 + i); h_gref[i] = (int)(p0 + i); }
+        }
+        CE_CUDA(cudaMemcpyAsync(c.d_idx, c.h_idx, 3 * B * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        const int* d_ridx = c.d_idx;
+        const int* d_uniq = c.d_idx + B;
+        const int* d_gref = c.d_idx + 2 * B;
+        bool contiguous = true;
+        for (size_t r = 1; r < R; r++) contiguous = contiguous && h_uniq[r] == h_uniq[r - 1] + 1;
+
         double* d_raw = reinterpret_cast<double*>(c.d_results);
         unsigned long long* d_sse = reinterpret_cast<unsigned long long*>(d_raw);
         double* d_s2 = d_raw + B;
         double* d_ds = d_s2 + B * 108;
         double* d_ba = d_ds + B * 10;
-        const uint8_t* ref = d_ref + p0 * img_bytes;
         const uint8_t* dist = d_dist + p0 * img_bytes;
-        if (cfg.xyb_roundtrip) {  // reference only, before every metric (src/eval/session.rs:447-456)
-            uint8_t* rt = c.arena.alloc<uint8_t>(B * img_bytes);
-            launch_xyb_roundtrip(c, ref, B * npix, rt);
-            ref = rt;
+        // reference images of this sub-batch: (ref_base, ref_src) with ref_src a device index array or
+        // nullptr for "image r of ref_base"; (ref_base, sse_idx) the same per pair
+        const uint8_t* ref_base = d_ref;
+        const int* ref_src = d_uniq;
+        const int* sse_idx = d_gref;
+        if (contiguous) { ref_base = d_ref + (size_t)h_uniq[0] * img_bytes; ref_src = nullptr; sse_idx = d_ridx; }
+        if (cfg.xyb_roundtrip) {  // distinct references only, before every metric (src/eval/session.rs:447-456)
+            uint8_t* rt = c.arena.alloc<uint8_t>(R * img_bytes);
+            for (size_t r = 0; r < R;) {   // one launch per run of consecutive source images
+                size_t e = r + 1;
+                while (e < R && h_uniq[e] == h_uniq[e - 1] + 1) e++;
+                launch_xyb_roundtrip(c, d_ref + (size_t)h_uniq[r] * img_bytes, (e - r) * npix, rt + r * img_bytes);
+                r = e;
+            }
+            ref_base = rt; ref_src = nullptr; sse_idx = d_ridx;
         }
-        if (cfg.psnr) launch_sse(c, ref, dist, B, img_bytes, d_sse);
+        if (cfg.psnr) launch_sse(c, ref_base, sse_idx, dist, B, img_bytes, d_sse);
         int s2_ns = 0, ds_ns = 0;
         if (perceptual) {
-            float* lin = c.arena.alloc<float>(2 * B * 3 * npix);
-            float* lin2 = lin + B * 3 * npix;
-            launch_srgb8_to_linear(c, ref, B, npix, lin);
-            launch_srgb8_to_linear(c, dist, B, npix, lin2);
-            if (cfg.dssim) ds_ns = dssim_run(c, lin, lin2, nullptr, nullptr, B, w, h, d_ds, dbg ? dbg->ds_map0 : nullptr);
-            if (cfg.ssimulacra2 && !small) s2_ns = ssim2_run(c, lin, lin2, B, w, h, d_s2, dbg ? dbg->s2_planes : nullptr);
-            if (cfg.butteraugli && !small) butteraugli_run(c, lin, lin2, B, w, h, intensity, d_ba, dbg ? dbg->ba_diffmap : nullptr);
+            const size_t NI = R + B;
+            float* lin = c.arena.alloc<float>(NI * 3 * npix);
+            launch_srgb8_to_linear(c, ref_base, ref_src, R, npix, lin);
+            launch_srgb8_to_linear(c, dist, nullptr, B, npix, lin + R * 3 * npix);
+            // fork: DSSIM and SSIMULACRA2 on the side streams, Butteraugli on the main one.  Each metric keeps
+            // its arena region (no release between them) because their kernels overlap in time.
+            const bool fork = c.concurrent && !c.prof.enabled;
+            cudaStream_t main_stream = c.stream;
+            if (fork) CE_CUDA(cudaEventRecord(c.ev_fork, main_stream));
+            int used = 0;
+            auto on_side = [&](auto&& fn) {
+                if (!fork) { fn(); return; }
+                cudaStream_t s = c.side[used];
+                CE_CUDA(cudaStreamWaitEvent(s, c.ev_fork, 0));
+                c.stream = s;
+                c.arena.high = c.arena.off;
+                try { fn(); } catch (...) { c.stream = main_stream; throw; }
+                c.arena.off = c.arena.high;   // keep the metric's workspace reserved until the join
+                c.stream = main_stream;
+                CE_CUDA(cudaEventRecord(c.ev_join[used], s));
+                used++;
+            };
+            if (cfg.dssim) on_side([&] { ds_ns = dssim_run(c, lin, nullptr, R, d_ridx, B, w, h, d_ds, dbg ? dbg->ds_map0 : nullptr); });
+            if (cfg.ssimulacra2 && !small) on_side([&] { s2_ns = ssim2_run(c, lin, R, d_ridx, B, w, h, d_s2, dbg ? dbg->s2_planes : nullptr); });
+            if (cfg.butteraugli && !small) butteraugli_run(c, lin, R, d_ridx, B, w, h, intensity, d_ba, dbg ? dbg->ba_diffmap : nullptr);
+            for (int i = 0; i < used; i++) CE_CUDA(cudaStreamWaitEvent(main_stream, c.ev_join[i], 0));
         }
         CE_CUDA(cudaMemcpyAsync(c.h_pinned, d_raw, B * raw_doubles * 8, cudaMemcpyDeviceToHost, c.stream));
         CE_CUDA(cudaStreamSynchronize(c.stream));
@@ -373,10 +447,15 @@ CE_API int ce_ctx_create(ce_ctx** out, int device, size_t workspace_bytes) {
         c.sm_count = prop.multiProcessorCount;
         CE_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
         c.stream = c.own_stream;
+        for (int i = 0; i < 2; i++) {
+            CE_CUDA(cudaStreamCreateWithFlags(&c.side[i], cudaStreamNonBlocking));
+            CE_CUDA(cudaEventCreateWithFlags(&c.ev_join[i], cudaEventDisableTiming));
+        }
+        CE_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
         if (workspace_bytes == 0) {
             size_t free_b = 0, total_b = 0;
             CE_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            workspace_bytes = std::min<size_t>(free_b / 2, (size_t)24 << 30);
+            workspace_bytes = std::min<size_t>(free_b / 2, (size_t)64 << 30);
         }
         CE_CUDA(cudaMalloc(&c.arena.base, workspace_bytes));
         c.arena.cap = workspace_bytes;
@@ -407,9 +486,16 @@ CE_API void ce_ctx_destroy(ce_ctx* ctx) {
     if (c.h_pinned) cudaFreeHost(c.h_pinned);
     if (c.d_results) cudaFree(c.d_results);
     if (c.d_in) cudaFree(c.d_in);
+    if (c.h_idx) cudaFreeHost(c.h_idx);
+    if (c.d_idx) cudaFree(c.d_idx);
     for (auto& kv : c.ba_inv_cache) cudaFree(kv.second);
     c.prof_collect();
     for (auto e : c.prof.pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        if (c.side[i]) { cudaStreamSynchronize(c.side[i]); cudaStreamDestroy(c.side[i]); }
+        if (c.ev_join[i]) cudaEventDestroy(c.ev_join[i]);
+    }
+    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     delete ctx;
 }
@@ -461,7 +547,29 @@ CE_API int ce_evaluate_batch_device(ce_ctx* ctx, const uint8_t* d_ref, const uin
     Context& c = ctx->c;
     CE_TRY(c, {
         CE_CUDA(cudaSetDevice(c.device));
-        run_device_batch(c, d_ref, d_dist, n, width, height, *cfg, intensity_target, out, nullptr);
+        run_device_batch(c, d_ref, n, d_dist, n, nullptr, width, height, *cfg, intensity_target, out, nullptr);
+    })
+    return CE_OK;
+}
+
+CE_API int ce_evaluate_batch_device_grouped(ce_ctx* ctx, const uint8_t* d_ref, size_t n_ref, const uint8_t* d_dist, size_t n,
+                                            const uint32_t* ref_index, uint32_t width, uint32_t height,
+                                            const ce_metric_config* cfg, float intensity_target, ce_result* out) {
+    if (!ctx || !cfg || (n && (!out || !d_ref || !d_dist || !ref_index || n_ref == 0))) return CE_ERR_INVALID_ARGUMENT;
+    if (n == 0) return CE_OK;
+    if (width == 0 || height == 0) {
+        ctx->c.last_error = "zero-sized image";
+        return CE_ERR_INVALID_ARGUMENT;
+    }
+    for (size_t i = 0; i < n; i++)
+        if (ref_index[i] >= n_ref) {
+            ctx->c.last_error = "ref_index out of range";
+            return CE_ERR_INVALID_ARGUMENT;
+        }
+    Context& c = ctx->c;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        run_device_batch(c, d_ref, n_ref, d_dist, n, ref_index, width, height, *cfg, intensity_target, out, nullptr);
     })
     return CE_OK;
 }
@@ -497,23 +605,35 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
         groups[{pairs[i].width, pairs[i].height}].push_back(i);
     }
     std::vector<ce_result> tmp;
+    std::vector<uint32_t> ref_of;
     for (auto& g : groups) {
         const size_t w = g.first.first, h = g.first.second, img_bytes = w * h * 3;
         const std::vector<size_t>& idx = g.second;
-        // staging: at most 4 GiB of input per chunk
+        // staging: at most 2 GiB of distorted input per chunk
         size_t chunk = std::max<size_t>(1, std::min<size_t>(idx.size(), ((size_t)2 << 30) / std::max<size_t>(img_bytes, 1)));
         for (size_t k0 = 0; k0 < idx.size(); k0 += chunk) {
             const size_t B = std::min(chunk, idx.size() - k0);
-            c.ensure_input(2 * B * img_bytes);
-            uint8_t* d_ref = c.d_in;
-            uint8_t* d_dist = c.d_in + B * img_bytes;
+            // distinct reference buffers of the chunk (same host pointer == same image: evaluate_image compares one
+            // reference with every codec x quality output, src/eval/session.rs:375-431) are uploaded once
+            std::map<const uint8_t*, uint32_t> seen;
+            std::vector<const uint8_t*> urefs;
+            ref_of.resize(B);
             for (size_t k = 0; k < B; k++) {
                 const ce_pair& p = pairs[idx[k0 + k]];
-                CE_CUDA(cudaMemcpyAsync(d_ref + k * img_bytes, p.ref, img_bytes, cudaMemcpyHostToDevice, c.stream));
-                CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, p.dist, img_bytes, cudaMemcpyHostToDevice, c.stream));
+                auto it = seen.find(p.ref);
+                if (it == seen.end()) { it = seen.emplace(p.ref, (uint32_t)urefs.size()).first; urefs.push_back(p.ref); }
+                ref_of[k] = it->second;
             }
+            const size_t Ru = urefs.size();
+            c.ensure_input((Ru + B) * img_bytes);
+            uint8_t* d_ref = c.d_in;
+            uint8_t* d_dist = c.d_in + Ru * img_bytes;
+            for (size_t r = 0; r < Ru; r++)
+                CE_CUDA(cudaMemcpyAsync(d_ref + r * img_bytes, urefs[r], img_bytes, cudaMemcpyHostToDevice, c.stream));
+            for (size_t k = 0; k < B; k++)
+                CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, pairs[idx[k0 + k]].dist, img_bytes, cudaMemcpyHostToDevice, c.stream));
             tmp.resize(B);
-            run_device_batch(c, d_ref, d_dist, B, w, h, cfg, intensity, tmp.data(), dbg);
+            run_device_batch(c, d_ref, Ru, d_dist, B, ref_of.data(), w, h, cfg, intensity, tmp.data(), dbg);
             for (size_t k = 0; k < B; k++) out[idx[k0 + k]] = tmp[k];
         }
     }
@@ -616,13 +736,16 @@ CE_API int ce_dssim_rgbaf32(ce_ctx* ctx, const float* ref, size_t ref_w, size_t 
         float* d_t = c.arena.alloc<float>(test_stride * h * 4);
         CE_CUDA(cudaMemcpyAsync(d_r, ref, ref_stride * (h - 1) * 16 + w * 16, cudaMemcpyHostToDevice, c.stream));
         CE_CUDA(cudaMemcpyAsync(d_t, test, test_stride * (h - 1) * 16 + w * 16, cudaMemcpyHostToDevice, c.stream));
-        float* p1 = c.arena.alloc<float>(4 * n);
-        float* p2 = c.arena.alloc<float>(4 * n);
-        launch_rgba_to_planar(c, d_r, w, h, ref_stride, p1);
-        launch_rgba_to_planar(c, d_t, w, h, test_stride, p2);
+        float* lin = c.arena.alloc<float>(2 * 3 * n);   // [2 images][3][n]
+        float* alpha = c.arena.alloc<float>(2 * n);     // [2 images][n]
+        launch_rgba_to_planar(c, d_r, w, h, ref_stride, lin, alpha);
+        launch_rgba_to_planar(c, d_t, w, h, test_stride, lin + 3 * n, alpha + n);
         c.ensure_results(10 * 8);
+        c.ensure_idx(1);
+        c.h_idx[0] = 0;
+        CE_CUDA(cudaMemcpyAsync(c.d_idx, c.h_idx, sizeof(int), cudaMemcpyHostToDevice, c.stream));
         double* d_ds = reinterpret_cast<double*>(c.d_results);
-        int ns = dssim_run(c, p1, p2, p1 + 3 * n, p2 + 3 * n, 1, w, h, d_ds, nullptr);
+        int ns = dssim_run(c, lin, alpha, 1, c.d_idx, 1, w, h, d_ds, nullptr);
         CE_CUDA(cudaMemcpyAsync(c.h_pinned, d_ds, 10 * 8, cudaMemcpyDeviceToHost, c.stream));
         CE_CUDA(cudaStreamSynchronize(c.stream));
         if (dssim) *dssim = finalize_dssim(reinterpret_cast<const double*>(c.h_pinned), ns, w, h, nullptr);
@@ -731,15 +854,14 @@ CE_API int ce_reference_compare_many(ce_ctx* ctx, ce_ref* ref, const uint8_t* co
         }
         const size_t B = ok.size();
         if (B) {
-            c.ensure_input(2 * B * img_bytes);
-            uint8_t* d_ref = c.d_in;
-            uint8_t* d_dist = c.d_in + B * img_bytes;
-            for (size_t k = 0; k < B; k++) {
-                CE_CUDA(cudaMemcpyAsync(d_ref + k * img_bytes, ref->d_ref, img_bytes, cudaMemcpyDeviceToDevice, c.stream));
+            c.ensure_input(B * img_bytes);
+            uint8_t* d_dist = c.d_in;
+            for (size_t k = 0; k < B; k++)
                 CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, dists[ok[k]], img_bytes, cudaMemcpyHostToDevice, c.stream));
-            }
             std::vector<ce_result> tmp(B);
-            run_device_batch(c, d_ref, d_dist, B, ref->width, ref->height, ref->cfg, intensity_target, tmp.data(), nullptr);
+            std::vector<uint32_t> ref_of(B, 0u);   // every distortion compares against the one resident reference
+            run_device_batch(c, ref->d_ref, 1, d_dist, B, ref_of.data(), ref->width, ref->height, ref->cfg, intensity_target,
+                             tmp.data(), nullptr);
             for (size_t k = 0; k < B; k++) out[ok[k]] = tmp[k];
         }
     })
@@ -851,7 +973,7 @@ static int debug_ba_image(ce_ctx* ctx, const uint8_t* rgb, size_t width, size_t 
         float* lin = c.arena.alloc<float>(3 * n);
         float* d_out = c.arena.alloc<float>((size_t)nplanes * n);
         CE_CUDA(cudaMemcpyAsync(d_in, rgb, n * 3, cudaMemcpyHostToDevice, c.stream));
-        launch_srgb8_to_linear(c, d_in, 1, n, lin);
+        launch_srgb8_to_linear(c, d_in, nullptr, 1, n, lin);
         if (opsin) butteraugli_debug_opsin(c, lin, width, height, intensity, d_out);
         else butteraugli_debug_psycho(c, lin, width, height, intensity, d_out);
         CE_CUDA(cudaMemcpyAsync(planes, d_out, (size_t)nplanes * n * 4, cudaMemcpyDeviceToHost, c.stream));

@@ -90,11 +90,20 @@ struct Context {
     size_t d_results_bytes = 0;
     uint8_t* d_in = nullptr;      // device input staging for host-pointer entries
     size_t d_in_bytes = 0;
+    int* h_idx = nullptr;         // pinned + device index staging (reference index tables of a sub-batch)
+    int* d_idx = nullptr;
+    size_t idx_cap = 0;
     RGaussCoef rg;
     std::string last_error;
     uint64_t launches = 0;
     std::map<uint64_t, float*> ba_inv_cache;  // Butteraugli border-renormalisation tables
     int sm_count = 148;
+
+    // the three perceptual metrics of a sub-batch run concurrently on the main stream + two side streams
+    // (disabled while the per-kernel profiler is on, so its event pairs bracket one kernel each)
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    bool concurrent = true;
 
     Profiler prof;
     void prof_begin(const char* name, double bytes);
@@ -102,6 +111,7 @@ struct Context {
     void prof_collect();   // call after the stream is synchronised
     void ensure_input(size_t bytes);
     void ensure_results(size_t bytes);
+    void ensure_idx(size_t count);
 };
 
 // every kernel launch of the library goes through this: counts it, and (when profiling) brackets it with events
@@ -116,33 +126,37 @@ inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ---------------- k_color.cu ----------------
 // RGB8 interleaved [n_img][h*w][3] -> planar fp32 [n_img][3][h*w] through the LUT
-void launch_srgb8_to_linear(Context& c, const uint8_t* d_rgb, size_t n_img, size_t npix, float* d_planes);
+// src_index (device, nullable): output image i is converted from source image src_index[i]
+void launch_srgb8_to_linear(Context& c, const uint8_t* d_rgb, const int* src_index, size_t n_img, size_t npix, float* d_planes);
 // exact integer SSE per pair: d_sse[n] (zeroed inside)
-void launch_sse(Context& c, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, size_t bytes_per_img,
+// ref_index (device, nullable): pair i compares reference image ref_index[i] (identity when null)
+void launch_sse(Context& c, const uint8_t* d_ref, const int* ref_index, const uint8_t* d_dist, size_t n, size_t bytes_per_img,
                 unsigned long long* d_sse);
 void launch_xyb_roundtrip(Context& c, const uint8_t* d_rgb, size_t npix_total, uint8_t* d_out);
 void launch_rgb8_to_rgba_linear(Context& c, const uint8_t* d_in, size_t npix, int in_channels, float* d_out);
-void launch_rgba_to_planar(Context& c, const float* d_rgba, size_t w, size_t h, size_t stride, float* d_planes4);
+void launch_rgba_to_planar(Context& c, const float* d_rgba, size_t w, size_t h, size_t stride, float* d_planes3, float* d_alpha);
+
+// Image convention of the three perceptual metrics: one array of NI = R + B images, the R distinct
+// references of the sub-batch first, then the B distorted images; pair b compares image ridx[b] (< R)
+// with image R + b.  ridx is a device array.  Reference-side work is done once per distinct reference.
 
 // ---------------- k_ssim2.cu ----------------
-// lin1/lin2: [B][3][h*w] linear planes (consumed: downsampled in place into scratch);
-// d_sums: [B][6][18] doubles.  Returns number of scales.
-int ssim2_run(Context& c, const float* lin1, const float* lin2, size_t B, size_t w, size_t h, double* d_sums,
+// lin: [NI][3][h*w] linear planes; d_sums: [B][6][18] doubles.  Returns number of scales.
+int ssim2_run(Context& c, const float* lin, size_t R, const int* ridx, size_t B, size_t w, size_t h, double* d_sums,
               float* dbg_planes /* nullable, B==1: 3*7*h*w */);
 size_t ssim2_workspace_per_pair(size_t w, size_t h);
 void ssim2_init(Context& c);  // uploads the recursive-Gaussian coefficients
 
 // ---------------- k_dssim.cu ----------------
-// lin1/lin2: [B][3][h*w]; alpha1/alpha2 nullable [B][h*w]; d_out: [B][5][2] doubles (sum_map, sum_absdev)
-int dssim_run(Context& c, const float* lin1, const float* lin2, const float* alpha1, const float* alpha2, size_t B,
-              size_t w, size_t h, double* d_out, float* dbg_map0 /* nullable */);
+// lin: [NI][3][h*w]; alpha nullable [NI][h*w]; d_out: [B][5][2] doubles (sum_map, sum_absdev)
+int dssim_run(Context& c, const float* lin, const float* alpha, size_t R, const int* ridx, size_t B, size_t w, size_t h,
+              double* d_out, float* dbg_map0 /* nullable */);
 size_t dssim_workspace_per_pair(size_t w, size_t h);
 int dssim_num_scales(size_t w, size_t h, size_t* ws, size_t* hs);
 
 // ---------------- k_butteraugli.cu ----------------
-// lin1: [2B][3][h*w] with the B distorted images following the B references (lin2 == lin1 + B*3*h*w);
-// d_out: [B][4] doubles (max, sum d^3, sum d^6, sum d^12)
-void butteraugli_run(Context& c, const float* lin1, const float* lin2, size_t B, size_t w, size_t h, float intensity,
+// lin: [NI][3][h*w]; d_out: [B][4] doubles (max, sum d^3, sum d^6, sum d^12)
+void butteraugli_run(Context& c, const float* lin, size_t R, const int* ridx, size_t B, size_t w, size_t h, float intensity,
                      double* d_out, float* dbg_diffmap /* nullable, B==1 */);
 size_t butteraugli_workspace_per_pair(size_t w, size_t h);
 void butteraugli_init(Context& c);  // uploads the blur kernels

@@ -2,7 +2,9 @@
 // site src/metrics/butteraugli.rs:72-80) for a batch of B pairs: max and libjxl 3-norm of the
 // two-resolution diffmap.
 //
-// Image index convention: NI = 2B images, image i = which*B + b (which 0 = reference).
+// Image index convention: NI = R + B images: the R distinct references of the sub-batch, then the B
+// distorted images; pair b compares image ridx[b] with image R + b.  Per-image stages (everything up to
+// the Malta filters) run once per image, so a reference shared by several pairs is processed once.
 // Kernels per resolution (each stage's pointwise epilogue is fused into the blur that feeds it):
 //   k_ba_opsin   : sigma-1.2 blur (5-tap mirror, H+V through a smem tile) + opsin dynamics      lin -> xyb
 //   k_ba_blur_h  : sigma-7.16 (33 taps) along x                                               xyb -> tmp
@@ -524,7 +526,8 @@ struct MaltaParams2 {
 // pair.  uhf,hf: [NI][2][n]; mf: [NI][3][n]  ->  diff [B][2 ch][3 bands][n].  One thread = 4 pixels (VEC) or 1.
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_ba_malta_diff(const float* __restrict__ uhf, const float* __restrict__ hf,
-                                                        const float* __restrict__ mf, size_t n, size_t B,
+                                                        const float* __restrict__ mf, size_t n, size_t B, size_t R,
+                                                        const int* __restrict__ ridx,
                                                         const __grid_constant__ MaltaParams2 prm2, float* __restrict__ diff) {
     const size_t per = VEC ? n / 4 : n;
     const size_t total = B * 2 * per;
@@ -533,8 +536,9 @@ __global__ void __launch_bounds__(256) k_ba_malta_diff(const float* __restrict__
         const size_t b = bc >> 1;
         const int C = (int)(bc & 1);
         const size_t i = VEC ? q * 4 : q;
-        const float* p0[3] = {uhf + (b * 2 + C) * n + i, hf + (b * 2 + C) * n + i, mf + (b * 3 + C) * n + i};
-        const float* p1[3] = {uhf + ((B + b) * 2 + C) * n + i, hf + ((B + b) * 2 + C) * n + i, mf + ((B + b) * 3 + C) * n + i};
+        const size_t i0 = (size_t)ridx[b], i1 = R + b;
+        const float* p0[3] = {uhf + (i0 * 2 + C) * n + i, hf + (i0 * 2 + C) * n + i, mf + (i0 * 3 + C) * n + i};
+        const float* p1[3] = {uhf + (i1 * 2 + C) * n + i, hf + (i1 * 2 + C) * n + i, mf + (i1 * 3 + C) * n + i};
         float* o = diff + bc * 3 * n + i;
         if (VEC) {
             float4 a[3], d[3];
@@ -562,7 +566,8 @@ __global__ void __launch_bounds__(256) k_ba_malta_diff(const float* __restrict__
 // cp.async; each thread then pulls the 9x12 window of its 4 pixels into registers (27 LDS.128 per band)
 // and evaluates the 16 oriented line sums per pixel from there.
 __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ diff, const float* __restrict__ hf,
-                                                      const float* __restrict__ mf, int w, int h, size_t n, size_t B,
+                                                      const float* __restrict__ mf, int w, int h, size_t n, size_t R,
+                                                      const int* __restrict__ ridx,
                                                       const __grid_constant__ MaltaParams2 prm2, float* __restrict__ ac) {
     __shared__ __align__(16) float s_d[3][MT_ROWS * MT_P];
     const size_t b = blockIdx.z >> 1;
@@ -599,10 +604,11 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
     }
     if (!live) return;
     const size_t idx = (size_t)(live ? y : 0) * w + (live ? x : 0);
-    const float* h0 = hf + (b * 2 + C) * n + idx;
-    const float* h1 = hf + ((B + b) * 2 + C) * n + idx;
-    const float* m0 = mf + (b * 3 + C) * n + idx;
-    const float* m1 = mf + ((B + b) * 3 + C) * n + idx;
+    const size_t im0 = (size_t)ridx[b], im1 = R + b;
+    const float* h0 = hf + (im0 * 2 + C) * n + idx;
+    const float* h1 = hf + (im1 * 2 + C) * n + idx;
+    const float* m0 = mf + (im0 * 3 + C) * n + idx;
+    const float* m1 = mf + (im1 * 3 + C) * n + idx;
     float hv0[4], hv1[4], mv0[4], mv1[4];
     if (vec) {
         const float4 a = *reinterpret_cast<const float4*>(h0), q = *reinterpret_cast<const float4*>(h1);
@@ -662,13 +668,15 @@ CE_DEVINL void store_min3(float v, float& m0, float& m1, float& m2) {
 // bl: [NI][n] blurred mask inputs; ac: [B][2][n]; mf, lf: [NI][3][n]; diffmap out [B][n]
 __global__ void __launch_bounds__(256) k_ba_combine(const float* __restrict__ bl, const float* __restrict__ ac,
                                                      const float* __restrict__ mf, const float* __restrict__ lf, int w, int h,
-                                                     size_t n, size_t B, float xmul, float* __restrict__ diffmap) {
+                                                     size_t n, size_t B, size_t R, const int* __restrict__ ridx, float xmul,
+                                                     float* __restrict__ diffmap) {
     const size_t total = B * n;
     const int S = 3;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         size_t b = t / n, i = t - b * n;
         int y = (int)(i / w), x = (int)(i - (size_t)y * w);
-        const float* from = bl + b * n;
+        const size_t i0 = (size_t)ridx[b], i1 = R + b;
+        const float* from = bl + i0 * n;
         float m0 = from[i], m1 = 2.0f * m0, m2 = m1;
         if (x >= S) {
             store_min3(from[i - S], m0, m1, m2);
@@ -684,14 +692,14 @@ __global__ void __launch_bounds__(256) k_ba_combine(const float* __restrict__ bl
         if (y < h - S) store_min3(from[i + (size_t)S * w], m0, m1, m2);
         float mask = (0.45f * m0 + 0.3f * m1) + 0.25f * m2;
 
-        float dmk = from[i] - bl[(B + b) * n + i];
+        float dmk = from[i] - bl[i1 * n + i];
         float ac0 = ac[(b * 2 + 0) * n + i];
         float ac1 = ac[(b * 2 + 1) * n + i];
         ac1 += (10.0f * dmk) * dmk;
-        const float* M0 = mf + b * 3 * n + i;
-        const float* M1 = mf + (B + b) * 3 * n + i;
-        const float* L0 = lf + b * 3 * n + i;
-        const float* L1 = lf + (B + b) * 3 * n + i;
+        const float* M0 = mf + i0 * 3 * n + i;
+        const float* M1 = mf + i1 * 3 * n + i;
+        const float* L0 = lf + i0 * 3 * n + i;
+        const float* L1 = lf + i1 * 3 * n + i;
         float d2 = M0[2 * n] - M1[2 * n];
         float ac2 = (d2 * d2) * 16.2176043152f;
         float e0 = L0[0] - L1[0], e1 = L0[n] - L1[n], e2 = L0[2 * n] - L1[2 * n];
@@ -820,29 +828,29 @@ static MaltaParams make_malta_params(int c, float hf_asym) {
 struct BaLevelBufs {
     float *xyb, *tmp, *lf, *mf_pre, *mf, *ac;
     float *hf_pre, *hf, *uhf, *m, *bl;   // views, strides below
-    float* mdiff;                        // [B][2][3][n] Malta difference planes = tmp (dead after the HF blur)
+    float* mdiff;                        // [B][2][3][n] Malta difference planes
     BlurTables tables;
 };
 
 static size_t ba_level_floats_per_pair(size_t n) {
-    // per image: xyb 3, tmp 3, lf 3, mf_pre 3, mf 3 = 15; x2 images = 30; pair: ac 2
-    return 32 * n;
+    // per image: xyb 3, tmp 3, lf 3, mf_pre 3, mf 3 = 15; at most 2 images per pair = 30; pair: ac 2, Malta diffs 6
+    return 38 * n;
 }
 
 static unsigned ew_blocks(Context& c, size_t total) {
     return (unsigned)std::min<size_t>(cdiv(total, 256), (size_t)c.sm_count * 32);
 }
 
-static void ba_alloc_level(Context& c, size_t B, size_t w, size_t h, BaLevelBufs& L) {
-    const size_t n = w * h, NI = 2 * B;
+static void ba_alloc_level(Context& c, size_t NI, size_t B, size_t w, size_t h, BaLevelBufs& L) {
+    const size_t n = w * h;
     L.xyb = c.arena.alloc<float>(NI * 3 * n);
     L.tmp = c.arena.alloc<float>(NI * 3 * n);
     L.lf = c.arena.alloc<float>(NI * 3 * n);
     L.mf_pre = c.arena.alloc<float>(NI * 3 * n);
     L.mf = c.arena.alloc<float>(NI * 3 * n);
     L.ac = c.arena.alloc<float>(B * 2 * n);
+    L.mdiff = c.arena.alloc<float>(B * 6 * n);
     L.hf_pre = L.tmp;                  // [NI][2][n]
-    L.mdiff = L.tmp;                   // [B][2][3][n] == NI*3*n floats
     L.hf = L.xyb;                      // [NI][2][n]
     L.m = L.xyb + NI * 2 * n;          // [NI][n]
     L.uhf = L.mf_pre;                  // [NI][2][n]
@@ -888,12 +896,13 @@ static void ba_psycho_level(Context& c, const float* lin, size_t NI, size_t w, s
 }
 
 // full diffmap of one resolution for B pairs; lin: [2B][3][n]
-static void ba_diffmap_level(Context& c, const float* lin, size_t B, size_t w, size_t h, float intensity, float* diffmap) {
-    const size_t n = w * h, NI = 2 * B;
+static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* ridx, size_t B, size_t w, size_t h,
+                             float intensity, float* diffmap) {
+    const size_t n = w * h, NI = R + B;
     const float hf_asym = 1.0f, xmul = 1.0f;
     size_t mark = c.arena.mark();
     BaLevelBufs L;
-    ba_alloc_level(c, B, w, h, L);
+    ba_alloc_level(c, NI, B, w, h, L);
     ba_psycho_level(c, lin, NI, w, h, intensity, L, nullptr);
     {
         dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), (unsigned)NI);
@@ -907,16 +916,16 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t B, size_t w, s
         mp.ch[1] = make_malta_params(1, hf_asym);
         if (n % 4 == 0)
             CE_LAUNCH(c, "k_ba_malta_diff", (double)B * n * 72,
-                      k_ba_malta_diff<true><<<ew_blocks(c, B * 2 * (n / 4)), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, mp, L.mdiff));
+                      k_ba_malta_diff<true><<<ew_blocks(c, B * 2 * (n / 4)), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
         else
             CE_LAUNCH(c, "k_ba_malta_diff", (double)B * n * 72,
-                      k_ba_malta_diff<false><<<ew_blocks(c, B * 2 * n), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, mp, L.mdiff));
+                      k_ba_malta_diff<false><<<ew_blocks(c, B * 2 * n), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
         dim3 grid(cdiv(w, MT_TW), cdiv(h, MT_TH), (unsigned)(2 * B));
         CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
-                  k_ba_malta<<<grid, 256, 0, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, B, mp, L.ac));
+                  k_ba_malta<<<grid, 256, 0, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, L.ac));
     }
     CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,
-              k_ba_combine<<<ew_blocks(c, B * n), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, xmul, diffmap));
+              k_ba_combine<<<ew_blocks(c, B * n), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul, diffmap));
     CE_CUDA(cudaGetLastError());
     c.arena.release(mark);
 }
@@ -928,24 +937,23 @@ size_t butteraugli_workspace_per_pair(size_t w, size_t h) {
     return (ba_level_floats_per_pair(n) + n + 7 * sn) * 4 + BA_RED_BLOCKS * 4 * 8 + 65536;
 }
 
-void butteraugli_run(Context& c, const float* lin, const float* lin2, size_t B, size_t w, size_t h, float intensity,
+void butteraugli_run(Context& c, const float* lin, size_t R, const int* ridx, size_t B, size_t w, size_t h, float intensity,
                      double* d_out, float* dbg_diffmap) {
-    const size_t n = w * h;
-    if (lin2 != lin + B * 3 * n) throw CudaError("butteraugli_run expects lin2 == lin1 + B*3*n");
-    check_grid_z(B * 6);
+    const size_t n = w * h, NI = R + B;
+    check_grid_z(NI * 3);
     size_t mark = c.arena.mark();
     float* diffmap = c.arena.alloc<float>(B * n);
     double* partial = c.arena.alloc<double>(B * BA_RED_BLOCKS * 4);
-    ba_diffmap_level(c, lin, B, w, h, intensity, diffmap);
+    ba_diffmap_level(c, lin, R, ridx, B, w, h, intensity, diffmap);
     const size_t sw = (w + 1) / 2, sh = (h + 1) / 2, sn = sw * sh;
     float* sub = nullptr;
     if (sw >= 8 && sh >= 8) {
-        float* slin = c.arena.alloc<float>(2 * B * 3 * sn);
+        float* slin = c.arena.alloc<float>(NI * 3 * sn);
         sub = c.arena.alloc<float>(B * sn);
-        size_t total = 2 * B * 3 * sn;
+        size_t total = NI * 3 * sn;
         CE_LAUNCH(c, "k_ba_subsample", (double)total * 20,
                   k_ba_subsample<<<ew_blocks(c, total), 256, 0, c.stream>>>(lin, (int)w, (int)h, n, (int)sw, (int)sh, sn, total, slin));
-        ba_diffmap_level(c, slin, B, sw, sh, intensity, sub);
+        ba_diffmap_level(c, slin, R, ridx, B, sw, sh, intensity, sub);
     }
     for (size_t b0 = 0; b0 < B; b0 += 32768) {
         unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
@@ -967,7 +975,7 @@ void butteraugli_debug_psycho(Context& c, const float* lin, size_t w, size_t h, 
     const size_t n = w * h;
     size_t mark = c.arena.mark();
     BaLevelBufs L;
-    ba_alloc_level(c, 1, w, h, L);
+    ba_alloc_level(c, 2, 1, w, h, L);
     // with NI = 1 the alias views must be re-based on one image
     L.m = L.xyb + 2 * n;
     L.bl = L.mf_pre + 2 * n;
@@ -981,7 +989,7 @@ void butteraugli_debug_psycho(Context& c, const float* lin, size_t w, size_t h, 
 void butteraugli_debug_opsin(Context& c, const float* lin, size_t w, size_t h, float intensity, float* d_planes3) {
     size_t mark = c.arena.mark();
     BaLevelBufs L;
-    ba_alloc_level(c, 1, w, h, L);
+    ba_alloc_level(c, 2, 1, w, h, L);
     L.m = L.xyb + 2 * w * h;
     L.bl = L.mf_pre + 2 * w * h;
     ba_psycho_level(c, lin, 1, w, h, intensity, L, d_planes3);
@@ -992,7 +1000,7 @@ void butteraugli_debug_blur(Context& c, const float* in, size_t w, size_t h, flo
     const size_t n = w * h;
     size_t mark = c.arena.mark();
     BaLevelBufs L;
-    ba_alloc_level(c, 1, w, h, L);
+    ba_alloc_level(c, 2, 1, w, h, L);
     const int vec = (w % 4 == 0) ? 1 : 0;
     dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), 1);
     if (fabsf(sigma - 1.2f) < 1e-6f) {

@@ -12,7 +12,7 @@ namespace ce {
 // 256-entry table holding exactly those fp32 values.
 // One thread = 16 pixels = 48 B in (3 x LDG.128), 3 x 4 x STG.128 out.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_srgb8_to_linear_v16(const uint8_t* __restrict__ rgb,
+__global__ void __launch_bounds__(256) k_srgb8_to_linear_v16(const uint8_t* __restrict__ rgb, const int* __restrict__ src_index,
                                                               const float* __restrict__ lut, size_t n_groups,
                                                               size_t groups_per_img, size_t npix,
                                                               float* __restrict__ planes) {
@@ -20,7 +20,10 @@ __global__ void __launch_bounds__(256) k_srgb8_to_linear_v16(const uint8_t* __re
     s_lut[threadIdx.x] = lut[threadIdx.x];
     __syncthreads();
     for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < n_groups; g += (size_t)gridDim.x * blockDim.x) {
-        const uint4* src = reinterpret_cast<const uint4*>(rgb + g * 48);
+        const size_t img = g / groups_per_img;
+        const size_t gi = g - img * groups_per_img;
+        const size_t simg = src_index ? (size_t)src_index[img] : img;   // output image `img` reads source image simg
+        const uint4* src = reinterpret_cast<const uint4*>(rgb + (simg * groups_per_img + gi) * 48);
         uint4 a = ldg_stream_u4(src), b = ldg_stream_u4(src + 1), c = ldg_stream_u4(src + 2);
         uint32_t wds[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
         float ch[3][16];
@@ -29,8 +32,7 @@ __global__ void __launch_bounds__(256) k_srgb8_to_linear_v16(const uint8_t* __re
             uint32_t byte = (wds[k >> 2] >> ((k & 3) * 8)) & 0xffu;
             ch[k % 3][k / 3] = s_lut[byte];
         }
-        size_t img = g / groups_per_img;
-        size_t p0 = (g - img * groups_per_img) * 16;
+        size_t p0 = gi * 16;
         float* base = planes + img * 3 * npix + p0;
 #pragma unroll
         for (int cc = 0; cc < 3; cc++) {
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(256) k_srgb8_to_linear_v16(const uint8_t* __re
 }
 
 // generic fallback for npix % 16 != 0: one thread per pixel
-__global__ void __launch_bounds__(256) k_srgb8_to_linear_px(const uint8_t* __restrict__ rgb,
+__global__ void __launch_bounds__(256) k_srgb8_to_linear_px(const uint8_t* __restrict__ rgb, const int* __restrict__ src_index,
                                                              const float* __restrict__ lut, size_t n_total, size_t npix,
                                                              float* __restrict__ planes) {
     __shared__ float s_lut[256];
@@ -51,26 +53,28 @@ __global__ void __launch_bounds__(256) k_srgb8_to_linear_px(const uint8_t* __res
     __syncthreads();
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n_total; p += (size_t)gridDim.x * blockDim.x) {
         size_t img = p / npix, i = p - img * npix;
+        const size_t simg = src_index ? (size_t)src_index[img] : img;
+        const uint8_t* q = rgb + (simg * npix + i) * 3;
         float* base = planes + img * 3 * npix + i;
-        base[0] = s_lut[rgb[3 * p]];
-        base[npix] = s_lut[rgb[3 * p + 1]];
-        base[2 * npix] = s_lut[rgb[3 * p + 2]];
+        base[0] = s_lut[q[0]];
+        base[npix] = s_lut[q[1]];
+        base[2 * npix] = s_lut[q[2]];
     }
 }
 
-void launch_srgb8_to_linear(Context& c, const uint8_t* d_rgb, size_t n_img, size_t npix, float* d_planes) {
+void launch_srgb8_to_linear(Context& c, const uint8_t* d_rgb, const int* src_index, size_t n_img, size_t npix, float* d_planes) {
     if (n_img == 0 || npix == 0) return;
     const int wave = c.sm_count * 8;
     if (npix % 16 == 0 && (reinterpret_cast<uintptr_t>(d_rgb) & 15) == 0) {
         size_t gpi = npix / 16, ng = gpi * n_img;
         unsigned blocks = (unsigned)std::min<size_t>(cdiv(ng, 256), (size_t)wave * 4);
         CE_LAUNCH(c, "k_srgb8_to_linear_v16", n_img * npix * 15,
-                  k_srgb8_to_linear_v16<<<blocks, 256, 0, c.stream>>>(d_rgb, c.d_lut, ng, gpi, npix, d_planes));
+                  k_srgb8_to_linear_v16<<<blocks, 256, 0, c.stream>>>(d_rgb, src_index, c.d_lut, ng, gpi, npix, d_planes));
     } else {
         size_t nt = npix * n_img;
         unsigned blocks = (unsigned)std::min<size_t>(cdiv(nt, 256), (size_t)wave * 4);
         CE_LAUNCH(c, "k_srgb8_to_linear_px", n_img * npix * 15,
-                  k_srgb8_to_linear_px<<<blocks, 256, 0, c.stream>>>(d_rgb, c.d_lut, nt, npix, d_planes));
+                  k_srgb8_to_linear_px<<<blocks, 256, 0, c.stream>>>(d_rgb, src_index, c.d_lut, nt, npix, d_planes));
     }
     CE_CUDA(cudaGetLastError());
 }
@@ -87,10 +91,11 @@ CE_DEVINL uint32_t sq4(uint32_t a, uint32_t b, uint32_t acc) {
     return __dp4a(d, d, acc);
 }
 
-__global__ void __launch_bounds__(256) k_sse(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ dist,
-                                              size_t bytes_per_img, unsigned long long* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_sse(const uint8_t* __restrict__ ref, const int* __restrict__ ref_index,
+                                              const uint8_t* __restrict__ dist, size_t bytes_per_img,
+                                              unsigned long long* __restrict__ out) {
     const size_t pair = blockIdx.y;
-    const uint8_t* r = ref + pair * bytes_per_img;
+    const uint8_t* r = ref + (ref_index ? (size_t)ref_index[pair] : pair) * bytes_per_img;
     const uint8_t* d = dist + pair * bytes_per_img;
     // head bytes until 16-B alignment (ref and dist arrays share the same offset modulo 16
     // only if both bases are 16-B aligned; checked by the launcher)
@@ -146,10 +151,11 @@ __global__ void __launch_bounds__(256) k_sse(const uint8_t* __restrict__ ref, co
 }
 
 // scalar kernel for the (never expected) case of mutually misaligned arrays
-__global__ void __launch_bounds__(256) k_sse_scalar(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ dist,
-                                                     size_t bytes_per_img, unsigned long long* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_sse_scalar(const uint8_t* __restrict__ ref, const int* __restrict__ ref_index,
+                                                     const uint8_t* __restrict__ dist, size_t bytes_per_img,
+                                                     unsigned long long* __restrict__ out) {
     const size_t pair = blockIdx.y;
-    const uint8_t* r = ref + pair * bytes_per_img;
+    const uint8_t* r = ref + (ref_index ? (size_t)ref_index[pair] : pair) * bytes_per_img;
     const uint8_t* d = dist + pair * bytes_per_img;
     unsigned long long total = 0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < bytes_per_img; i += (size_t)gridDim.x * blockDim.x) {
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(256) k_sse_scalar(const uint8_t* __restrict__ 
     if ((threadIdx.x & 31) == 0 && total) atomicAdd(out + pair, total);
 }
 
-void launch_sse(Context& c, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, size_t bytes_per_img,
+void launch_sse(Context& c, const uint8_t* d_ref, const int* ref_index, const uint8_t* d_dist, size_t n, size_t bytes_per_img,
                 unsigned long long* d_sse) {
     if (n == 0) return;
     CE_CUDA(cudaMemsetAsync(d_sse, 0, n * sizeof(unsigned long long), c.stream));
@@ -173,14 +179,17 @@ void launch_sse(Context& c, const uint8_t* d_ref, const uint8_t* d_dist, size_t 
     for (size_t p0 = 0; p0 < n; p0 += 65535) {
         unsigned np = (unsigned)std::min<size_t>(65535, n - p0);
         dim3 grid(chunks, np);
-        const uint8_t* r = d_ref + p0 * bytes_per_img;
+        const uint8_t* r = ref_index ? d_ref : d_ref + p0 * bytes_per_img;
+        const int* ri = ref_index ? ref_index + p0 : nullptr;
         const uint8_t* d = d_dist + p0 * bytes_per_img;
-        bool same_align = ((reinterpret_cast<uintptr_t>(r) ^ reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+        // the vector kernel needs every ref / dist image pair to share its offset modulo 16
+        bool same_align = ((reinterpret_cast<uintptr_t>(d_ref) ^ reinterpret_cast<uintptr_t>(d_dist)) & 15) == 0 &&
+                          (bytes_per_img % 16 == 0 || !ref_index);
         if (same_align)
-            CE_LAUNCH(c, "k_sse", (double)np * (2 * bytes_per_img + 8), k_sse<<<grid, 256, 0, c.stream>>>(r, d, bytes_per_img, d_sse + p0));
+            CE_LAUNCH(c, "k_sse", (double)np * (2 * bytes_per_img + 8), k_sse<<<grid, 256, 0, c.stream>>>(r, ri, d, bytes_per_img, d_sse + p0));
         else
             CE_LAUNCH(c, "k_sse_scalar", (double)np * (2 * bytes_per_img + 8),
-                      k_sse_scalar<<<grid, 256, 0, c.stream>>>(r, d, bytes_per_img, d_sse + p0));
+                      k_sse_scalar<<<grid, 256, 0, c.stream>>>(r, ri, d, bytes_per_img, d_sse + p0));
     }
     CE_CUDA(cudaGetLastError());
 }
@@ -276,9 +285,9 @@ void launch_rgb8_to_rgba_linear(Context& c, const uint8_t* d_in, size_t npix, in
     CE_CUDA(cudaGetLastError());
 }
 
-// linear RGBA f32 interleaved (row stride in pixels) -> 4 planes [r,g,b,a][h*w]
+// linear RGBA f32 interleaved (row stride in pixels) -> 3 planes [r,g,b][h*w] + alpha plane [h*w]
 __global__ void __launch_bounds__(256) k_rgba_to_planar(const float4* __restrict__ in, size_t w, size_t h, size_t stride,
-                                                         float* __restrict__ planes) {
+                                                         float* __restrict__ planes, float* __restrict__ alpha) {
     size_t n = w * h;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         size_t y = i / w, x = i - y * w;
@@ -286,14 +295,14 @@ __global__ void __launch_bounds__(256) k_rgba_to_planar(const float4* __restrict
         planes[i] = v.x;
         planes[n + i] = v.y;
         planes[2 * n + i] = v.z;
-        planes[3 * n + i] = v.w;
+        alpha[i] = v.w;
     }
 }
-void launch_rgba_to_planar(Context& c, const float* d_rgba, size_t w, size_t h, size_t stride, float* d_planes4) {
+void launch_rgba_to_planar(Context& c, const float* d_rgba, size_t w, size_t h, size_t stride, float* d_planes3, float* d_alpha) {
     if (w * h == 0) return;
     unsigned blocks = (unsigned)std::min<size_t>(cdiv(w * h, 256), (size_t)c.sm_count * 32);
     CE_LAUNCH(c, "k_rgba_to_planar", w * h * 32,
-              k_rgba_to_planar<<<blocks, 256, 0, c.stream>>>(reinterpret_cast<const float4*>(d_rgba), w, h, stride, d_planes4));
+              k_rgba_to_planar<<<blocks, 256, 0, c.stream>>>(reinterpret_cast<const float4*>(d_rgba), w, h, stride, d_planes3, d_alpha));
     CE_CUDA(cudaGetLastError());
 }
 

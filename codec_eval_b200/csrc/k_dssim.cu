@@ -79,11 +79,11 @@ __global__ void __launch_bounds__(256) k_ds_down(const float* __restrict__ in, i
 }
 
 // ------------------------------------------------------------------ Lab (+ next scale)
-// thread = one 2x2 block of the current scale.  linear rgb [B][3][n] (+ alpha [B][n]) of image `which` ->
-//   img[(b*2+which)*3 + 0] = L;  chroma[(b*2+which)*2 + {0,1}] = a, b (un-blurred);
-//   nlin [B][3][on] = 2x2 average of the linear planes (floor size: a trailing odd row / column is dropped).
+// thread = one 2x2 block of the current scale; grid.z = image.  linear rgb [NI][3][n] (+ alpha [NI][n]) ->
+//   img[i*3 + 0] = L;  chroma[i*2 + {0,1}] = a, b (un-blurred);
+//   nlin [NI][3][on] = 2x2 average of the linear planes (floor size: a trailing odd row / column is dropped).
 __global__ void __launch_bounds__(256) k_ds_lab(const float* __restrict__ lin, const float* __restrict__ alpha, int w, int h,
-                                                 size_t n, int which, float* __restrict__ img, float* __restrict__ chroma,
+                                                 size_t n, float* __restrict__ img, float* __restrict__ chroma,
                                                  int has_next, int ow, int oh, size_t on, float* __restrict__ nlin) {
     const int ox = blockIdx.x * 64 + (threadIdx.x & 63);
     const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(256) k_ds_lab(const float* __restrict__ lin, c
         for (int c = 0; c < 3; c++)
             nlin[(b * 3 + c) * on + (size_t)oy * ow + ox] = (((p[c][0] + p[c][1]) + p[c][2]) + p[c][3]) * 0.25f;
     }
-    float* Lp = img + ((b * 2 + which) * 3) * n;
-    float* Ap = chroma + ((b * 2 + which) * 2) * n;
+    float* Lp = img + (b * 3) * n;
+    float* Ap = chroma + (b * 2) * n;
     float* Bp = Ap + n;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) k_ds_lab(const float* __restrict__ lin, c
 }
 
 // ------------------------------------------------------------------ chroma pre-blur (3x3 kernel applied twice)
-// grid (tiles_x, tiles_y, 2B): blockIdx.z = b*2 + which; chroma [2B][2][n] -> img[(z*3) + 1 + {0,1}].
+// grid (tiles_x, tiles_y, NI): blockIdx.z = image; chroma [NI][2][n] -> img[(z*3) + 1 + {0,1}].
 // Both planes of a 64x16 tile (+ halo 2, clamped) are staged; each pass evaluates 4 positions per thread
 // from 128-bit shared loads.
 __global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chroma, int w, int h, size_t n,
@@ -178,13 +178,15 @@ __global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chro
 }
 
 // ------------------------------------------------------------------ statistics + SSIM map
-// grid (tiles_x, tiles_y, B), block 320; img: [B][2][3][n]; map: [B][n]; partial: [B][tiles] doubles.
+// grid (tiles_x, tiles_y, B), block 320; img: [NI][3][n], pair b = images ridx[b] and R + b; map: [B][n];
+// partial: [B][tiles] doubles.
 // Per channel: the two image tiles (+ halo 2, clamped) are staged; the first 3x3 pass of the five quantities
 // {ch1, ch2, ch1^2, ch2^2, ch1*ch2} is evaluated 4 positions per thread from 128-bit shared loads, the second
 // pass likewise for the thread's 4 pixels; channel sums are accumulated in the upstream order.
 #define DS_ST_THREADS 320
-__global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __restrict__ img, int w, int h, size_t n,
-                                                             float* __restrict__ map, double* __restrict__ partial) {
+__global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __restrict__ img, size_t R,
+                                                                const int* __restrict__ ridx, int w, int h, size_t n,
+                                                                float* __restrict__ map, double* __restrict__ partial) {
     __shared__ __align__(16) float s_in[2][DS_IH * DS_IW];
     __shared__ __align__(16) float s_f[5][DS_FH * DS_FW];
     __shared__ double scratch[32];
@@ -196,8 +198,8 @@ __global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __re
     float sm11[4], sm12[4], sm22[4], ss1[4], ss2[4], ss12[4];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const float* p1 = img + ((b * 2 + 0) * 3 + c) * n;
-        const float* pq = img + ((b * 2 + 1) * 3 + c) * n;
+        const float* p1 = img + ((size_t)ridx[b] * 3 + c) * n;
+        const float* pq = img + ((R + b) * 3 + c) * n;
         __syncthreads();  // previous channel's s_f / s_in no longer read
         load_tile<2, DS_IW / 4>(s_in[0], DS_IW, p1, w, h, x0 - 4, y0 - 2, DS_IH, vec);
         load_tile<2, DS_IW / 4>(s_in[1], DS_IW, pq, w, h, x0 - 4, y0 - 2, DS_IH, vec);
@@ -338,67 +340,64 @@ size_t dssim_workspace_per_pair(size_t w, size_t h) {
     return (6 * n + 4 * n + n + 4 * n) * 4 + (tiles + DS_MAD_BLOCKS + 4) * 8 + 8192;
 }
 
-int dssim_run(Context& c, const float* lin1_in, const float* lin2_in, const float* alpha1_in, const float* alpha2_in, size_t B,
-              size_t w, size_t h, double* d_out, float* dbg_map0) {
+int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, const int* ridx, size_t B, size_t w, size_t h,
+              double* d_out, float* dbg_map0) {
     size_t ws[5], hs[5];
     const int ns = dssim_num_scales(w, h, ws, hs);
     size_t mark = c.arena.mark();
-    const size_t n0 = w * h;
-    float* img = c.arena.alloc<float>(B * 6 * n0);
-    float* chroma = c.arena.alloc<float>(B * 4 * n0);
+    const size_t n0 = w * h, NI = R + B;
+    if (NI > 65535) throw CudaError("dssim sub-batch too large for one launch");
+    float* img = c.arena.alloc<float>(NI * 3 * n0);
+    float* chroma = c.arena.alloc<float>(NI * 2 * n0);
     float* map = c.arena.alloc<float>(B * n0);
     const size_t tiles0 = (size_t)cdiv(w, DS_TW) * cdiv(h, DS_TH);
     double* partial = c.arena.alloc<double>(B * std::max<size_t>(tiles0, DS_MAD_BLOCKS));
     double* avg = c.arena.alloc<double>(B);
-    const bool has_alpha = alpha1_in != nullptr;
-    const int npl = has_alpha ? 4 : 3;
-    // next-scale planes: [pingpong][img] each [B][npl][n/4]; alpha stored as plane 3 of each pair
-    float* nl[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    const bool has_alpha = alpha_in != nullptr;
+    // next-scale planes, ping-pong: [NI][3][n/4] (+ alpha [NI][n/4])
+    float* nl[2] = {nullptr, nullptr};
+    float* nal[2] = {nullptr, nullptr};
     if (ns > 1)
-        for (int i = 0; i < 2; i++)
-            for (int j = 0; j < 2; j++) nl[i][j] = c.arena.alloc<float>(B * 3 * ws[1] * hs[1]);
-    float* nal[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    if (ns > 1 && has_alpha)
-        for (int i = 0; i < 2; i++)
-            for (int j = 0; j < 2; j++) nal[i][j] = c.arena.alloc<float>(B * ws[1] * hs[1]);
-    (void)npl;
+        for (int i = 0; i < 2; i++) {
+            nl[i] = c.arena.alloc<float>(NI * 3 * ws[1] * hs[1]);
+            if (has_alpha) nal[i] = c.arena.alloc<float>(NI * ws[1] * hs[1]);
+        }
 
-    const float* l[2] = {lin1_in, lin2_in};
-    const float* al[2] = {alpha1_in, alpha2_in};
+    const float* l = lin_in;
+    const float* al = alpha_in;
     const unsigned wave = (unsigned)c.sm_count * 8;
     for (int s = 0; s < ns; s++) {
         const size_t cw = ws[s], ch = hs[s], n = cw * ch;
         const bool has_next = s + 1 < ns;
         const size_t nw = has_next ? ws[s + 1] : 0, nh = has_next ? hs[s + 1] : 0, nn = nw * nh;
         const unsigned tx = cdiv(cw, DS_TW), ty = cdiv(ch, DS_TH);
-        if (B > 65535) throw CudaError("dssim sub-batch too large for one launch");
-        for (int im = 0; im < 2; im++) {
-            float* dst = has_next ? nl[(s + 1) & 1][im] : nullptr;
-            dim3 grid(cdiv((cw + 1) / 2, 64), cdiv((ch + 1) / 2, 4), (unsigned)B);
-            CE_LAUNCH(c, "k_ds_lab", (double)B * (n * (has_alpha ? 28 : 24) + nn * 12),
-                      k_ds_lab<<<grid, 256, 0, c.stream>>>(l[im], has_alpha ? al[im] : nullptr, (int)cw, (int)ch, n, im, img, chroma,
+        {
+            float* dst = has_next ? nl[(s + 1) & 1] : nullptr;
+            dim3 grid(cdiv((cw + 1) / 2, 64), cdiv((ch + 1) / 2, 4), (unsigned)NI);
+            CE_LAUNCH(c, "k_ds_lab", (double)NI * (n * (has_alpha ? 28 : 24) + nn * 12),
+                      k_ds_lab<<<grid, 256, 0, c.stream>>>(l, has_alpha ? al : nullptr, (int)cw, (int)ch, n, img, chroma,
                                                           has_next ? 1 : 0, (int)nw, (int)nh, nn, dst));
             if (has_next && has_alpha) {
-                float* adst = nal[(s + 1) & 1][im];
-                size_t atotal = B * nn;
+                float* adst = nal[(s + 1) & 1];
+                size_t atotal = NI * nn;
                 CE_LAUNCH(c, "k_ds_down", (double)atotal * 20,
                           k_ds_down<<<std::min<unsigned>(cdiv(atotal, 256), wave * 4), 256, 0, c.stream>>>(
-                              al[im], (int)cw, n, (int)nw, (int)nh, nn, atotal, adst));
-                al[im] = adst;
+                              al, (int)cw, n, (int)nw, (int)nh, nn, atotal, adst));
+                al = adst;
             }
-            if (has_next) l[im] = dst;
+            if (has_next) l = dst;
         }
         {
-            if (2 * B > 65535) throw CudaError("dssim sub-batch too large for one launch");
-            dim3 grid(tx, ty, (unsigned)(2 * B));
-            CE_LAUNCH(c, "k_ds_blur2", (double)B * n * 32, k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img));
+            dim3 grid(tx, ty, (unsigned)NI);
+            CE_LAUNCH(c, "k_ds_blur2", (double)NI * n * 16, k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img));
         }
         const int ntiles = (int)(tx * ty);
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
             dim3 grid(tx, ty, nb);
             CE_LAUNCH(c, "k_ds_stats", (double)nb * n * 28,
-                      k_ds_stats<<<grid, DS_ST_THREADS, 0, c.stream>>>(img + b0 * 6 * n, (int)cw, (int)ch, n, map + b0 * n, partial + b0 * ntiles));
+                      k_ds_stats<<<grid, DS_ST_THREADS, 0, c.stream>>>(img, R + b0, ridx + b0, (int)cw, (int)ch, n, map + b0 * n,
+                                                                        partial + b0 * ntiles));
         }
         CE_LAUNCH(c, "k_ds_mean", (double)B * (ntiles + 2) * 8,
                   k_ds_mean<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, ntiles, B, n, s, d_out, avg));

@@ -20,19 +20,17 @@ namespace ce {
 __constant__ RGaussCoef c_rg;
 
 // ------------------------------------------------------------------ xyb + down2
-// thread = one 2x2 block of the current scale (= one pixel of the next scale)
-__global__ void __launch_bounds__(256) k_s2_xyb_down(const float* __restrict__ lin1, const float* __restrict__ lin2,
-                                                      int w, int h, int ow, int oh, size_t n, size_t on,
-                                                      float* __restrict__ xyb, float* __restrict__ nlin1,
-                                                      float* __restrict__ nlin2, int write_down) {
+// thread = one 2x2 block of the current scale (= one pixel of the next scale); grid.z = image
+__global__ void __launch_bounds__(256) k_s2_xyb_down(const float* __restrict__ lin_all, int w, int h, int ow, int oh,
+                                                      size_t n, size_t on, float* __restrict__ xyb,
+                                                      float* __restrict__ nlin, int write_down) {
     const int ox = blockIdx.x * 64 + (threadIdx.x & 63);
     const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
-    const size_t b = blockIdx.z >> 1;
-    const int img = blockIdx.z & 1;
+    const size_t im = blockIdx.z;
     if (ox >= ow || oy >= oh) return;
-    const float* lin = (img ? lin2 : lin1) + b * 3 * n;
-    float* xo = xyb + (b * 2 + img) * 3 * n;
-    float* no = (img ? nlin2 : nlin1) + b * 3 * on;
+    const float* lin = lin_all + im * 3 * n;
+    float* xo = xyb + im * 3 * n;
+    float* no = nlin + im * 3 * on;
     const int x0 = 2 * ox, y0 = 2 * oy;
     const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
     const bool vx = (x0 + 1 < w), vy = (y0 + 1 < h);
@@ -104,8 +102,8 @@ CE_DEVINL float rg_step(RGState& s, float sum) {
 // recurrence runs 4 columns behind the loads: chunk k (input columns k*HP_COLS ..) produces output columns
 // k*HP_COLS-4 .. ; the first four steps are the upstream warm-up (n = -4 .. -1), and
 // ceil((w+4)/HP_COLS) chunks reach the last column.  Each warp writes out the plane it produced.
-__global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb, float* __restrict__ hb, int w, int h,
-                                                   size_t n, int vec) {
+__global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb, size_t R, const int* __restrict__ ridx,
+                                                   float* __restrict__ hb, int w, int h, size_t n, int vec) {
     extern __shared__ __align__(16) float s_dyn[];   // HP_SMEM_BYTES (> 48 KB: opt-in dynamic shared memory)
     float* s_in = s_dyn;
     const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
@@ -113,8 +111,8 @@ __global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb,
     const size_t b = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
     const int row0 = blockIdx.x * HP_ROWS;
-    const float* i1 = xyb + ((b * 2 + 0) * 3 + c) * n;
-    const float* i2 = xyb + ((b * 2 + 1) * 3 + c) * n;
+    const float* i1 = xyb + ((size_t)ridx[b] * 3 + c) * n;
+    const float* i2 = xyb + ((R + b) * 3 + c) * n;
     float* op = hb + ((b * 3 + c) * 5 + p) * n;
     const int nchunks = (w + 4 + HP_COLS - 1) / HP_COLS;
     // product roles
@@ -218,9 +216,9 @@ __global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb,
 // arithmetic in the loop); the five blurred values of each pixel meet in shared memory and, one batch
 // later, warp r evaluates the SSIM / edge-artifact / detail-loss terms of row r of that batch -- so there
 // is ONE block barrier per 5 rows.  partials: [(b*3+c)][gridDim.x][6]
-__global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb, const float* __restrict__ hb,
-                                                   int w, int h, size_t n, double* __restrict__ partials,
-                                                   float* __restrict__ dbg, int vec) {
+__global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb, size_t R, const int* __restrict__ ridx,
+                                                   const float* __restrict__ hb, int w, int h, size_t n,
+                                                   double* __restrict__ partials, float* __restrict__ dbg, int vec) {
     __shared__ __align__(16) float s_ld[VP_SLOTS * VP_SLOT_FLOATS];   // [slot][row r][plane][col]
     __shared__ float s_v[2][VP_BATCH][5][VP_COLS];
     __shared__ double scratch[6 * 32];
@@ -230,8 +228,8 @@ __global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb,
     const size_t b = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
     const bool active = x < w;
-    const float* i1 = xyb + ((b * 2 + 0) * 3 + c) * n;
-    const float* i2 = xyb + ((b * 2 + 1) * 3 + c) * n;
+    const float* i1 = xyb + ((size_t)ridx[b] * 3 + c) * n;
+    const float* i2 = xyb + ((R + b) * 3 + c) * n;
     const float* hp = hb + ((b * 3 + c) * 5) * n;
     const int total = h + 4;  // input rows j = 0 .. h+3 (rows >= h are zero); output row y = j - 4
     const int nbatch = (total + VP_BATCH - 1) / VP_BATCH;
@@ -290,7 +288,7 @@ __global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb,
             const float a1 = slot[5 * VP_COLS], a2 = slot[6 * VP_COLS];
             if (dbg) {
                 float* d = dbg + (size_t)c * 7 * n + (size_t)y * w + x;
-                d[2 * n] = m1; d[3 * n] = m2; d[4 * n] = s11; d[5 * n] = s22; d[6 * n] = s12;
+                d[0] = a1; d[n] = a2; d[2 * n] = m1; d[3 * n] = m2; d[4 * n] = s11; d[5 * n] = s22; d[6 * n] = s12;
             }
             // ssim_map
             const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
@@ -373,26 +371,25 @@ void ssim2_init(Context& c) {
 
 size_t ssim2_workspace_per_pair(size_t w, size_t h) {
     size_t n = w * h;
-    // next-scale linear (2*3*n/4 .. geometric), xyb 6n, hb 15n, partials
+    // xyb 6n (two images), row-pass planes 15n, next-scale linear ping-pong 2 x 2 x 3 x n/4, partials
     size_t bytes = (6 * n + 15 * n) * 4 + (2 * 3 * ((w + 1) / 2) * ((h + 1) / 2)) * 4 * 2 + 3 * cdiv(w, VP_COLS) * 6 * 8 + 4096;
     return bytes;
 }
 
-int ssim2_run(Context& c, const float* lin1_in, const float* lin2_in, size_t B, size_t w, size_t h, double* d_sums,
+int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t B, size_t w, size_t h, double* d_sums,
               float* dbg_planes) {
     size_t mark = c.arena.mark();
-    const size_t n0 = w * h;
-    float* xyb = c.arena.alloc<float>(B * 6 * n0);
+    const size_t n0 = w * h, NI = R + B;
+    if (NI > 65535 || B * 3 > 65535) throw CudaError("ssimulacra2 sub-batch too large for one launch");
+    float* xyb = c.arena.alloc<float>(NI * 3 * n0);
     float* hb = c.arena.alloc<float>(B * 15 * n0);
     const size_t ow0 = (w + 1) / 2, oh0 = (h + 1) / 2;
-    float* nl[2][2];  // ping-pong next-scale linear buffers [pingpong][img]
-    for (int i = 0; i < 2; i++)
-        for (int j = 0; j < 2; j++) nl[i][j] = c.arena.alloc<float>(B * 3 * ow0 * oh0);
+    float* nl[2];  // ping-pong next-scale linear buffers, [NI][3][n/4]
+    for (int i = 0; i < 2; i++) nl[i] = c.arena.alloc<float>(NI * 3 * ow0 * oh0);
     const int nblk0 = cdiv(w, VP_COLS);
     double* partials = c.arena.alloc<double>(B * 3 * nblk0 * 6);
 
-    const float* l1 = lin1_in;
-    const float* l2 = lin2_in;
+    const float* l = lin_in;
     size_t cw = w, ch = h;
     int ns = 0;
     for (int scale = 0; scale < 6; scale++) {
@@ -400,40 +397,34 @@ int ssim2_run(Context& c, const float* lin1_in, const float* lin2_in, size_t B, 
         const size_t ow = (cw + 1) / 2, oh = (ch + 1) / 2;
         // does a next scale exist? (check on the current size, as upstream does at the top of its loop)
         const bool has_next = (scale + 1 < 6) && !(cw < 8 || ch < 8);
-        float* d1 = nl[scale & 1][0];
-        float* d2 = nl[scale & 1][1];
+        float* d = nl[scale & 1];
         {
-            dim3 grid(cdiv(ow, 64), cdiv(oh, 4), (unsigned)(B * 2));
-            CE_LAUNCH(c, "k_s2_xyb_down", (double)B * 4 * (12 * n + (has_next ? 6 * ow * oh : 0)),
-                      k_s2_xyb_down<<<grid, 256, 0, c.stream>>>(l1, l2, (int)cw, (int)ch, (int)ow, (int)oh, n, ow * oh, xyb, d1,
-                                                                 d2, has_next ? 1 : 0));
+            dim3 grid(cdiv(ow, 64), cdiv(oh, 4), (unsigned)NI);
+            CE_LAUNCH(c, "k_s2_xyb_down", (double)NI * 4 * (6 * n + (has_next ? 3 * ow * oh : 0)),
+                      k_s2_xyb_down<<<grid, 256, 0, c.stream>>>(l, (int)cw, (int)ch, (int)ow, (int)oh, n, ow * oh, xyb, d,
+                                                                 has_next ? 1 : 0));
         }
         {
             dim3 grid(cdiv(ch, HP_ROWS), (unsigned)(B * 3));
-            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4, k_s2_hpass<<<grid, 160, HP_SMEM_BYTES, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, (cw % 4 == 0) ? 1 : 0));
+            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4,
+                      k_s2_hpass<<<grid, 160, HP_SMEM_BYTES, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, (cw % 4 == 0) ? 1 : 0));
         }
         const int nblk = cdiv(cw, VP_COLS);
         float* dbg = (dbg_planes && scale == 0) ? dbg_planes : nullptr;
         {
             dim3 grid(nblk, (unsigned)(B * 3));
             CE_LAUNCH(c, "k_s2_vpass", (double)B * 3 * 7 * n * 4,
-                      k_s2_vpass<<<grid, 160, 0, c.stream>>>(xyb, hb, (int)cw, (int)ch, n, partials, dbg, (cw % 4 == 0) ? 1 : 0));
+                      k_s2_vpass<<<grid, 160, 0, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, partials, dbg, (cw % 4 == 0) ? 1 : 0));
         }
         {
             size_t total = B * 3 * 6;
             CE_LAUNCH(c, "k_s2_reduce", (double)total * (nblk + 1) * 8,
                       k_s2_reduce<<<cdiv(total, 128), 128, 0, c.stream>>>(partials, nblk, total, scale, d_sums));
         }
-        if (dbg) {
-            for (int cc = 0; cc < 3; cc++) {
-                CE_CUDA(cudaMemcpyAsync(dbg + (size_t)cc * 7 * n, xyb + (size_t)cc * n, n * 4, cudaMemcpyDeviceToDevice, c.stream));
-                CE_CUDA(cudaMemcpyAsync(dbg + (size_t)cc * 7 * n + n, xyb + (size_t)(3 + cc) * n, n * 4, cudaMemcpyDeviceToDevice, c.stream));
-            }
-        }
         CE_CUDA(cudaGetLastError());
         ns++;
         if (!has_next) break;
-        l1 = d1; l2 = d2; cw = ow; ch = oh;
+        l = d; cw = ow; ch = oh;
     }
     c.arena.release(mark);
     return ns;

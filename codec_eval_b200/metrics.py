@@ -371,6 +371,22 @@ class GpuMetrics:
         return out
 
 
+    def evaluate_batch_device_grouped(self, d_ref: int, n_ref: int, d_dist: int, n: int, ref_index, width: int, height: int,
+                                      config: MetricConfig, intensity_target: float = 80.0):
+        """Device-resident batch with shared references: pair i = (reference ref_index[i], distorted i).
+        Reference-side work is done once per distinct reference (evaluate_image's shape, session.rs:375-431)."""
+        out = (_lib.CeResult * max(n, 1))()
+        cfg = config._c()
+        ri = np.ascontiguousarray(ref_index, dtype=np.uint32)
+        assert ri.size == n
+        st = self._L.ce_evaluate_batch_device_grouped(self._h, C.c_void_p(d_ref), n_ref, C.c_void_p(d_dist), n,
+                                                      ri.ctypes.data_as(C.POINTER(C.c_uint32)), width, height, C.byref(cfg),
+                                                      intensity_target, out)
+        if st != _lib.CE_OK:
+            self._raise(st, "batch")
+        return out
+
+
 class GpuReference:
     """Reference image kept on the device; mirrors fast_ssim2::Ssimulacra2Reference::new / .compare
     as used by crates/codec-iter/src/eval.rs:138-149,84-88."""

@@ -78,7 +78,7 @@ typedef struct {
 
 /* replaces GpuSsim2::new (crates/codec-iter/src/gpu.rs:40-77).  workspace_bytes
  * = device scratch for intermediates (0 = default: half of free memory, at most
- * 24 GiB); batches larger than the workspace are processed in sub-batches. */
+ * 64 GiB); batches larger than the workspace are processed in sub-batches. */
 CE_API int ce_ctx_create(ce_ctx** out, int device, size_t workspace_bytes);
 CE_API void ce_ctx_destroy(ce_ctx* ctx);
 /* run all work on the caller's CUDA stream (cudaStream_t); NULL = the context's own stream */
@@ -113,6 +113,15 @@ CE_API int ce_evaluate_batch(ce_ctx* ctx, const ce_pair* pairs, size_t n, const 
 CE_API int ce_evaluate_batch_device(ce_ctx* ctx, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, uint32_t width,
                                     uint32_t height, const ce_metric_config* cfg, float intensity_target,
                                     ce_result* out);
+
+/* Device-resident batch with shared references: n_ref reference images, n distorted images, pair i compares
+ * reference ref_index[i] (host array) with distorted image i.  This is evaluate_image's shape -- one reference
+ * against every codec x quality output (src/eval/session.rs:375-431) -- and what Ssimulacra2Reference::new /
+ * .compare exploits on the CPU (crates/codec-iter/src/eval.rs:138-149): reference-side work is done once per
+ * distinct reference.  ce_evaluate_batch does the same automatically for pairs whose `ref` pointers are equal. */
+CE_API int ce_evaluate_batch_device_grouped(ce_ctx* ctx, const uint8_t* d_ref, size_t n_ref, const uint8_t* d_dist, size_t n,
+                                            const uint32_t* ref_index, uint32_t width, uint32_t height,
+                                            const ce_metric_config* cfg, float intensity_target, ce_result* out);
 
 /* ---- single-pair mirrors of src/metrics ----------------------------- */
 

@@ -393,3 +393,48 @@ def test_device_batch_sub_batching_and_determinism(gpu, O):
         assert abs(a[i].ssimulacra2 - O.ssimulacra2(refs[i], dists[i], w, h)) < S2_TOL
         assert rel(a[i].dssim, O.dssim(refs[i], dists[i], w, h)) < DS_RTOL
         assert rel(a[i].butteraugli, O.butteraugli(refs[i], dists[i], w, h)[0]) < BA_RTOL
+
+
+def test_shared_reference_batches_match_independent_pairs(gpu, O):
+    """evaluate_image's shape: one reference against several distortions.  Pairs that share the reference buffer are
+    grouped (reference-side work once); the scores must be bit-identical to evaluating every pair on its own."""
+    import torch
+
+    from codec_eval_b200.metrics import MetricConfig
+
+    w, h = 160, 96
+    refs = [G(i, w, h) for i in range(3)]
+    pairs, ref_index, dists = [], [], []
+    for i, r in enumerate(refs):
+        for q in (35, 60, 85):
+            d = cheap_distort(r, q, seed=10 * i + q)
+            pairs.append((r, d, w, h))
+            ref_index.append(i)
+            dists.append(d)
+    cfg = MetricConfig.all()
+    grouped = gpu.evaluate_batch(pairs, cfg)
+    single = [gpu.evaluate_batch([p], cfg)[0] for p in pairs]
+    for a, b in zip(grouped, single):
+        assert (a.sse, a.psnr, a.ssimulacra2, a.dssim, a.butteraugli, a.butteraugli_pnorm3) == \
+               (b.sse, b.psnr, b.ssimulacra2, b.dssim, b.butteraugli, b.butteraugli_pnorm3)
+    # same through the device-resident grouped entry, references in a shuffled order
+    order = [2, 0, 1]
+    d_ref = torch.from_numpy(np.stack([refs[k] for k in order])).cuda()
+    d_dist = torch.from_numpy(np.stack(dists)).cuda()
+    ri = [order.index(i) for i in ref_index]
+    out = gpu.evaluate_batch_device_grouped(d_ref.data_ptr(), 3, d_dist.data_ptr(), len(dists), ri, w, h, cfg)
+    torch.cuda.synchronize()
+    for k, b in enumerate(single):
+        assert out[k].status == 0 and out[k].sse == b.sse and out[k].ssimulacra2 == b.ssimulacra2
+        assert out[k].dssim == b.dssim and out[k].butteraugli == b.butteraugli
+    # with the XYB round-trip applied to the (distinct) references
+    g2 = gpu.evaluate_batch(pairs, cfg.with_xyb_roundtrip())
+    s2 = gpu.evaluate_batch([pairs[4]], cfg.with_xyb_roundtrip())[0]
+    assert (g2[4].sse, g2[4].ssimulacra2, g2[4].dssim, g2[4].butteraugli) == (s2.sse, s2.ssimulacra2, s2.dssim, s2.butteraugli)
+    rt = O.xyb_roundtrip(refs[1], w, h)
+    assert g2[4].sse == O.sse(rt, dists[4])
+    # out-of-range index is rejected
+    from codec_eval_b200.metrics import CudaError
+
+    with pytest.raises((AssertionError, CudaError)):
+        gpu.evaluate_batch_device_grouped(d_ref.data_ptr(), 3, d_dist.data_ptr(), 2, [0, 3], w, h, cfg)
