@@ -34,6 +34,14 @@ void Context::ensure_input(size_t bytes) {
     CE_CUDA(cudaMalloc(&d_in, bytes));
     d_in_bytes = bytes;
 }
+void Context::ensure_stage(int slot, size_t bytes) {
+    if (bytes <= d_stage_bytes[slot]) return;
+    if (d_stage[slot]) CE_CUDA(cudaFree(d_stage[slot]));
+    d_stage[slot] = nullptr;
+    d_stage_bytes[slot] = 0;
+    CE_CUDA(cudaMalloc(&d_stage[slot], bytes));
+    d_stage_bytes[slot] = bytes;
+}
 void Context::ensure_results(size_t bytes) {
     if (bytes <= h_pinned_bytes) return;
     if (h_pinned) CE_CUDA(cudaFreeHost(h_pinned));
@@ -452,6 +460,8 @@ CE_API int ce_ctx_create(ce_ctx** out, int device, size_t workspace_bytes) {
             CE_CUDA(cudaEventCreateWithFlags(&c.ev_join[i], cudaEventDisableTiming));
         }
         CE_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+        CE_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) CE_CUDA(cudaEventCreateWithFlags(&c.ev_copy[i], cudaEventDisableTiming));
         if (workspace_bytes == 0) {
             size_t free_b = 0, total_b = 0;
             CE_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -496,6 +506,11 @@ CE_API void ce_ctx_destroy(ce_ctx* ctx) {
         if (c.ev_join[i]) cudaEventDestroy(c.ev_join[i]);
     }
     if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+    if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); }
+    for (int i = 0; i < 2; i++) {
+        if (c.ev_copy[i]) cudaEventDestroy(c.ev_copy[i]);
+        if (c.d_stage[i]) cudaFree(c.d_stage[i]);
+    }
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     delete ctx;
 }
@@ -605,36 +620,59 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
         groups[{pairs[i].width, pairs[i].height}].push_back(i);
     }
     std::vector<ce_result> tmp;
-    std::vector<uint32_t> ref_of;
+    struct Staged {
+        size_t k0 = 0, B = 0, Ru = 0;
+        std::vector<uint32_t> ref_of;
+    } st[2];
     for (auto& g : groups) {
         const size_t w = g.first.first, h = g.first.second, img_bytes = w * h * 3;
         const std::vector<size_t>& idx = g.second;
-        // staging: at most 2 GiB of distorted input per chunk
-        size_t chunk = std::max<size_t>(1, std::min<size_t>(idx.size(), ((size_t)2 << 30) / std::max<size_t>(img_bytes, 1)));
-        for (size_t k0 = 0; k0 < idx.size(); k0 += chunk) {
-            const size_t B = std::min(chunk, idx.size() - k0);
+        // The group is cut into up to 4 chunks (at most 2 GiB of distorted input each): chunk k+1 is copied to the
+        // device on the copy stream while chunk k computes.
+        size_t nchunks = std::min<size_t>(4, (idx.size() + 7) / 8);
+        size_t chunk = (idx.size() + nchunks - 1) / nchunks;
+        chunk = std::max<size_t>(1, std::min<size_t>(chunk, ((size_t)2 << 30) / std::max<size_t>(img_bytes, 1)));
+        nchunks = (idx.size() + chunk - 1) / chunk;
+        auto stage = [&](size_t ci) {
+            Staged& s = st[ci & 1];
+            s.k0 = ci * chunk;
+            s.B = std::min(chunk, idx.size() - s.k0);
             // distinct reference buffers of the chunk (same host pointer == same image: evaluate_image compares one
             // reference with every codec x quality output, src/eval/session.rs:375-431) are uploaded once
             std::map<const uint8_t*, uint32_t> seen;
             std::vector<const uint8_t*> urefs;
-            ref_of.resize(B);
-            for (size_t k = 0; k < B; k++) {
-                const ce_pair& p = pairs[idx[k0 + k]];
+            s.ref_of.resize(s.B);
+            for (size_t k = 0; k < s.B; k++) {
+                const ce_pair& p = pairs[idx[s.k0 + k]];
                 auto it = seen.find(p.ref);
                 if (it == seen.end()) { it = seen.emplace(p.ref, (uint32_t)urefs.size()).first; urefs.push_back(p.ref); }
-                ref_of[k] = it->second;
+                s.ref_of[k] = it->second;
             }
-            const size_t Ru = urefs.size();
-            c.ensure_input((Ru + B) * img_bytes);
-            uint8_t* d_ref = c.d_in;
-            uint8_t* d_dist = c.d_in + Ru * img_bytes;
-            for (size_t r = 0; r < Ru; r++)
-                CE_CUDA(cudaMemcpyAsync(d_ref + r * img_bytes, urefs[r], img_bytes, cudaMemcpyHostToDevice, c.stream));
-            for (size_t k = 0; k < B; k++)
-                CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, pairs[idx[k0 + k]].dist, img_bytes, cudaMemcpyHostToDevice, c.stream));
-            tmp.resize(B);
-            run_device_batch(c, d_ref, Ru, d_dist, B, ref_of.data(), w, h, cfg, intensity, tmp.data(), dbg);
-            for (size_t k = 0; k < B; k++) out[idx[k0 + k]] = tmp[k];
+            s.Ru = urefs.size();
+            c.ensure_stage((int)(ci & 1), (s.Ru + s.B) * img_bytes);
+            uint8_t* d_ref = c.d_stage[ci & 1];
+            uint8_t* d_dist = d_ref + s.Ru * img_bytes;
+            for (size_t r = 0; r < s.Ru; r++)
+                CE_CUDA(cudaMemcpyAsync(d_ref + r * img_bytes, urefs[r], img_bytes, cudaMemcpyHostToDevice, c.copy_stream));
+            for (size_t k = 0; k < s.B; k++)
+                CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, pairs[idx[s.k0 + k]].dist, img_bytes, cudaMemcpyHostToDevice,
+                                        c.copy_stream));
+            CE_CUDA(cudaEventRecord(c.ev_copy[ci & 1], c.copy_stream));
+        };
+        try {
+            stage(0);
+            for (size_t ci = 0; ci < nchunks; ci++) {
+                if (ci + 1 < nchunks) stage(ci + 1);   // its slot was last read by chunk ci-1, which has completed
+                Staged& s = st[ci & 1];
+                CE_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy[ci & 1], 0));
+                tmp.resize(s.B);
+                run_device_batch(c, c.d_stage[ci & 1], s.Ru, c.d_stage[ci & 1] + s.Ru * img_bytes, s.B, s.ref_of.data(), w, h,
+                                 cfg, intensity, tmp.data(), dbg);
+                for (size_t k = 0; k < s.B; k++) out[idx[s.k0 + k]] = tmp[k];
+            }
+        } catch (...) {
+            cudaStreamSynchronize(c.copy_stream);   // no copy may outlive the caller's buffers
+            throw;
         }
     }
 }

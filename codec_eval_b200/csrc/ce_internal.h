@@ -90,6 +90,11 @@ struct Context {
     size_t d_results_bytes = 0;
     uint8_t* d_in = nullptr;      // device input staging for host-pointer entries
     size_t d_in_bytes = 0;
+    // double-buffered staging of ce_evaluate_batch: chunk k+1 is copied on copy_stream while chunk k computes
+    uint8_t* d_stage[2] = {nullptr, nullptr};
+    size_t d_stage_bytes[2] = {0, 0};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     int* h_idx = nullptr;         // pinned + device index staging (reference index tables of a sub-batch)
     int* d_idx = nullptr;
     size_t idx_cap = 0;
@@ -110,6 +115,7 @@ struct Context {
     void prof_end();
     void prof_collect();   // call after the stream is synchronised
     void ensure_input(size_t bytes);
+    void ensure_stage(int slot, size_t bytes);
     void ensure_results(size_t bytes);
     void ensure_idx(size_t count);
 };
