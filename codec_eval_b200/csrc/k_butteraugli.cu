@@ -21,6 +21,7 @@
 // borders of libjxl's ConvolveBorderColumn); tile loads are 128-bit where the row pitch allows.
 #include "ce_common.cuh"
 #include "ce_internal.h"
+#include "ba_weights.inc"
 
 #include <math.h>
 
@@ -32,6 +33,12 @@ struct BaConst {
     float w5[3];      // sigma 1.2: w0 (centre), w1, w2 pre-normalised
 };
 __constant__ BaConst c_ba;
+
+// blur weights as compile-time literals (FFMA immediates); SLOT as in c_ba.w
+template <int SLOT>
+CE_DEVINL constexpr float baw(int t) {
+    return SLOT == 0 ? kBaW16[t < 33 ? t : 0] : SLOT == 1 ? kBaW7[t < 15 ? t : 0] : SLOT == 2 ? kBaW3[t < 7 ? t : 0] : kBaW6[t < 13 ? t : 0];
+}
 
 static const float kSigmas[4] = {7.15593339443f, 3.22489901262f, 1.56416327805f, 2.7f};
 static const int kRadii[4] = {16, 7, 3, 6};
@@ -67,6 +74,13 @@ void butteraugli_init(Context& c) {
     k.w5[2] = w5[0] * scale;
     g_ba_host = k;
     CE_CUDA(cudaMemcpyToSymbol(c_ba, &k, sizeof(k), 0, cudaMemcpyHostToDevice));
+    // the kernels use the generated literals of ba_weights.inc; they must equal this run-time computation
+    const float* lit[4] = {hBaW16, hBaW7, hBaW3, hBaW6};
+    for (int s = 0; s < 4; s++)
+        for (int t = 0; t <= 2 * kRadii[s]; t++)
+            if (lit[s][t] != k.w[s][t]) throw CudaError("ba_weights.inc is stale: regenerate with tools/gen_ba_weights.py");
+    for (int t = 0; t < 3; t++)
+        if (hBaW5[t] != k.w5[t]) throw CudaError("ba_weights.inc is stale: regenerate with tools/gen_ba_weights.py");
 }
 
 // inv[x] = 1 / sum of in-range taps (ascending tap order, fp32) for a line of length len
@@ -94,9 +108,10 @@ static float* ba_inv_table(Context& c, int slot, size_t len) {
     if (it != c.ba_inv_cache.end()) return it->second;
     std::vector<float> inv;
     ba_host_inv_weights(slot, len, inv);
+    inv.resize(((len + 3) & ~size_t(3)) + 4, 0.0f);   // zero padding: kernels read 4 entries at a time
     float* d = nullptr;
-    CE_CUDA(cudaMalloc(&d, len * sizeof(float)));
-    CE_CUDA(cudaMemcpy(d, inv.data(), len * sizeof(float), cudaMemcpyHostToDevice));
+    CE_CUDA(cudaMalloc(&d, inv.size() * sizeof(float)));
+    CE_CUDA(cudaMemcpy(d, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice));
     c.ba_inv_cache[key] = d;
     return d;
 }
@@ -109,7 +124,7 @@ static float* ba_inv_table(Context& c, int slot, size_t len) {
 #define OP_ROWS (OP_TH + 4)   // rows y0-2 .. y0+17
 
 CE_DEVINL float blur5(float l2, float l1, float c, float r1, float r2) {
-    return __fmaf_rn(l2 + r2, c_ba.w5[2], __fmaf_rn(l1 + r1, c_ba.w5[1], c * c_ba.w5[0]));  // libjxl Separable5 MulAdd chain
+    return __fmaf_rn(l2 + r2, kBaW5[2], __fmaf_rn(l1 + r1, kBaW5[1], c * kBaW5[0]));  // libjxl Separable5 MulAdd chain
 }
 
 // OPSIN = true : lin [NI][3][n] -> xyb [NI][3][n] (blur + OpsinDynamicsImage), grid.z = image
@@ -124,7 +139,7 @@ __global__ void __launch_bounds__(256) k_ba_opsin(const float* __restrict__ lin,
     const float* src = lin + (size_t)blockIdx.z * NPL * n;
     float* dst = out + (size_t)blockIdx.z * NPL * n;
 #pragma unroll
-    for (int c = 0; c < NPL; c++) load_tile<1, OP_P / 4>(s_in[c], OP_P, src + (size_t)c * n, w, h, x0 - 4, y0 - 2, OP_ROWS, vec != 0);
+    for (int c = 0; c < NPL; c++) load_tile<1, OP_P / 4, OP_ROWS, 256>(s_in[c], OP_P, src + (size_t)c * n, w, h, x0 - 4, y0 - 2, vec != 0);
     __syncthreads();
     // horizontal pass: (row, 4-column group) items
     for (int e = threadIdx.x; e < OP_ROWS * (OP_TW / 4); e += 256) {
@@ -204,7 +219,7 @@ __global__ void __launch_bounds__(256) k_ba_blur_h(const float* __restrict__ in,
     const int x0 = blockIdx.x * 128, y0 = blockIdx.y * 8;
     const float* p = in + (size_t)blockIdx.z * n;
     float* o = out + (size_t)blockIdx.z * n;
-    load_tile<0, PITCH / 4>(s, PITCH, p, w, h, x0 - RUP, y0, 8, vec != 0);
+    load_tile<0, PITCH / 4, 8, 256>(s, PITCH, p, w, h, x0 - RUP, y0, vec != 0);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int y = y0 + ty, x = x0 + tx * 4;
@@ -215,15 +230,17 @@ __global__ void __launch_bounds__(256) k_ba_blur_h(const float* __restrict__ in,
         float4 f = *reinterpret_cast<const float4*>(&s[ty * PITCH + tx * 4 + q * 4]);
         v[q * 4] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
     }
+    const float4 iv = *reinterpret_cast<const float4*>(inv + x);   // zero-padded table
+    const float ivk[4] = {iv.x, iv.y, iv.z, iv.w};
     float res[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         float sum = 0.0f;
 #pragma unroll
-        for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], c_ba.w[SLOT][t], sum);
-        res[k] = sum * (x + k < w ? inv[x + k] : 0.0f);
+        for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], baw<SLOT>(t), sum);
+        res[k] = sum * ivk[k];
     }
-    float* d = o + (size_t)y * w + x;
+    float* d = o + (y * w + x);
     if (vec) *reinterpret_cast<float4*>(d) = make_float4(res[0], res[1], res[2], res[3]);
     else {
 #pragma unroll
@@ -250,7 +267,7 @@ __global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in,
 #pragma unroll
     for (int c = 0; c < NPL; c++) {
         if (c) __syncthreads();
-        load_tile<0, 8>(s, 32, in + base + (size_t)c * n, w, h, x0, y0 - R, ROWS, vec);
+        load_tile<0, 8, ROWS, 256>(s, 32, in + base + (size_t)c * n, w, h, x0, y0 - R, vec);
         __syncthreads();
         float v[8 + 2 * R];
 #pragma unroll
@@ -260,7 +277,7 @@ __global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in,
             const int y = y0 + g * 8 + k;
             float sum = 0.0f;
 #pragma unroll
-            for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], c_ba.w[SLOT][t], sum);
+            for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], baw<SLOT>(t), sum);
             res[c][k] = sum * (y < h ? inv[y] : 0.0f);
         }
     }
@@ -314,7 +331,7 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
 #pragma unroll
     for (int c = 0; c < NPL; c++) {
         if (c) __syncthreads();
-        load_tile<0, PITCH / 4>(s_in, PITCH, in + (img * NPL + c) * n, w, h, x0 - RUP, y0 - R, ROWS, vec);
+        load_tile<0, PITCH / 4, ROWS, 256>(s_in, PITCH, in + (img * NPL + c) * n, w, h, x0 - RUP, y0 - R, vec);
         __syncthreads();
         for (int e = threadIdx.x; e < ROWS * (B2_TW / 4); e += 256) {
             const int r = e >> 4, q4 = e & 15;
@@ -324,14 +341,15 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
                 float4 f = *reinterpret_cast<const float4*>(&s_in[r * PITCH + q4 * 4 + q * 4]);
                 v[q * 4] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
             }
+            const float4 iv = *reinterpret_cast<const float4*>(inv_x + min(x0 + q4 * 4, (w + 3) & ~3));   // zero-padded table
+            const float ivk[4] = {iv.x, iv.y, iv.z, iv.w};
             float o4[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int xx = x0 + q4 * 4 + k;
                 float sum = 0.0f;
 #pragma unroll
-                for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], c_ba.w[SLOT][t], sum);
-                o4[k] = sum * (xx < w ? inv_x[xx] : 0.0f);
+                for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], baw<SLOT>(t), sum);
+                o4[k] = sum * ivk[k];
             }
             *reinterpret_cast<float4*>(&s_h[r * B2_TW + q4 * 4]) = make_float4(o4[0], o4[1], o4[2], o4[3]);
         }
@@ -348,7 +366,7 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
             const int y = y0 + g * 8 + k;
             float sum = 0.0f;
 #pragma unroll
-            for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], c_ba.w[SLOT][t], sum);
+            for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], baw<SLOT>(t), sum);
             res[c][k] = sum * (y < h ? inv_y[y] : 0.0f);
         }
     }
@@ -578,7 +596,7 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
     const bool vec = (w & 3) == 0;
 #pragma unroll
     for (int bd = 0; bd < 3; bd++)
-        load_tile_async<MT_P / 4>(s_d[bd], MT_P, diff + ((size_t)blockIdx.z * 3 + bd) * n, w, h, tx0 - 4, ty0 - 4, MT_ROWS, vec);
+        load_tile_async<MT_P / 4, MT_ROWS, 256>(s_d[bd], MT_P, diff + ((size_t)blockIdx.z * 3 + bd) * n, w, h, tx0 - 4, ty0 - 4, vec);
     cp_async_commit();
     const int x = tx0 + 4 * g, y = ty0 + oy;
     const bool live = y < h && x < w;

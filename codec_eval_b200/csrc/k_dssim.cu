@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chro
     const size_t z = blockIdx.z;
     const bool vec = (w & 3) == 0;
 #pragma unroll
-    for (int pl = 0; pl < 2; pl++) load_tile<2, DS_IW / 4>(s_ab[pl], DS_IW, chroma + (z * 2 + pl) * n, w, h, x0 - 4, y0 - 2, DS_IH, vec);
+    for (int pl = 0; pl < 2; pl++) load_tile<2, DS_IW / 4, DS_IH, 256>(s_ab[pl], DS_IW, chroma + (z * 2 + pl) * n, w, h, x0 - 4, y0 - 2, vec);
     __syncthreads();
     // first 3x3 pass over the positions the second pass needs
     for (int e = threadIdx.x; e < 2 * DS_FH * DS_FG; e += 256) {
@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __re
         const float* p1 = img + ((size_t)ridx[b] * 3 + c) * n;
         const float* pq = img + ((R + b) * 3 + c) * n;
         __syncthreads();  // previous channel's s_f / s_in no longer read
-        load_tile<2, DS_IW / 4>(s_in[0], DS_IW, p1, w, h, x0 - 4, y0 - 2, DS_IH, vec);
-        load_tile<2, DS_IW / 4>(s_in[1], DS_IW, pq, w, h, x0 - 4, y0 - 2, DS_IH, vec);
+        load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[0], DS_IW, p1, w, h, x0 - 4, y0 - 2, vec);
+        load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[1], DS_IW, pq, w, h, x0 - 4, y0 - 2, vec);
         __syncthreads();
         if (threadIdx.x < DS_FH * DS_FG) {
             const int ry = threadIdx.x / DS_FG, q = threadIdx.x - ry * DS_FG;
