@@ -178,86 +178,126 @@ __global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chro
 }
 
 // ------------------------------------------------------------------ statistics + SSIM map
-// grid (tiles_x, tiles_y, B), block 320; img: [NI][3][n], pair b = images ridx[b] and R + b; map: [B][n];
-// partial: [B][tiles] doubles.
-// Per channel: the two image tiles (+ halo 2, clamped) are staged; the first 3x3 pass of the five quantities
-// {ch1, ch2, ch1^2, ch2^2, ch1*ch2} is evaluated 4 positions per thread from 128-bit shared loads, the second
-// pass likewise for the thread's 4 pixels; channel sums are accumulated in the upstream order.
+// The five double-3x3 blurs {ch1, ch2, ch1^2, ch2^2, ch1*ch2} per channel split by who owns them:
+//   k_ds_stats<0> (grid.z = distinct reference): mu1 = blur2(ch1), e11 = blur2(ch1^2) -> refstat [R][3][2][n],
+//                  once per reference however many distortions it is compared with;
+//   k_ds_stats<1> (grid.z = pair): blur2 of {ch2, ch2^2, ch1*ch2}, then the channel-averaged SSIM map
+//                  (written once) + fp64 block partial of its sum.  partial: [B][tiles] doubles.
+// Block 320, 64x16 tile: the image tile(s) (+ halo 2, clamped) are staged per channel; the first 3x3 pass is
+// evaluated 4 positions per thread from 128-bit shared loads, the second pass likewise for the thread's 4
+// pixels; every quantity keeps the upstream operation sequence, channel sums accumulate in upstream order.
 #define DS_ST_THREADS 320
+template <int MODE>
 __global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __restrict__ img, size_t R,
                                                                 const int* __restrict__ ridx, int w, int h, size_t n,
-                                                                float* __restrict__ map, double* __restrict__ partial) {
-    __shared__ __align__(16) float s_in[2][DS_IH * DS_IW];
-    __shared__ __align__(16) float s_f[5][DS_FH * DS_FW];
+                                                                float* __restrict__ refstat, float* __restrict__ map,
+                                                                double* __restrict__ partial) {
+    constexpr int NQ = MODE == 0 ? 2 : 3;
+    __shared__ __align__(16) float s_in[MODE == 0 ? 1 : 2][DS_IH * DS_IW];
+    __shared__ __align__(16) float s_f[NQ][DS_FH * DS_FW];
     __shared__ double scratch[32];
     const int x0 = blockIdx.x * DS_TW, y0 = blockIdx.y * DS_TH;
     const size_t b = blockIdx.z;
+    const size_t im1 = MODE == 0 ? b : (size_t)ridx[b];   // reference image
+    const size_t im2 = R + b;                             // distorted image (pair mode)
     const bool vec = (w & 3) == 0;
     const int g = threadIdx.x & 15, oy = threadIdx.x >> 4;   // second pass: threads 0..255
     const bool p2 = threadIdx.x < 256;
+    const int x = x0 + 4 * g, y = y0 + oy;
+    const bool live = p2 && x < w && y < h;
+    const int pix = live ? y * w + x : 0;
     float sm11[4], sm12[4], sm22[4], ss1[4], ss2[4], ss12[4];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const float* p1 = img + ((size_t)ridx[b] * 3 + c) * n;
-        const float* pq = img + ((R + b) * 3 + c) * n;
         __syncthreads();  // previous channel's s_f / s_in no longer read
-        load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[0], DS_IW, p1, w, h, x0 - 4, y0 - 2, vec);
-        load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[1], DS_IW, pq, w, h, x0 - 4, y0 - 2, vec);
+        load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[0], DS_IW, img + (im1 * 3 + c) * n, w, h, x0 - 4, y0 - 2, vec);
+        if (MODE == 1)
+            load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[MODE], DS_IW, img + (im2 * 3 + c) * n, w, h, x0 - 4, y0 - 2, vec);
         __syncthreads();
         if (threadIdx.x < DS_FH * DS_FG) {
             const int ry = threadIdx.x / DS_FG, q = threadIdx.x - ry * DS_FG;
-            float u[3][8], v[3][8], t[3][8];
+            float u[3][8], t[3][8];
 #pragma unroll
-            for (int r = 0; r < 3; r++) {
-                ds_ld8(s_in[0] + (ry + r) * DS_IW + 4 * q, u[r]);
-                ds_ld8(s_in[1] + (ry + r) * DS_IW + 4 * q, v[r]);
-            }
+            for (int r = 0; r < 3; r++) ds_ld8(s_in[0] + (ry + r) * DS_IW + 4 * q, u[r]);
             float* o = &s_f[0][ry * DS_FW + 4 * q];
-            *reinterpret_cast<float4*>(o) = ds_k9x4(u[0], u[1], u[2]);
-            *reinterpret_cast<float4*>(o + DS_FH * DS_FW) = ds_k9x4(v[0], v[1], v[2]);
+            if (MODE == 0) {
+                *reinterpret_cast<float4*>(o) = ds_k9x4(u[0], u[1], u[2]);
 #pragma unroll
-            for (int r = 0; r < 3; r++)
+                for (int r = 0; r < 3; r++)
 #pragma unroll
-                for (int i = 1; i < 7; i++) t[r][i] = u[r][i] * u[r][i];
-            *reinterpret_cast<float4*>(o + 2 * DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
+                    for (int i = 1; i < 7; i++) t[r][i] = u[r][i] * u[r][i];
+                *reinterpret_cast<float4*>(o + DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
+            } else {
+                float v[3][8];
 #pragma unroll
-            for (int r = 0; r < 3; r++)
+                for (int r = 0; r < 3; r++) ds_ld8(s_in[MODE] + (ry + r) * DS_IW + 4 * q, v[r]);
+                *reinterpret_cast<float4*>(o) = ds_k9x4(v[0], v[1], v[2]);
 #pragma unroll
-                for (int i = 1; i < 7; i++) t[r][i] = v[r][i] * v[r][i];
-            *reinterpret_cast<float4*>(o + 3 * DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
+                for (int r = 0; r < 3; r++)
 #pragma unroll
-            for (int r = 0; r < 3; r++)
+                    for (int i = 1; i < 7; i++) t[r][i] = v[r][i] * v[r][i];
+                *reinterpret_cast<float4*>(o + DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
 #pragma unroll
-                for (int i = 1; i < 7; i++) t[r][i] = u[r][i] * v[r][i];
-            *reinterpret_cast<float4*>(o + 4 * DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int i = 1; i < 7; i++) t[r][i] = u[r][i] * v[r][i];
+                *reinterpret_cast<float4*>(o + 2 * DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
+            }
         }
         __syncthreads();
-        ds_fix_border(&s_f[0][0], 5, DS_FH * DS_FW, w, h, x0, y0);
+        ds_fix_border(&s_f[0][0], NQ, DS_FH * DS_FW, w, h, x0, y0);
         __syncthreads();
         if (p2) {
-            float q[5][4];
+            float q[NQ][4];
 #pragma unroll
-            for (int f = 0; f < 5; f++) {
+            for (int f = 0; f < NQ; f++) {
                 float r0[8], r1[8], r2[8];
                 const float* base = s_f[f] + oy * DS_FW + 4 * g;
                 ds_ld8(base, r0); ds_ld8(base + DS_FW, r1); ds_ld8(base + 2 * DS_FW, r2);
                 const float4 o = ds_k9x4(r0, r1, r2);
                 q[f][0] = o.x; q[f][1] = o.y; q[f][2] = o.z; q[f][3] = o.w;
             }
+            if (MODE == 0) {
+                if (live) {
+                    float* d0 = refstat + ((b * 3 + c) * 2) * n + pix;
+                    if (vec) {
+                        *reinterpret_cast<float4*>(d0) = make_float4(q[0][0], q[0][1], q[0][2], q[0][3]);
+                        *reinterpret_cast<float4*>(d0 + n) = make_float4(q[1][0], q[1][1], q[1][2], q[1][3]);
+                    } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float mu1 = q[0][k], mu2 = q[1][k];
-                const float m11 = mu1 * mu1, m12 = mu1 * mu2, m22 = mu2 * mu2;
-                const float s1 = q[2][k] - m11, s2 = q[3][k] - m22, s12 = q[4][k] - m12;
-                if (c == 0) { sm11[k] = m11; sm12[k] = m12; sm22[k] = m22; ss1[k] = s1; ss2[k] = s2; ss12[k] = s12; }
-                else { sm11[k] += m11; sm12[k] += m12; sm22[k] += m22; ss1[k] += s1; ss2[k] += s2; ss12[k] += s12; }
+                        for (int k = 0; k < 4; k++)
+                            if (x + k < w) { d0[k] = q[0][k]; d0[n + k] = q[1][k]; }
+                    }
+                }
+            } else {
+                float r_mu[4] = {0, 0, 0, 0}, r_e[4] = {0, 0, 0, 0};
+                if (live) {
+                    const float* s0 = refstat + ((im1 * 3 + c) * 2) * n + pix;
+                    if (vec) {
+                        const float4 a = *reinterpret_cast<const float4*>(s0), e = *reinterpret_cast<const float4*>(s0 + n);
+                        r_mu[0] = a.x; r_mu[1] = a.y; r_mu[2] = a.z; r_mu[3] = a.w;
+                        r_e[0] = e.x; r_e[1] = e.y; r_e[2] = e.z; r_e[3] = e.w;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (x + k < w) { r_mu[k] = s0[k]; r_e[k] = s0[n + k]; }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float mu1 = r_mu[k], mu2 = q[0][k];
+                    const float m11 = mu1 * mu1, m12 = mu1 * mu2, m22 = mu2 * mu2;
+                    const float s1 = r_e[k] - m11, s2 = q[1][k] - m22, s12 = q[NQ - 1][k] - m12;
+                    if (c == 0) { sm11[k] = m11; sm12[k] = m12; sm22[k] = m22; ss1[k] = s1; ss2[k] = s2; ss12[k] = s12; }
+                    else { sm11[k] += m11; sm12[k] += m12; sm22[k] += m22; ss1[k] += s1; ss2[k] += s2; ss12[k] += s12; }
+                }
             }
         }
     }
+    if (MODE == 0) return;
     const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f, third = 1.0f / 3.0f;
     double acc = 0.0;
-    const int x = x0 + 4 * g, y = y0 + oy;
-    if (p2 && x < w && y < h) {
+    if (live) {
         float vv[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -266,7 +306,7 @@ __global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __re
             vv[k] = (__fmaf_rn(2.0f, mu1_mu2, c1) * __fmaf_rn(2.0f, sigma12, c2)) /
                     (((mu1_sq + mu2_sq) + c1) * ((sigma1_sq + sigma2_sq) + c2));
         }
-        float* d = map + b * n + (size_t)y * w + x;
+        float* d = map + b * n + pix;
         if (vec) {
             *reinterpret_cast<float4*>(d) = make_float4(vv[0], vv[1], vv[2], vv[3]);
             acc = (((double)vv[0] + (double)vv[1]) + (double)vv[2]) + (double)vv[3];
@@ -336,8 +376,8 @@ int dssim_num_scales(size_t w, size_t h, size_t* ws, size_t* hs) {
 size_t dssim_workspace_per_pair(size_t w, size_t h) {
     size_t n = w * h;
     size_t tiles = (size_t)cdiv(w, DS_TW) * cdiv(h, DS_TH);
-    // img 6n, chroma 4n, map n, next-scale rgb(a) ping-pong 2*2*4*(n/4)
-    return (6 * n + 4 * n + n + 4 * n) * 4 + (tiles + DS_MAD_BLOCKS + 4) * 8 + 8192;
+    // img 6n, chroma 4n, map n, reference statistics 6n, next-scale rgb(a) ping-pong 2*2*4*(n/4)
+    return (6 * n + 4 * n + n + 6 * n + 4 * n) * 4 + (tiles + DS_MAD_BLOCKS + 4) * 8 + 8192;
 }
 
 int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, const int* ridx, size_t B, size_t w, size_t h,
@@ -350,6 +390,7 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
     float* img = c.arena.alloc<float>(NI * 3 * n0);
     float* chroma = c.arena.alloc<float>(NI * 2 * n0);
     float* map = c.arena.alloc<float>(B * n0);
+    float* refstat = c.arena.alloc<float>(R * 6 * n0);   // per reference: [3 channels][mu1, blur2(ch1^2)]
     const size_t tiles0 = (size_t)cdiv(w, DS_TW) * cdiv(h, DS_TH);
     double* partial = c.arena.alloc<double>(B * std::max<size_t>(tiles0, DS_MAD_BLOCKS));
     double* avg = c.arena.alloc<double>(B);
@@ -392,12 +433,17 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
             CE_LAUNCH(c, "k_ds_blur2", (double)NI * n * 16, k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img));
         }
         const int ntiles = (int)(tx * ty);
+        {
+            dim3 grid(tx, ty, (unsigned)R);
+            CE_LAUNCH(c, "k_ds_stats<ref>", (double)R * n * 36,
+                      k_ds_stats<0><<<grid, DS_ST_THREADS, 0, c.stream>>>(img, R, nullptr, (int)cw, (int)ch, n, refstat, nullptr, nullptr));
+        }
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
             dim3 grid(tx, ty, nb);
-            CE_LAUNCH(c, "k_ds_stats", (double)nb * n * 28,
-                      k_ds_stats<<<grid, DS_ST_THREADS, 0, c.stream>>>(img, R + b0, ridx + b0, (int)cw, (int)ch, n, map + b0 * n,
-                                                                        partial + b0 * ntiles));
+            CE_LAUNCH(c, "k_ds_stats<pair>", (double)nb * n * 52,
+                      k_ds_stats<1><<<grid, DS_ST_THREADS, 0, c.stream>>>(img, R + b0, ridx + b0, (int)cw, (int)ch, n, refstat,
+                                                                           map + b0 * n, partial + b0 * ntiles));
         }
         CE_LAUNCH(c, "k_ds_mean", (double)B * (ntiles + 2) * 8,
                   k_ds_mean<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, ntiles, B, n, s, d_out, avg));
