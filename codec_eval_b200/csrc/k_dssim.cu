@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __re
                                                                 float* __restrict__ refstat, float* __restrict__ map,
                                                                 double* __restrict__ partial) {
     constexpr int NQ = MODE == 0 ? 2 : 3;
-    __shared__ __align__(16) float s_in[MODE == 0 ? 1 : 2][DS_IH * DS_IW];
+    constexpr int NIMG = MODE == 0 ? 1 : 2;
+    __shared__ __align__(16) float s_in[2][NIMG][DS_IH * DS_IW];   // [channel parity][image]: next channel prefetched
     __shared__ __align__(16) float s_f[NQ][DS_FH * DS_FW];
     __shared__ double scratch[32];
     const int x0 = blockIdx.x * DS_TW, y0 = blockIdx.y * DS_TH;
@@ -207,18 +208,37 @@ __global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __re
     const bool live = p2 && x < w && y < h;
     const int pix = live ? y * w + x : 0;
     float sm11[4], sm12[4], sm22[4], ss1[4], ss2[4], ss12[4];
+    // Tiles whose halo lies inside the image (block-uniform) are staged with cp.async one channel ahead; tiles on
+    // the image border need clamped coordinates and are loaded synchronously.
+    const bool interior = vec && x0 - 4 >= 0 && x0 - 4 + DS_IW <= w && y0 - 2 >= 0 && y0 - 2 + DS_IH <= h;
+    auto prefetch = [&](int c) {
+        if (interior) {
+            load_tile_async<DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[c & 1][0], DS_IW, img + (im1 * 3 + c) * n, w, h, x0 - 4, y0 - 2, true);
+            if (MODE == 1)
+                load_tile_async<DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[c & 1][NIMG - 1], DS_IW, img + (im2 * 3 + c) * n, w, h, x0 - 4,
+                                                                 y0 - 2, true);
+        }
+        cp_async_commit();
+    };
+    prefetch(0);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        __syncthreads();  // previous channel's s_f / s_in no longer read
-        load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[0], DS_IW, img + (im1 * 3 + c) * n, w, h, x0 - 4, y0 - 2, vec);
-        if (MODE == 1)
-            load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[MODE], DS_IW, img + (im2 * 3 + c) * n, w, h, x0 - 4, y0 - 2, vec);
-        __syncthreads();
+        // everyone is past the first pass of channel c-1 (it read buffer (c+1) & 1) -- see the barriers below
+        if (c + 1 < 3) prefetch(c + 1);
+        if (interior) {
+            if (c + 1 < 3) cp_async_wait<1>(); else cp_async_wait<0>();
+        } else {
+            load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[c & 1][0], DS_IW, img + (im1 * 3 + c) * n, w, h, x0 - 4, y0 - 2, vec);
+            if (MODE == 1)
+                load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[c & 1][NIMG - 1], DS_IW, img + (im2 * 3 + c) * n, w, h, x0 - 4,
+                                                              y0 - 2, vec);
+        }
+        __syncthreads();   // tiles of channel c visible; previous channel's second pass is done with s_f
         if (threadIdx.x < DS_FH * DS_FG) {
             const int ry = threadIdx.x / DS_FG, q = threadIdx.x - ry * DS_FG;
             float u[3][8], t[3][8];
 #pragma unroll
-            for (int r = 0; r < 3; r++) ds_ld8(s_in[0] + (ry + r) * DS_IW + 4 * q, u[r]);
+            for (int r = 0; r < 3; r++) ds_ld8(s_in[c & 1][0] + (ry + r) * DS_IW + 4 * q, u[r]);
             float* o = &s_f[0][ry * DS_FW + 4 * q];
             if (MODE == 0) {
                 *reinterpret_cast<float4*>(o) = ds_k9x4(u[0], u[1], u[2]);
@@ -230,7 +250,7 @@ __global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __re
             } else {
                 float v[3][8];
 #pragma unroll
-                for (int r = 0; r < 3; r++) ds_ld8(s_in[MODE] + (ry + r) * DS_IW + 4 * q, v[r]);
+                for (int r = 0; r < 3; r++) ds_ld8(s_in[c & 1][NIMG - 1] + (ry + r) * DS_IW + 4 * q, v[r]);
                 *reinterpret_cast<float4*>(o) = ds_k9x4(v[0], v[1], v[2]);
 #pragma unroll
                 for (int r = 0; r < 3; r++)
