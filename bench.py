@@ -200,6 +200,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w, h, _, _, desc = WORKLOADS[args.workload]
