@@ -438,3 +438,63 @@ def test_shared_reference_batches_match_independent_pairs(gpu, O):
 
     with pytest.raises((AssertionError, CudaError)):
         gpu.evaluate_batch_device_grouped(d_ref.data_ptr(), 3, d_dist.data_ptr(), 2, [0, 3], w, h, cfg)
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes
+def test_full_size_1024_all_metrics_vs_oracle(gpu, O):
+    """cfg5 shape (1024x1024, all metrics): one pair against the oracle, plus batch invariance."""
+    from codec_eval_b200.metrics import MetricConfig
+
+    w = h = 1024
+    ref = G(5, w, h)
+    dist = cheap_distort(ref, 75, seed=5)
+    r = gpu.evaluate_batch([(ref, dist, w, h)], MetricConfig.all())[0]
+    assert r.sse == O.sse(ref, dist)
+    assert abs(r.ssimulacra2 - O.ssimulacra2(ref, dist, w, h)) < S2_TOL
+    assert rel(r.dssim, O.dssim(ref, dist, w, h)) < DS_RTOL
+    emx, epn = O.butteraugli(ref, dist, w, h)
+    assert rel(r.butteraugli, emx) < BA_RTOL and rel(r.butteraugli_pnorm3, epn) < BA_RTOL
+    # the same pair inside a larger shared-reference batch gives the same bits
+    d2 = cheap_distort(ref, 50, seed=6)
+    many = gpu.evaluate_batch([(ref, d2, w, h), (ref, dist, w, h), (ref, ref, w, h)], MetricConfig.all())
+    assert (many[1].sse, many[1].ssimulacra2, many[1].dssim, many[1].butteraugli) == (r.sse, r.ssimulacra2, r.dssim, r.butteraugli)
+    assert many[2].sse == 0 and many[2].ssimulacra2 == 100.0 and many[2].dssim == 0.0 and many[2].butteraugli == 0.0
+    # stronger distortion scores worse on every metric
+    assert many[0].sse > r.sse and many[0].ssimulacra2 < r.ssimulacra2 and many[0].dssim > r.dssim and many[0].butteraugli > r.butteraugli
+
+
+def test_full_size_4k_dssim_butteraugli_vs_oracle(gpu, O):
+    """cfg4 shape (3840x2160, Butteraugli + DSSIM): odd pyramid levels (2160 -> ... -> 135 -> 67), one pair against the
+    oracle; identical pair is exactly zero."""
+    from codec_eval_b200.metrics import MetricConfig
+
+    w, h = 3840, 2160
+    ref = G(9, w, h)
+    dist = cheap_distort(ref, 85, seed=9)
+    cfg = MetricConfig(dssim=True, butteraugli=True, psnr=True)
+    r = gpu.evaluate_batch([(ref, dist, w, h), (ref, ref, w, h)], cfg)
+    assert r[0].sse == O.sse(ref, dist)
+    assert rel(r[0].dssim, O.dssim(ref, dist, w, h)) < DS_RTOL
+    emx, epn = O.butteraugli(ref, dist, w, h)
+    assert rel(r[0].butteraugli, emx) < BA_RTOL and rel(r[0].butteraugli_pnorm3, epn) < BA_RTOL
+    assert r[0].ssimulacra2 is None
+    assert r[1].sse == 0 and r[1].dssim == 0.0 and r[1].butteraugli == 0.0 and np.isinf(r[1].psnr)
+
+
+def test_codec_iter_sweep_shape_ssim2_only(gpu, O):
+    """cfg3 shape: 512x512 references x 3 qualities x {plain, XYB round-tripped reference}, SSIMULACRA2 only, through
+    the reference handle (Ssimulacra2Reference::new / .compare, crates/codec-iter/src/eval.rs:138-149)."""
+    from codec_eval_b200.metrics import GpuReference, MetricConfig
+
+    w = h = 512
+    for i in range(2):
+        ref = G(20 + i, w, h)
+        dists = [cheap_distort(ref, q, seed=i) for q in (75, 85, 95)]
+        for cfg in (MetricConfig.ssimulacra2_only(), MetricConfig.ssimulacra2_only().with_xyb_roundtrip()):
+            handle = GpuReference(gpu, ref, w, h, cfg)
+            got = [m.ssimulacra2 for m in handle.compare_many(dists)]
+            handle.close()
+            base = O.xyb_roundtrip(ref, w, h).reshape(h, w, 3) if cfg.xyb_roundtrip else ref
+            for g_, d in zip(got, dists):
+                assert abs(g_ - O.ssimulacra2(np.ascontiguousarray(base), d, w, h)) < S2_TOL
+            assert got[0] < got[1] < got[2]
