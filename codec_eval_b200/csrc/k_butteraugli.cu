@@ -249,7 +249,15 @@ __global__ void __launch_bounds__(256) k_ba_blur_h(const float* __restrict__ in,
     }
 }
 
-// vertical: tile 32 x 64, thread = 8 consecutive outputs of one column, NPL planes per image in one block.
+// splat of a blur weight over both lanes of a packed pair
+template <int SLOT>
+CE_DEVINL f32x2 baw2(int t) {
+    return pk2(baw<SLOT>(t), baw<SLOT>(t));
+}
+
+// vertical: tile 32 x 64, thread = 4 consecutive outputs of TWO adjacent columns held as packed fp32x2 pairs
+// (LDS.64 delivers the pair; FFMA2 = the scalar fused multiply-add in each lane, half the issue slots).  The NPL
+// planes of an image go through one block; plane c+1 is staged with cp.async while plane c is computed.
 // EPI 0: out[pl] = blurred plane (grid.z counts plane groups of NPL)
 // EPI 1 (NPL = 3): LF epilogue -- lf = blurred xyb; mf_pre = xyb - lf; lf scaled (XybLowFreqToVals)
 template <int SLOT, int R, int NPL, int EPI>
@@ -257,48 +265,66 @@ __global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in,
                                                     const float* __restrict__ inv, float* __restrict__ out,
                                                     const float* __restrict__ xyb, float* __restrict__ mf_pre) {
     constexpr int ROWS = 64 + 2 * R;
-    __shared__ __align__(16) float s[ROWS * 32];
+    __shared__ __align__(16) float s[2][ROWS * 32];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 64;
-    const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int x = x0 + cx;
+    const int cp = threadIdx.x & 15, g = threadIdx.x >> 4;   // 16 column pairs x 16 groups of 4 rows
+    const int x = x0 + 2 * cp;
     const size_t base = (size_t)blockIdx.z * NPL * n;
     const bool vec = (w & 3) == 0;
-    float res[NPL][8];
+    float res[NPL][4][2];
+    load_tile_async<8, ROWS, 256>(s[0], 32, in + base, w, h, x0, y0 - R, vec);
+    cp_async_commit();
 #pragma unroll
     for (int c = 0; c < NPL; c++) {
-        if (c) __syncthreads();
-        load_tile<0, 8, ROWS, 256>(s, 32, in + base + (size_t)c * n, w, h, x0, y0 - R, vec);
-        __syncthreads();
-        float v[8 + 2 * R];
-#pragma unroll
-        for (int q = 0; q < 8 + 2 * R; q++) v[q] = s[(g * 8 + q) * 32 + cx];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int y = y0 + g * 8 + k;
-            float sum = 0.0f;
-#pragma unroll
-            for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], baw<SLOT>(t), sum);
-            res[c][k] = sum * (y < h ? inv[y] : 0.0f);
+        if (c + 1 < NPL) {
+            load_tile_async<8, ROWS, 256>(s[(c + 1) & 1], 32, in + base + (size_t)(c + 1) * n, w, h, x0, y0 - R, vec);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
+        __syncthreads();
+        const float* sc = s[c & 1];
+        f32x2 v[4 + 2 * R];
+#pragma unroll
+        for (int q = 0; q < 4 + 2 * R; q++) v[q] = *reinterpret_cast<const f32x2*>(&sc[(g * 4 + q) * 32 + 2 * cp]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int y = y0 + g * 4 + k;
+            f32x2 sum = 0ULL;   // (+0, +0)
+#pragma unroll
+            for (int t = 0; t <= 2 * R; t++) sum = fma2(v[k + t], baw2<SLOT>(t), sum);
+            const float iy = y < h ? inv[y] : 0.0f;
+            float lo, hi;
+            unpk2(sum, lo, hi);
+            res[c][k][0] = lo * iy;
+            res[c][k][1] = hi * iy;
+        }
+        __syncthreads();   // plane c's buffer is refilled two planes later
     }
     if (x >= w) return;
+    const bool two = x + 1 < w;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int y = y0 + g * 8 + k;
+    for (int k = 0; k < 4; k++) {
+        const int y = y0 + g * 4 + k;
         if (y >= h) break;
         const size_t idx = base + (size_t)y * w + x;
-        if (EPI == 0) {
 #pragma unroll
-            for (int c = 0; c < NPL; c++) out[idx + (size_t)c * n] = res[c][k];
-        } else {
-            const float lx = res[0][k], ly = res[NPL > 1 ? 1 : 0][k], lb = res[NPL > 2 ? 2 : 0][k];
-            mf_pre[idx] = xyb[idx] - lx;
-            mf_pre[idx + n] = xyb[idx + n] - ly;
-            mf_pre[idx + 2 * n] = xyb[idx + 2 * n] - lb;
-            const float bb = __fmaf_rn(-0.362267051518f, ly, lb);
-            out[idx + 2 * n] = bb * 49.87984651440f;
-            out[idx] = lx * 33.832837186260f;
-            out[idx + n] = ly * 14.458268100570f;
+        for (int j = 0; j < 2; j++) {
+            if (j == 1 && !two) break;
+            if (EPI == 0) {
+#pragma unroll
+                for (int c = 0; c < NPL; c++) out[idx + j + (size_t)c * n] = res[c][k][j];
+            } else {
+                const float lx = res[0][k][j], ly = res[NPL > 1 ? 1 : 0][k][j], lb = res[NPL > 2 ? 2 : 0][k][j];
+                mf_pre[idx + j] = xyb[idx + j] - lx;
+                mf_pre[idx + j + n] = xyb[idx + j + n] - ly;
+                mf_pre[idx + j + 2 * n] = xyb[idx + j + 2 * n] - lb;
+                const float bb = __fmaf_rn(-0.362267051518f, ly, lb);
+                out[idx + j + 2 * n] = bb * 49.87984651440f;
+                out[idx + j] = lx * 33.832837186260f;
+                out[idx + j + n] = ly * 14.458268100570f;
+            }
         }
     }
 }
@@ -320,19 +346,28 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
     constexpr int RUP = (R + 3) & ~3;
     constexpr int PITCH = B2_TW + 2 * RUP;
     constexpr int ROWS = B2_TH + 2 * R;
-    __shared__ __align__(16) float s_in[ROWS * PITCH];
+    __shared__ __align__(16) float s_in2[2][ROWS * PITCH];   // plane c+1 is staged with cp.async while plane c is computed
     __shared__ __align__(16) float s_h[ROWS * B2_TW];
     const int x0 = blockIdx.x * B2_TW, y0 = blockIdx.y * B2_TH;
     const size_t img = blockIdx.z;
     const bool vec = (w & 3) == 0;
-    const int cx = threadIdx.x & 63, g = threadIdx.x >> 6;   // vertical pass: column cx, rows g*8 .. g*8+7
-    const int x = x0 + cx;
-    float res[NPL][8], ctr[NPL][8];
+    // vertical pass: thread = 4 rows (g*4 ..) of the two adjacent columns 2*cp, 2*cp+1, held as packed fp32x2 pairs
+    const int cp = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int x = x0 + 2 * cp;
+    float res[NPL][4][2], ctr[NPL][4][2];
+    load_tile_async<PITCH / 4, ROWS, 256>(s_in2[0], PITCH, in + (img * NPL) * n, w, h, x0 - RUP, y0 - R, vec);
+    cp_async_commit();
 #pragma unroll
     for (int c = 0; c < NPL; c++) {
-        if (c) __syncthreads();
-        load_tile<0, PITCH / 4, ROWS, 256>(s_in, PITCH, in + (img * NPL + c) * n, w, h, x0 - RUP, y0 - R, vec);
-        __syncthreads();
+        if (c + 1 < NPL) {
+            load_tile_async<PITCH / 4, ROWS, 256>(s_in2[(c + 1) & 1], PITCH, in + (img * NPL + c + 1) * n, w, h, x0 - RUP, y0 - R, vec);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();   // plane c staged; the previous plane's vertical pass is done with s_h
+        const float* s_in = s_in2[c & 1];
         for (int e = threadIdx.x; e < ROWS * (B2_TW / 4); e += 256) {
             const int r = e >> 4, q4 = e & 15;
             float v[4 + 2 * RUP];
@@ -355,37 +390,48 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
         }
         if (EPI != 0) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) ctr[c][k] = s_in[(g * 8 + k + R) * PITCH + cx + RUP];
+            for (int k = 0; k < 4; k++) {
+                const float2 t = *reinterpret_cast<const float2*>(&s_in[(g * 4 + k + R) * PITCH + 2 * cp + RUP]);
+                ctr[c][k][0] = t.x; ctr[c][k][1] = t.y;
+            }
         }
         __syncthreads();
-        float v[8 + 2 * R];
+        f32x2 v[4 + 2 * R];
 #pragma unroll
-        for (int q = 0; q < 8 + 2 * R; q++) v[q] = s_h[(g * 8 + q) * B2_TW + cx];
+        for (int q = 0; q < 4 + 2 * R; q++) v[q] = *reinterpret_cast<const f32x2*>(&s_h[(g * 4 + q) * B2_TW + 2 * cp]);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int y = y0 + g * 8 + k;
-            float sum = 0.0f;
+        for (int k = 0; k < 4; k++) {
+            const int y = y0 + g * 4 + k;
+            f32x2 sum = 0ULL;
 #pragma unroll
-            for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + t], baw<SLOT>(t), sum);
-            res[c][k] = sum * (y < h ? inv_y[y] : 0.0f);
+            for (int t = 0; t <= 2 * R; t++) sum = fma2(v[k + t], baw2<SLOT>(t), sum);
+            const float iy = y < h ? inv_y[y] : 0.0f;
+            float lo, hi;
+            unpk2(sum, lo, hi);
+            res[c][k][0] = lo * iy;
+            res[c][k][1] = hi * iy;
         }
     }
     if (x >= w) return;
+    const bool two = x + 1 < w;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int y = y0 + g * 8 + k;
+    for (int k = 0; k < 4; k++) {
+        const int y = y0 + g * 4 + k;
         if (y >= h) break;
-        const size_t i = (size_t)y * w + x;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+        if (j == 1 && !two) break;
+        const size_t i = (size_t)y * w + x + j;
         if (EPI == 0) {
 #pragma unroll
-            for (int c = 0; c < NPL; c++) out_a[(img * NPL + c) * n + i] = res[c][k];
+            for (int c = 0; c < NPL; c++) out_a[(img * NPL + c) * n + i] = res[c][k][j];
         } else if (EPI == 2) {
-            const float bx = res[0][k], by = res[NPL > 1 ? 1 : 0][k];
-            const float hfx = ctr[0][k] - bx, hfy = ctr[NPL > 1 ? 1 : 0][k] - by;
+            const float bx = res[0][k][j], by = res[NPL > 1 ? 1 : 0][k][j];
+            const float hfx = ctr[0][k][j] - bx, hfy = ctr[NPL > 1 ? 1 : 0][k][j] - by;
             float* M = out_a + img * 3 * n + i;
             M[0] = ba_remove_range(bx, 0.29f);
             M[n] = ba_amplify_range(by, 0.1f);
-            M[2 * n] = res[NPL > 2 ? 2 : 0][k];
+            M[2 * n] = res[NPL > 2 ? 2 : 0][k][j];
             const float scaler = __fmaf_rn(46.0f / __fmaf_rn(hfy, hfy, 46.0f), (float)(1.0 - 0.653020556257), 0.653020556257f);
             float* H = out_b + img * 2 * n + i;
             H[0] = scaler * hfx;
@@ -395,13 +441,13 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
             float* U = out_b + img * 2 * n + i;
             float hx, ux, hy, uy;
             {
-                const float hb = res[0][k];
-                ux = ba_remove_range(ctr[0][k] - hb, 0.04f);
+                const float hb = res[0][k][j];
+                ux = ba_remove_range(ctr[0][k][j] - hb, 0.04f);
                 hx = ba_remove_range(hb, 1.5f);
             }
             {
-                float hb = ba_max_clamp(res[NPL > 1 ? 1 : 0][k], 28.4691806922f);
-                float u = ctr[NPL > 1 ? 1 : 0][k] - hb;
+                float hb = ba_max_clamp(res[NPL > 1 ? 1 : 0][k][j], 28.4691806922f);
+                float u = ctr[NPL > 1 ? 1 : 0][k][j] - hb;
                 u = ba_max_clamp(u, 5.19175294647f);
                 uy = u * 2.69313763794f;
                 hb = hb * 2.155f;
@@ -415,6 +461,7 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
             const float yd = uy * 0.4f + hy * 0.4f;
             const float vv = sqrtf(xd * xd + yd * yd);
             out_c[img * n + i] = sqrtf(kMul * fabsf(vv) + bias) - sqrtf(bias);
+        }
         }
     }
 }
