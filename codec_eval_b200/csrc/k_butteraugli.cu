@@ -778,6 +778,92 @@ __global__ void __launch_bounds__(256) k_ba_combine(const float* __restrict__ bl
     }
 }
 
+// 4 pixels per thread (w % 4 == 0): the 3x3 stride-3 neighbourhood of the mask comes from three aligned
+// 128-bit loads per row (columns x-4 .. x+7), everything else from one 128-bit load per plane.
+__global__ void __launch_bounds__(256) k_ba_combine4(const float* __restrict__ bl, const float* __restrict__ ac,
+                                                      const float* __restrict__ mf, const float* __restrict__ lf, int w, int h,
+                                                      size_t n, size_t B, size_t R, const int* __restrict__ ridx, float xmul,
+                                                      float* __restrict__ diffmap) {
+    const int S = 3;
+    const int w4 = w >> 2;
+    const size_t per = n >> 2, total = B * per;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = t / per;
+        const int q = (int)(t - b * per);
+        const int y = q / w4, x = (q - y * w4) * 4;
+        const int i = y * w + x;
+        const size_t i0 = (size_t)ridx[b], i1 = R + b;
+        const float* from = bl + i0 * n;
+        // rows y-3, y, y+3, columns x-4 .. x+7 (values outside the image are never selected)
+        float win[3][12];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int yy = y + (r - 1) * S;
+            const bool yok = yy >= 0 && yy < h;
+#pragma unroll
+            for (int c4 = 0; c4 < 3; c4++) {
+                const int xx = x - 4 + 4 * c4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (yok && xx >= 0 && xx < w) v = *reinterpret_cast<const float4*>(from + yy * w + xx);
+                win[r][4 * c4] = v.x; win[r][4 * c4 + 1] = v.y; win[r][4 * c4 + 2] = v.z; win[r][4 * c4 + 3] = v.w;
+            }
+        }
+        const float4 b1 = *reinterpret_cast<const float4*>(bl + i1 * n + i);
+        const float4 a0 = *reinterpret_cast<const float4*>(ac + (b * 2 + 0) * n + i);
+        const float4 a1 = *reinterpret_cast<const float4*>(ac + (b * 2 + 1) * n + i);
+        const float4 m0 = *reinterpret_cast<const float4*>(mf + (i0 * 3 + 2) * n + i);
+        const float4 m1 = *reinterpret_cast<const float4*>(mf + (i1 * 3 + 2) * n + i);
+        float4 l0[3], l1[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            l0[c] = *reinterpret_cast<const float4*>(lf + (i0 * 3 + c) * n + i);
+            l1[c] = *reinterpret_cast<const float4*>(lf + (i1 * 3 + c) * n + i);
+        }
+        const float b1v[4] = {b1.x, b1.y, b1.z, b1.w}, a0v[4] = {a0.x, a0.y, a0.z, a0.w}, a1v[4] = {a1.x, a1.y, a1.z, a1.w};
+        const float m0v[4] = {m0.x, m0.y, m0.z, m0.w}, m1v[4] = {m1.x, m1.y, m1.z, m1.w};
+        const float l0v[3][4] = {{l0[0].x, l0[0].y, l0[0].z, l0[0].w}, {l0[1].x, l0[1].y, l0[1].z, l0[1].w}, {l0[2].x, l0[2].y, l0[2].z, l0[2].w}};
+        const float l1v[3][4] = {{l1[0].x, l1[0].y, l1[0].z, l1[0].w}, {l1[1].x, l1[1].y, l1[1].z, l1[1].w}, {l1[2].x, l1[2].y, l1[2].z, l1[2].w}};
+        float res[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int xk = x + k;
+            const int c = 4 + k;   // centre column in the window
+            const float ctr = win[1][c];
+            float mn0 = ctr, mn1 = 2.0f * mn0, mn2 = mn1;
+            const bool up = y >= S, dn = y < h - S;
+            if (xk >= S) {
+                store_min3(win[1][c - S], mn0, mn1, mn2);
+                if (up) store_min3(win[0][c - S], mn0, mn1, mn2);
+                if (dn) store_min3(win[2][c - S], mn0, mn1, mn2);
+            }
+            if (xk < w - S) {
+                store_min3(win[1][c + S], mn0, mn1, mn2);
+                if (up) store_min3(win[0][c + S], mn0, mn1, mn2);
+                if (dn) store_min3(win[2][c + S], mn0, mn1, mn2);
+            }
+            if (up) store_min3(win[0][c], mn0, mn1, mn2);
+            if (dn) store_min3(win[2][c], mn0, mn1, mn2);
+            const float mask = (0.45f * mn0 + 0.3f * mn1) + 0.25f * mn2;
+
+            const float dmk = ctr - b1v[k];
+            const float ac0 = a0v[k];
+            float ac1 = a1v[k];
+            ac1 += (10.0f * dmk) * dmk;
+            const float d2 = m0v[k] - m1v[k];
+            const float ac2 = (d2 * d2) * 16.2176043152f;
+            const float e0 = l0v[0][k] - l1v[0][k], e1 = l0v[1][k] - l1v[1][k], e2 = l0v[2][k] - l1v[2][k];
+            const float dc0 = (e0 * e0) * 29.2353797994f;
+            const float dc1 = (e1 * e1) * 0.844626970982f;
+            const float dc2 = (e2 * e2) * 0.703646627719f;
+            const float maskval = ba_mask_y(mask), dc_maskval = ba_mask_dc_y(mask);
+            const float dsum = ((dc0 * xmul) * dc_maskval + dc1 * dc_maskval) + dc2 * dc_maskval;
+            const float asum = ((ac0 * xmul) * maskval + ac1 * maskval) + ac2 * maskval;
+            res[k] = sqrtf(dsum + asum);
+        }
+        *reinterpret_cast<float4*>(diffmap + b * n + i) = make_float4(res[0], res[1], res[2], res[3]);
+    }
+}
+
 // ---------------------------------------------------------------- multi-resolution
 // SubSample2x on linear planes: [np][n] -> [np][on]; ((a+b)+c)+d)*0.25 with the x2 fix-ups
 __global__ void __launch_bounds__(256) k_ba_subsample(const float* __restrict__ in, int w, int h, size_t n, int ow, int oh,
@@ -989,8 +1075,13 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
         CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
                   k_ba_malta<<<grid, 256, 0, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, L.ac));
     }
-    CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,
-              k_ba_combine<<<ew_blocks(c, B * n), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul, diffmap));
+    if (w % 4 == 0)
+        CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,
+                  k_ba_combine4<<<ew_blocks(c, B * (n / 4)), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul,
+                                                                                diffmap));
+    else
+        CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,
+                  k_ba_combine<<<ew_blocks(c, B * n), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul, diffmap));
     CE_CUDA(cudaGetLastError());
     c.arena.release(mark);
 }
