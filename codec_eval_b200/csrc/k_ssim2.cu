@@ -242,25 +242,29 @@ __global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb,
     const int e_pl = threadIdx.x / 40, e_r = (threadIdx.x % 40) >> 3;   // threads 0..79: plane 5 + e_pl, row e_r
     const float* src_e = (e_pl ? i2 : i1) + x0 + 4 * cc4;
 
+    // issue() is called for t = 0, 1, 2, ... in order, so the source pointers just advance by 5 rows per call
+    const ptrdiff_t step = (ptrdiff_t)VP_BATCH * w;
+    const float* pp = src_p + (ptrdiff_t)cr * w;             // row j0 + cr of this warp's plane
+    const float* p4 = src_p + (ptrdiff_t)4 * w;              // row j0 + 4
+    const float* pe = src_e + ((ptrdiff_t)e_r - 4) * w;      // image row j0 + e_r - 4 (dereferenced only when inside)
+    int jn = 0;                                              // j0 of the next batch to issue
     auto issue = [&](int t) {
         if (t < nbatch) {
             float* slot = s_ld + (t & (VP_SLOTS - 1)) * VP_SLOT_FLOATS;
-            const int j0 = t * VP_BATCH;
+            const int j0 = jn;
             if (vec) {
                 {
-                    const int j = j0 + cr;
-                    const bool ok = cx_ok && j < h;
-                    cp_async16(slot + (cr * VP_PLANES + p) * VP_COLS + 4 * cc4, ok ? src_p + (size_t)j * w : hp, ok);
+                    const bool ok = cx_ok && j0 + cr < h;
+                    cp_async16(slot + (cr * VP_PLANES + p) * VP_COLS + 4 * cc4, ok ? pp : hp, ok);
                 }
                 if (lane < 8) {
-                    const int j = j0 + 4;
-                    const bool ok = cx_ok && j < h;
-                    cp_async16(slot + (4 * VP_PLANES + p) * VP_COLS + 4 * cc4, ok ? src_p + (size_t)j * w : hp, ok);
+                    const bool ok = cx_ok && j0 + 4 < h;
+                    cp_async16(slot + (4 * VP_PLANES + p) * VP_COLS + 4 * cc4, ok ? p4 : hp, ok);
                 }
                 if (threadIdx.x < 80) {
                     const int y = j0 + e_r - 4;
                     const bool ok = cx_ok && y >= 0 && y < h;
-                    cp_async16(slot + (e_r * VP_PLANES + 5 + e_pl) * VP_COLS + 4 * cc4, ok ? src_e + (size_t)y * w : hp, ok);
+                    cp_async16(slot + (e_r * VP_PLANES + 5 + e_pl) * VP_COLS + 4 * cc4, ok ? pe : hp, ok);
                 }
             } else {
                 for (int e = threadIdx.x; e < VP_BATCH * VP_PLANES * VP_COLS; e += 160) {
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb,
                     cp_async4(slot + (r * VP_PLANES + pl) * VP_COLS + cx, ok ? base + (size_t)row * w + xx : base, ok);
                 }
             }
+            pp += step; p4 += step; pe += step; jn += VP_BATCH;
         }
         cp_async_commit();
     };
