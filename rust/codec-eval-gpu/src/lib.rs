@@ -1,0 +1,95 @@
+//! Safe wrapper over `ce-gpu-sys` with codec-eval's types (src/metrics/mod.rs:45-149, src/error.rs:33-47).
+//! `GpuMetrics::evaluate_batch` is the batched entry `EvalSession::evaluate_image` (src/eval/session.rs:368-434)
+//! dispatches into; see `evaluate_image_batched` at the bottom for the session-side loop.
+use ce_gpu_sys as sys;
+use std::ffi::CStr;
+
+#[derive(Debug, Clone, Copy, Default, PartialEq)]
+pub struct MetricConfig { pub dssim: bool, pub ssimulacra2: bool, pub butteraugli: bool, pub psnr: bool, pub xyb_roundtrip: bool }
+
+#[derive(Debug, Clone, Default, PartialEq)]
+pub struct MetricResult { pub dssim: Option<f64>, pub ssimulacra2: Option<f64>, pub butteraugli: Option<f64>, pub psnr: Option<f64> }
+
+#[derive(Debug)]
+pub enum Error {
+    DimensionMismatch { expected: (usize, usize), actual: (usize, usize) },
+    MetricCalculation { metric: String, reason: String },
+}
+pub type Result<T> = std::result::Result<T, Error>;
+
+/// One CUDA device + stream + workspace.  Single owner (`!Sync`), like `GpuSsim2`
+/// (crates/codec-iter/src/gpu.rs:21-38).
+pub struct GpuMetrics { ctx: *mut sys::ce_ctx }
+unsafe impl Send for GpuMetrics {}
+
+impl GpuMetrics {
+    pub fn new(device: i32) -> Result<Self> {
+        let mut ctx = std::ptr::null_mut();
+        let st = unsafe { sys::ce_ctx_create(&mut ctx, device, 0) };
+        if st != sys::CE_OK {
+            let reason = unsafe { CStr::from_ptr(sys::ce_last_error(std::ptr::null())) }.to_string_lossy().into_owned();
+            return Err(Error::MetricCalculation { metric: "GPU".into(), reason });
+        }
+        Ok(Self { ctx })
+    }
+
+    fn last_error(&self) -> String {
+        unsafe { CStr::from_ptr(sys::ce_last_error(self.ctx)) }.to_string_lossy().into_owned()
+    }
+
+    /// Batched `calculate_metrics` (src/eval/session.rs:437-497).  Pairs that borrow the same reference slice are
+    /// grouped inside the library: the reference is uploaded and pre-processed once.
+    pub fn evaluate_batch(&mut self, pairs: &[(&[u8], &[u8], u32, u32)], cfg: &MetricConfig) -> Vec<Result<MetricResult>> {
+        let c_pairs: Vec<sys::ce_pair> = pairs.iter().enumerate().map(|(i, (r, t, w, h))| sys::ce_pair {
+            reference: r.as_ptr(), dist: t.as_ptr(), ref_len: r.len(), dist_len: t.len(),
+            width: *w, height: *h, ref_id: i as u32, reserved: 0,
+        }).collect();
+        let c_cfg = sys::ce_metric_config {
+            dssim: cfg.dssim as u8, ssimulacra2: cfg.ssimulacra2 as u8, butteraugli: cfg.butteraugli as u8,
+            psnr: cfg.psnr as u8, xyb_roundtrip: cfg.xyb_roundtrip as u8,
+        };
+        let mut out = vec![sys::ce_result::default(); pairs.len()];
+        let st = unsafe { sys::ce_evaluate_batch(self.ctx, c_pairs.as_ptr(), c_pairs.len(), &c_cfg, 80.0, out.as_mut_ptr()) };
+        if st != sys::CE_OK {
+            let reason = self.last_error();
+            return pairs.iter().map(|_| Err(Error::MetricCalculation { metric: "GPU".into(), reason: reason.clone() })).collect();
+        }
+        out.iter().zip(pairs).map(|(r, p)| match r.status {
+            sys::CE_OK => Ok(MetricResult {
+                dssim: (r.valid & 1 != 0).then_some(r.dssim),
+                ssimulacra2: (r.valid & 2 != 0).then_some(r.ssimulacra2),
+                butteraugli: (r.valid & 4 != 0).then_some(r.butteraugli),
+                psnr: (r.valid & 8 != 0).then_some(r.psnr),
+            }),
+            sys::CE_ERR_DIMENSION_MISMATCH => Err(Error::DimensionMismatch {        // src/metrics/ssimulacra2.rs:65-70
+                expected: (p.2 as usize, p.3 as usize),
+                actual: (p.1.len() / 3 / (p.3 as usize).max(1), p.3 as usize),
+            }),
+            _ => Err(Error::MetricCalculation { metric: "GPU".into(), reason: self.last_error() }),
+        }).collect()
+    }
+
+    /// `calculate_ssimulacra2` (src/metrics/ssimulacra2.rs:59-100) for one pair.
+    pub fn calculate_ssimulacra2(&mut self, reference: &[u8], test: &[u8], width: usize, height: usize) -> Result<f64> {
+        let mut score = 0.0f64;
+        let st = unsafe { sys::ce_ssimulacra2(self.ctx, reference.as_ptr(), reference.len(), test.as_ptr(), test.len(), width, height, &mut score) };
+        match st {
+            sys::CE_OK => Ok(score),
+            sys::CE_ERR_DIMENSION_MISMATCH => Err(Error::DimensionMismatch { expected: (width, height), actual: (test.len() / 3 / height.max(1), height) }),
+            _ => Err(Error::MetricCalculation { metric: "SSIMULACRA2".into(), reason: self.last_error() }),
+        }
+    }
+}
+
+impl Drop for GpuMetrics {
+    fn drop(&mut self) { unsafe { sys::ce_ctx_destroy(self.ctx) } }
+}
+
+/// The dispatch change inside `EvalSession::evaluate_image` (src/eval/session.rs:375-431): the caller has already
+/// encoded/decoded every (codec, quality) output of one reference; this fills the metric slots in order with ONE
+/// GPU call instead of one `calculate_metrics` call per output.
+pub fn evaluate_image_batched(gpu: &mut GpuMetrics, reference_rgb: &[u8], decoded_rgb: &[Vec<u8>], width: u32, height: u32,
+                              cfg: &MetricConfig) -> Result<Vec<MetricResult>> {
+    let pairs: Vec<(&[u8], &[u8], u32, u32)> = decoded_rgb.iter().map(|d| (reference_rgb, d.as_slice(), width, height)).collect();
+    gpu.evaluate_batch(&pairs, cfg).into_iter().collect()      // first per-pair error, like the `?` chain today
+}
