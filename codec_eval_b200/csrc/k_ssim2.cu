@@ -92,53 +92,71 @@ CE_DEVINL float rg_step(RGState& s, float sum) {
 #define HP_C4 (HP_COLS / 4)
 #define HP_PITCH (HP_COLS + 4)   // 16-B aligned rows; lane = row reads LDS.128 at chunk (C4+1)*row + q: conflict-free per quarter warp
 #define HP_SLOTS 3
-#define HP_SMEM_BYTES ((HP_SLOTS * 2 + 5) * HP_ROWS * HP_PITCH * 4)
 
-// grid (ceil(h/32), 3*B); block 160 = 5 warps (product) x 32 lanes (row).
-// warp p blurs product p of the band's 32 rows: 0 i1, 1 i2, 2 i1*i1, 3 i2*i2, 4 i1*i2 (one code path for all
-// five so the loop body stays inside the instruction cache).
+// Which blurs a launch computes.  The reference-side statistics (mu1 = blur(i1), blur(i1^2)) do not depend on the
+// distorted image, so when a sub-batch has shared references they are computed once per distinct reference
+// (S2_REF) and the per-pair launch (S2_PAIR) does the other three -- fast_ssim2's Ssimulacra2Reference split.
+enum { S2_ALL = 0, S2_REF = 1, S2_PAIR = 2 };
+template <int MODE> struct S2Mode {
+    static constexpr int NW = MODE == S2_ALL ? 5 : MODE == S2_REF ? 2 : 3;     // products = warps per block
+    static constexpr int NIN = MODE == S2_REF ? 1 : 2;                          // image planes staged by the row pass
+    static constexpr int HP_SMEM = (HP_SLOTS * NIN + NW) * HP_ROWS * HP_PITCH * 4;
+};
+
+// grid (ceil(h/32), 3*units); block NW warps (product) x 32 lanes (row); unit = pair (S2_ALL, S2_PAIR) or distinct
+// reference (S2_REF).  Warp p blurs one product of the band's 32 rows:
+//   S2_ALL: i1, i2, i1*i1, i2*i2, i1*i2      S2_REF: i1, i1*i1      S2_PAIR: i2, i2*i2, i1*i2
+// (one code path for all warps so the loop body stays inside the instruction cache).
 // The row is walked in HP_COLS-column chunks staged by cp.async (three slots, two chunks in flight,
 // zero-filled past the image, one block barrier per chunk).  Output n needs in[n+4] and in[n-6], so the
 // recurrence runs 4 columns behind the loads: chunk k (input columns k*HP_COLS ..) produces output columns
 // k*HP_COLS-4 .. ; the first four steps are the upstream warm-up (n = -4 .. -1), and
 // ceil((w+4)/HP_COLS) chunks reach the last column.  Each warp writes out the plane it produced.
-__global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb, size_t R, const int* __restrict__ ridx,
-                                                   float* __restrict__ hb, int w, int h, size_t n, int vec) {
-    extern __shared__ __align__(16) float s_dyn[];   // HP_SMEM_BYTES (> 48 KB: opt-in dynamic shared memory)
+// hb: [unit][3][NW][n].
+template <int MODE>
+__global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float* __restrict__ xyb, size_t R,
+                                                                     const int* __restrict__ ridx, float* __restrict__ hb,
+                                                                     int w, int h, size_t n, int vec) {
+    constexpr int NW = S2Mode<MODE>::NW, NIN = S2Mode<MODE>::NIN, NT = NW * 32;
+    extern __shared__ __align__(16) float s_dyn[];   // opt-in dynamic shared memory (> 48 KB)
     float* s_in = s_dyn;
     const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
-    float* so = s_dyn + HP_SLOTS * 2 * HP_ROWS * HP_PITCH + p * (HP_ROWS * HP_PITCH);
-    const size_t b = blockIdx.y / 3;
+    float* so = s_dyn + HP_SLOTS * NIN * HP_ROWS * HP_PITCH + p * (HP_ROWS * HP_PITCH);
+    const size_t u = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
     const int row0 = blockIdx.x * HP_ROWS;
-    const float* i1 = xyb + ((size_t)ridx[b] * 3 + c) * n;
-    const float* i2 = xyb + ((R + b) * 3 + c) * n;
-    float* op = hb + ((b * 3 + c) * 5 + p) * n;
+    const float* i1 = xyb + ((MODE == S2_REF ? u : (size_t)ridx[u]) * 3 + c) * n;
+    const float* i2 = xyb + ((R + u) * 3 + c) * n;   // unused by S2_REF
+    float* op = hb + ((u * 3 + c) * NW + p) * n;
     const int nchunks = (w + 4 + HP_COLS - 1) / HP_COLS;
-    // product roles
-    const int offA = (p == 1 || p == 3) ? HP_ROWS * HP_PITCH : 0;   // plane of the first factor
-    const int offB = (p >= 3) ? HP_ROWS * HP_PITCH : 0;             // plane of the second factor
-    const bool mul = p >= 2;
-    // loader role (threads 0..127): plane lpl, rows lr0 + (64/C4)*i, 16-B column group lc4
-    const int lpl = (threadIdx.x >> 6) & 1, lu = threadIdx.x & 63, lr0 = lu / HP_C4, lc4 = lu % HP_C4;
-    const float* lbase = lpl ? i2 : i1;
+    // product roles: plane of the first / second factor, and whether there is a second factor
+    int offA, offB;
+    bool mul;
+    if (MODE == S2_ALL) { offA = (p == 1 || p == 3) ? HP_ROWS * HP_PITCH : 0; offB = (p >= 3) ? HP_ROWS * HP_PITCH : 0; mul = p >= 2; }
+    else if (MODE == S2_REF) { offA = 0; offB = 0; mul = p == 1; }
+    else { offA = (p == 2) ? 0 : HP_ROWS * HP_PITCH; offB = HP_ROWS * HP_PITCH; mul = p >= 1; }
 
     auto issue = [&](int k) {
-        if (p < 4 && k < nchunks) {
-            const int x = k * HP_COLS + 4 * lc4;
-            float* dst = s_in + (((k % HP_SLOTS) * 2 + lpl) * HP_ROWS + lr0) * HP_PITCH + 4 * lc4;
+        if (k < nchunks) {
+            constexpr int ITEMS = NIN * HP_ROWS * HP_C4;
+            float* slot = s_in + (k % HP_SLOTS) * NIN * HP_ROWS * HP_PITCH;
 #pragma unroll
-            for (int i = 0; i < HP_C4 / 2; i++) {
-                const int rr = (64 / HP_C4) * i;
-                const int y = row0 + lr0 + rr;
+            for (int it = 0; it < (ITEMS + NT - 1) / NT; it++) {
+                const int e = (int)threadIdx.x + it * NT;
+                if (ITEMS % NT != 0 && e >= ITEMS) break;
+                const int pl = e / (HP_ROWS * HP_C4), rem = e - pl * (HP_ROWS * HP_C4);
+                const int rr = rem / HP_C4, c4 = rem - rr * HP_C4;
+                const int y = row0 + rr, x = k * HP_COLS + 4 * c4;
+                const float* base = (NIN == 2 && pl) ? i2 : i1;
+                float* dst = slot + (pl * HP_ROWS + rr) * HP_PITCH + 4 * c4;
                 if (vec) {
                     const bool ok = y < h && x < w;
-                    cp_async16(dst + rr * HP_PITCH, ok ? lbase + (size_t)y * w + x : lbase, ok);
+                    cp_async16(dst, ok ? base + (size_t)y * w + x : base, ok);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const bool ok = y < h && x + j < w;
-                        cp_async4(dst + rr * HP_PITCH + j, ok ? lbase + (size_t)y * w + x + j : lbase, ok);
+                        cp_async4(dst + j, ok ? base + (size_t)y * w + x + j : base, ok);
                     }
                 }
             }
@@ -154,7 +172,7 @@ __global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb,
         cp_async_wait<1>();
         __syncthreads();   // chunk k visible to all; every warp is past its reads of slot (k-1) % 3
         issue(k + 2);      // -> slot (k-1) % 3
-        const float* a = s_in + ((k % HP_SLOTS) * 2 * HP_ROWS + lane) * HP_PITCH;
+        const float* a = s_in + ((k % HP_SLOTS) * NIN * HP_ROWS + lane) * HP_PITCH;
 #pragma unroll 1
         for (int m0 = 0; m0 < HP_C4; m0 += 4) {
 #pragma unroll
@@ -169,13 +187,13 @@ __global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb,
                 float4 o;
                 float* L0 = (mm == 0) ? Q1 : (mm == 1) ? Q2 : (mm == 2) ? Q3 : Q0;   // group holding c-12..c-9
                 float* L1 = (mm == 0) ? Q2 : (mm == 1) ? Q3 : (mm == 2) ? Q0 : Q1;   // group holding c-8..c-5
-                float* NW = (mm == 0) ? Q0 : (mm == 1) ? Q1 : (mm == 2) ? Q2 : Q3;   // oldest group, replaced by the new one
+                float* NWQ = (mm == 0) ? Q0 : (mm == 1) ? Q1 : (mm == 2) ? Q2 : Q3;  // oldest group, replaced by the new one
                 o.x = rg_step(st, L0[2] + g4.x);
                 o.y = rg_step(st, L0[3] + g4.y);
                 o.z = rg_step(st, L1[0] + g4.z);
                 o.w = rg_step(st, L1[1] + g4.w);
                 *reinterpret_cast<float4*>(so + lane * HP_PITCH + 4 * m) = o;
-                NW[0] = g4.x; NW[1] = g4.y; NW[2] = g4.z; NW[3] = g4.w;
+                NWQ[0] = g4.x; NWQ[1] = g4.y; NWQ[2] = g4.z; NWQ[3] = g4.w;
             }
         }
         __syncwarp();
@@ -207,90 +225,114 @@ __global__ void __launch_bounds__(160) k_s2_hpass(const float* __restrict__ xyb,
 #define VP_COLS 32
 #define VP_BATCH 5
 #define VP_SLOTS 4
-#define VP_PLANES 7   // 5 row-pass planes + i1 + i2
-#define VP_SLOT_FLOATS (VP_BATCH * VP_PLANES * VP_COLS)
+#define VP_MAXITEMS 3   // staged 16-B items per thread and batch
 
-// grid (ceil(w/32), 3*B); block 160 = 5 warps x 32 lanes.  lane = column.  Each warp runs the recurrence of
-// ONE product down the column strip (10-row register delay line).  Rows arrive in batches of 5 through a
-// 4-slot cp.async ring (two batches in flight; every thread owns fixed copy slots so there is no index
-// arithmetic in the loop); the five blurred values of each pixel meet in shared memory and, one batch
-// later, warp r evaluates the SSIM / edge-artifact / detail-loss terms of row r of that batch -- so there
-// is ONE block barrier per 5 rows.  partials: [(b*3+c)][gridDim.x][6]
-__global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb, size_t R, const int* __restrict__ ridx,
-                                                   const float* __restrict__ hb, int w, int h, size_t n,
-                                                   double* __restrict__ partials, float* __restrict__ dbg, int vec) {
-    __shared__ __align__(16) float s_ld[VP_SLOTS * VP_SLOT_FLOATS];   // [slot][row r][plane][col]
-    __shared__ float s_v[2][VP_BATCH][5][VP_COLS];
+// grid (ceil(w/32), 3*units); block NW warps x 32 lanes.  lane = column.  Each warp runs the recurrence of ONE
+// product down the column strip (10-row register delay line).  Rows arrive in batches of 5 through a 4-slot
+// cp.async ring (two batches in flight; every thread owns fixed copy slots whose source pointers just advance).
+//   S2_ALL : ring planes = 5 row-pass planes + i1 + i2; the five blurred values of each pixel meet in shared memory
+//            and, one batch later, warp r evaluates the SSIM / edge-artifact / detail-loss terms of row r.
+//   S2_REF : ring planes = 2 row-pass planes; the finished mu1 / blur(i1^2) rows go to vref [r][3][2][n].
+//   S2_PAIR: ring planes = 3 row-pass planes + i1 + i2 + the reference's mu1 and blur(i1^2) rows (vref); the
+//            map rows of a batch are dealt over the three warps.
+// ONE block barrier per 5 rows.  partials: [(unit*3+c)][gridDim.x][6]
+template <int MODE>
+__global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float* __restrict__ xyb, size_t R,
+                                                                     const int* __restrict__ ridx,
+                                                                     const float* __restrict__ hb, float* __restrict__ vref,
+                                                                     int w, int h, size_t n, double* __restrict__ partials,
+                                                                     float* __restrict__ dbg, int vec) {
+    constexpr int NW = S2Mode<MODE>::NW, NT = NW * 32;
+    constexpr int NPL = MODE == S2_REF ? 2 : 7;          // ring planes
+    constexpr int SLOT_FLOATS = VP_BATCH * NPL * VP_COLS;
+    __shared__ __align__(16) float s_ld[VP_SLOTS * SLOT_FLOATS];   // [slot][row r][plane][col]
+    __shared__ float s_v[MODE == S2_REF ? 1 : 2][VP_BATCH][NW][VP_COLS];
     __shared__ double scratch[6 * 32];
     const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
     const int x0 = blockIdx.x * VP_COLS;
     const int x = x0 + lane;
-    const size_t b = blockIdx.y / 3;
+    const size_t u = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
     const bool active = x < w;
-    const float* i1 = xyb + ((size_t)ridx[b] * 3 + c) * n;
-    const float* i2 = xyb + ((R + b) * 3 + c) * n;
-    const float* hp = hb + ((b * 3 + c) * 5) * n;
+    const size_t iref = MODE == S2_REF ? u : (size_t)ridx[u];
+    const float* i1 = xyb + (iref * 3 + c) * n;
+    const float* i2 = xyb + ((R + u) * 3 + c) * n;
+    const float* hp = hb + ((u * 3 + c) * NW) * n;
+    const float* vr = MODE == S2_PAIR ? vref + ((iref * 3 + c) * 2) * n : nullptr;
     const int total = h + 4;  // input rows j = 0 .. h+3 (rows >= h are zero); output row y = j - 4
     const int nbatch = (total + VP_BATCH - 1) / VP_BATCH;
 
-    // copy roles.  vec: warp p brings plane p: lane -> (row lane/8, 16-B group lane%8) for rows 0..3, lanes 0..7 also row 4;
-    // threads 0..79 bring i1 / i2 (rows shifted by -4).
-    const int cr = lane >> 3, cc4 = lane & 7;
-    const bool cx_ok = x0 + 4 * cc4 < w;
-    const float* src_p = hp + (size_t)p * n + x0 + 4 * cc4;
-    const int e_pl = threadIdx.x / 40, e_r = (threadIdx.x % 40) >> 3;   // threads 0..79: plane 5 + e_pl, row e_r
-    const float* src_e = (e_pl ? i2 : i1) + x0 + 4 * cc4;
-
-    // issue() is called for t = 0, 1, 2, ... in order, so the source pointers just advance by 5 rows per call
+    // copy roles: item e -> (row r of the batch, ring plane pl, 16-B group c4); planes < NW are row-pass planes
+    // (row j0 + r), the others are image-space planes (row j0 + r - 4).
+    constexpr int ITEMS = VP_BATCH * NPL * (VP_COLS / 4);
+    const float* src[VP_MAXITEMS];
+    int srow[VP_MAXITEMS], sdst[VP_MAXITEMS];
+    static_assert((ITEMS + NT - 1) / NT <= VP_MAXITEMS, "copy roles");
+#pragma unroll
+    for (int it = 0; it < VP_MAXITEMS; it++) {
+        const int e = (int)threadIdx.x + it * NT;
+        src[it] = nullptr; srow[it] = 0; sdst[it] = 0;
+        if (e < ITEMS) {
+            const int r = e / (NPL * 8), rem = e - r * (NPL * 8), pl = rem >> 3, c4 = rem & 7;
+            const float* base;
+            if (pl < NW) base = hp + (size_t)pl * n;
+            else if (MODE == S2_ALL) base = (pl == 5) ? i1 : i2;
+            else base = (pl == 3) ? i1 : (pl == 4) ? i2 : vr + (size_t)(pl - 5) * n;
+            srow[it] = (pl < NW) ? r : r - 4;
+            sdst[it] = (r * NPL + pl) * VP_COLS + 4 * c4;
+            src[it] = (x0 + 4 * c4 < w) ? base + (ptrdiff_t)srow[it] * w + x0 + 4 * c4 : nullptr;
+        }
+    }
     const ptrdiff_t step = (ptrdiff_t)VP_BATCH * w;
-    const float* pp = src_p + (ptrdiff_t)cr * w;             // row j0 + cr of this warp's plane
-    const float* p4 = src_p + (ptrdiff_t)4 * w;              // row j0 + 4
-    const float* pe = src_e + ((ptrdiff_t)e_r - 4) * w;      // image row j0 + e_r - 4 (dereferenced only when inside)
-    int jn = 0;                                              // j0 of the next batch to issue
-    auto issue = [&](int t) {
+    int jn = 0;   // rows already issued
+    auto issue = [&](int t) {   // called for t = 0, 1, 2, ... in order
         if (t < nbatch) {
-            float* slot = s_ld + (t & (VP_SLOTS - 1)) * VP_SLOT_FLOATS;
-            const int j0 = jn;
+            float* slot = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS;
             if (vec) {
-                {
-                    const bool ok = cx_ok && j0 + cr < h;
-                    cp_async16(slot + (cr * VP_PLANES + p) * VP_COLS + 4 * cc4, ok ? pp : hp, ok);
-                }
-                if (lane < 8) {
-                    const bool ok = cx_ok && j0 + 4 < h;
-                    cp_async16(slot + (4 * VP_PLANES + p) * VP_COLS + 4 * cc4, ok ? p4 : hp, ok);
-                }
-                if (threadIdx.x < 80) {
-                    const int y = j0 + e_r - 4;
-                    const bool ok = cx_ok && y >= 0 && y < h;
-                    cp_async16(slot + (e_r * VP_PLANES + 5 + e_pl) * VP_COLS + 4 * cc4, ok ? pe : hp, ok);
+#pragma unroll
+                for (int it = 0; it < VP_MAXITEMS; it++) {
+                    if ((int)threadIdx.x + it * NT < ITEMS) {
+                        const int row = jn + srow[it];
+                        const bool ok = src[it] != nullptr && row >= 0 && row < h;
+                        cp_async16(slot + sdst[it], ok ? src[it] : hp, ok);
+                        if (src[it]) src[it] += step;
+                    }
                 }
             } else {
-                for (int e = threadIdx.x; e < VP_BATCH * VP_PLANES * VP_COLS; e += 160) {
-                    const int cx = e & 31, pl = (e >> 5) % VP_PLANES, r = e / (VP_PLANES * 32);
+                for (int e = threadIdx.x; e < VP_BATCH * NPL * VP_COLS; e += NT) {
+                    const int cx = e & 31, pl = (e >> 5) % NPL, r = e / (NPL * 32);
                     const int xx = x0 + cx;
-                    const int row = (pl < 5) ? j0 + r : j0 + r - 4;
-                    const float* base = (pl < 5) ? hp + (size_t)pl * n : (pl == 5 ? i1 : i2);
+                    const float* base;
+                    if (pl < NW) base = hp + (size_t)pl * n;
+                    else if (MODE == S2_ALL) base = (pl == 5) ? i1 : i2;
+                    else base = (pl == 3) ? i1 : (pl == 4) ? i2 : vr + (size_t)(pl - 5) * n;
+                    const int row = (pl < NW) ? jn + r : jn + r - 4;
                     const bool ok = row >= 0 && row < h && xx < w;
-                    cp_async4(slot + (r * VP_PLANES + pl) * VP_COLS + cx, ok ? base + (size_t)row * w + xx : base, ok);
+                    cp_async4(slot + (r * NPL + pl) * VP_COLS + cx, ok ? base + (size_t)row * w + xx : base, ok);
                 }
             }
-            pp += step; p4 += step; pe += step; jn += VP_BATCH;
+            jn += VP_BATCH;
         }
         cp_async_commit();
     };
 
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    // SSIM / edge terms of row r = p of batch t (values in s_v[t & 1], image rows in slot t % VP_SLOTS)
-    auto map_rows = [&](int t) {
-        const int y = t * VP_BATCH + p - 4;
+    // SSIM / edge terms of row r of batch t (blurred values in s_v[t & 1], image-space rows in slot t % VP_SLOTS)
+    auto map_row = [&](int t, int r) {
+        const int y = t * VP_BATCH + r - 4;
         if (y >= 0 && y < h && active) {
             const int bf = t & 1;
-            const float m1 = s_v[bf][p][0][lane], m2 = s_v[bf][p][1][lane], s11 = s_v[bf][p][2][lane],
-                        s22 = s_v[bf][p][3][lane], s12 = s_v[bf][p][4][lane];
-            const float* slot = s_ld + (t & (VP_SLOTS - 1)) * VP_SLOT_FLOATS + (p * VP_PLANES) * VP_COLS + lane;
-            const float a1 = slot[5 * VP_COLS], a2 = slot[6 * VP_COLS];
+            const float* slot = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS + (r * NPL) * VP_COLS + lane;
+            float m1, m2, s11, s22, s12, a1, a2;
+            if (MODE == S2_ALL) {
+                m1 = s_v[bf][r][0][lane]; m2 = s_v[bf][r][1][lane]; s11 = s_v[bf][r][2][lane];
+                s22 = s_v[bf][r][NW > 3 ? 3 : 0][lane]; s12 = s_v[bf][r][NW > 4 ? 4 : 0][lane];
+                a1 = slot[5 * VP_COLS]; a2 = slot[6 * VP_COLS];
+            } else {
+                m2 = s_v[bf][r][0][lane]; s22 = s_v[bf][r][1][lane]; s12 = s_v[bf][r][NW > 2 ? 2 : 0][lane];
+                a1 = slot[3 * VP_COLS]; a2 = slot[4 * VP_COLS];
+                m1 = slot[(NPL > 5 ? 5 : 0) * VP_COLS]; s11 = slot[(NPL > 6 ? 6 : 0) * VP_COLS];
+            }
             if (dbg) {
                 float* d = dbg + (size_t)c * 7 * n + (size_t)y * w + x;
                 d[0] = a1; d[n] = a2; d[2 * n] = m1; d[3 * n] = m2; d[4 * n] = s11; d[5 * n] = s22; d[6 * n] = s12;
@@ -317,6 +359,14 @@ __global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb,
             acc[5] += l2 * l2;
         }
     };
+    // rows of a batch are dealt over the warps: warp p takes rows p, p + NW, ...
+    auto map_rows = [&](int t) {
+#pragma unroll
+        for (int r0 = 0; r0 < VP_BATCH; r0 += NW) {
+            const int r = r0 + p;
+            if (r < VP_BATCH) map_row(t, r);
+        }
+    };
 
     issue(0);
     issue(1);
@@ -324,6 +374,7 @@ __global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb,
     float ring[2 * VP_BATCH];
 #pragma unroll
     for (int j = 0; j < 2 * VP_BATCH; j++) ring[j] = 0.0f;
+    float* vout = MODE == S2_REF ? vref + ((u * 3 + c) * 2 + p) * n : nullptr;
     for (int t0 = 0; t0 < nbatch; t0 += 2) {
 #pragma unroll
         for (int half = 0; half < 2; half++) {
@@ -332,18 +383,25 @@ __global__ void __launch_bounds__(160) k_s2_vpass(const float* __restrict__ xyb,
                 cp_async_wait<1>();
                 __syncthreads();   // batch t landed; s_v of batch t-1 complete; slot (t-2) % 4 free
                 issue(t + 2);
-                const float* in = s_ld + (t & (VP_SLOTS - 1)) * VP_SLOT_FLOATS + p * VP_COLS + lane;
+                const float* in = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS + p * VP_COLS + lane;
 #pragma unroll
                 for (int r = 0; r < VP_BATCH; r++) {
-                    const float rv = in[r * VP_PLANES * VP_COLS];
+                    const float rv = in[r * NPL * VP_COLS];
                     const float l = ring[half * VP_BATCH + r];
                     ring[half * VP_BATCH + r] = rv;
-                    s_v[half][r][p][lane] = rg_step(st, l + rv);
+                    const float o = rg_step(st, l + rv);
+                    if (MODE == S2_REF) {
+                        const int y = t * VP_BATCH + r - 4;
+                        if (y >= 0 && y < h && active) vout[(size_t)y * w + x] = o;
+                    } else {
+                        s_v[half][r][p][lane] = o;
+                    }
                 }
-                if (t > 0) map_rows(t - 1);
+                if (MODE != S2_REF && t > 0) map_rows(t - 1);
             }
         }
     }
+    if (MODE == S2_REF) return;
     __syncthreads();
     map_rows(nbatch - 1);
     block_sum<6>(acc, scratch);
@@ -371,7 +429,9 @@ __global__ void k_s2_reduce(const double* __restrict__ partials, int nblk, size_
 
 void ssim2_init(Context& c) {
     CE_CUDA(cudaMemcpyToSymbol(c_rg, &c.rg, sizeof(RGaussCoef), 0, cudaMemcpyHostToDevice));
-    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, HP_SMEM_BYTES));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_ALL>::HP_SMEM));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_REF>::HP_SMEM));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_PAIR>::HP_SMEM));
 }
 
 size_t ssim2_workspace_per_pair(size_t w, size_t h) {
@@ -387,7 +447,19 @@ int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t
     const size_t n0 = w * h, NI = R + B;
     if (NI > 65535 || B * 3 > 65535) throw CudaError("ssimulacra2 sub-batch too large for one launch");
     float* xyb = c.arena.alloc<float>(NI * 3 * n0);
-    float* hb = c.arena.alloc<float>(B * 15 * n0);
+    // shared references (on average >= 2 distortions each): reference-side blurs once per distinct reference
+    const bool split = 2 * R <= B;
+    float* hb = nullptr;    // [B][3][5][n]  (S2_ALL)
+    float* hbr = nullptr;   // [R][3][2][n]  row pass of {i1, i1^2}
+    float* vref = nullptr;  // [R][3][2][n]  finished mu1, blur(i1^2)
+    float* hbp = nullptr;   // [B][3][3][n]  row pass of {i2, i2^2, i1*i2}
+    if (split) {
+        hbr = c.arena.alloc<float>(R * 6 * n0);
+        vref = c.arena.alloc<float>(R * 6 * n0);
+        hbp = c.arena.alloc<float>(B * 9 * n0);
+    } else {
+        hb = c.arena.alloc<float>(B * 15 * n0);
+    }
     const size_t ow0 = (w + 1) / 2, oh0 = (h + 1) / 2;
     float* nl[2];  // ping-pong next-scale linear buffers, [NI][3][n/4]
     for (int i = 0; i < 2; i++) nl[i] = c.arena.alloc<float>(NI * 3 * ow0 * oh0);
@@ -409,17 +481,26 @@ int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t
                       k_s2_xyb_down<<<grid, 256, 0, c.stream>>>(l, (int)cw, (int)ch, (int)ow, (int)oh, n, ow * oh, xyb, d,
                                                                  has_next ? 1 : 0));
         }
-        {
-            dim3 grid(cdiv(ch, HP_ROWS), (unsigned)(B * 3));
-            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4,
-                      k_s2_hpass<<<grid, 160, HP_SMEM_BYTES, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, (cw % 4 == 0) ? 1 : 0));
-        }
+        const int vecf = (cw % 4 == 0) ? 1 : 0;
         const int nblk = cdiv(cw, VP_COLS);
         float* dbg = (dbg_planes && scale == 0) ? dbg_planes : nullptr;
-        {
-            dim3 grid(nblk, (unsigned)(B * 3));
+        if (split) {
+            dim3 ghr(cdiv(ch, HP_ROWS), (unsigned)(R * 3)), ghp(cdiv(ch, HP_ROWS), (unsigned)(B * 3));
+            dim3 gvr(nblk, (unsigned)(R * 3)), gvp(nblk, (unsigned)(B * 3));
+            CE_LAUNCH(c, "k_s2_hpass<ref>", (double)R * 3 * 3 * n * 4,
+                      k_s2_hpass<S2_REF><<<ghr, 64, S2Mode<S2_REF>::HP_SMEM, c.stream>>>(xyb, R, ridx, hbr, (int)cw, (int)ch, n, vecf));
+            CE_LAUNCH(c, "k_s2_vpass<ref>", (double)R * 3 * 4 * n * 4,
+                      k_s2_vpass<S2_REF><<<gvr, 64, 0, c.stream>>>(xyb, R, ridx, hbr, vref, (int)cw, (int)ch, n, nullptr, nullptr, vecf));
+            CE_LAUNCH(c, "k_s2_hpass<pair>", (double)B * 3 * 5 * n * 4,
+                      k_s2_hpass<S2_PAIR><<<ghp, 96, S2Mode<S2_PAIR>::HP_SMEM, c.stream>>>(xyb, R, ridx, hbp, (int)cw, (int)ch, n, vecf));
+            CE_LAUNCH(c, "k_s2_vpass<pair>", (double)B * 3 * 7 * n * 4,
+                      k_s2_vpass<S2_PAIR><<<gvp, 96, 0, c.stream>>>(xyb, R, ridx, hbp, vref, (int)cw, (int)ch, n, partials, dbg, vecf));
+        } else {
+            dim3 gh(cdiv(ch, HP_ROWS), (unsigned)(B * 3)), gv(nblk, (unsigned)(B * 3));
+            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4,
+                      k_s2_hpass<S2_ALL><<<gh, 160, S2Mode<S2_ALL>::HP_SMEM, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, vecf));
             CE_LAUNCH(c, "k_s2_vpass", (double)B * 3 * 7 * n * 4,
-                      k_s2_vpass<<<grid, 160, 0, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, partials, dbg, (cw % 4 == 0) ? 1 : 0));
+                      k_s2_vpass<S2_ALL><<<gv, 160, 0, c.stream>>>(xyb, R, ridx, hb, nullptr, (int)cw, (int)ch, n, partials, dbg, vecf));
         }
         {
             size_t total = B * 3 * 6;
