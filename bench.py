@@ -171,6 +171,28 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: everything else (NCCL's version banner, library chatter) is sent to
+    stderr by pointing fd 1 at fd 2; emit() writes the line to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +206,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -373,7 +396,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "per_metric": per_metric, "kernels": kernels, "sanity": sanity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
         if args.profile_out:
             with open(args.profile_out, "w") as f:
                 json.dump({"workload": desc, "steps": args.steps, "kernels": kernels, "roofline": roofline,
