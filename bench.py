@@ -168,7 +168,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "MPix-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 _REAL_STDOUT = None
