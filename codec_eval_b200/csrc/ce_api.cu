@@ -282,7 +282,7 @@ static void run_device_batch(Context& c, const uint8_t* d_ref, size_t n_ref, con
     const size_t fixed = 1 << 20;
     if (c.arena.cap < ppb + fixed) throw OomError("workspace too small for one pair of this size");
     size_t Bmax = (c.arena.cap - fixed) / ppb;
-    Bmax = std::min<size_t>(Bmax, 16384);
+    Bmax = std::min<size_t>(Bmax, 10000);   // keeps every grid.z (up to 3 planes x 2 images per pair) under 65535
     // raw per-pair device results: sse(1 u64) + s2 sums(108) + ds(10) + ba(4) doubles
     const size_t raw_doubles = 1 + 108 + 10 + 4;
     std::vector<int> local_of(ref_of ? n_ref : 0, -1);

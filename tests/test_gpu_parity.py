@@ -498,3 +498,37 @@ def test_codec_iter_sweep_shape_ssim2_only(gpu, O):
             for g_, d in zip(got, dists):
                 assert abs(g_ - O.ssimulacra2(np.ascontiguousarray(base), d, w, h)) < S2_TOL
             assert got[0] < got[1] < got[2]
+
+
+def test_many_tiny_pairs_and_workspace_limits(gpu, O):
+    """More pairs than one sub-batch may hold (grid.z limits), smallest legal size, and a workspace that cannot hold
+    one pair (CE_ERR_OUT_OF_MEMORY, no crash)."""
+    import torch
+
+    from codec_eval_b200 import _lib
+    from codec_eval_b200.metrics import CudaError, GpuMetrics, MetricConfig
+
+    w = h = 8
+    n = 12000
+    rng = np.random.default_rng(1)
+    refs = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    dists = np.clip(refs.astype(int) + rng.integers(-9, 10, refs.shape), 0, 255).astype(np.uint8)
+    d_ref, d_dist = torch.from_numpy(refs).cuda(), torch.from_numpy(dists).cuda()
+    out = gpu.evaluate_batch_device(d_ref.data_ptr(), d_dist.data_ptr(), n, w, h, MetricConfig.all())
+    torch.cuda.synchronize()
+    for i in (0, 4999, 9999, 10000, 11999):     # both sides of the sub-batch boundary
+        assert out[i].status == 0 and out[i].valid == 15
+        assert out[i].sse == O.sse(refs[i], dists[i])
+        assert abs(out[i].ssimulacra2 - O.ssimulacra2(refs[i], dists[i], w, h)) < S2_TOL
+        assert rel(out[i].dssim, O.dssim(refs[i], dists[i], w, h)) < DS_RTOL
+        assert rel(out[i].butteraugli, O.butteraugli(refs[i], dists[i], w, h)[0]) < BA_RTOL
+    tiny = GpuMetrics(0, workspace_bytes=8 << 20)
+    try:
+        big = np.zeros(1024 * 1024 * 3, np.uint8)
+        with pytest.raises(CudaError) as e:
+            tiny.evaluate_batch([(big, big, 1024, 1024)], MetricConfig.all())
+        assert f"status {_lib.CE_ERR_OUT_OF_MEMORY}" in str(e.value)
+        # the context is still usable afterwards
+        assert tiny.calculate_psnr(big[:192], big[:192], 8, 8) == float("inf")
+    finally:
+        tiny.close()
