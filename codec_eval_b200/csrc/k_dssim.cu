@@ -6,9 +6,9 @@
 //                  2x2 average of the linear planes for the next scale                 [HBM-bound]
 //   k_ds_blur2   : chroma pre-blur: the 3x3 kernel applied twice (clamp-replicate per pass) through a
 //                  shared-memory tile, 4 positions per thread from 128-bit shared loads [HBM-bound]
-//   k_ds_stats   : per channel the five double-3x3 blurs {ch1,ch2,ch1^2,ch2^2,ch1*ch2} of a 64x16 tile,
-//                  4 positions per thread from 128-bit shared loads; channel-averaged SSIM map
-//                  written once + fp64 block partial of its sum                        [FP32-issue bound]
+//   k_ds_stream  : per channel the five double-3x3 blurs {ch1,ch2,ch1^2,ch2^2,ch1*ch2}: a warp streams down a
+//                  60-column strip with both 3x3 passes as register windows (shared products and row sums);
+//                  channel-averaged SSIM map written once + fp64 partial of its sum    [FP32-issue bound]
 //   k_ds_mean    : fixed-order reduce -> sum(map), avg = max(mean,0)^(0.5^scale)
 //   k_ds_mad     : sum |avg - map_i| in fp64 -> block partials; k_ds_mad_reduce fixes the order
 #include "ce_common.cuh"
@@ -177,168 +177,318 @@ __global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chro
     }
 }
 
-// ------------------------------------------------------------------ statistics + SSIM map
+// ------------------------------------------------------------------ statistics + SSIM map (streaming)
 // The five double-3x3 blurs {ch1, ch2, ch1^2, ch2^2, ch1*ch2} per channel split by who owns them:
-//   k_ds_stats<0> (grid.z = distinct reference): mu1 = blur2(ch1), e11 = blur2(ch1^2) -> refstat [R][3][2][n],
+//   k_ds_stream<0> (grid.z = distinct reference): mu1 = blur2(ch1), e11 = blur2(ch1^2) -> refstat [R][3][2][n],
 //                  once per reference however many distortions it is compared with;
-//   k_ds_stats<1> (grid.z = pair): blur2 of {ch2, ch2^2, ch1*ch2}, then the channel-averaged SSIM map
-//                  (written once) + fp64 block partial of its sum.  partial: [B][tiles] doubles.
-// Block 320, 64x16 tile: the image tile(s) (+ halo 2, clamped) are staged per channel; the first 3x3 pass is
-// evaluated 4 positions per thread from 128-bit shared loads, the second pass likewise for the thread's 4
-// pixels; every quantity keeps the upstream operation sequence, channel sums accumulate in upstream order.
-#define DS_ST_THREADS 320
+//   k_ds_stream<1> (grid.z = pair): blur2 of {ch2, ch2^2, ch1*ch2}, then the channel-averaged SSIM map
+//                  (written once) + fp64 partial of its sum.  partial: [B][strips] doubles.
+//
+// One warp owns a strip of 60 output columns (lane = 2 adjacent columns; lanes 0 and 31 are halo lanes) and
+// walks down DSS rows, all three channels in registers, no shared memory and no block barrier.  The 3x3 pass
+//     out = ((v00*k0 + v01*k1) + v02*k0) + ((v10*k1 + v11*k4) + v12*k1) + ((v20*k0 + v21*k1) + v22*k0)
+// is evaluated with the upstream operation sequence, but every product v*k is formed once per input element and
+// the row sums  A = (p0[x-1] + p1[x]) + p0[x+1]  (top and bottom rows use the same weights) and
+// B = (p1[x-1] + p4[x]) + p1[x+1]  once per row:  out(r) = (A(r-1) + B(r)) + A(r+1).  That is 11 instead of 17
+// fp32 instructions per 3x3 evaluation with bit-identical results.  Both passes run as two chained 3-row
+// windows (6 registers per column and quantity); the clamp-replicate rule between the passes (a first-pass
+// value outside the image is the nearest inside first-pass value) is applied explicitly: horizontally by a
+// shuffle from the lane holding column 0 / w-1, vertically by pushing the first / last row twice.
+#define DSS_OUT 60
+#define DSS_PITCH 68     // floats per staged plane row: 2 pad + 64 window columns + 2 pad
+#define DSS_SLOTS 4      // ring depth (three rows in flight ahead of the one being consumed)
+
+// two-row window of one quantity: a[par] = A(r-2), a[par ^ 1] = A(r-1) for the tick parity par, b = B(r-1).
+// Pushing writes the new A over the oldest one, so with the tick loop unrolled by two no register moves remain.
+struct DsWin {
+    f32x2 a[2], b;   // each holds the lane's two columns
+};
+// row sums of the two columns of this lane from the four values at columns c0-1 .. c0+2
+// The products are scalar FMULs, the sums packed FADD2s (one issue slot for both columns); a packed multiply
+// feeding a packed add would be contracted into FFMA2 by ptxas and round differently from dssim-core's chain.
+CE_DEVINL void ds_rowsums(float vm, float v0, float v1, float v2, f32x2& A, f32x2& B) {
+    const float k0 = 0.095332f, k1 = 0.118095f, k4 = 0.146293f;
+    const float p0m = vm * k0, p00 = v0 * k0, p01 = v1 * k0, p02 = v2 * k0;
+    const float p1m = vm * k1, p10 = v0 * k1, p11 = v1 * k1, p12 = v2 * k1;
+    const float p40 = v0 * k4, p41 = v1 * k4;
+    A = add2(add2(pk2(p0m, p00), pk2(p10, p11)), pk2(p01, p02));
+    B = add2(add2(pk2(p1m, p10), pk2(p40, p41)), pk2(p11, p12));
+}
+CE_DEVINL void cp_async8(float* smem, const float* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(DS_ST_THREADS, 3) k_ds_stats(const float* __restrict__ img, size_t R,
-                                                                const int* __restrict__ ridx, int w, int h, size_t n,
-                                                                float* __restrict__ refstat, float* __restrict__ map,
-                                                                double* __restrict__ partial) {
-    constexpr int NQ = MODE == 0 ? 2 : 3;
-    constexpr int NIMG = MODE == 0 ? 1 : 2;
-    __shared__ __align__(16) float s_in[2][NIMG][DS_IH * DS_IW];   // [channel parity][image]: next channel prefetched
-    __shared__ __align__(16) float s_f[NQ][DS_FH * DS_FW];
-    __shared__ double scratch[32];
-    const int x0 = blockIdx.x * DS_TW, y0 = blockIdx.y * DS_TH;
+struct DsStream {
+    static constexpr int NQ = MODE == 0 ? 2 : 3;
+    static constexpr int NPL = MODE == 0 ? 3 : 12;   // staged planes per tick: inputs (+ the reference statistics)
+    static constexpr int SLOT = NPL * DSS_PITCH;
+    static constexpr unsigned FULL = 0xffffffffu;
+
+    DsWin s1[3][NQ], s2[3][NQ];
+    float sm11[2], sm12[2], sm22[2], ss1[2], ss2[2], ss12[2];
+    double acc;
+    int lane, c0, w;
+    bool left_edge, right_edge, st0, st1, v2ok;
+    int rsrc, rel;
+
+    // one channel's terms of the output row: o = second-pass values {mu2, e22, e12}, rs = staged {mu1, e11}
+    CE_DEVINL void terms(int c, const float (&o)[NQ][2], const float (&rmu)[2], const float (&re)[2]) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float mu1 = rmu[e], mu2 = o[0][e];
+            const float m11 = mu1 * mu1, m12 = mu1 * mu2, m22 = mu2 * mu2;
+            const float t1 = re[e] - m11, t2 = o[1][e] - m22, t12 = o[NQ - 1][e] - m12;
+            if (c == 0) { sm11[e] = m11; sm12[e] = m12; sm22[e] = m22; ss1[e] = t1; ss2[e] = t2; ss12[e] = t12; }
+            else { sm11[e] += m11; sm12[e] += m12; sm22[e] += m22; ss1[e] += t1; ss2[e] += t2; ss12[e] += t12; }
+        }
+    }
+    CE_DEVINL void store_ref(float* __restrict__ d0, size_t n, const float (&o)[NQ][2]) {   // d0: plane mu1 at the row start
+        if (v2ok && st0) {
+            *reinterpret_cast<float2*>(d0 + c0) = make_float2(o[0][0], o[0][1]);
+            *reinterpret_cast<float2*>(d0 + n + c0) = make_float2(o[1][0], o[1][1]);
+        } else {
+            if (st0 && c0 >= 0) { d0[c0] = o[0][0]; d0[n + c0] = o[1][0]; }
+            if (st1 && c0 + 1 >= 0) { d0[c0 + 1] = o[0][1]; d0[n + c0 + 1] = o[1][1]; }
+        }
+    }
+    CE_DEVINL void finish_row(float* __restrict__ d, bool emit) {   // d: map row start
+        const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f, third = 1.0f / 3.0f;
+        float vv[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float mu1_sq = sm11[e] * third, mu2_sq = sm22[e] * third, mu1_mu2 = sm12[e] * third;
+            const float sigma1_sq = ss1[e] * third, sigma2_sq = ss2[e] * third, sigma12 = ss12[e] * third;
+            vv[e] = (__fmaf_rn(2.0f, mu1_mu2, c1) * __fmaf_rn(2.0f, sigma12, c2)) /
+                    (((mu1_sq + mu2_sq) + c1) * ((sigma1_sq + sigma2_sq) + c2));
+        }
+        if (!emit) return;
+        if (v2ok && st0) {
+            *reinterpret_cast<float2*>(d + c0) = make_float2(vv[0], vv[1]);
+            acc += (double)vv[0] + (double)vv[1];
+        } else {
+            if (st0 && c0 >= 0) { d[c0] = vv[0]; acc += (double)vv[0]; }
+            if (st1 && c0 + 1 >= 0) { d[c0 + 1] = vv[1]; acc += (double)vv[1]; }
+        }
+    }
+
+    // One tick: consume the staged input row (slot), advance the first pass, push the finished first-pass row into
+    // the second pass and form the output row.  Straight-line code: during the first ticks of a strip the windows
+    // are still filling and the values are meaningless; only the stores and the pooled sum are predicated (emit).
+    template <int PAR>
+    CE_DEVINL void tick(const float* __restrict__ slot, bool emit, float* __restrict__ ref_row, size_t n,
+                        float* __restrict__ map_row) {
+        const float* sl = slot + 2 * lane + 1;   // column c0 - 1 of plane 0
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float in[NQ][4];
+            {
+                const float* pa = sl + c * DSS_PITCH;
+                const float am = pa[0], a3 = pa[3];
+                const float2 a12 = *reinterpret_cast<const float2*>(pa + 1);
+                if (MODE == 0) {
+                    in[0][0] = am; in[0][1] = a12.x; in[0][2] = a12.y; in[0][3] = a3;
+                    in[1][0] = am * am; in[1][1] = a12.x * a12.x; in[1][2] = a12.y * a12.y; in[1][3] = a3 * a3;
+                } else {
+                    const float* pb = sl + (3 + c) * DSS_PITCH;
+                    const float bm = pb[0], b3 = pb[3];
+                    const float2 b12 = *reinterpret_cast<const float2*>(pb + 1);
+                    in[0][0] = bm; in[0][1] = b12.x; in[0][2] = b12.y; in[0][3] = b3;
+                    in[1][0] = bm * bm; in[1][1] = b12.x * b12.x; in[1][2] = b12.y * b12.y; in[1][3] = b3 * b3;
+                    in[NQ - 1][0] = am * bm; in[NQ - 1][1] = a12.x * b12.x; in[NQ - 1][2] = a12.y * b12.y; in[NQ - 1][3] = a3 * b3;
+                }
+            }
+            float f[NQ][2];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                f32x2 A, B;
+                ds_rowsums(in[q][0], in[q][1], in[q][2], in[q][3], A, B);
+                DsWin& s = s1[c][q];
+                unpk2(add2(add2(s.a[PAR], s.b), A), f[q][0], f[q][1]);
+                s.a[PAR] = A;
+                s.b = B;
+            }
+            // clamp-replicate of the first pass in x: columns < 0 take column 0, columns > w-1 take column w-1
+            if (left_edge) {
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    const float t = __shfl_sync(FULL, f[q][0], 1);
+                    if (lane == 0) { f[q][0] = t; f[q][1] = t; }
+                }
+            }
+            if (right_edge) {
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    const float t = __shfl_sync(FULL, rel ? f[q][1] : f[q][0], rsrc);
+                    if (c0 > w - 1) f[q][0] = t;
+                    if (c0 + 1 > w - 1) f[q][1] = t;
+                }
+            }
+            float o[NQ][2];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const float fm = __shfl_up_sync(FULL, f[q][1], 1), f2 = __shfl_down_sync(FULL, f[q][0], 1);
+                f32x2 A, B;
+                ds_rowsums(fm, f[q][0], f[q][1], f2, A, B);
+                DsWin& s = s2[c][q];
+                unpk2(add2(add2(s.a[PAR], s.b), A), o[q][0], o[q][1]);
+                s.a[PAR] = A;
+                s.b = B;
+            }
+            if (MODE == 0) {
+                if (emit) store_ref(ref_row + (size_t)c * 2 * n, n, o);
+            } else {
+                const float2 mu = *reinterpret_cast<const float2*>(sl + (6 + 2 * c) * DSS_PITCH + 1);
+                const float2 ee = *reinterpret_cast<const float2*>(sl + (7 + 2 * c) * DSS_PITCH + 1);
+                const float rmu[2] = {mu.x, mu.y}, re[2] = {ee.x, ee.y};
+                terms(c, o, rmu, re);
+            }
+        }
+        if (MODE == 1) finish_row(map_row, emit);
+    }
+    // row 0 also stands for row -1: the second-pass window holds its row sums twice
+    CE_DEVINL void dup_top() {
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int q = 0; q < NQ; q++) s2[c][q].a[1] = s2[c][q].a[0];
+    }
+};
+
+// grid (column strips, row strips, units); block = one warp; unit = distinct reference (MODE 0) or pair (MODE 1)
+template <int MODE>
+__global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ img, size_t R, const int* __restrict__ ridx, int w,
+                                                   int h, size_t n, int rows_per_strip, float* __restrict__ refstat,
+                                                   float* __restrict__ map, double* __restrict__ partial) {
+    typedef DsStream<MODE> S;
+    constexpr int NQ = S::NQ;
+    __shared__ __align__(16) float ring[DSS_SLOTS * S::SLOT];
+    S st;
+    const int lane = threadIdx.x;
+    const int xw = (int)blockIdx.x * DSS_OUT - 2;   // first column of the warp's 64-column window
+    const int c0 = xw + 2 * lane;                   // this lane's columns c0, c0 + 1 (may lie outside the image)
+    const int ys = (int)blockIdx.y * rows_per_strip, ye = min(ys + rows_per_strip, h);
     const size_t b = blockIdx.z;
     const size_t im1 = MODE == 0 ? b : (size_t)ridx[b];   // reference image
     const size_t im2 = R + b;                             // distorted image (pair mode)
-    const bool vec = (w & 3) == 0;
-    const int g = threadIdx.x & 15, oy = threadIdx.x >> 4;   // second pass: threads 0..255
-    const bool p2 = threadIdx.x < 256;
-    const int x = x0 + 4 * g, y = y0 + oy;
-    const bool live = p2 && x < w && y < h;
-    const int pix = live ? y * w + x : 0;
-    float sm11[4], sm12[4], sm22[4], ss1[4], ss2[4], ss12[4];
-    // Tiles whose halo lies inside the image (block-uniform) are staged with cp.async one channel ahead; tiles on
-    // the image border need clamped coordinates and are loaded synchronously.
-    const bool interior = vec && x0 - 4 >= 0 && x0 - 4 + DS_IW <= w && y0 - 2 >= 0 && y0 - 2 + DS_IH <= h;
-    auto prefetch = [&](int c) {
-        if (interior) {
-            load_tile_async<DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[c & 1][0], DS_IW, img + (im1 * 3 + c) * n, w, h, x0 - 4, y0 - 2, true);
-            if (MODE == 1)
-                load_tile_async<DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[c & 1][NIMG - 1], DS_IW, img + (im2 * 3 + c) * n, w, h, x0 - 4,
-                                                                 y0 - 2, true);
+    const int cc0 = min(max(c0, 0), w - 1), cc1 = min(max(c0 + 1, 0), w - 1);
+    const bool allvec = (w & 1) == 0 && xw >= 0 && xw + 63 < w;   // warp-uniform: every lane's pair is inside and 8-B aligned
+    st.lane = lane; st.c0 = c0; st.w = w;
+    st.v2ok = (w & 1) == 0 && c0 >= 0 && c0 + 1 < w;
+    st.left_edge = xw < 0; st.right_edge = xw + 63 > w - 1;
+    st.rsrc = (w - 1 - xw) >> 1; st.rel = (w - 1 - xw) & 1;   // lane / element holding column w-1
+    st.st0 = lane >= 1 && lane <= 30 && c0 < w; st.st1 = lane >= 1 && lane <= 30 && c0 + 1 < w;
+    st.acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                st.s1[c][q].a[k] = 0ull; st.s2[c][q].a[k] = 0ull;
+                st.s1[c][q].b = 0ull; st.s2[c][q].b = 0ull;
+            }
+
+    // first-pass rows needed: r_lo .. r_hi; input rows r_lo-1 .. r_hi+1 (clamped); tick k consumes input row r_lo-1+k,
+    // finishes first-pass row r_lo+k-2 and (k >= kfirst) output row ys + k - kfirst
+    const int r_lo = max(ys - 1, 0), r_hi = min(ye, h - 1);
+    const int nin = r_hi - r_lo + 3;
+    const int kfirst = ys == 0 ? 3 : 4;
+    const float* p1 = img + im1 * 3 * n;
+    const float* p2 = img + im2 * 3 * n;                 // unused in ref mode
+    const float* prs = refstat + im1 * 6 * n;            // pair mode: [3][2][n] statistics of the reference
+    float* my = ring + 2 + 2 * lane;                     // this lane's two columns of plane 0, slot 0
+    auto issue = [&](int k) {
+        if (k < nin) {
+            float* d = my + (k & (DSS_SLOTS - 1)) * S::SLOT;
+            const size_t ro = (size_t)min(max(r_lo - 1 + k, 0), h - 1) * w;
+            const int y = ys + k - kfirst;
+            const bool stats = MODE == 1 && k >= kfirst && y < h;
+            const size_t so = (size_t)min(max(y, 0), h - 1) * w;
+            if (allvec) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    cp_async8(d + c * DSS_PITCH, p1 + c * n + ro + c0);
+                    if (MODE == 1) cp_async8(d + (3 + c) * DSS_PITCH, p2 + c * n + ro + c0);
+                }
+                if (stats) {
+#pragma unroll
+                    for (int j = 0; j < 6; j++) cp_async8(d + (6 + j) * DSS_PITCH, prs + j * n + so + c0);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    cp_async4(d + c * DSS_PITCH, p1 + c * n + ro + cc0, true);
+                    cp_async4(d + c * DSS_PITCH + 1, p1 + c * n + ro + cc1, true);
+                    if (MODE == 1) {
+                        cp_async4(d + (3 + c) * DSS_PITCH, p2 + c * n + ro + cc0, true);
+                        cp_async4(d + (3 + c) * DSS_PITCH + 1, p2 + c * n + ro + cc1, true);
+                    }
+                }
+                if (stats) {
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        cp_async4(d + (6 + j) * DSS_PITCH, prs + j * n + so + cc0, true);
+                        cp_async4(d + (6 + j) * DSS_PITCH + 1, prs + j * n + so + cc1, true);
+                    }
+                }
+            }
         }
         cp_async_commit();
     };
-    prefetch(0);
+    issue(0);
+    issue(1);
+    issue(2);
+    float* ref_out = MODE == 0 ? refstat + b * 6 * n : nullptr;
+    float* map_out = MODE == 1 ? map + b * n : nullptr;
+    for (int k = 0; k < nin; k += 2) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        // everyone is past the first pass of channel c-1 (it read buffer (c+1) & 1) -- see the barriers below
-        if (c + 1 < 3) prefetch(c + 1);
-        if (interior) {
-            if (c + 1 < 3) cp_async_wait<1>(); else cp_async_wait<0>();
-        } else {
-            load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[c & 1][0], DS_IW, img + (im1 * 3 + c) * n, w, h, x0 - 4, y0 - 2, vec);
-            if (MODE == 1)
-                load_tile<2, DS_IW / 4, DS_IH, DS_ST_THREADS>(s_in[c & 1][NIMG - 1], DS_IW, img + (im2 * 3 + c) * n, w, h, x0 - 4,
-                                                              y0 - 2, vec);
-        }
-        __syncthreads();   // tiles of channel c visible; previous channel's second pass is done with s_f
-        if (threadIdx.x < DS_FH * DS_FG) {
-            const int ry = threadIdx.x / DS_FG, q = threadIdx.x - ry * DS_FG;
-            float u[3][8], t[3][8];
-#pragma unroll
-            for (int r = 0; r < 3; r++) ds_ld8(s_in[c & 1][0] + (ry + r) * DS_IW + 4 * q, u[r]);
-            float* o = &s_f[0][ry * DS_FW + 4 * q];
-            if (MODE == 0) {
-                *reinterpret_cast<float4*>(o) = ds_k9x4(u[0], u[1], u[2]);
-#pragma unroll
-                for (int r = 0; r < 3; r++)
-#pragma unroll
-                    for (int i = 1; i < 7; i++) t[r][i] = u[r][i] * u[r][i];
-                *reinterpret_cast<float4*>(o + DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
-            } else {
-                float v[3][8];
-#pragma unroll
-                for (int r = 0; r < 3; r++) ds_ld8(s_in[c & 1][NIMG - 1] + (ry + r) * DS_IW + 4 * q, v[r]);
-                *reinterpret_cast<float4*>(o) = ds_k9x4(v[0], v[1], v[2]);
-#pragma unroll
-                for (int r = 0; r < 3; r++)
-#pragma unroll
-                    for (int i = 1; i < 7; i++) t[r][i] = v[r][i] * v[r][i];
-                *reinterpret_cast<float4*>(o + DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
-#pragma unroll
-                for (int r = 0; r < 3; r++)
-#pragma unroll
-                    for (int i = 1; i < 7; i++) t[r][i] = u[r][i] * v[r][i];
-                *reinterpret_cast<float4*>(o + 2 * DS_FH * DS_FW) = ds_k9x4(t[0], t[1], t[2]);
+        for (int par = 0; par < 2; par++) {
+            const int kk = k + par;
+            if (kk < nin) {   // warp-uniform
+                cp_async_wait<2>();
+                __syncwarp();   // row kk landed for every lane; every lane is past its reads of slot (kk - 1) & 3
+                issue(kk + 3);
+                const int y = ys + kk - kfirst;
+                const bool emit = kk >= kfirst;
+                const float* slot = ring + (kk & (DSS_SLOTS - 1)) * S::SLOT;
+                float* rr = MODE == 0 ? ref_out + (size_t)max(y, 0) * w : nullptr;
+                float* mr = MODE == 1 ? map_out + (size_t)max(y, 0) * w : nullptr;
+                if (par == 0) st.template tick<0>(slot, emit, rr, n, mr);
+                else st.template tick<1>(slot, emit, rr, n, mr);
+                if (kk == 2 && ys == 0) st.dup_top();   // tick 2 (parity 0) pushed first-pass row 0
             }
         }
-        __syncthreads();
-        ds_fix_border(&s_f[0][0], NQ, DS_FH * DS_FW, w, h, x0, y0);
-        __syncthreads();
-        if (p2) {
-            float q[NQ][4];
+    }
+    cp_async_wait<0>();
+    if (ye == h) {
+        // the last first-pass row also stands for row h: one more output row, y = h-1, from the window as it is:
+        // A(h-2) = a[par], B(h-1) = b, A(h) := A(h-1) = a[par ^ 1] where par is the parity after the last tick
+        const int par = nin & 1;
+        const int y = h - 1;
 #pragma unroll
-            for (int f = 0; f < NQ; f++) {
-                float r0[8], r1[8], r2[8];
-                const float* base = s_f[f] + oy * DS_FW + 4 * g;
-                ds_ld8(base, r0); ds_ld8(base + DS_FW, r1); ds_ld8(base + 2 * DS_FW, r2);
-                const float4 o = ds_k9x4(r0, r1, r2);
-                q[f][0] = o.x; q[f][1] = o.y; q[f][2] = o.z; q[f][3] = o.w;
+        for (int c = 0; c < 3; c++) {
+            float o[NQ][2];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const DsWin& s = st.s2[c][q];
+                const f32x2 a_old = par ? s.a[1] : s.a[0], a_new = par ? s.a[0] : s.a[1];
+                unpk2(add2(add2(a_old, s.b), a_new), o[q][0], o[q][1]);
             }
-            if (MODE == 0) {
-                if (live) {
-                    float* d0 = refstat + ((b * 3 + c) * 2) * n + pix;
-                    if (vec) {
-                        *reinterpret_cast<float4*>(d0) = make_float4(q[0][0], q[0][1], q[0][2], q[0][3]);
-                        *reinterpret_cast<float4*>(d0 + n) = make_float4(q[1][0], q[1][1], q[1][2], q[1][3]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if (x + k < w) { d0[k] = q[0][k]; d0[n + k] = q[1][k]; }
-                    }
-                }
-            } else {
-                float r_mu[4] = {0, 0, 0, 0}, r_e[4] = {0, 0, 0, 0};
-                if (live) {
-                    const float* s0 = refstat + ((im1 * 3 + c) * 2) * n + pix;
-                    if (vec) {
-                        const float4 a = *reinterpret_cast<const float4*>(s0), e = *reinterpret_cast<const float4*>(s0 + n);
-                        r_mu[0] = a.x; r_mu[1] = a.y; r_mu[2] = a.z; r_mu[3] = a.w;
-                        r_e[0] = e.x; r_e[1] = e.y; r_e[2] = e.z; r_e[3] = e.w;
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if (x + k < w) { r_mu[k] = s0[k]; r_e[k] = s0[n + k]; }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float mu1 = r_mu[k], mu2 = q[0][k];
-                    const float m11 = mu1 * mu1, m12 = mu1 * mu2, m22 = mu2 * mu2;
-                    const float s1 = r_e[k] - m11, s2 = q[1][k] - m22, s12 = q[NQ - 1][k] - m12;
-                    if (c == 0) { sm11[k] = m11; sm12[k] = m12; sm22[k] = m22; ss1[k] = s1; ss2[k] = s2; ss12[k] = s12; }
-                    else { sm11[k] += m11; sm12[k] += m12; sm22[k] += m22; ss1[k] += s1; ss2[k] += s2; ss12[k] += s12; }
-                }
+            if (MODE == 0) st.store_ref(ref_out + (size_t)y * w + (size_t)c * 2 * n, n, o);
+            else {
+                float rmu[2], re[2];
+                const float* q0 = prs + (size_t)(2 * c) * n + (size_t)y * w;
+                rmu[0] = q0[cc0]; rmu[1] = q0[cc1]; re[0] = q0[n + cc0]; re[1] = q0[n + cc1];
+                st.terms(c, o, rmu, re);
             }
         }
+        if (MODE == 1) st.finish_row(map_out + (size_t)y * w, true);
     }
     if (MODE == 0) return;
-    const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f, third = 1.0f / 3.0f;
-    double acc = 0.0;
-    if (live) {
-        float vv[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float mu1_sq = sm11[k] * third, mu2_sq = sm22[k] * third, mu1_mu2 = sm12[k] * third;
-            const float sigma1_sq = ss1[k] * third, sigma2_sq = ss2[k] * third, sigma12 = ss12[k] * third;
-            vv[k] = (__fmaf_rn(2.0f, mu1_mu2, c1) * __fmaf_rn(2.0f, sigma12, c2)) /
-                    (((mu1_sq + mu2_sq) + c1) * ((sigma1_sq + sigma2_sq) + c2));
-        }
-        float* d = map + b * n + pix;
-        if (vec) {
-            *reinterpret_cast<float4*>(d) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-            acc = (((double)vv[0] + (double)vv[1]) + (double)vv[2]) + (double)vv[3];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (x + k < w) { d[k] = vv[k]; acc += (double)vv[k]; }
-        }
-    }
-    double a1[1] = {acc};
-    block_sum<1>(a1, scratch);
-    if (threadIdx.x == 0) partial[(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a1[0];
+    const double tot = warp_sum(st.acc);
+    if (lane == 0) partial[(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
 }
 
 // one thread per pair: sum partials in fixed order; out[b][scale][0] = sum; avg[b] = max(mean,0)^(0.5^scale)
@@ -395,7 +545,7 @@ int dssim_num_scales(size_t w, size_t h, size_t* ws, size_t* hs) {
 
 size_t dssim_workspace_per_pair(size_t w, size_t h) {
     size_t n = w * h;
-    size_t tiles = (size_t)cdiv(w, DS_TW) * cdiv(h, DS_TH);
+    size_t tiles = (size_t)cdiv(w, DSS_OUT) * cdiv(h, 16);
     // img 6n, chroma 4n, map n, reference statistics 6n, next-scale rgb(a) ping-pong 2*2*4*(n/4)
     return (6 * n + 4 * n + n + 6 * n + 4 * n) * 4 + (tiles + DS_MAD_BLOCKS + 4) * 8 + 8192;
 }
@@ -411,8 +561,8 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
     float* chroma = c.arena.alloc<float>(NI * 2 * n0);
     float* map = c.arena.alloc<float>(B * n0);
     float* refstat = c.arena.alloc<float>(R * 6 * n0);   // per reference: [3 channels][mu1, blur2(ch1^2)]
-    const size_t tiles0 = (size_t)cdiv(w, DS_TW) * cdiv(h, DS_TH);
-    double* partial = c.arena.alloc<double>(B * std::max<size_t>(tiles0, DS_MAD_BLOCKS));
+    const size_t strips0 = (size_t)cdiv(w, DSS_OUT) * cdiv(h, 16);   // most strips any scale can have
+    double* partial = c.arena.alloc<double>(B * std::max<size_t>(strips0, DS_MAD_BLOCKS));
     double* avg = c.arena.alloc<double>(B);
     const bool has_alpha = alpha_in != nullptr;
     // next-scale planes, ping-pong: [NI][3][n/4] (+ alpha [NI][n/4])
@@ -452,18 +602,23 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
             dim3 grid(tx, ty, (unsigned)NI);
             CE_LAUNCH(c, "k_ds_blur2", (double)NI * n * 16, k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img));
         }
-        const int ntiles = (int)(tx * ty);
+        // row strips: 64 rows per warp, fewer when the launch would not fill the machine
+        int rows = 64;
+        const unsigned sx = cdiv(cw, DSS_OUT);
+        while (rows > 16 && (size_t)sx * cdiv(ch, rows) * B < (size_t)c.sm_count * 32) rows /= 2;
+        const unsigned sy = cdiv(ch, rows);
+        const int ntiles = (int)(sx * sy);
         {
-            dim3 grid(tx, ty, (unsigned)R);
+            dim3 grid(sx, sy, (unsigned)R);
             CE_LAUNCH(c, "k_ds_stats<ref>", (double)R * n * 36,
-                      k_ds_stats<0><<<grid, DS_ST_THREADS, 0, c.stream>>>(img, R, nullptr, (int)cw, (int)ch, n, refstat, nullptr, nullptr));
+                      k_ds_stream<0><<<grid, 32, 0, c.stream>>>(img, R, nullptr, (int)cw, (int)ch, n, rows, refstat, nullptr, nullptr));
         }
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
-            dim3 grid(tx, ty, nb);
+            dim3 grid(sx, sy, nb);
             CE_LAUNCH(c, "k_ds_stats<pair>", (double)nb * n * 52,
-                      k_ds_stats<1><<<grid, DS_ST_THREADS, 0, c.stream>>>(img, R + b0, ridx + b0, (int)cw, (int)ch, n, refstat,
-                                                                           map + b0 * n, partial + b0 * ntiles));
+                      k_ds_stream<1><<<grid, 32, 0, c.stream>>>(img, R + b0, ridx + b0, (int)cw, (int)ch, n, rows, refstat,
+                                                                 map + b0 * n, partial + b0 * ntiles));
         }
         CE_LAUNCH(c, "k_ds_mean", (double)B * (ntiles + 2) * 8,
                   k_ds_mean<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, ntiles, B, n, s, d_out, avg));
