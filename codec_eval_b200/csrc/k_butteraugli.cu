@@ -54,8 +54,10 @@ static void ba_host_kernel(float sigma, int* radius, float* w) {
 
 static BaConst g_ba_host;
 
+static void ba_set_kernel_attributes();
 void butteraugli_init(Context& c) {
     (void)c;
+    ba_set_kernel_attributes();
     BaConst k;
     memset(&k, 0, sizeof(k));
     for (int s = 0; s < 4; s++) {
@@ -179,9 +181,9 @@ __global__ void __launch_bounds__(256) k_ba_opsin(const float* __restrict__ lin,
             float p0, p1, p2;
             ba_opsin_absorbance(bl[0][k] * intensity, bl[NPL > 1 ? 1 : 0][k] * intensity, bl[NPL > 2 ? 2 : 0][k] * intensity, p0, p1, p2);
             p0 = fmaxf(p0, 1e-4f); p1 = fmaxf(p1, 1e-4f); p2 = fmaxf(p2, 1e-4f);
-            const float s0 = fmaxf(ba_gamma(p0) / p0, 1e-4f);
-            const float s1 = fmaxf(ba_gamma(p1) / p1, 1e-4f);
-            const float s2 = fmaxf(ba_gamma(p2) / p2, 1e-4f);
+            const float s0 = fmaxf(__fdividef(ba_gamma(p0), p0), 1e-4f);
+            const float s1 = fmaxf(__fdividef(ba_gamma(p1), p1), 1e-4f);
+            const float s2 = fmaxf(__fdividef(ba_gamma(p2), p2), 1e-4f);
             const int ci = (r + 2) * OP_P + 4 * g + 4 + k;
             float c0, c1, c2;
             ba_opsin_absorbance(s_in[0][ci] * intensity, s_in[NPL > 1 ? 1 : 0][ci] * intensity, s_in[NPL > 2 ? 2 : 0][ci] * intensity, c0, c1, c2);
@@ -477,77 +479,89 @@ struct BlurTables {
 #define MT_P (MT_TW + 8)
 #define MT_ROWS (MT_TH + 8)
 #define D(dy, dx) win[(dy) + 4][(dx) + 4 + K]
+// The 16 line sums of a pixel share sub-sums (the centre triples of the four principal directions, the pairs
+// next to the centre of the "knight" lines); they are formed once per pixel.  Mathematically the upstream sums;
+// the association differs, i.e. ~1e-7 relative per sum.
 template <int K>
 CE_DEVINL float malta_hf(const float (&win)[9][12]) {  // pixel K of the thread's 4; window rows -4..4, cols -4..7
+    const float c = D(0,0);
+    const float V3 = (D(-1,0) + c) + D(1,0), H3 = (D(0,-1) + c) + D(0,1);
+    const float D3 = (D(-1,-1) + c) + D(1,1), A3 = (D(-1,1) + c) + D(1,-1);
+    const float H2 = c + D(0,1), V2 = c + D(1,0);
+    const float R12 = D(-1,2) + D(-1,3), R13 = D(1,2) + D(1,3);
+    const float B14 = D(2,1) + D(3,1), B15 = D(2,-1) + D(3,-1);
     float acc = 0.0f, t;
-    t = D(0,-4) + D(0,-3) + D(0,-2) + D(0,-1) + D(0,0) + D(0,1) + D(0,2) + D(0,3) + D(0,4);
+    t = ((D(0,-4) + D(0,-3)) + (D(0,-2) + H3)) + ((D(0,2) + D(0,3)) + D(0,4));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,0) + D(-3,0) + D(-2,0) + D(-1,0) + D(0,0) + D(1,0) + D(2,0) + D(3,0) + D(4,0);
+    t = ((D(-4,0) + D(-3,0)) + (D(-2,0) + V3)) + ((D(2,0) + D(3,0)) + D(4,0));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-3,-3) + D(-2,-2) + D(-1,-1) + D(0,0) + D(1,1) + D(2,2) + D(3,3);
+    t = ((D(-3,-3) + D(-2,-2)) + D3) + (D(2,2) + D(3,3));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-3,3) + D(-2,2) + D(-1,1) + D(0,0) + D(1,-1) + D(2,-2) + D(3,-3);
+    t = ((D(-3,3) + D(-2,2)) + A3) + (D(2,-2) + D(3,-3));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,1) + D(-3,1) + D(-2,1) + D(-1,0) + D(0,0) + D(1,0) + D(2,-1) + D(3,-1) + D(4,-1);
+    t = ((D(-4,1) + D(-3,1)) + (D(-2,1) + V3)) + (B15 + D(4,-1));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,-1) + D(-3,-1) + D(-2,-1) + D(-1,0) + D(0,0) + D(1,0) + D(2,1) + D(3,1) + D(4,1);
+    t = ((D(-4,-1) + D(-3,-1)) + (D(-2,-1) + V3)) + (B14 + D(4,1));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-1,-4) + D(-1,-3) + D(-1,-2) + D(0,-1) + D(0,0) + D(0,1) + D(1,2) + D(1,3) + D(1,4);
+    t = ((D(-1,-4) + D(-1,-3)) + (D(-1,-2) + H3)) + (R13 + D(1,4));
     acc = __fmaf_rn(t, t, acc);
-    t = D(1,-4) + D(1,-3) + D(1,-2) + D(0,-1) + D(0,0) + D(0,1) + D(-1,2) + D(-1,3) + D(-1,4);
+    t = ((D(1,-4) + D(1,-3)) + (D(1,-2) + H3)) + (R12 + D(-1,4));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-3,-2) + D(-2,-1) + D(-1,-1) + D(0,0) + D(1,1) + D(2,1) + D(3,2);
+    t = ((D(-3,-2) + D(-2,-1)) + D3) + (D(2,1) + D(3,2));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-3,2) + D(-2,1) + D(-1,1) + D(0,0) + D(1,-1) + D(2,-1) + D(3,-2);
+    t = ((D(-3,2) + D(-2,1)) + A3) + (D(2,-1) + D(3,-2));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-2,-3) + D(-1,-2) + D(-1,-1) + D(0,0) + D(1,1) + D(1,2) + D(2,3);
+    t = ((D(-2,-3) + D(-1,-2)) + D3) + (D(1,2) + D(2,3));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-2,3) + D(-1,2) + D(-1,1) + D(0,0) + D(1,-1) + D(1,-2) + D(2,-3);
+    t = ((D(-2,3) + D(-1,2)) + A3) + (D(1,-2) + D(2,-3));
     acc = __fmaf_rn(t, t, acc);
-    t = D(2,-4) + D(2,-3) + D(1,-2) + D(1,-1) + D(0,0) + D(0,1) + D(-1,2) + D(-1,3);
+    t = ((D(2,-4) + D(2,-3)) + (D(1,-2) + D(1,-1))) + (H2 + R12);
     acc = __fmaf_rn(t, t, acc);
-    t = D(-2,-4) + D(-2,-3) + D(-1,-2) + D(-1,-1) + D(0,0) + D(0,1) + D(1,2) + D(1,3);
+    t = ((D(-2,-4) + D(-2,-3)) + (D(-1,-2) + D(-1,-1))) + (H2 + R13);
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,-2) + D(-3,-2) + D(-2,-1) + D(-1,-1) + D(0,0) + D(1,0) + D(2,1) + D(3,1);
+    t = ((D(-4,-2) + D(-3,-2)) + (D(-2,-1) + D(-1,-1))) + (V2 + B14);
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,2) + D(-3,2) + D(-2,1) + D(-1,1) + D(0,0) + D(1,0) + D(2,-1) + D(3,-1);
+    t = ((D(-4,2) + D(-3,2)) + (D(-2,1) + D(-1,1))) + (V2 + B15);
     acc = __fmaf_rn(t, t, acc);
     return acc;
 }
 template <int K>
 CE_DEVINL float malta_lf(const float (&win)[9][12]) {
+    const float c = D(0,0);
+    const float Ia = (c + D(-2,-1)) + D(2,1), Ib = (c + D(-2,1)) + D(2,-1);
+    const float Ic = (c + D(-1,-2)) + D(1,2), Id = (c + D(-1,2)) + D(1,-2);
     float acc = 0.0f, t;
-    t = D(0,-4) + D(0,-2) + D(0,0) + D(0,2) + D(0,4);
+    t = ((D(0,-4) + D(0,-2)) + c) + (D(0,2) + D(0,4));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,0) + D(-2,0) + D(0,0) + D(2,0) + D(4,0);
+    t = ((D(-4,0) + D(-2,0)) + c) + (D(2,0) + D(4,0));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-3,-3) + D(-2,-2) + D(0,0) + D(2,2) + D(3,3);
+    t = ((D(-3,-3) + D(-2,-2)) + c) + (D(2,2) + D(3,3));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-3,3) + D(-2,2) + D(0,0) + D(2,-2) + D(3,-3);
+    t = ((D(-3,3) + D(-2,2)) + c) + (D(2,-2) + D(3,-3));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,1) + D(-2,1) + D(0,0) + D(2,-1) + D(4,-1);
+    t = Ib + (D(-4,1) + D(4,-1));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,-1) + D(-2,-1) + D(0,0) + D(2,1) + D(4,1);
+    t = Ia + (D(-4,-1) + D(4,1));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-1,-4) + D(-1,-2) + D(0,0) + D(1,2) + D(1,4);
+    t = Ic + (D(-1,-4) + D(1,4));
     acc = __fmaf_rn(t, t, acc);
-    t = D(1,-4) + D(1,-2) + D(0,0) + D(-1,2) + D(-1,4);
+    t = Id + (D(1,-4) + D(-1,4));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-3,-2) + D(-2,-1) + D(0,0) + D(2,1) + D(3,2);
+    t = Ia + (D(-3,-2) + D(3,2));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-3,2) + D(-2,1) + D(0,0) + D(2,-1) + D(3,-2);
+    t = Ib + (D(-3,2) + D(3,-2));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-2,-3) + D(-1,-2) + D(0,0) + D(1,2) + D(2,3);
+    t = Ic + (D(-2,-3) + D(2,3));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-2,3) + D(-1,2) + D(0,0) + D(1,-2) + D(2,-3);
+    t = Id + (D(-2,3) + D(2,-3));
     acc = __fmaf_rn(t, t, acc);
-    t = D(2,-4) + D(1,-2) + D(0,0) + D(-1,2) + D(-2,4);
+    t = Id + (D(2,-4) + D(-2,4));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-2,-4) + D(-1,-2) + D(0,0) + D(1,2) + D(2,4);
+    t = Ic + (D(-2,-4) + D(2,4));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,-2) + D(-2,-1) + D(0,0) + D(2,1) + D(4,2);
+    t = Ia + (D(-4,-2) + D(4,2));
     acc = __fmaf_rn(t, t, acc);
-    t = D(-4,2) + D(-2,1) + D(0,0) + D(2,-1) + D(4,-2);
+    t = Ib + (D(-4,2) + D(4,-2));
     acc = __fmaf_rn(t, t, acc);
     return acc;
 }
@@ -626,99 +640,115 @@ __global__ void __launch_bounds__(256) k_ba_malta_diff(const float* __restrict__
     }
 }
 
-// grid (tiles_x, tiles_y, 2B): blockIdx.z = b*2 + C.  diff: [B][2][3][n]; hf: [NI][2][n]; mf: [NI][3][n];
-// ac out: [B][2][n] plane C.  The three band tiles (+ halo 4, zero outside the image) are staged with
-// cp.async; each thread then pulls the 9x12 window of its 4 pixels into registers (27 LDS.128 per band)
-// and evaluates the 16 oriented line sums per pixel from there.
+// grid (tiles_x, ceil(tiles_y / MT_NT), 2B): blockIdx.z = b*2 + C.  diff: [B][2][3][n]; hf: [NI][2][n]; mf: [NI][3][n];
+// ac out: [B][2][n] plane C.  A block walks down MT_NT vertically adjacent 64x16 tiles.  Per tile the three band
+// tiles (+ halo 4, zero outside the image) and the four pointwise inputs of the L2 terms are staged with cp.async
+// into one of two buffers, so the loads of tile t+1 run under the arithmetic of tile t.  Each thread pulls the
+// 9x12 window of its 4 pixels into registers (27 LDS.128 per band) and evaluates the 16 oriented line sums per
+// pixel from there.
+#define MT_NT 4
+#define MT_BAND_FLOATS (MT_ROWS * MT_P)
+#define MT_BUF_FLOATS (3 * MT_BAND_FLOATS + 4 * MT_TH * MT_TW)
+#define MT_SMEM (2 * MT_BUF_FLOATS * 4)
 __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ diff, const float* __restrict__ hf,
                                                       const float* __restrict__ mf, int w, int h, size_t n, size_t R,
                                                       const int* __restrict__ ridx,
                                                       const __grid_constant__ MaltaParams2 prm2, float* __restrict__ ac) {
-    __shared__ __align__(16) float s_d[3][MT_ROWS * MT_P];
+    extern __shared__ __align__(16) float s_mt[];   // [2 buffers][3 band tiles | hf0 hf1 mf0 mf1 tiles]
     const size_t b = blockIdx.z >> 1;
     const int C = blockIdx.z & 1;
     const MaltaParams& prm = prm2.ch[C];
-    const int tx0 = blockIdx.x * MT_TW, ty0 = blockIdx.y * MT_TH;
+    const int tx0 = blockIdx.x * MT_TW;
+    const int tiles_y = (h + MT_TH - 1) / MT_TH;
+    const int t_begin = blockIdx.y * MT_NT, nt = min(MT_NT, tiles_y - t_begin);
     const int g = threadIdx.x & 15, oy = threadIdx.x >> 4;
     const bool vec = (w & 3) == 0;
+    const size_t im0 = (size_t)ridx[b], im1 = R + b;
+    const float* e_src[4] = {hf + (im0 * 2 + C) * n, hf + (im1 * 2 + C) * n, mf + (im0 * 3 + C) * n, mf + (im1 * 3 + C) * n};
+    auto issue = [&](int t) {
+        if (t < nt) {
+            float* buf = s_mt + (t & 1) * MT_BUF_FLOATS;
+            const int ty0 = (t_begin + t) * MT_TH;
 #pragma unroll
-    for (int bd = 0; bd < 3; bd++)
-        load_tile_async<MT_P / 4, MT_ROWS, 256>(s_d[bd], MT_P, diff + ((size_t)blockIdx.z * 3 + bd) * n, w, h, tx0 - 4, ty0 - 4, vec);
-    cp_async_commit();
-    const int x = tx0 + 4 * g, y = ty0 + oy;
-    const bool live = y < h && x < w;
-    cp_async_wait<0>();
-    __syncthreads();
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int bd = 0; bd < 3; bd++)
+                load_tile_async<MT_P / 4, MT_ROWS, 256>(buf + bd * MT_BAND_FLOATS, MT_P, diff + ((size_t)blockIdx.z * 3 + bd) * n, w, h,
+                                                        tx0 - 4, ty0 - 4, vec);
 #pragma unroll
-    for (int bd = 0; bd < 3; bd++) {
-        float win[9][12];
+            for (int e = 0; e < 4; e++)
+                load_tile_async<MT_TW / 4, MT_TH, 256>(buf + 3 * MT_BAND_FLOATS + e * MT_TH * MT_TW, MT_TW, e_src[e], w, h, tx0, ty0, vec);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    const int x = tx0 + 4 * g;
+    for (int t = 0; t < nt; t++) {
+        cp_async_wait<1>();
+        __syncthreads();   // tile t visible to all
+        const float* buf = s_mt + (t & 1) * MT_BUF_FLOATS;
+        const int y = (t_begin + t) * MT_TH + oy;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int r = 0; r < 9; r++) {
+        for (int bd = 0; bd < 3; bd++) {
+            float win[9][12];
+            const float* sb = buf + bd * MT_BAND_FLOATS;
 #pragma unroll
-            for (int q = 0; q < 3; q++) {
-                const float4 f = *reinterpret_cast<const float4*>(&s_d[bd][(oy + r) * MT_P + 4 * g + 4 * q]);
-                win[r][4 * q] = f.x; win[r][4 * q + 1] = f.y; win[r][4 * q + 2] = f.z; win[r][4 * q + 3] = f.w;
+            for (int r = 0; r < 9; r++) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const float4 f = *reinterpret_cast<const float4*>(&sb[(oy + r) * MT_P + 4 * g + 4 * q]);
+                    win[r][4 * q] = f.x; win[r][4 * q + 1] = f.y; win[r][4 * q + 2] = f.z; win[r][4 * q + 3] = f.w;
+                }
+            }
+            if (bd == 0) {
+                acc[0] += malta_hf<0>(win); acc[1] += malta_hf<1>(win); acc[2] += malta_hf<2>(win); acc[3] += malta_hf<3>(win);
+            } else {
+                acc[0] += malta_lf<0>(win); acc[1] += malta_lf<1>(win); acc[2] += malta_lf<2>(win); acc[3] += malta_lf<3>(win);
             }
         }
-        if (bd == 0) {
-            acc[0] += malta_hf<0>(win); acc[1] += malta_hf<1>(win); acc[2] += malta_hf<2>(win); acc[3] += malta_hf<3>(win);
-        } else {
-            acc[0] += malta_lf<0>(win); acc[1] += malta_lf<1>(win); acc[2] += malta_lf<2>(win); acc[3] += malta_lf<3>(win);
-        }
-    }
-    if (!live) return;
-    const size_t idx = (size_t)(live ? y : 0) * w + (live ? x : 0);
-    const size_t im0 = (size_t)ridx[b], im1 = R + b;
-    const float* h0 = hf + (im0 * 2 + C) * n + idx;
-    const float* h1 = hf + (im1 * 2 + C) * n + idx;
-    const float* m0 = mf + (im0 * 3 + C) * n + idx;
-    const float* m1 = mf + (im1 * 3 + C) * n + idx;
-    float hv0[4], hv1[4], mv0[4], mv1[4];
-    if (vec) {
-        const float4 a = *reinterpret_cast<const float4*>(h0), q = *reinterpret_cast<const float4*>(h1);
-        const float4 m = *reinterpret_cast<const float4*>(m0), o = *reinterpret_cast<const float4*>(m1);
-        hv0[0] = a.x; hv0[1] = a.y; hv0[2] = a.z; hv0[3] = a.w; hv1[0] = q.x; hv1[1] = q.y; hv1[2] = q.z; hv1[3] = q.w;
-        mv0[0] = m.x; mv0[1] = m.y; mv0[2] = m.z; mv0[3] = m.w; mv1[0] = o.x; mv1[1] = o.y; mv1[2] = o.z; mv1[3] = o.w;
-    } else {
+        const float* se = buf + 3 * MT_BAND_FLOATS + oy * MT_TW + 4 * g;
+        const float4 a = *reinterpret_cast<const float4*>(se), q = *reinterpret_cast<const float4*>(se + MT_TH * MT_TW);
+        const float4 m = *reinterpret_cast<const float4*>(se + 2 * MT_TH * MT_TW), o4 = *reinterpret_cast<const float4*>(se + 3 * MT_TH * MT_TW);
+        __syncthreads();   // everyone is done reading buffer t & 1
+        issue(t + 2);
+        const float hv0[4] = {a.x, a.y, a.z, a.w}, hv1[4] = {q.x, q.y, q.z, q.w};
+        const float mv0[4] = {m.x, m.y, m.z, m.w}, mv1[4] = {o4.x, o4.y, o4.z, o4.w};
+        float tot[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const bool ok = live && x + k < w;
-            hv0[k] = ok ? h0[k] : 0.0f; hv1[k] = ok ? h1[k] : 0.0f;
-            mv0[k] = ok ? m0[k] : 0.0f; mv1[k] = ok ? m1[k] : 0.0f;
+            // the three L2 products, added after the Malta sums in the upstream order
+            const float v0 = hv0[k], v1 = hv1[k];
+            const float df = v0 - v1;
+            const float l2a = df * df;
+            const float fabs0 = fabsf(v0);
+            const float too_small = 0.4f * fabs0, too_big = fabs0;
+            const float if_neg = v1 > -too_small ? v1 + too_small : (v1 < -too_big ? -v1 - too_big : 0.0f);
+            const float if_pos = v1 < too_small ? too_small - v1 : (v1 > too_big ? v1 - too_big : 0.0f);
+            const float v = v0 < 0.0f ? if_neg : if_pos;
+            const float l2b = v * v;
+            const float dm = mv0[k] - mv1[k];
+            const float l2c = dm * dm;
+            float total = acc[k];
+            total = __fmaf_rn(l2a, prm.l2_hf_gt, total);   // L2DiffAsymmetric on hf
+            total = __fmaf_rn(prm.l2_hf_lt, l2b, total);
+            total = __fmaf_rn(l2c, prm.l2_mf, total);      // L2Diff on mf
+            tot[k] = total;
+        }
+        if (y < h && x < w) {
+            float* o = ac + (b * 2 + C) * n + (size_t)y * w + x;
+            if (vec) *reinterpret_cast<float4*>(o) = make_float4(tot[0], tot[1], tot[2], tot[3]);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (x + k < w) o[k] = tot[k];
+            }
         }
     }
-    float l2a[4], l2b[4], l2c[4];   // the three L2 products, added after the Malta sums in the upstream order
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const float v0 = hv0[k], v1 = hv1[k];
-        const float df = v0 - v1;
-        l2a[k] = df * df;
-        const float fabs0 = fabsf(v0);
-        const float too_small = 0.4f * fabs0, too_big = fabs0;
-        const float if_neg = v1 > -too_small ? v1 + too_small : (v1 < -too_big ? -v1 - too_big : 0.0f);
-        const float if_pos = v1 < too_small ? too_small - v1 : (v1 > too_big ? v1 - too_big : 0.0f);
-        const float v = v0 < 0.0f ? if_neg : if_pos;
-        l2b[k] = v * v;
-        const float dm = mv0[k] - mv1[k];
-        l2c[k] = dm * dm;
-    }
-    float tot[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        float total = acc[k];
-        total = __fmaf_rn(l2a[k], prm.l2_hf_gt, total);   // L2DiffAsymmetric on hf
-        total = __fmaf_rn(prm.l2_hf_lt, l2b[k], total);
-        total = __fmaf_rn(l2c[k], prm.l2_mf, total);      // L2Diff on mf
-        tot[k] = total;
-    }
-    float* o = ac + (b * 2 + C) * n + idx;
-    if (vec) *reinterpret_cast<float4*>(o) = make_float4(tot[0], tot[1], tot[2], tot[3]);
-    else {
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (x + k < w) o[k] = tot[k];
-    }
+    cp_async_wait<0>();
+}
+
+static void ba_set_kernel_attributes() {
+    CE_CUDA(cudaFuncSetAttribute(k_ba_malta, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
 }
 
 // ---------------------------------------------------------------- combine
@@ -1071,9 +1101,9 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
         else
             CE_LAUNCH(c, "k_ba_malta_diff", (double)B * n * 72,
                       k_ba_malta_diff<false><<<ew_blocks(c, B * 2 * n), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
-        dim3 grid(cdiv(w, MT_TW), cdiv(h, MT_TH), (unsigned)(2 * B));
+        dim3 grid(cdiv(w, MT_TW), cdiv(cdiv(h, MT_TH), MT_NT), (unsigned)(2 * B));
         CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
-                  k_ba_malta<<<grid, 256, 0, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, L.ac));
+                  k_ba_malta<<<grid, 256, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, L.ac));
     }
     if (w % 4 == 0)
         CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,

