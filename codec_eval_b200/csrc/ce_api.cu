@@ -819,6 +819,127 @@ CE_API int ce_rgba8_to_dssim_image(ce_ctx* ctx, const uint8_t* data, size_t len,
     return to_dssim_image(ctx, data, len, width, height, 4, out);
 }
 
+// ------------------------------------------------------------------ on-device distortion source
+static int jpeg_args_ok(Context& c, int subsampling, const int* qualities, size_t n_q) {
+    if (subsampling != 0 && subsampling != 2) {
+        c.last_error = "subsampling must be 0 (4:4:4) or 2 (4:2:0)";
+        return 0;
+    }
+    for (size_t k = 0; k < n_q; k++)
+        if (qualities[k] < 1 || qualities[k] > 100) {
+            c.last_error = "quality must be in 1..100";
+            return 0;
+        }
+    return 1;
+}
+
+CE_API int ce_jpeg_roundtrip_device(ce_ctx* ctx, const uint8_t* d_refs, size_t n_ref, uint32_t width, uint32_t height,
+                                    const int* qualities, size_t n_q, int subsampling, uint8_t* d_out) {
+    if (!ctx || ((n_ref && n_q) && (!d_refs || !d_out || !qualities))) return CE_ERR_INVALID_ARGUMENT;
+    if (n_ref == 0 || n_q == 0) return CE_OK;
+    Context& c = ctx->c;
+    if (width == 0 || height == 0) {
+        c.last_error = "zero-sized image";
+        return CE_ERR_INVALID_ARGUMENT;
+    }
+    if (!jpeg_args_ok(c, subsampling, qualities, n_q)) return CE_ERR_INVALID_ARGUMENT;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        const size_t img_bytes = (size_t)width * height * 3;
+        const size_t per_ref = jpeg_workspace_bytes(1, n_q, width, height, subsampling);
+        if (c.arena.cap < per_ref + (1 << 20)) throw OomError("workspace too small for one reference of this size");
+        const size_t step = std::max<size_t>(1, std::min<size_t>((c.arena.cap - (1 << 20)) / per_ref, 65535 / n_q));
+        for (size_t r0 = 0; r0 < n_ref; r0 += step) {
+            const size_t nr = std::min(step, n_ref - r0);
+            c.arena.reset();
+            jpeg_roundtrip_run(c, d_refs + r0 * img_bytes, nr, width, height, qualities, n_q, subsampling,
+                               d_out + r0 * n_q * img_bytes);
+        }
+    })
+    return CE_OK;
+}
+
+CE_API int ce_jpeg_roundtrip(ce_ctx* ctx, const uint8_t* rgb, size_t len, size_t width, size_t height, int quality,
+                             int subsampling, uint8_t* out) {
+    if (!ctx || !rgb || !out) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    if (width == 0 || height == 0 || len != width * height * 3) {
+        c.last_error = "Buffer size mismatch";
+        return CE_ERR_INVALID_ARGUMENT;
+    }
+    if (!jpeg_args_ok(c, subsampling, &quality, 1)) return CE_ERR_INVALID_ARGUMENT;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        c.ensure_input(2 * len);
+        CE_CUDA(cudaMemcpyAsync(c.d_in, rgb, len, cudaMemcpyHostToDevice, c.stream));
+        c.arena.reset();
+        jpeg_roundtrip_run(c, c.d_in, 1, width, height, &quality, 1, subsampling, c.d_in + len);
+        CE_CUDA(cudaMemcpyAsync(out, c.d_in + len, len, cudaMemcpyDeviceToHost, c.stream));
+        CE_CUDA(cudaStreamSynchronize(c.stream));
+    })
+    return CE_OK;
+}
+
+CE_API int ce_evaluate_jpeg_sweep(ce_ctx* ctx, const uint8_t* const* refs, size_t n_ref, uint32_t width, uint32_t height,
+                                  const int* qualities, size_t n_q, int subsampling, const ce_metric_config* cfg,
+                                  float intensity_target, ce_result* out) {
+    if (!ctx || !cfg || ((n_ref && n_q) && (!refs || !qualities || !out))) return CE_ERR_INVALID_ARGUMENT;
+    if (n_ref == 0 || n_q == 0) return CE_OK;
+    Context& c = ctx->c;
+    if (width == 0 || height == 0) {
+        c.last_error = "zero-sized image";
+        return CE_ERR_INVALID_ARGUMENT;
+    }
+    for (size_t r = 0; r < n_ref; r++)
+        if (!refs[r]) return CE_ERR_INVALID_ARGUMENT;
+    if (!jpeg_args_ok(c, subsampling, qualities, n_q)) return CE_ERR_INVALID_ARGUMENT;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        const size_t w = width;
+        const size_t h = height;
+        const size_t img_bytes = w * h * 3;
+        const size_t per_ref = jpeg_workspace_bytes(1, n_q, w, h, subsampling);
+        if (c.arena.cap < per_ref + (1 << 20)) throw OomError("workspace too small for one reference of this size");
+        // references per chunk: up to 4 chunks, at most 2 GiB of generated images each, JPEG temporaries inside the arena
+        size_t nchunks = std::min<size_t>(4, (n_ref + 1) / 2);
+        size_t chunk = (n_ref + nchunks - 1) / nchunks;
+        chunk = std::min<size_t>(chunk, std::max<size_t>(1, ((size_t)2 << 30) / (n_q * img_bytes)));
+        chunk = std::min<size_t>(chunk, (c.arena.cap - (1 << 20)) / per_ref);
+        chunk = std::max<size_t>(1, std::min<size_t>(chunk, 65535 / n_q));
+        nchunks = (n_ref + chunk - 1) / chunk;
+        auto stage = [&](size_t ci) {
+            const size_t r0 = ci * chunk;
+            const size_t nr = std::min(chunk, n_ref - r0);
+            c.ensure_stage((int)(ci & 1), nr * (1 + n_q) * img_bytes);
+            for (size_t r = 0; r < nr; r++)
+                CE_CUDA(cudaMemcpyAsync(c.d_stage[ci & 1] + r * img_bytes, refs[r0 + r], img_bytes, cudaMemcpyHostToDevice,
+                                        c.copy_stream));
+            CE_CUDA(cudaEventRecord(c.ev_copy[ci & 1], c.copy_stream));
+        };
+        std::vector<uint32_t> ref_of;
+        try {
+            stage(0);
+            for (size_t ci = 0; ci < nchunks; ci++) {
+                if (ci + 1 < nchunks) stage(ci + 1);
+                const size_t r0 = ci * chunk;
+                const size_t nr = std::min(chunk, n_ref - r0);
+                uint8_t* d_ref = c.d_stage[ci & 1];
+                uint8_t* d_dist = d_ref + nr * img_bytes;
+                CE_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy[ci & 1], 0));
+                c.arena.reset();
+                jpeg_roundtrip_run(c, d_ref, nr, w, h, qualities, n_q, subsampling, d_dist);
+                ref_of.resize(nr * n_q);
+                for (size_t i = 0; i < nr * n_q; i++) ref_of[i] = (uint32_t)(i / n_q);
+                run_device_batch(c, d_ref, nr, d_dist, nr * n_q, ref_of.data(), w, h, *cfg, intensity_target, out + r0 * n_q, nullptr);
+            }
+        } catch (...) {
+            cudaStreamSynchronize(c.copy_stream);
+            throw;
+        }
+    })
+    return CE_OK;
+}
+
 CE_API int ce_xyb_roundtrip(ce_ctx* ctx, const uint8_t* rgb, size_t len, size_t width, size_t height, uint8_t* out) {
     if (!ctx || !rgb || !out) return CE_ERR_INVALID_ARGUMENT;
     Context& c = ctx->c;

@@ -387,6 +387,61 @@ class GpuMetrics:
         return out
 
 
+    # -- on-device distortion source (the step before the metric path in codec-iter's run_eval,
+    #    crates/codec-iter/src/eval.rs:153-172)
+    def jpeg_roundtrip(self, rgb, width: int, height: int, quality: int, subsampling: int = 2) -> np.ndarray:
+        """Decoded image of a baseline JPEG(quality, subsampling 0 = 4:4:4 / 2 = 4:2:0) of `rgb`, computed on the
+        device; bit-exact with libjpeg-turbo's encode -> decode.  uint8 [height, width, 3]."""
+        d = _as_u8(rgb)
+        assert d.size == width * height * 3, "Buffer size mismatch"
+        out = np.empty((height, width, 3), np.uint8)
+        st = self._L.ce_jpeg_roundtrip(self._h, d.ctypes.data, d.size, width, height, int(quality), int(subsampling),
+                                       out.ctypes.data)
+        self._raise(st, "JPEG")
+        return out
+
+    def jpeg_roundtrip_device(self, d_refs: int, n_ref: int, width: int, height: int, qualities, subsampling: int, d_out: int):
+        """Device-resident: d_out[r * len(qualities) + k] = reference r at qualities[k] (raw device pointers)."""
+        q = (C.c_int * len(qualities))(*[int(v) for v in qualities])
+        st = self._L.ce_jpeg_roundtrip_device(self._h, C.c_void_p(d_refs), n_ref, width, height, q, len(qualities),
+                                              int(subsampling), C.c_void_p(d_out))
+        self._raise(st, "JPEG")
+
+    def evaluate_jpeg_sweep_raw(self, refs, width: int, height: int, qualities, config: MetricConfig, subsampling: int = 2,
+                                intensity_target: float = 80.0):
+        """Quality sweep: every reference against its own JPEG round trip at every quality, distortions generated on
+        the device (only the references are uploaded).  Returns ce_result[len(refs) * len(qualities)], reference-major."""
+        keep = [_as_u8(r) for r in refs]
+        for r in keep:
+            assert r.size == width * height * 3, "Buffer size mismatch"
+        n_ref, n_q = len(keep), len(qualities)
+        ptrs = (C.c_void_p * max(n_ref, 1))(*[r.ctypes.data for r in keep])
+        q = (C.c_int * max(n_q, 1))(*[int(v) for v in qualities])
+        out = (_lib.CeResult * max(n_ref * n_q, 1))()
+        cfg = config._c()
+        st = self._L.ce_evaluate_jpeg_sweep(self._h, ptrs, n_ref, width, height, q, n_q, int(subsampling), C.byref(cfg),
+                                            intensity_target, out)
+        if st != _lib.CE_OK:
+            self._raise(st, "batch")
+        return out
+
+    def evaluate_jpeg_sweep(self, refs, width: int, height: int, qualities, config: MetricConfig, subsampling: int = 2,
+                            intensity_target: float = 80.0) -> List[List[MetricResult]]:
+        """[reference][quality] MetricResult table of evaluate_jpeg_sweep_raw."""
+        out = self.evaluate_jpeg_sweep_raw(refs, width, height, qualities, config, subsampling, intensity_target)
+        n_q = len(qualities)
+        table = []
+        for r in range(len(refs)):
+            row = []
+            for k in range(n_q):
+                o = out[r * n_q + k]
+                if o.status != _lib.CE_OK:
+                    self._raise(o.status, "SSIMULACRA2" if config.ssimulacra2 else "Butteraugli", (width, height), (width, height))
+                row.append(_result_from_c(o))
+            table.append(row)
+        return table
+
+
 class GpuReference:
     """Reference image kept on the device; mirrors fast_ssim2::Ssimulacra2Reference::new / .compare
     as used by crates/codec-iter/src/eval.rs:138-149,84-88."""

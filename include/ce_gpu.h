@@ -161,6 +161,29 @@ CE_API int ce_reference_compare_many(ce_ctx* ctx, ce_ref* ref, const uint8_t* co
                                      size_t n_dist, float intensity_target, ce_result* out);
 CE_API void ce_reference_destroy(ce_ref* ref);
 
+/* ---- on-device distortion source -------------- */
+/* The step BEFORE the metric path in codec-iter's eval loop is encode -> decode per quality level
+ * (crates/codec-iter/src/eval.rs:153-172, run_eval: `decode -> compare`).  These entry points produce the decoded
+ * image of a baseline JPEG (IJG / libjpeg-turbo defaults: islow DCT, Annex-K tables scaled by `quality`,
+ * subsampling 0 = 4:4:4 or 2 = 4:2:0 with fancy upsampling) directly on the device, bit-exact with
+ * libjpeg-turbo's encode -> decode, so a quality sweep uploads only the reference images.  No bitstream is
+ * produced (entropy coding is lossless and skipped): file sizes still come from the real encoder. */
+
+/* one host image -> its JPEG(quality, subsampling) round trip; out = width*height*3 bytes */
+CE_API int ce_jpeg_roundtrip(ce_ctx* ctx, const uint8_t* rgb, size_t len, size_t width, size_t height, int quality,
+                             int subsampling, uint8_t* out);
+/* device-resident: n_ref tightly packed RGB8 references -> d_out[(r * n_q + k)] = reference r at qualities[k]
+ * (qualities: host array) */
+CE_API int ce_jpeg_roundtrip_device(ce_ctx* ctx, const uint8_t* d_refs, size_t n_ref, uint32_t width, uint32_t height,
+                                    const int* qualities, size_t n_q, int subsampling, uint8_t* d_out);
+/* Quality sweep in one call: n_ref HOST references (refs[r], width*height*3 bytes each) x n_q qualities ->
+ * out[r * n_q + k] = metrics of reference r against its own JPEG(qualities[k]) round trip.  Only the references
+ * cross PCIe; reference-side metric work is shared by the n_q distortions of a reference
+ * (Ssimulacra2Reference reuse, crates/codec-iter/src/eval.rs:138-149). */
+CE_API int ce_evaluate_jpeg_sweep(ce_ctx* ctx, const uint8_t* const* refs, size_t n_ref, uint32_t width, uint32_t height,
+                                  const int* qualities, size_t n_q, int subsampling, const ce_metric_config* cfg,
+                                  float intensity_target, ce_result* out);
+
 /* ---- stage-level entry points (parity tests; device does the work) -- */
 /* Each runs ONE pipeline stage on the device for a single host image / pair
  * and returns the intermediate, so tests can localise a mismatch against the

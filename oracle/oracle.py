@@ -17,8 +17,8 @@ _SO = os.path.join(_HERE, "libce_oracle.so")
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "ce_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("ce_oracle.c", "ce_oracle_jpeg.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libce_oracle.so"], stdout=subprocess.DEVNULL)
     return _SO
 
@@ -86,6 +86,9 @@ def lib():
         L.ceo_evaluate_pair.argtypes = [u8p, u8p, sz, sz, C.c_uint32, C.c_float, C.POINTER(Result)]
         L.ceo_evaluate_batch.argtypes = [u8p, u8p, sz, sz, sz, C.c_uint32, C.c_float, C.c_int, C.POINTER(Result)]
         L.ceo_max_threads.restype = C.c_int
+        L.ceo_jpeg_roundtrip.restype = C.c_int
+        L.ceo_jpeg_roundtrip.argtypes = [u8p, sz, sz, C.c_int, C.c_int, u8p]
+        L.ceo_jpeg_qtable.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint16)]
         _lib = L
     return _lib
 
@@ -316,3 +319,20 @@ def evaluate_batch(refs, dists, w, h, flags, intensity=80.0, threads=0):
 
 def max_threads() -> int:
     return int(lib().ceo_max_threads())
+
+
+def jpeg_roundtrip(rgb, w, h, quality, subsampling=2) -> np.ndarray:
+    """Baseline JPEG encode -> decode in the sample domain (ce_oracle_jpeg.c); uint8 [h, w, 3]."""
+    r, rp = _u8(rgb)
+    assert r.size == w * h * 3
+    out = np.empty((h, w, 3), np.uint8)
+    st = lib().ceo_jpeg_roundtrip(rp, w, h, int(quality), int(subsampling), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    if st != 0:
+        raise OracleError(st)
+    return out
+
+
+def jpeg_qtable(chroma: bool, quality: int) -> np.ndarray:
+    t = np.zeros(64, np.uint16)
+    lib().ceo_jpeg_qtable(int(chroma), int(quality), t.ctypes.data_as(C.POINTER(C.c_uint16)))
+    return t
