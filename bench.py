@@ -321,10 +321,10 @@ def main():
             except Exception:
                 traffic = None
         # what ncu says binds the kernels that are not HBM bound (profiles/README.md)
-        issue_bound = {"k_ba_malta": "FP32 issue (16 oriented 9-tap line sums per pixel and band, ~300 FADD per pixel-channel): 62 % issue-active, DRAM 21 %",
-                       "k_ds_stats<pair>": "FP32 issue (un-fused 3x3 mul+add chains kept for bit parity with dssim-core): 54 % issue-active",
-                       "k_s2_vpass<pair>": "FP32/FP64 issue (recurrence + fp64 SSIM / edge terms): 78 % issue-active",
-                       "k_s2_vpass": "FP32/FP64 issue (recurrence + fp64 SSIM / edge terms): 78 % issue-active"}
+        issue_bound = {"k_ba_malta": "FP32 issue (16 oriented line sums per pixel and band, ~235 fp32 instructions per pixel-channel after sharing sub-sums), not HBM",
+                       "k_ds_stats<pair>": "FP32 issue (un-fused 3x3 mul+add chains kept for bit parity with dssim-core, 11 instructions per 3x3), not HBM",
+                       "k_s2_vpass<pair>": "FP32 issue (three recurrences + SSIM / edge terms per pixel), not HBM",
+                       "k_s2_vpass": "FP32 issue (five recurrences + SSIM / edge terms per pixel), not HBM"}
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "binding_resource": issue_bound.get(name, "HBM"),
                     "traffic": traffic, "peak_source": peak_src, "launches": v["launches"],
@@ -372,6 +372,27 @@ def main():
     e2e = {"value": e2e_val, "unit": "MPix-pairs/s", "h2d_bytes_per_step": (n + n_ref) * img_bytes,
            "d2h_bytes_per_step": n * (1 + 108 + 10 + 4) * 8, "ms_per_step": e2e_ms / args.steps}
 
+    # ---- the same sweep with the distortions generated ON the device: host references in, results
+    # out; only the references cross PCIe.  Same references and quality ladder, 4:2:0 everywhere.
+    _, _, _, quals, _ = WORKLOADS[args.workload]
+    sweep = None
+    if w * h <= 1024 * 1024:
+        ref_ptrs = (C.c_void_p * n_ref)(*[h_ref.data_ptr() + i * img_bytes for i in range(n_ref)])
+        qarr = (C.c_int * len(quals))(*quals)
+        sw_out = (_lib.CeResult * (n_ref * len(quals)))()
+
+        def step_sweep():
+            st = L.ce_evaluate_jpeg_sweep(ctx._h, ref_ptrs, n_ref, w, h, qarr, len(quals), 2, C.byref(ccfg), 80.0, sw_out)
+            if st != 0:
+                raise RuntimeError(f"ce_evaluate_jpeg_sweep failed: {st} {ctx.last_error()}")
+
+        sw_ms = timed(step_sweep, args.steps, 2)
+        sweep = {"value": n_ref * len(quals) * w * h / 1e6 * world * args.steps / (sw_ms / 1e3), "unit": "MPix-pairs/s",
+                 "ms_per_step": sw_ms / args.steps, "h2d_bytes_per_step": n_ref * img_bytes,
+                 "d2h_bytes_per_step": n_ref * len(quals) * (1 + 108 + 10 + 4) * 8,
+                 "what": "ce_evaluate_jpeg_sweep: host references -> on-device baseline-JPEG round trips (bit-exact with "
+                         "libjpeg-turbo) -> all four metrics"}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -393,7 +414,7 @@ def main():
                        "references": f"{n_ref} distinct references, {n // max(n_ref, 1)} distortions each; reference-side work is done once per distinct reference (the reference's Ssimulacra2Reference reuse, generalised)",
                        "l2": f"no explicit flush: {(n + n_ref) * img_bytes / 1e6:.0f} MB of inputs and >1 GB of fp32 intermediates per step exceed the 126 MB L2",
                        "parallelism": f"pairs sharded over {world} rank(s), NCCL all_gather of 56 B/pair results"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sweep_e2e": sweep, "gpu_launches": launches, "clocks": clocks,
             "per_metric": per_metric, "kernels": kernels, "sanity": sanity,
         }
         emit(line)

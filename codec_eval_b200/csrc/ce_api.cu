@@ -830,6 +830,10 @@ static int jpeg_args_ok(Context& c, int subsampling, const int* qualities, size_
             c.last_error = "quality must be in 1..100";
             return 0;
         }
+    if (n_q > 32) {
+        c.last_error = "at most 32 quality levels per call";
+        return 0;
+    }
     return 1;
 }
 
@@ -855,6 +859,7 @@ CE_API int ce_jpeg_roundtrip_device(ce_ctx* ctx, const uint8_t* d_refs, size_t n
             jpeg_roundtrip_run(c, d_refs + r0 * img_bytes, nr, width, height, qualities, n_q, subsampling,
                                d_out + r0 * n_q * img_bytes);
         }
+        CE_CUDA(cudaStreamSynchronize(c.stream));
     })
     return CE_OK;
 }
@@ -900,8 +905,10 @@ CE_API int ce_evaluate_jpeg_sweep(ce_ctx* ctx, const uint8_t* const* refs, size_
         const size_t img_bytes = w * h * 3;
         const size_t per_ref = jpeg_workspace_bytes(1, n_q, w, h, subsampling);
         if (c.arena.cap < per_ref + (1 << 20)) throw OomError("workspace too small for one reference of this size");
-        // references per chunk: up to 4 chunks, at most 2 GiB of generated images each, JPEG temporaries inside the arena
-        size_t nchunks = std::min<size_t>(4, (n_ref + 1) / 2);
+        // references per chunk: only the references are uploaded, so chunks exist to overlap that copy when it is
+        // large (one chunk per 64 MB of references, at most 4), to keep the generated images of a chunk under 2 GiB and
+        // the JPEG temporaries inside the arena
+        size_t nchunks = std::min<size_t>(4, std::max<size_t>(1, n_ref * img_bytes / ((size_t)64 << 20)));
         size_t chunk = (n_ref + nchunks - 1) / nchunks;
         chunk = std::min<size_t>(chunk, std::max<size_t>(1, ((size_t)2 << 30) / (n_q * img_bytes)));
         chunk = std::min<size_t>(chunk, (c.arena.cap - (1 << 20)) / per_ref);

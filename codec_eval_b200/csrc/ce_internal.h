@@ -172,7 +172,7 @@ void butteraugli_debug_blur(Context& c, const float* in, size_t w, size_t h, flo
 
 // ---------------- k_jpeg.cu ----------------
 // baseline-JPEG sample-domain round trip: d_refs [n_ref][h][w][3] -> d_out [n_ref * n_q][h][w][3]; temporaries from
-// the arena; synchronises the stream before returning
+// the arena; stream-ordered (no host synchronisation); at most 32 qualities per call
 void jpeg_roundtrip_run(Context& c, const uint8_t* d_refs, size_t n_ref, size_t w, size_t h, const int* qualities, size_t n_q,
                         int subsampling, uint8_t* d_out);
 size_t jpeg_workspace_bytes(size_t n_ref, size_t n_q, size_t w, size_t h, int subsampling);

@@ -136,15 +136,33 @@ CE_DEVINL void jpg_idct8(int& d0, int& d1, int& d2, int& d3, int& d4, int& d5, i
     d3 = JDESCALE(tmp13 + tmp0, N); d4 = JDESCALE(tmp13 - tmp0, N);
 }
 
+// Annex-K base tables (natural order): [0] luminance, [1] chrominance
+__constant__ uint8_t c_jpg_base[2][64] = {
+    {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,  14, 13, 16, 24, 40,  57,  69,  56,
+     14, 17, 22, 29, 51,  87,  80,  62,  18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+     49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99},
+    {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+     99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99}};
+
+#define JPG_MAXQ 32
+struct JpgQualities {
+    int q[JPG_MAXQ];
+};
+
 // grid (ceil(blocks/128), 3 components, n_ref * n_q), block 128; thread = one 8x8 block.
-// ycc: [n_ref][3][plane_stride] -> rt: [n_ref * n_q][3][plane_stride]; qt: [n_q][2][64] (luma, chroma).
-__global__ void __launch_bounds__(128) k_jpg_dct(const uint8_t* __restrict__ ycc, JpgGeom g, const uint16_t* __restrict__ qt,
+// ycc: [n_ref][3][plane_stride] -> rt: [n_ref * n_q][3][plane_stride].  The quantisation table of (quality,
+// component) is formed per block: jcparam.c jpeg_quality_scaling + jpeg_add_quant_table(force_baseline = TRUE).
+__global__ void __launch_bounds__(128) k_jpg_dct(const uint8_t* __restrict__ ycc, JpgGeom g, const __grid_constant__ JpgQualities ql,
                                                   int n_q, uint8_t* __restrict__ rt) {
     __shared__ int s_q[64];
     const int comp = blockIdx.y;
     const size_t rk = blockIdx.z, r = rk / n_q;
     const int k = (int)(rk - r * n_q);
-    if (threadIdx.x < 64) s_q[threadIdx.x] = qt[(k * 2 + (comp ? 1 : 0)) * 64 + threadIdx.x];
+    if (threadIdx.x < 64) {
+        const int quality = min(max(ql.q[k], 1), 100);
+        const int scale = quality < 50 ? 5000 / quality : 200 - 2 * quality;
+        s_q[threadIdx.x] = min(max(((int)c_jpg_base[comp ? 1 : 0][threadIdx.x] * scale + 50) / 100, 1), 255);
+    }
     __syncthreads();
     const int pw = comp ? g.cpw : g.pw, ph = comp ? g.cph : g.ph;
     const int bw = pw >> 3, nblk = bw * (ph >> 3);
@@ -240,25 +258,6 @@ __global__ void __launch_bounds__(256) k_jpg_rgb(const uint8_t* __restrict__ rt,
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-static const uint8_t kStdLum[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
-                                    14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
-                                    18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
-                                    49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
-static const uint8_t kStdChr[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99,
-                                    99, 99, 47, 66, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
-                                    99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
-
-// jcparam.c jpeg_quality_scaling + jpeg_add_quant_table(force_baseline = TRUE)
-static void jpg_host_qtable(int chroma, int quality, uint16_t* out) {
-    quality = std::min(std::max(quality, 1), 100);
-    const int scale = quality < 50 ? 5000 / quality : 200 - 2 * quality;
-    const uint8_t* base = chroma ? kStdChr : kStdLum;
-    for (int i = 0; i < 64; i++) {
-        long t = ((long)base[i] * scale + 50L) / 100L;
-        out[i] = (uint16_t)std::min(std::max(t, 1L), 255L);
-    }
-}
-
 static JpgGeom jpg_geom(size_t w, size_t h, int ss) {
     JpgGeom g;
     const size_t m = ss ? 16 : 8;
@@ -272,25 +271,20 @@ static JpgGeom jpg_geom(size_t w, size_t h, int ss) {
 
 size_t jpeg_workspace_bytes(size_t n_ref, size_t n_q, size_t w, size_t h, int ss) {
     const JpgGeom g = jpg_geom(w, h, ss);
-    return (n_ref + n_ref * n_q) * 3 * g.plane_stride + n_q * 2 * 64 * sizeof(uint16_t) + 4096;
+    return (n_ref + n_ref * n_q) * 3 * g.plane_stride + 4096;
 }
 
 // d_refs: [n_ref][h][w][3] -> d_out: [n_ref * n_q][h][w][3], image r * n_q + k = reference r at qualities[k].
-// Temporaries come from the arena (the caller resets / releases it).
+// Temporaries come from the arena (the caller resets / releases it); everything is stream-ordered, no host sync.
 void jpeg_roundtrip_run(Context& c, const uint8_t* d_refs, size_t n_ref, size_t w, size_t h, const int* qualities, size_t n_q,
                         int ss, uint8_t* d_out) {
     const JpgGeom g = jpg_geom(w, h, ss);
     if (n_ref * n_q > 65535) throw CudaError("jpeg sweep sub-batch too large for one launch");
     uint8_t* ycc = c.arena.alloc<uint8_t>(n_ref * 3 * g.plane_stride);
     uint8_t* rt = c.arena.alloc<uint8_t>(n_ref * n_q * 3 * g.plane_stride);
-    uint16_t* d_qt = c.arena.alloc<uint16_t>(n_q * 2 * 64);
-    std::vector<uint16_t> h_qt(n_q * 2 * 64);
-    for (size_t k = 0; k < n_q; k++) {
-        jpg_host_qtable(0, qualities[k], &h_qt[(k * 2) * 64]);
-        jpg_host_qtable(1, qualities[k], &h_qt[(k * 2 + 1) * 64]);
-    }
-    // pageable source: the copy is staged by the runtime before the call returns
-    CE_CUDA(cudaMemcpyAsync(d_qt, h_qt.data(), h_qt.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c.stream));
+    if (n_q > JPG_MAXQ) throw CudaError("at most 32 quality levels per call");
+    JpgQualities ql;
+    for (size_t k = 0; k < JPG_MAXQ; k++) ql.q[k] = k < n_q ? qualities[k] : 1;
     const dim3 blk(32, 8);
     const double in_bytes = (double)n_ref * w * h * 3, plane_bytes = (double)g.pw * g.ph + 2.0 * g.cpw * g.cph;
     if (ss) {
@@ -303,7 +297,7 @@ void jpeg_roundtrip_run(Context& c, const uint8_t* d_refs, size_t n_ref, size_t 
     {
         const unsigned nblk = (unsigned)((g.pw / 8) * (g.ph / 8));
         dim3 grid(cdiv(nblk, 128), 3, (unsigned)(n_ref * n_q));
-        CE_LAUNCH(c, "k_jpg_dct", 2.0 * n_ref * n_q * plane_bytes, k_jpg_dct<<<grid, 128, 0, c.stream>>>(ycc, g, d_qt, (int)n_q, rt));
+        CE_LAUNCH(c, "k_jpg_dct", 2.0 * n_ref * n_q * plane_bytes, k_jpg_dct<<<grid, 128, 0, c.stream>>>(ycc, g, ql, (int)n_q, rt));
     }
     if (ss) {
         dim3 grid(cdiv(g.cw, 32), cdiv(g.ch, 8), (unsigned)(n_ref * n_q));
@@ -313,7 +307,6 @@ void jpeg_roundtrip_run(Context& c, const uint8_t* d_refs, size_t n_ref, size_t 
         CE_LAUNCH(c, "k_jpg_rgb", (double)n_ref * n_q * (plane_bytes + (double)w * h * 3), k_jpg_rgb<0><<<grid, blk, 0, c.stream>>>(rt, g, d_out));
     }
     CE_CUDA(cudaGetLastError());
-    CE_CUDA(cudaStreamSynchronize(c.stream));   // h_qt must outlive the copy
 }
 
 }  // namespace ce
