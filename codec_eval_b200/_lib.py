@@ -41,7 +41,7 @@ EXPORTS = [
     "ce_evaluate_batch", "ce_evaluate_batch_device", "ce_evaluate_batch_device_grouped", "ce_psnr", "ce_ssimulacra2", "ce_butteraugli", "ce_dssim_rgb8",
     "ce_dssim_rgbaf32", "ce_rgb8_to_dssim_image", "ce_rgba8_to_dssim_image", "ce_xyb_roundtrip",
     "ce_reference_create", "ce_reference_compare", "ce_reference_compare_many", "ce_reference_destroy",
-    "ce_jpeg_roundtrip", "ce_jpeg_roundtrip_device", "ce_evaluate_jpeg_sweep",
+    "ce_jpeg_roundtrip", "ce_jpeg_roundtrip_device", "ce_evaluate_jpeg_sweep", "ce_transform_to_srgb",
     "ce_debug_ssim2_sums", "ce_debug_ssim2_scale0_planes", "ce_debug_dssim_scales", "ce_debug_butteraugli_diffmap",
     "ce_debug_butteraugli_psycho", "ce_debug_butteraugli_opsin", "ce_debug_ba_blur",
 ]
@@ -96,6 +96,7 @@ def load():
     L.ce_jpeg_roundtrip_device.argtypes = [vp, vp, sz, C.c_uint32, C.c_uint32, C.POINTER(C.c_int), sz, C.c_int, vp]
     L.ce_evaluate_jpeg_sweep.argtypes = [vp, C.POINTER(vp), sz, C.c_uint32, C.c_uint32, C.POINTER(C.c_int), sz, C.c_int, cfgp,
                                          C.c_float, resp]
+    L.ce_transform_to_srgb.argtypes = [vp, u8p, sz, sz, sz, u8p, sz, u8p]
     L.ce_debug_ssim2_sums.argtypes = [vp, u8p, u8p, sz, sz, f64p, C.POINTER(C.c_int)]
     L.ce_debug_ssim2_scale0_planes.argtypes = [vp, u8p, u8p, sz, sz, f32p]
     L.ce_debug_dssim_scales.argtypes = [vp, u8p, u8p, sz, sz, f64p, C.POINTER(C.c_int), f32p]

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libce_gpu.so")
-SOURCES = ["ce_api.cu", "k_color.cu", "k_ssim2.cu", "k_dssim.cu", "k_butteraugli.cu", "k_jpeg.cu"]
+SOURCES = ["ce_api.cu", "k_color.cu", "k_ssim2.cu", "k_dssim.cu", "k_butteraugli.cu", "k_jpeg.cu", "k_icc.cu"]
 NVCC = os.environ.get("CE_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17",

@@ -947,6 +947,37 @@ CE_API int ce_evaluate_jpeg_sweep(ce_ctx* ctx, const uint8_t* const* refs, size_
     return CE_OK;
 }
 
+// transform_to_srgb, src/metrics/icc.rs:69-103
+CE_API int ce_transform_to_srgb(ce_ctx* ctx, const uint8_t* rgb, size_t len, size_t width, size_t height, const uint8_t* icc,
+                                size_t icc_len, uint8_t* out) {
+    if (!ctx || !rgb || !out) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    if (len != width * height * 3) {
+        c.last_error = "Buffer size mismatch";
+        return CE_ERR_INVALID_ARGUMENT;
+    }
+    if (len == 0) return CE_OK;
+    if (!icc || icc_len == 0) {   // ColorProfile::Srgb => rgb.to_vec()
+        memmove(out, rgb, len);
+        return CE_OK;
+    }
+    std::string why;
+    if (!icc_is_usable(icc, icc_len, &why)) {
+        c.last_error = why;
+        return CE_ERR_METRIC_CALCULATION;
+    }
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        c.ensure_input(2 * len);
+        CE_CUDA(cudaMemcpyAsync(c.d_in, rgb, len, cudaMemcpyHostToDevice, c.stream));
+        c.arena.reset();
+        icc_to_srgb_run(c, c.d_in, width * height, icc, icc_len, c.d_in + len);
+        CE_CUDA(cudaMemcpyAsync(out, c.d_in + len, len, cudaMemcpyDeviceToHost, c.stream));
+        CE_CUDA(cudaStreamSynchronize(c.stream));
+    })
+    return CE_OK;
+}
+
 CE_API int ce_xyb_roundtrip(ce_ctx* ctx, const uint8_t* rgb, size_t len, size_t width, size_t height, uint8_t* out) {
     if (!ctx || !rgb || !out) return CE_ERR_INVALID_ARGUMENT;
     Context& c = ctx->c;

@@ -177,4 +177,10 @@ void jpeg_roundtrip_run(Context& c, const uint8_t* d_refs, size_t n_ref, size_t 
                         int subsampling, uint8_t* d_out);
 size_t jpeg_workspace_bytes(size_t n_ref, size_t n_q, size_t w, size_t h, int subsampling);
 
+// ---------------- k_icc.cu ----------------
+// matrix/TRC ICC profile -> sRGB, d_rgb [npix][3] -> d_out [npix][3]; throws std::runtime_error with the reason when
+// the profile is not a usable matrix/TRC RGB profile
+void icc_to_srgb_run(Context& c, const uint8_t* d_rgb, size_t npix, const uint8_t* icc, size_t icc_len, uint8_t* d_out);
+bool icc_is_usable(const uint8_t* icc, size_t icc_len, std::string* why);
+
 }  // namespace ce

@@ -387,6 +387,18 @@ class GpuMetrics:
         return out
 
 
+    def transform_to_srgb(self, rgb, width: int, height: int, icc_profile: Optional[bytes]) -> np.ndarray:
+        """src/metrics/icc.rs:69-103: RGB8 in the colour space of `icc_profile` -> RGB8 sRGB on the device (matrix/TRC
+        profiles).  None / empty = ColorProfile::Srgb (copy).  An unusable profile raises MetricCalculation("ICC", ..)."""
+        d = _as_u8(rgb)
+        assert d.size == width * height * 3, "Buffer size mismatch"
+        out = np.empty(d.size, np.uint8)
+        icc = bytes(icc_profile) if icc_profile else b""
+        st = self._L.ce_transform_to_srgb(self._h, d.ctypes.data, d.size, width, height, icc if icc else None, len(icc),
+                                          out.ctypes.data)
+        self._raise(st, "ICC")
+        return out
+
     # -- on-device distortion source (SURVEY.md 8(f) rank 2; the step before the metric path in codec-iter's run_eval,
     #    crates/codec-iter/src/eval.rs:153-172)
     def jpeg_roundtrip(self, rgb, width: int, height: int, quality: int, subsampling: int = 2) -> np.ndarray:

@@ -68,12 +68,16 @@ class ImageData:
             return self.data
         return np.ascontiguousarray(self.data.reshape(-1, 4)[:, :3]).reshape(-1)
 
-    def to_rgb8_srgb(self) -> np.ndarray:
-        """session.rs:143-147.  The ICC -> sRGB transform (src/metrics/icc.rs, moxcms) is upstream of the GPU path and
-        out of scope here: an attached profile is refused rather than silently ignored."""
-        if self.icc_profile is not None:
-            raise NotImplementedError("ICC -> sRGB conversion is not part of the GPU metric path; convert before evaluating")
-        return self.to_rgb8_vec()
+    def to_rgb8_srgb(self, metrics=None) -> np.ndarray:
+        """session.rs:143-147: to_rgb8_vec, then the ICC -> sRGB transform (src/metrics/icc.rs:69-103) when a profile is
+        attached -- here on the device (matrix/TRC profiles; others raise MetricCalculation("ICC", ..))."""
+        rgb = self.to_rgb8_vec()
+        if not self.icc_profile:
+            return rgb
+        from .metrics import default_context
+
+        ctx = metrics or default_context()
+        return ctx.transform_to_srgb(rgb, self.width(), self.height(), self.icc_profile)
 
 
 @dataclass

@@ -184,6 +184,15 @@ CE_API int ce_evaluate_jpeg_sweep(ce_ctx* ctx, const uint8_t* const* refs, size_
                                   const int* qualities, size_t n_q, int subsampling, const ce_metric_config* cfg,
                                   float intensity_target, ce_result* out);
 
+/* ---- ICC -> sRGB on the device ---------------- */
+/* transform_to_srgb, src/metrics/icc.rs:69-103 (what ImageData::to_rgb8_srgb applies before the metrics,
+ * src/eval/session.rs:143-147): RGB8 in the colour space of `icc` -> RGB8 sRGB; out = width*height*3 bytes.
+ * icc == NULL or icc_len == 0 is ColorProfile::Srgb (bytes are copied, icc.rs:73).  Matrix/TRC RGB profiles
+ * (rXYZ/gXYZ/bXYZ + rTRC/gTRC/bTRC, curveType or parametricCurveType) are supported; anything else returns
+ * CE_ERR_METRIC_CALCULATION with the reason in ce_last_error(), i.e. Error::MetricCalculation{metric:"ICC"}. */
+CE_API int ce_transform_to_srgb(ce_ctx* ctx, const uint8_t* rgb, size_t len, size_t width, size_t height,
+                                const uint8_t* icc, size_t icc_len, uint8_t* out);
+
 /* ---- stage-level entry points (parity tests; device does the work) -- */
 /* Each runs ONE pipeline stage on the device for a single host image / pair
  * and returns the intermediate, so tests can localise a mismatch against the

@@ -101,8 +101,8 @@ def test_image_data_and_config_defaults():
     d = ImageData.rgba8(rgba)
     assert (d.width(), d.height()) == (3, 2)
     assert np.array_equal(d.to_rgb8_vec(), rgba[:, :, :3].reshape(-1))                               # alpha dropped, session.rs:100-114
-    with pytest.raises(NotImplementedError):
-        ImageData.rgb_slice_with_icc(np.zeros(12, np.uint8), 2, 2, b"icc").to_rgb8_srgb()
+    # an attached profile is applied on the device (tests/test_icc.py); untagged data passes through untouched
+    assert np.array_equal(ImageData.rgb_slice(np.arange(12, dtype=np.uint8), 2, 2).to_rgb8_srgb(), np.arange(12, dtype=np.uint8))
     with pytest.raises(ValueError):
         ImageData.rgb_slice(np.zeros(11, np.uint8), 2, 2)
     c = EvalConfig.builder().report_dir("/tmp/x").build()
