@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-per-metric", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (profiling runs only: the line then has e2e = null)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel table (JSON) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -367,16 +368,18 @@ def main():
             gather_in.copy_(torch.frombuffer(e2e_out, dtype=torch.uint8))
             dist.all_gather_into_tensor(gather_out, gather_in)
 
-    e2e_ms = timed(step_e2e, args.steps, 2)
-    e2e_val = mpix * world * args.steps / (e2e_ms / 1e3)
-    e2e = {"value": e2e_val, "unit": "MPix-pairs/s", "h2d_bytes_per_step": (n + n_ref) * img_bytes,
-           "d2h_bytes_per_step": n * (1 + 108 + 10 + 4) * 8, "ms_per_step": e2e_ms / args.steps}
+    e2e = None
+    if not args.no_e2e:
+        e2e_ms = timed(step_e2e, args.steps, 2)
+        e2e_val = mpix * world * args.steps / (e2e_ms / 1e3)
+        e2e = {"value": e2e_val, "unit": "MPix-pairs/s", "h2d_bytes_per_step": (n + n_ref) * img_bytes,
+               "d2h_bytes_per_step": n * (1 + 108 + 10 + 4) * 8, "ms_per_step": e2e_ms / args.steps}
 
     # ---- the same sweep with the distortions generated ON the device: host references in, results
     # out; only the references cross PCIe.  Same references and quality ladder, 4:2:0 everywhere.
     _, _, _, quals, _ = WORKLOADS[args.workload]
     sweep = None
-    if w * h <= 1024 * 1024:
+    if w * h <= 1024 * 1024 and not args.no_e2e:
         ref_ptrs = (C.c_void_p * n_ref)(*[h_ref.data_ptr() + i * img_bytes for i in range(n_ref)])
         qarr = (C.c_int * len(quals))(*quals)
         sw_out = (_lib.CeResult * (n_ref * len(quals)))()

@@ -4,8 +4,9 @@
 // Per scale (<= 5 scales, floor-halving with crop on LINEAR rgb(a)):
 //   k_ds_lab     : pointwise, thread = 2x2 block: linear -> L (final), a/b (to be pre-blurred), and the
 //                  2x2 average of the linear planes for the next scale                 [issue: 6 IEEE divisions / px]
-//   k_ds_blur2s  : chroma pre-blur: the 3x3 kernel applied twice (clamp-replicate per pass); a warp streams
-//                  down a 60-column strip with both passes as register windows         [HBM-bound]
+//   k_ds_blur2   : chroma pre-blur: the 3x3 kernel applied twice (clamp-replicate per pass) through a
+//                  shared-memory tile, 4 positions per thread from 128-bit shared loads [HBM / latency]
+//                  (a streaming-warp version like k_ds_stream measured 7-25 % slower: 256-B row segments)
 //   k_ds_stream  : per channel the five double-3x3 blurs {ch1,ch2,ch1^2,ch2^2,ch1*ch2}: a warp streams down a
 //                  60-column strip with both 3x3 passes as register windows (shared products and row sums);
 //                  channel-averaged SSIM map written once + fp64 partial of its sum    [FP32-issue bound]
@@ -18,6 +19,55 @@
 
 namespace ce {
 
+#define DS_TW 64
+#define DS_TH 16
+#define DS_IW (DS_TW + 8)   // staged columns x0-4 .. x0+67 (16-B aligned start; the blurs need x0-2 .. x0+65)
+#define DS_IH (DS_TH + 4)   // rows y0-2 .. y0+17
+#define DS_FW (DS_TW + 4)   // first-pass positions x0-2 .. x0+65 (column j <-> x = x0-2+j; j < 66 used)
+#define DS_FH (DS_TH + 2)   // first-pass rows y0-1 .. y0+16
+#define DS_FG (DS_FW / 4)   // 17 four-column groups per first-pass row
+
+__constant__ float c_dsk[9] = {0.095332f, 0.118095f, 0.095332f, 0.118095f, 0.146293f,
+                               0.118095f, 0.095332f, 0.118095f, 0.095332f};
+
+CE_DEVINL float ds_k9(float v00, float v01, float v02, float v10, float v11, float v12, float v20, float v21, float v22) {
+    float a = (v00 * c_dsk[0] + v01 * c_dsk[1]) + v02 * c_dsk[2];
+    float b = (v10 * c_dsk[3] + v11 * c_dsk[4]) + v12 * c_dsk[5];
+    float c = (v20 * c_dsk[6] + v21 * c_dsk[7]) + v22 * c_dsk[8];
+    return (a + b) + c;
+}
+
+// 3 rows x 8 staged columns (i = 4q .. 4q+7) -> the 3x3 blur at the 4 positions j = 4q .. 4q+3 (centre column i = j+2)
+CE_DEVINL float4 ds_k9x4(const float (&r0)[8], const float (&r1)[8], const float (&r2)[8]) {
+    float4 o;
+    o.x = ds_k9(r0[1], r0[2], r0[3], r1[1], r1[2], r1[3], r2[1], r2[2], r2[3]);
+    o.y = ds_k9(r0[2], r0[3], r0[4], r1[2], r1[3], r1[4], r2[2], r2[3], r2[4]);
+    o.z = ds_k9(r0[3], r0[4], r0[5], r1[3], r1[4], r1[5], r2[3], r2[4], r2[5]);
+    o.w = ds_k9(r0[4], r0[5], r0[6], r1[4], r1[5], r1[6], r2[4], r2[5], r2[6]);
+    return o;
+}
+CE_DEVINL void ds_ld8(const float* s, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// The second 3x3 pass reads its input with clamped coordinates, so a first-pass value at a position outside
+// the image is the first-pass value at the nearest inside position.  Border tiles patch those entries.
+CE_DEVINL void ds_fix_border(float* __restrict__ s_f, int nplanes, int plane_stride, int w, int h, int x0, int y0) {
+    const bool border = x0 - 2 < 0 || x0 + DS_TW + 1 >= w || y0 - 1 < 0 || y0 + DS_TH >= h;
+    if (!border) return;   // block-uniform
+    for (int e = threadIdx.x; e < DS_FH * DS_FW; e += blockDim.x) {
+        const int ry = e / DS_FW, j = e - ry * DS_FW;
+        const int x = x0 - 2 + j, y = y0 - 1 + ry;
+        const int cx = min(max(x, 0), w - 1), cy = min(max(y, 0), h - 1);
+        if (cx != x || cy != y) {
+            const int cj = cx - (x0 - 2), cr = cy - (y0 - 1);
+            if (cj >= 0 && cj < DS_FW && cr >= 0 && cr < DS_FH)
+                for (int f = 0; f < nplanes; f++) s_f[f * plane_stride + e] = s_f[f * plane_stride + cr * DS_FW + cj];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ downsample (alpha plane / generic)
 // planes: [nplanes][n] -> [nplanes][on]; floor size, (a+b+c+d)*0.25
 __global__ void __launch_bounds__(256) k_ds_down(const float* __restrict__ in, int w, size_t n, int ow, int oh, size_t on,
@@ -28,6 +78,53 @@ __global__ void __launch_bounds__(256) k_ds_down(const float* __restrict__ in, i
         const float* top = in + pl * n + (size_t)(2 * y) * w + 2 * x;
         const float* bot = top + w;
         out[t] = (((top[0] + top[1]) + bot[0]) + bot[1]) * 0.25f;
+    }
+}
+
+// ------------------------------------------------------------------ chroma pre-blur (3x3 kernel applied twice)
+// grid (tiles_x, tiles_y, NI): blockIdx.z = image; chroma [NI][2][n] -> img[(z*3) + 1 + {0,1}].
+// Both planes of a 64x16 tile (+ halo 2, clamped) are staged; each pass evaluates 4 positions per thread
+// from 128-bit shared loads.
+__global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chroma, int w, int h, size_t n,
+                                                   float* __restrict__ img) {
+    __shared__ __align__(16) float s_ab[2][DS_IH * DS_IW];
+    __shared__ __align__(16) float s_f[2][DS_FH * DS_FW];
+    const int x0 = blockIdx.x * DS_TW, y0 = blockIdx.y * DS_TH;
+    const size_t z = blockIdx.z;
+    const bool vec = (w & 3) == 0;
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++) load_tile<2, DS_IW / 4, DS_IH, 256>(s_ab[pl], DS_IW, chroma + (z * 2 + pl) * n, w, h, x0 - 4, y0 - 2, vec);
+    __syncthreads();
+    // first 3x3 pass over the positions the second pass needs
+    for (int e = threadIdx.x; e < 2 * DS_FH * DS_FG; e += 256) {
+        const int pl = e / (DS_FH * DS_FG), r = e - pl * (DS_FH * DS_FG);
+        const int ry = r / DS_FG, q = r - ry * DS_FG;
+        float r0[8], r1[8], r2[8];
+        const float* base = s_ab[pl] + ry * DS_IW + 4 * q;
+        ds_ld8(base, r0); ds_ld8(base + DS_IW, r1); ds_ld8(base + 2 * DS_IW, r2);
+        *reinterpret_cast<float4*>(&s_f[pl][ry * DS_FW + 4 * q]) = ds_k9x4(r0, r1, r2);
+    }
+    __syncthreads();
+    ds_fix_border(&s_f[0][0], 2, DS_FH * DS_FW, w, h, x0, y0);
+    __syncthreads();
+    // second pass -> the 4 pixels of this thread
+    const int g = threadIdx.x & 15, oy = threadIdx.x >> 4;
+    const int x = x0 + 4 * g, y = y0 + oy;
+    if (x >= w || y >= h) return;
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++) {
+        float r0[8], r1[8], r2[8];
+        const float* base = s_f[pl] + oy * DS_FW + 4 * g;
+        ds_ld8(base, r0); ds_ld8(base + DS_FW, r1); ds_ld8(base + 2 * DS_FW, r2);
+        const float4 o = ds_k9x4(r0, r1, r2);
+        float* d = img + (z * 3 + 1 + pl) * n + (size_t)y * w + x;
+        if (vec) *reinterpret_cast<float4*>(d) = o;
+        else {
+            d[0] = o.x;
+            if (x + 1 < w) d[1] = o.y;
+            if (x + 2 < w) d[2] = o.z;
+            if (x + 3 < w) d[3] = o.w;
+        }
     }
 }
 
@@ -397,114 +494,6 @@ __global__ void __launch_bounds__(256) k_ds_lab(const float* __restrict__ lin, c
     }
 }
 
-// ------------------------------------------------------------------ chroma pre-blur (3x3 kernel applied twice, streaming)
-// One warp per 60-column strip walks down the rows of one image's a / b planes with the same two chained register
-// windows as k_ds_stream (clamp-replicate per pass).  grid (column strips, row strips, NI);
-// chroma [NI][2][n] -> img[(z*3) + 1 + {0,1}].
-__global__ void __launch_bounds__(32, 16) k_ds_blur2s(const float* __restrict__ chroma, int w, int h, size_t n, int rows_per_strip,
-                                                       float* __restrict__ img) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x;
-    const int xw = (int)blockIdx.x * DSS_OUT - 2;
-    const int c0 = xw + 2 * lane;
-    const int ys = (int)blockIdx.y * rows_per_strip, ye = min(ys + rows_per_strip, h);
-    const size_t z = blockIdx.z;
-    const int cc0 = min(max(c0, 0), w - 1), cc1 = min(max(c0 + 1, 0), w - 1);
-    const bool v2ok = (w & 1) == 0 && c0 >= 0 && c0 + 1 < w;
-    const bool left_edge = xw < 0, right_edge = xw + 63 > w - 1;
-    const int rsrc = (w - 1 - xw) >> 1, rel = (w - 1 - xw) & 1;
-    const bool st0 = lane >= 1 && lane <= 30 && c0 < w, st1 = lane >= 1 && lane <= 30 && c0 + 1 < w;
-    const int r_lo = max(ys - 1, 0), r_hi = min(ye, h - 1);
-    const int nin = r_hi - r_lo + 3;
-    const int kfirst = ys == 0 ? 3 : 4;
-    const float* src = chroma + z * 2 * n;
-    float* dimg = img + (z * 3 + 1) * n;
-    DsWin s1[2], s2[2];
-#pragma unroll
-    for (int q = 0; q < 2; q++) { s1[q].a[0] = s1[q].a[1] = s1[q].b = 0ull; s2[q].a[0] = s2[q].a[1] = s2[q].b = 0ull; }
-    constexpr int AHEAD = 3;   // input rows in flight
-    float nx[AHEAD][2][2];
-    auto load = [&](int k, float (&d)[2][2]) {
-        const size_t ro = (size_t)min(max(r_lo - 1 + min(k, nin - 1), 0), h - 1) * w;
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const float* pl = src + (size_t)q * n + ro;
-            if (v2ok) {
-                const float2 t = *reinterpret_cast<const float2*>(pl + c0);
-                d[q][0] = t.x; d[q][1] = t.y;
-            } else {
-                d[q][0] = pl[cc0]; d[q][1] = pl[cc1];
-            }
-        }
-    };
-    auto store2 = [&](float* row, float v0, float v1) {   // row start of a plane
-        if (v2ok && st0) *reinterpret_cast<float2*>(row + c0) = make_float2(v0, v1);
-        else {
-            if (st0 && c0 >= 0) row[c0] = v0;
-            if (st1 && c0 + 1 >= 0) row[c0 + 1] = v1;
-        }
-    };
-    auto tick = [&](auto parc, int k, const float (&cur)[2][2]) {
-        constexpr int PAR = decltype(parc)::value;
-        float o[2][2];
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const float v0 = cur[q][0], v1 = cur[q][1];
-            const float vm = __shfl_up_sync(FULL, v1, 1), v2 = __shfl_down_sync(FULL, v0, 1);
-            f32x2 RA, RB;
-            ds_rowsums(vm, v0, v1, v2, RA, RB);
-            float f0, f1;
-            unpk2(add2(add2(s1[q].a[PAR], s1[q].b), RA), f0, f1);
-            s1[q].a[PAR] = RA; s1[q].b = RB;
-            if (left_edge) {
-                const float t = __shfl_sync(FULL, f0, 1);
-                if (lane == 0) { f0 = t; f1 = t; }
-            }
-            if (right_edge) {
-                const float t = __shfl_sync(FULL, rel ? f1 : f0, rsrc);
-                if (c0 > w - 1) f0 = t;
-                if (c0 + 1 > w - 1) f1 = t;
-            }
-            const float fm = __shfl_up_sync(FULL, f1, 1), f2 = __shfl_down_sync(FULL, f0, 1);
-            ds_rowsums(fm, f0, f1, f2, RA, RB);
-            unpk2(add2(add2(s2[q].a[PAR], s2[q].b), RA), o[q][0], o[q][1]);
-            s2[q].a[PAR] = RA; s2[q].b = RB;
-        }
-        if (k >= kfirst) {
-            const int y = ys + k - kfirst;
-            store2(dimg + (size_t)y * w, o[0][0], o[0][1]);
-            store2(dimg + n + (size_t)y * w, o[1][0], o[1][1]);
-        }
-        if (k == 2 && ys == 0) { s2[0].a[1] = s2[0].a[0]; s2[1].a[1] = s2[1].a[0]; }   // row 0 also stands for row -1
-    };
-#pragma unroll
-    for (int j = 0; j < AHEAD; j++) load(j, nx[j]);
-    // ticks in groups of 6 (= lcm of the window parity 2 and the AHEAD ring 3) so every index is compile-time
-    for (int k = 0; k < nin; k += 6) {
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-            if (k + j < nin) {   // warp-uniform
-                float cur[2][2];
-#pragma unroll
-                for (int q = 0; q < 2; q++) { cur[q][0] = nx[j % AHEAD][q][0]; cur[q][1] = nx[j % AHEAD][q][1]; }
-                load(k + j + AHEAD, nx[j % AHEAD]);
-                if (j & 1) tick(std::integral_constant<int, 1>(), k + j, cur);
-                else tick(std::integral_constant<int, 0>(), k + j, cur);
-            }
-        }
-    }
-    if (ye == h) {   // the last first-pass row also stands for row h: output row h-1 from the window as it is
-        const int par = nin & 1;
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const f32x2 a_old = par ? s2[q].a[1] : s2[q].a[0], a_new = par ? s2[q].a[0] : s2[q].a[1];
-            float o0, o1;
-            unpk2(add2(add2(a_old, s2[q].b), a_new), o0, o1);
-            store2(dimg + (size_t)q * n + (size_t)(h - 1) * w, o0, o1);
-        }
-    }
-}
-
 // one thread per pair: sum partials in fixed order; out[b][scale][0] = sum; avg[b] = max(mean,0)^(0.5^scale)
 __global__ void k_ds_mean(const double* __restrict__ partial, int ntiles, size_t B, size_t n, int scale, double* __restrict__ out,
                           double* __restrict__ avg) {
@@ -613,10 +602,8 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
             if (has_next) l = dst;
         }
         {
-            int lrows = 64;
-            while (lrows > 16 && (size_t)sx * cdiv(ch, lrows) * NI < (size_t)c.sm_count * 64) lrows /= 2;
-            dim3 grid(sx, cdiv(ch, lrows), (unsigned)NI);
-            CE_LAUNCH(c, "k_ds_blur2", (double)NI * n * 16, k_ds_blur2s<<<grid, 32, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, lrows, img));
+            dim3 grid(cdiv(cw, DS_TW), cdiv(ch, DS_TH), (unsigned)NI);
+            CE_LAUNCH(c, "k_ds_blur2", (double)NI * n * 16, k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img));
         }
         // row strips: 64 rows per warp, fewer when the launch would not fill the machine
         int rows = 64;
@@ -624,9 +611,11 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
         const unsigned sy = cdiv(ch, rows);
         const int ntiles = (int)(sx * sy);
         {
-            dim3 grid(sx, sy, (unsigned)R);
+            int rrows = 64;   // the reference launch has R, not B, images to spread over the machine
+            while (rrows > 16 && (size_t)sx * cdiv(ch, rrows) * R < (size_t)c.sm_count * 32) rrows /= 2;
+            dim3 grid(sx, cdiv(ch, rrows), (unsigned)R);
             CE_LAUNCH(c, "k_ds_stats<ref>", (double)R * n * 36,
-                      k_ds_stream<0><<<grid, 32, 0, c.stream>>>(img, R, nullptr, (int)cw, (int)ch, n, rows, refstat, nullptr, nullptr));
+                      k_ds_stream<0><<<grid, 32, 0, c.stream>>>(img, R, nullptr, (int)cw, (int)ch, n, rrows, refstat, nullptr, nullptr));
         }
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);

@@ -69,4 +69,16 @@ extern "C" {
                                      dist_lens: *const usize, n: usize, intensity_target: f32,
                                      out: *mut ce_result) -> c_int;
     pub fn ce_reference_destroy(r: *mut ce_ref);
+
+    // ---- on-device distortion source (baseline JPEG round trip, bit-exact with libjpeg-turbo) ----
+    pub fn ce_jpeg_roundtrip(ctx: *mut ce_ctx, rgb: *const u8, len: usize, width: usize, height: usize, quality: c_int,
+                             subsampling: c_int, out: *mut u8) -> c_int;
+    pub fn ce_jpeg_roundtrip_device(ctx: *mut ce_ctx, d_refs: *const u8, n_ref: usize, width: u32, height: u32,
+                                    qualities: *const c_int, n_q: usize, subsampling: c_int, d_out: *mut u8) -> c_int;
+    pub fn ce_evaluate_jpeg_sweep(ctx: *mut ce_ctx, refs: *const *const u8, n_ref: usize, width: u32, height: u32,
+                                  qualities: *const c_int, n_q: usize, subsampling: c_int, cfg: *const ce_metric_config,
+                                  intensity_target: f32, out: *mut ce_result) -> c_int;
+    // ---- src/metrics/icc.rs:69-103 transform_to_srgb (matrix/TRC profiles); icc == null => ColorProfile::Srgb ----
+    pub fn ce_transform_to_srgb(ctx: *mut ce_ctx, rgb: *const u8, len: usize, width: usize, height: usize, icc: *const u8,
+                                icc_len: usize, out: *mut u8) -> c_int;
 }
