@@ -124,6 +124,13 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(refs, dists, w, h, flags, sample_pairs, threads=0):
     """The oracle (port) on the host cores over a bounded sample of the same workload."""
     from oracle import oracle as O
@@ -145,15 +152,15 @@ def run_reference(args):
     w, h, _, _, desc = WORKLOADS[args.workload]
     urefs, dists, ref_index = make_pairs(args.workload, 0)
     refs = urefs[ref_index]
-    cores = O.max_threads()
+    cores = host_cores()   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core it is allowed to run on
     sample = max(cores, min(refs.shape[0], int(16 * (768 * 512) / (w * h)) or 1))
     sample = min(sample, refs.shape[0])
     flags = 15
     for _ in range(args.warmup):
-        O.evaluate_batch(refs[:sample], dists[:sample], w, h, flags)
+        O.evaluate_batch(refs[:sample], dists[:sample], w, h, flags, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.evaluate_batch(refs[:sample], dists[:sample], w, h, flags)
+        O.evaluate_batch(refs[:sample], dists[:sample], w, h, flags, threads=cores)
     dt = time.perf_counter() - t0
     val = sample * w * h / 1e6 * args.steps / dt
     line = {
@@ -401,9 +408,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
 
-        cores = O.max_threads()
+        cores = host_cores()
         sample = max(cores, 16)
-        v, ns, dt = cpu_baseline(urefs[ref_index[:sample]], dists, w, h, 15, sample)
+        v, ns, dt = cpu_baseline(urefs[ref_index[:sample]], dists, w, h, 15, sample, threads=cores)
         cpu = {"value": v, "unit": "MPix-pairs/s", "cores": cores, "kind": "port",
                "sample": f"{ns} of {n} pairs, all four metrics, OpenMP over pairs, {dt:.1f} s wall"}
 
