@@ -628,15 +628,44 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
         const size_t w = g.first.first, h = g.first.second, img_bytes = w * h * 3;
         const std::vector<size_t>& idx = g.second;
         // The group is cut into up to 4 chunks (at most 2 GiB of distorted input each): chunk k+1 is copied to the
-        // device on the copy stream while chunk k computes.
-        size_t nchunks = std::min<size_t>(4, (idx.size() + 7) / 8);
-        size_t chunk = (idx.size() + nchunks - 1) / nchunks;
-        chunk = std::max<size_t>(1, std::min<size_t>(chunk, ((size_t)2 << 30) / std::max<size_t>(img_bytes, 1)));
-        nchunks = (idx.size() + chunk - 1) / chunk;
+        // device on the copy stream while chunk k computes.  Only the first chunk's copy is exposed, so it is the
+        // small one (1/12 of the group); boundaries do not split a run of pairs that share a reference buffer.
+        size_t max_chunks = 4;
+        if (const char* e = getenv("CE_HOST_CHUNKS")) max_chunks = std::max<size_t>(1, (size_t)atoi(e));
+        const size_t cap = std::max<size_t>(1, ((size_t)2 << 30) / std::max<size_t>(img_bytes, 1));
+        std::vector<size_t> bounds(1, 0);
+        {
+            const size_t total = idx.size();
+            size_t want = std::min<size_t>(max_chunks, (total + 7) / 8);
+            want = std::max<size_t>(want, (total + cap - 1) / cap);
+            auto snap = [&](size_t b) {   // move a boundary to the end of the current same-reference run
+                while (b > 0 && b < total && pairs[idx[b]].ref == pairs[idx[b - 1]].ref) b++;
+                return b;
+            };
+            if (want > 1) {
+                const size_t first = snap(std::max<size_t>(1, total / 12));
+                if (first < total) bounds.push_back(first);
+                const size_t start = bounds.back(), rest = total - start, parts = want - 1;
+                for (size_t k = 1; k < parts; k++) {
+                    const size_t b = snap(start + rest * k / parts);
+                    if (b > bounds.back() && b < total) bounds.push_back(b);
+                }
+            }
+            // enforce the size cap
+            std::vector<size_t> capped(1, 0);
+            for (size_t k = 1; k <= bounds.size(); k++) {
+                const size_t end = k < bounds.size() ? bounds[k] : total;
+                while (end - capped.back() > cap) capped.push_back(capped.back() + cap);
+                if (end < total) capped.push_back(end);
+            }
+            bounds = capped;
+            bounds.push_back(total);
+        }
+        const size_t nchunks = bounds.size() - 1;
         auto stage = [&](size_t ci) {
             Staged& s = st[ci & 1];
-            s.k0 = ci * chunk;
-            s.B = std::min(chunk, idx.size() - s.k0);
+            s.k0 = bounds[ci];
+            s.B = bounds[ci + 1] - bounds[ci];
             // distinct reference buffers of the chunk (same host pointer == same image: evaluate_image compares one
             // reference with every codec x quality output, src/eval/session.rs:375-431) are uploaded once
             std::map<const uint8_t*, uint32_t> seen;

@@ -91,7 +91,9 @@ CE_DEVINL float rg_step(RGState& s, float sum) {
 #endif
 #define HP_C4 (HP_COLS / 4)
 #define HP_PITCH (HP_COLS + 4)   // 16-B aligned rows; lane = row reads LDS.128 at chunk (C4+1)*row + q: conflict-free per quarter warp
+#ifndef HP_SLOTS
 #define HP_SLOTS 3
+#endif
 
 // Which blurs a launch computes.  The reference-side statistics (mu1 = blur(i1), blur(i1^2)) do not depend on the
 // distorted image, so when a sub-batch has shared references they are computed once per distinct reference
@@ -164,14 +166,14 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float*
         cp_async_commit();
     };
     issue(0);
-    issue(1);
+    if (HP_SLOTS >= 3) issue(1);
     RGState st = {0, 0, 0, 0, 0, 0};
     // products of the previous 16 columns: Q0 = c-16..c-13, Q1 = c-12..c-9, Q2 = c-8..c-5, Q3 = c-4..c-1
     float Q0[4] = {0, 0, 0, 0}, Q1[4] = {0, 0, 0, 0}, Q2[4] = {0, 0, 0, 0}, Q3[4] = {0, 0, 0, 0};
     for (int k = 0; k < nchunks; k++) {
-        cp_async_wait<1>();
-        __syncthreads();   // chunk k visible to all; every warp is past its reads of slot (k-1) % 3
-        issue(k + 2);      // -> slot (k-1) % 3
+        if (HP_SLOTS >= 3) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();   // chunk k visible to all; every warp is past its reads of slot (k-1) % HP_SLOTS
+        issue(k + HP_SLOTS - 1);      // -> slot (k-1) % HP_SLOTS
         const float* a = s_in + ((k % HP_SLOTS) * NIN * HP_ROWS + lane) * HP_PITCH;
 #pragma unroll 1
         for (int m0 = 0; m0 < HP_C4; m0 += 4) {
