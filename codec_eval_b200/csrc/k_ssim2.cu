@@ -92,7 +92,7 @@ CE_DEVINL float rg_step(RGState& s, float sum) {
 #define HP_C4 (HP_COLS / 4)
 #define HP_PITCH (HP_COLS + 4)   // 16-B aligned rows; lane = row reads LDS.128 at chunk (C4+1)*row + q: conflict-free per quarter warp
 #ifndef HP_SLOTS
-#define HP_SLOTS 3
+#define HP_SLOTS 2
 #endif
 
 // Which blurs a launch computes.  The reference-side statistics (mu1 = blur(i1), blur(i1^2)) do not depend on the
