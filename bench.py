@@ -90,7 +90,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """start of the timed region: samples taken before it (warm-up, also under load) are only a fallback"""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -98,7 +102,10 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        inside = [r for t, r in self.rows if t >= t_mark]
+        rows = inside if len(inside) >= 2 else [r for _, r in self.rows]   # short timed regions: include the warm-up samples
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -294,10 +301,11 @@ def main():
     all_cfg = MetricConfig.all()
     step_all = make_step(all_cfg)
     sampler = ClockSampler(local_rank)
-    for _ in range(args.warmup):
+    sampler.start()                       # nvidia-smi needs ~0.2 s to deliver its first sample: start it under the warm-up
+    for _ in range(max(args.warmup, 12)):
         step_all()
     l0 = ctx.launch_count()
-    sampler.start()
+    sampler.mark()
     ms = timed(step_all, args.steps, 0)
     clocks = sampler.stop()
     launches = ctx.launch_count() - l0
