@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(256) k_ba_combine(const float* __restrict__ bl
 
 // 4 pixels per thread (w % 4 == 0): the 3x3 stride-3 neighbourhood of the mask comes from three aligned
 // 128-bit loads per row (columns x-4 .. x+7), everything else from one 128-bit load per plane.
-__global__ void __launch_bounds__(256) k_ba_combine4(const float* __restrict__ bl, const float* __restrict__ ac,
+__global__ void __launch_bounds__(256, 3) k_ba_combine4(const float* __restrict__ bl, const float* __restrict__ ac,
                                                       const float* __restrict__ mf, const float* __restrict__ lf, int w, int h,
                                                       size_t n, size_t B, size_t R, const int* __restrict__ ridx, float xmul,
                                                       float* __restrict__ diffmap) {
