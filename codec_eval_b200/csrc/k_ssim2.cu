@@ -267,37 +267,40 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
     // copy roles: item e -> (row r of the batch, ring plane pl, 16-B group c4); planes < NW are row-pass planes
     // (row j0 + r), the others are image-space planes (row j0 + r - 4).
     constexpr int ITEMS = VP_BATCH * NPL * (VP_COLS / 4);
-    const float* src[VP_MAXITEMS];
-    int srow[VP_MAXITEMS], sdst[VP_MAXITEMS];
+    // Per copy slot: the source address for batch row 0 and the range of batch start rows jn for which the source
+    // row lies inside the image (so the per-batch work is two compares, one 64-bit add and the copy).
+    const float* src0[VP_MAXITEMS];
+    int jlo[VP_MAXITEMS], jhi[VP_MAXITEMS], sdst[VP_MAXITEMS];
     static_assert((ITEMS + NT - 1) / NT <= VP_MAXITEMS, "copy roles");
 #pragma unroll
     for (int it = 0; it < VP_MAXITEMS; it++) {
         const int e = (int)threadIdx.x + it * NT;
-        src[it] = nullptr; srow[it] = 0; sdst[it] = 0;
+        src0[it] = hp; jlo[it] = 0x7fffffff; jhi[it] = 0; sdst[it] = 0;
         if (e < ITEMS) {
             const int r = e / (NPL * 8), rem = e - r * (NPL * 8), pl = rem >> 3, c4 = rem & 7;
             const float* base;
             if (pl < NW) base = hp + (size_t)pl * n;
             else if (MODE == S2_ALL) base = (pl == 5) ? i1 : i2;
             else base = (pl == 3) ? i1 : (pl == 4) ? i2 : vr + (size_t)(pl - 5) * n;
-            srow[it] = (pl < NW) ? r : r - 4;
+            const int srow = (pl < NW) ? r : r - 4;   // source row of this slot when the batch starts at row 0
             sdst[it] = (r * NPL + pl) * VP_COLS + 4 * c4;
-            src[it] = (x0 + 4 * c4 < w) ? base + (ptrdiff_t)srow[it] * w + x0 + 4 * c4 : nullptr;
+            if (x0 + 4 * c4 < w) {
+                src0[it] = base + (ptrdiff_t)srow * w + x0 + 4 * c4;
+                jlo[it] = -srow; jhi[it] = h - srow;
+            }
         }
     }
-    const ptrdiff_t step = (ptrdiff_t)VP_BATCH * w;
-    int jn = 0;   // rows already issued
     auto issue = [&](int t) {   // called for t = 0, 1, 2, ... in order
         if (t < nbatch) {
             float* slot = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS;
+            const int jn = t * VP_BATCH;   // first row of the batch
             if (vec) {
+                const size_t ro = (size_t)jn * w;
 #pragma unroll
                 for (int it = 0; it < VP_MAXITEMS; it++) {
                     if ((int)threadIdx.x + it * NT < ITEMS) {
-                        const int row = jn + srow[it];
-                        const bool ok = src[it] != nullptr && row >= 0 && row < h;
-                        cp_async16(slot + sdst[it], ok ? src[it] : hp, ok);
-                        if (src[it]) src[it] += step;
+                        const bool ok = jn >= jlo[it] && jn < jhi[it];
+                        cp_async16(slot + sdst[it], ok ? src0[it] + ro : hp, ok);
                     }
                 }
             } else {
@@ -313,7 +316,6 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
                     cp_async4(slot + (r * NPL + pl) * VP_COLS + cx, ok ? base + (size_t)row * w + xx : base, ok);
                 }
             }
-            jn += VP_BATCH;
         }
         cp_async_commit();
     };

@@ -1,25 +1,35 @@
 #!/usr/bin/env python
-"""Dynamic opcode mix of one kernel from an .ncu-rep source page: python tools/ncu_opmix.py rep kernel_regex"""
-import csv, subprocess, sys, collections
-out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'source', '--csv', '--kernel-name', 'regex:' + sys.argv[2]],
-                     capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hi = [i for i, r in enumerate(rows) if 'Source' in r and 'Instructions Executed' in r]
-seg = rows[hi[0] + 1: hi[1] - 1] if len(hi) > 1 else rows[hi[0] + 1:]
-h = rows[hi[0]]
-ie, src, smp = h.index('Instructions Executed'), h.index('Source'), h.index('# Samples')
-mix, tot, samp = collections.Counter(), 0, collections.Counter()
-for r in seg:
-    if len(r) <= ie: continue
-    try: n = int(r[ie])
-    except ValueError: continue
-    toks = r[src].split()
-    op = toks[1] if toks and toks[0].startswith('@') and len(toks) > 1 else (toks[0] if toks else '?')
-    op = op.split('.')[0].rstrip(';')
-    mix[op] += n; tot += n
-    try: samp[op] += int(r[smp])
-    except ValueError: pass
-print('total warp-instr', tot)
-ts = sum(samp.values())
-for op, n in mix.most_common(25):
-    print(f'{op:10s} {n:12d} {100*n/tot:5.1f}%   samples {100*samp[op]/max(ts,1):5.1f}%')
+"""Executed-instruction opcode mix per kernel from an .ncu-rep (SASS page; works without --import-source):
+  python tools/ncu_opmix.py rep kernel_substring [top]"""
+import csv, subprocess, sys
+from collections import Counter
+
+out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
+cur, hdr, per, smp = None, None, {}, {}
+idx = 0
+for r in csv.reader(out.splitlines()):
+    if len(r) >= 2 and r[0] in ('Kernel Name', 'Function Name'):
+        idx += 1
+        cur = f"{idx}:{r[1]}"
+        continue
+    if r and 'Instructions Executed' in r and 'Source' in r:
+        hdr = r
+        continue
+    if cur is None or hdr is None or len(r) < len(hdr) - 5:
+        continue
+    try:
+        n = int(r[hdr.index('Instructions Executed')]); s = int(r[hdr.index('# Samples')] or 0)
+    except ValueError:
+        continue
+    t = r[hdr.index('Source')].strip()
+    op = (t.split()[1] if t.startswith('@') else t.split()[0]).split('.')[0].rstrip(';')
+    per.setdefault(cur, Counter())[op] += n
+    smp.setdefault(cur, Counter())[op] += s
+want = sys.argv[2]
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+for k, c in per.items():
+    if want in k:
+        tot, ts = sum(c.values()), max(sum(smp[k].values()), 1)
+        print(k[:100], 'warp-instr', tot)
+        for op, n in c.most_common(top):
+            print(f'  {op:10s} {100 * n / tot:5.1f}% instr  {100 * smp[k][op] / ts:5.1f}% samples')
