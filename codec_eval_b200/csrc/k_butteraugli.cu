@@ -19,6 +19,8 @@
 // fp64 (warp shuffles -> block partials -> fixed order).
 // Blurs use zero padding + per-coordinate 1/sum(in-range taps) tables (the renormalised
 // borders of libjxl's ConvolveBorderColumn); tile loads are 128-bit where the row pitch allows.
+#include <cuda.h>
+
 #include "ce_common.cuh"
 #include "ce_internal.h"
 #include "ba_weights.inc"
@@ -650,11 +652,19 @@ __global__ void __launch_bounds__(256) k_ba_malta_diff(const float* __restrict__
 #define MT_BAND_FLOATS (MT_ROWS * MT_P)
 #define MT_BUF_FLOATS (3 * MT_BAND_FLOATS + 4 * MT_TH * MT_TW)
 #define MT_SMEM (2 * MT_BUF_FLOATS * 4)
+struct MaltaMaps {   // TMA descriptors (used by the TMA variant only): planes as the third tensor dimension
+    CUtensorMap diff;   // [B*2*3 planes][h][w]
+    CUtensorMap hf;     // [NI*2 planes][h][w]
+    CUtensorMap mf;     // [NI*3 planes][h][w]
+};
+template <bool TMA>
 __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ diff, const float* __restrict__ hf,
                                                       const float* __restrict__ mf, int w, int h, size_t n, size_t R,
                                                       const int* __restrict__ ridx,
-                                                      const __grid_constant__ MaltaParams2 prm2, float* __restrict__ ac) {
-    extern __shared__ __align__(16) float s_mt[];   // [2 buffers][3 band tiles | hf0 hf1 mf0 mf1 tiles]
+                                                      const __grid_constant__ MaltaParams2 prm2,
+                                                      const __grid_constant__ MaltaMaps maps, float* __restrict__ ac) {
+    extern __shared__ __align__(128) float s_mt[];   // [2 buffers][3 band tiles | hf0 hf1 mf0 mf1 tiles]
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const size_t b = blockIdx.z >> 1;
     const int C = blockIdx.z & 1;
     const MaltaParams& prm = prm2.ch[C];
@@ -666,6 +676,24 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
     const size_t im0 = (size_t)ridx[b], im1 = R + b;
     const float* e_src[4] = {hf + (im0 * 2 + C) * n, hf + (im1 * 2 + C) * n, mf + (im0 * 3 + C) * n, mf + (im1 * 3 + C) * n};
     auto issue = [&](int t) {
+        if (TMA) {
+            // one thread arms the buffer's barrier with the byte count and issues seven bulk tensor copies
+            if (threadIdx.x == 0 && t < nt) {
+                float* buf = s_mt + (t & 1) * MT_BUF_FLOATS;
+                const int ty0 = (t_begin + t) * MT_TH;
+                unsigned long long* bar = &s_bar[t & 1];
+                mbar_expect_tx(bar, MT_BUF_FLOATS * 4);
+#pragma unroll
+                for (int bd = 0; bd < 3; bd++)
+                    tma_load_3d(buf + bd * MT_BAND_FLOATS, &maps.diff, tx0 - 4, ty0 - 4, (int)blockIdx.z * 3 + bd, bar);
+                float* e = buf + 3 * MT_BAND_FLOATS;
+                tma_load_3d(e, &maps.hf, tx0, ty0, (int)(im0 * 2 + C), bar);
+                tma_load_3d(e + MT_TH * MT_TW, &maps.hf, tx0, ty0, (int)(im1 * 2 + C), bar);
+                tma_load_3d(e + 2 * MT_TH * MT_TW, &maps.mf, tx0, ty0, (int)(im0 * 3 + C), bar);
+                tma_load_3d(e + 3 * MT_TH * MT_TW, &maps.mf, tx0, ty0, (int)(im1 * 3 + C), bar);
+            }
+            return;
+        }
         if (t < nt) {
             float* buf = s_mt + (t & 1) * MT_BUF_FLOATS;
             const int ty0 = (t_begin + t) * MT_TH;
@@ -679,12 +707,24 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
         }
         cp_async_commit();
     };
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
     issue(0);
     issue(1);
     const int x = tx0 + 4 * g;
     for (int t = 0; t < nt; t++) {
-        cp_async_wait<1>();
-        __syncthreads();   // tile t visible to all
+        if (TMA) {
+            mbar_wait(&s_bar[t & 1], (unsigned)(t >> 1) & 1u);   // the bytes of tile t have landed
+        } else {
+            cp_async_wait<1>();
+            __syncthreads();   // tile t visible to all
+        }
         const float* buf = s_mt + (t & 1) * MT_BUF_FLOATS;
         const int y = (t_begin + t) * MT_TH + oy;
         float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -744,11 +784,41 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
             }
         }
     }
-    cp_async_wait<0>();
+    if (!TMA) cp_async_wait<0>();
 }
 
 static void ba_set_kernel_attributes() {
-    CE_CUDA(cudaFuncSetAttribute(k_ba_malta, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+    CE_CUDA(cudaFuncSetAttribute(k_ba_malta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+    CE_CUDA(cudaFuncSetAttribute(k_ba_malta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+// fp32 planes [nplanes][h][w] as a rank-3 tensor, box = (bw, bh, 1); zero fill outside.  w % 4 == 0 required.
+static bool make_plane_map(CUtensorMap* m, const float* base, size_t w, size_t h, size_t nplanes, unsigned bw, unsigned bh) {
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc || (w & 3) || nplanes == 0) return false;
+    const cuuint64_t dims[3] = {w, h, nplanes};
+    const cuuint64_t strides[2] = {w * 4, w * h * 4};
+    const cuuint32_t box[3] = {bw, bh, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---------------------------------------------------------------- combine
@@ -1102,8 +1172,17 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
             CE_LAUNCH(c, "k_ba_malta_diff", (double)B * n * 72,
                       k_ba_malta_diff<false><<<ew_blocks(c, B * 2 * n), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
         dim3 grid(cdiv(w, MT_TW), cdiv(cdiv(h, MT_TH), MT_NT), (unsigned)(2 * B));
-        CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
-                  k_ba_malta<<<grid, 256, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, L.ac));
+        MaltaMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        const bool tma = make_plane_map(&maps.diff, L.mdiff, w, h, B * 6, MT_P, MT_ROWS) &&
+                         make_plane_map(&maps.hf, L.hf, w, h, NI * 2, MT_TW, MT_TH) &&
+                         make_plane_map(&maps.mf, L.mf, w, h, NI * 3, MT_TW, MT_TH);
+        if (tma)
+            CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
+                      k_ba_malta<true><<<grid, 256, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));
+        else   // widths that are not a multiple of 4 cannot be described by a tensor map (16-byte row stride): cp.async tiles
+            CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
+                      k_ba_malta<false><<<grid, 256, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));
     }
     if (w % 4 == 0)
         CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,
