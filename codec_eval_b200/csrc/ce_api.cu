@@ -408,6 +408,36 @@ static void run_device_batch(Context& c, const uint8_t* d_ref, size_t n_ref, con
         c.last_error = cfg.ssimulacra2 ? "SSIMULACRA2: images must be at least 8x8 pixels" : "Butteraugli: images must be at least 8x8 pixels";
 }
 
+// ------------------------------------------------------------------ TMA descriptors
+namespace ce {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+bool tma_plane_map(CUtensorMap* m, const float* base, size_t w, size_t h, size_t nplanes, unsigned bw, unsigned bh, unsigned bz) {
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc || (w & 3) || nplanes == 0 || !base) return false;
+    const cuuint64_t dims[3] = {w, h, nplanes};
+    const cuuint64_t strides[2] = {w * 4, w * h * 4};
+    const cuuint32_t box[3] = {bw, bh, bz};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace ce
+
 // ------------------------------------------------------------------ C ABI
 #define CE_TRY(ctx_expr, body)                                   \
     try {                                                        \

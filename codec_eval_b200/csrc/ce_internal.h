@@ -1,6 +1,7 @@
 // ce_internal.h -- host-side internals of libce_gpu: context, workspace arena,
 // and the launchers each kernel file exports.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -127,6 +128,11 @@ struct Context {
         __VA_ARGS__;                                \
         (ctx).prof_end();                           \
     } while (0)
+
+// TMA descriptor of fp32 planes [nplanes][h][w] as a rank-3 tensor with box (bw, bh, bz) and zero fill outside
+// (cuTensorMapEncodeTiled through the runtime's driver entry point; libcuda is not linked).  False when the shape
+// cannot be described (w % 4 != 0: the row stride must be a multiple of 16 bytes) -- callers then use cp.async tiles.
+bool tma_plane_map(CUtensorMap* m, const float* base, size_t w, size_t h, size_t nplanes, unsigned bw, unsigned bh, unsigned bz);
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

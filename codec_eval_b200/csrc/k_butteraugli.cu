@@ -792,35 +792,6 @@ static void ba_set_kernel_attributes() {
     CE_CUDA(cudaFuncSetAttribute(k_ba_malta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn tma_encoder() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult st;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-        cudaGetLastError();
-    }
-    return fn;
-}
-// fp32 planes [nplanes][h][w] as a rank-3 tensor, box = (bw, bh, 1); zero fill outside.  w % 4 == 0 required.
-static bool make_plane_map(CUtensorMap* m, const float* base, size_t w, size_t h, size_t nplanes, unsigned bw, unsigned bh) {
-    EncodeTiledFn enc = tma_encoder();
-    if (!enc || (w & 3) || nplanes == 0) return false;
-    const cuuint64_t dims[3] = {w, h, nplanes};
-    const cuuint64_t strides[2] = {w * 4, w * h * 4};
-    const cuuint32_t box[3] = {bw, bh, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // ---------------------------------------------------------------- combine
 CE_DEVINL void store_min3(float v, float& m0, float& m1, float& m2) {
     if (v < m2) {
@@ -1174,9 +1145,9 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
         dim3 grid(cdiv(w, MT_TW), cdiv(cdiv(h, MT_TH), MT_NT), (unsigned)(2 * B));
         MaltaMaps maps;
         memset(&maps, 0, sizeof(maps));
-        const bool tma = make_plane_map(&maps.diff, L.mdiff, w, h, B * 6, MT_P, MT_ROWS) &&
-                         make_plane_map(&maps.hf, L.hf, w, h, NI * 2, MT_TW, MT_TH) &&
-                         make_plane_map(&maps.mf, L.mf, w, h, NI * 3, MT_TW, MT_TH);
+        const bool tma = tma_plane_map(&maps.diff, L.mdiff, w, h, B * 6, MT_P, MT_ROWS, 1) &&
+                         tma_plane_map(&maps.hf, L.hf, w, h, NI * 2, MT_TW, MT_TH, 1) &&
+                         tma_plane_map(&maps.mf, L.mf, w, h, NI * 3, MT_TW, MT_TH, 1);
         if (tma)
             CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
                       k_ba_malta<true><<<grid, 256, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));

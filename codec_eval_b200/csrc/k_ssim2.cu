@@ -12,6 +12,8 @@
 //   k_s2_reduce   : fixed-order sum of the block partials -> 18 sums per (pair, scale)
 // The recurrence is the exact operation sequence of the upstream code so the
 // result does not depend on the tiling.
+#include <cuda.h>
+
 #include "ce_common.cuh"
 #include "ce_internal.h"
 
@@ -238,16 +240,23 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float*
 //   S2_PAIR: ring planes = 3 row-pass planes + i1 + i2 + the reference's mu1 and blur(i1^2) rows (vref); the
 //            map rows of a batch are dealt over the three warps.
 // ONE block barrier per 5 rows.  partials: [(unit*3+c)][gridDim.x][6]
-template <int MODE>
+struct VpassMaps {   // TMA descriptors of the column pass (TMA variant): planes are the third tensor dimension
+    CUtensorMap hb;    // row-pass planes [units*3*NW][h][w], box (32, 5, NW)
+    CUtensorMap xyb;   // [NI*3][h][w], box (32, 5, 1)
+    CUtensorMap vr;    // reference statistics [R*3*2][h][w], box (32, 5, 2)
+};
+template <int MODE, bool TMA>
 __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float* __restrict__ xyb, size_t R,
                                                                      const int* __restrict__ ridx,
                                                                      const float* __restrict__ hb, float* __restrict__ vref,
                                                                      int w, int h, size_t n, double* __restrict__ partials,
-                                                                     float* __restrict__ dbg, int vec) {
+                                                                     float* __restrict__ dbg, int vec,
+                                                                     const __grid_constant__ VpassMaps maps) {
     constexpr int NW = S2Mode<MODE>::NW, NT = NW * 32;
     constexpr int NPL = MODE == S2_REF ? 2 : 7;          // ring planes
     constexpr int SLOT_FLOATS = VP_BATCH * NPL * VP_COLS;
-    __shared__ __align__(16) float s_ld[VP_SLOTS * SLOT_FLOATS];   // [slot][row r][plane][col]
+    __shared__ __align__(128) float s_ld[VP_SLOTS * SLOT_FLOATS];   // [slot][plane][row r][col]
+    __shared__ __align__(8) unsigned long long s_bar[VP_SLOTS];
     __shared__ float s_v[MODE == S2_REF ? 1 : 2][VP_BATCH][NW][VP_COLS];
     __shared__ double scratch[6 * 32];
     const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
             else if (MODE == S2_ALL) base = (pl == 5) ? i1 : i2;
             else base = (pl == 3) ? i1 : (pl == 4) ? i2 : vr + (size_t)(pl - 5) * n;
             const int srow = (pl < NW) ? r : r - 4;   // source row of this slot when the batch starts at row 0
-            sdst[it] = (r * NPL + pl) * VP_COLS + 4 * c4;
+            sdst[it] = (pl * VP_BATCH + r) * VP_COLS + 4 * c4;
             if (x0 + 4 * c4 < w) {
                 src0[it] = base + (ptrdiff_t)srow * w + x0 + 4 * c4;
                 jlo[it] = -srow; jhi[it] = h - srow;
@@ -291,6 +300,23 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
         }
     }
     auto issue = [&](int t) {   // called for t = 0, 1, 2, ... in order
+        if (TMA) {
+            // one thread: arm the slot's barrier with the byte count, then one bulk tensor copy per source tensor
+            // (rows / columns outside the image arrive as zeros)
+            if (threadIdx.x == 0 && t < nbatch) {
+                float* slot = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS;
+                unsigned long long* bar = &s_bar[t & (VP_SLOTS - 1)];
+                const int jn = t * VP_BATCH;
+                mbar_expect_tx(bar, SLOT_FLOATS * 4);
+                tma_load_3d(slot, &maps.hb, x0, jn, (int)((u * 3 + c) * NW), bar);
+                if (MODE != S2_REF) {
+                    tma_load_3d(slot + NW * VP_BATCH * VP_COLS, &maps.xyb, x0, jn - 4, (int)(iref * 3 + c), bar);
+                    tma_load_3d(slot + (NW + 1) * VP_BATCH * VP_COLS, &maps.xyb, x0, jn - 4, (int)((R + u) * 3 + c), bar);
+                }
+                if (MODE == S2_PAIR) tma_load_3d(slot + (NW + 2) * VP_BATCH * VP_COLS, &maps.vr, x0, jn - 4, (int)((iref * 3 + c) * 2), bar);
+            }
+            return;
+        }
         if (t < nbatch) {
             float* slot = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS;
             const int jn = t * VP_BATCH;   // first row of the batch
@@ -313,7 +339,7 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
                     else base = (pl == 3) ? i1 : (pl == 4) ? i2 : vr + (size_t)(pl - 5) * n;
                     const int row = (pl < NW) ? jn + r : jn + r - 4;
                     const bool ok = row >= 0 && row < h && xx < w;
-                    cp_async4(slot + (r * NPL + pl) * VP_COLS + cx, ok ? base + (size_t)row * w + xx : base, ok);
+                    cp_async4(slot + (pl * VP_BATCH + r) * VP_COLS + cx, ok ? base + (size_t)row * w + xx : base, ok);
                 }
             }
         }
@@ -326,16 +352,16 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
         const int y = t * VP_BATCH + r - 4;
         if (y >= 0 && y < h && active) {
             const int bf = t & 1;
-            const float* slot = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS + (r * NPL) * VP_COLS + lane;
+            const float* slot = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS + r * VP_COLS + lane;   // + plane * VP_BATCH * VP_COLS
             float m1, m2, s11, s22, s12, a1, a2;
             if (MODE == S2_ALL) {
                 m1 = s_v[bf][r][0][lane]; m2 = s_v[bf][r][1][lane]; s11 = s_v[bf][r][2][lane];
                 s22 = s_v[bf][r][NW > 3 ? 3 : 0][lane]; s12 = s_v[bf][r][NW > 4 ? 4 : 0][lane];
-                a1 = slot[5 * VP_COLS]; a2 = slot[6 * VP_COLS];
+                a1 = slot[5 * VP_BATCH * VP_COLS]; a2 = slot[6 * VP_BATCH * VP_COLS];
             } else {
                 m2 = s_v[bf][r][0][lane]; s22 = s_v[bf][r][1][lane]; s12 = s_v[bf][r][NW > 2 ? 2 : 0][lane];
-                a1 = slot[3 * VP_COLS]; a2 = slot[4 * VP_COLS];
-                m1 = slot[(NPL > 5 ? 5 : 0) * VP_COLS]; s11 = slot[(NPL > 6 ? 6 : 0) * VP_COLS];
+                a1 = slot[3 * VP_BATCH * VP_COLS]; a2 = slot[4 * VP_BATCH * VP_COLS];
+                m1 = slot[(NPL > 5 ? 5 : 0) * VP_BATCH * VP_COLS]; s11 = slot[(NPL > 6 ? 6 : 0) * VP_BATCH * VP_COLS];
             }
             if (dbg) {
                 float* d = dbg + (size_t)c * 7 * n + (size_t)y * w + x;
@@ -373,6 +399,14 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
         }
     };
 
+    if (TMA) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < VP_SLOTS; i++) mbar_init(&s_bar[i], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
     issue(0);
     issue(1);
     RGState st = {0, 0, 0, 0, 0, 0};
@@ -385,13 +419,14 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
         for (int half = 0; half < 2; half++) {
             const int t = t0 + half;
             if (t < nbatch) {   // block-uniform
-                cp_async_wait<1>();
+                if (TMA) mbar_wait(&s_bar[t & (VP_SLOTS - 1)], (unsigned)(t / VP_SLOTS) & 1u);
+                else cp_async_wait<1>();
                 __syncthreads();   // batch t landed; s_v of batch t-1 complete; slot (t-2) % 4 free
                 issue(t + 2);
-                const float* in = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS + p * VP_COLS + lane;
+                const float* in = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS + p * VP_BATCH * VP_COLS + lane;
 #pragma unroll
                 for (int r = 0; r < VP_BATCH; r++) {
-                    const float rv = in[r * NPL * VP_COLS];
+                    const float rv = in[r * VP_COLS];
                     const float l = ring[half * VP_BATCH + r];
                     ring[half * VP_BATCH + r] = rv;
                     const float o = rg_step(st, l + rv);
@@ -494,18 +529,41 @@ int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t
             dim3 gvr(nblk, (unsigned)(R * 3)), gvp(nblk, (unsigned)(B * 3));
             CE_LAUNCH(c, "k_s2_hpass<ref>", (double)R * 3 * 3 * n * 4,
                       k_s2_hpass<S2_REF><<<ghr, 64, S2Mode<S2_REF>::HP_SMEM, c.stream>>>(xyb, R, ridx, hbr, (int)cw, (int)ch, n, vecf));
-            CE_LAUNCH(c, "k_s2_vpass<ref>", (double)R * 3 * 4 * n * 4,
-                      k_s2_vpass<S2_REF><<<gvr, 64, 0, c.stream>>>(xyb, R, ridx, hbr, vref, (int)cw, (int)ch, n, nullptr, nullptr, vecf));
+            VpassMaps mr, mp;
+            memset(&mr, 0, sizeof(mr));
+            memset(&mp, 0, sizeof(mp));
+            const bool tma = tma_plane_map(&mr.hb, hbr, cw, ch, R * 6, VP_COLS, VP_BATCH, 2) &&
+                             tma_plane_map(&mp.hb, hbp, cw, ch, B * 9, VP_COLS, VP_BATCH, 3) &&
+                             tma_plane_map(&mp.xyb, xyb, cw, ch, NI * 3, VP_COLS, VP_BATCH, 1) &&
+                             tma_plane_map(&mp.vr, vref, cw, ch, R * 6, VP_COLS, VP_BATCH, 2);
+            if (tma)
+                CE_LAUNCH(c, "k_s2_vpass<ref>", (double)R * 3 * 4 * n * 4,
+                          k_s2_vpass<S2_REF, true><<<gvr, 64, 0, c.stream>>>(xyb, R, ridx, hbr, vref, (int)cw, (int)ch, n, nullptr, nullptr, vecf, mr));
+            else
+                CE_LAUNCH(c, "k_s2_vpass<ref>", (double)R * 3 * 4 * n * 4,
+                          k_s2_vpass<S2_REF, false><<<gvr, 64, 0, c.stream>>>(xyb, R, ridx, hbr, vref, (int)cw, (int)ch, n, nullptr, nullptr, vecf, mr));
             CE_LAUNCH(c, "k_s2_hpass<pair>", (double)B * 3 * 5 * n * 4,
                       k_s2_hpass<S2_PAIR><<<ghp, 96, S2Mode<S2_PAIR>::HP_SMEM, c.stream>>>(xyb, R, ridx, hbp, (int)cw, (int)ch, n, vecf));
-            CE_LAUNCH(c, "k_s2_vpass<pair>", (double)B * 3 * 7 * n * 4,
-                      k_s2_vpass<S2_PAIR><<<gvp, 96, 0, c.stream>>>(xyb, R, ridx, hbp, vref, (int)cw, (int)ch, n, partials, dbg, vecf));
+            if (tma)
+                CE_LAUNCH(c, "k_s2_vpass<pair>", (double)B * 3 * 7 * n * 4,
+                          k_s2_vpass<S2_PAIR, true><<<gvp, 96, 0, c.stream>>>(xyb, R, ridx, hbp, vref, (int)cw, (int)ch, n, partials, dbg, vecf, mp));
+            else
+                CE_LAUNCH(c, "k_s2_vpass<pair>", (double)B * 3 * 7 * n * 4,
+                          k_s2_vpass<S2_PAIR, false><<<gvp, 96, 0, c.stream>>>(xyb, R, ridx, hbp, vref, (int)cw, (int)ch, n, partials, dbg, vecf, mp));
         } else {
             dim3 gh(cdiv(ch, HP_ROWS), (unsigned)(B * 3)), gv(nblk, (unsigned)(B * 3));
             CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4,
                       k_s2_hpass<S2_ALL><<<gh, 160, S2Mode<S2_ALL>::HP_SMEM, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, vecf));
-            CE_LAUNCH(c, "k_s2_vpass", (double)B * 3 * 7 * n * 4,
-                      k_s2_vpass<S2_ALL><<<gv, 160, 0, c.stream>>>(xyb, R, ridx, hb, nullptr, (int)cw, (int)ch, n, partials, dbg, vecf));
+            VpassMaps ma;
+            memset(&ma, 0, sizeof(ma));
+            const bool tma = tma_plane_map(&ma.hb, hb, cw, ch, B * 15, VP_COLS, VP_BATCH, 5) &&
+                             tma_plane_map(&ma.xyb, xyb, cw, ch, NI * 3, VP_COLS, VP_BATCH, 1);
+            if (tma)
+                CE_LAUNCH(c, "k_s2_vpass", (double)B * 3 * 7 * n * 4,
+                          k_s2_vpass<S2_ALL, true><<<gv, 160, 0, c.stream>>>(xyb, R, ridx, hb, nullptr, (int)cw, (int)ch, n, partials, dbg, vecf, ma));
+            else
+                CE_LAUNCH(c, "k_s2_vpass", (double)B * 3 * 7 * n * 4,
+                          k_s2_vpass<S2_ALL, false><<<gv, 160, 0, c.stream>>>(xyb, R, ridx, hb, nullptr, (int)cw, (int)ch, n, partials, dbg, vecf, ma));
         }
         {
             size_t total = B * 3 * 6;
