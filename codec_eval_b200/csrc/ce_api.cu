@@ -426,6 +426,14 @@ static EncodeTiledFn tma_encoder() {
     }
     return fn;
 }
+bool tma_enabled(int group) {   // CE_TMA_MASK (debugging): bit per kernel group, default all on
+    static int mask = -2;
+    if (mask == -2) {
+        const char* e = getenv("CE_TMA_MASK");
+        mask = e ? atoi(e) : -1;
+    }
+    return (mask & (1 << group)) != 0;
+}
 bool tma_plane_map(CUtensorMap* m, const float* base, size_t w, size_t h, size_t nplanes, unsigned bw, unsigned bh, unsigned bz) {
     EncodeTiledFn enc = tma_encoder();
     if (!enc || (w & 3) || nplanes == 0 || !base) return false;

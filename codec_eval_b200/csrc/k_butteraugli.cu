@@ -214,17 +214,31 @@ __global__ void __launch_bounds__(256) k_ba_opsin(const float* __restrict__ lin,
 
 // ---------------------------------------------------------------- wide separable blur (sigma 7.16)
 // horizontal: tile 128 x 8, thread = 4 consecutive outputs of one row
-template <int SLOT, int R>
+// TMA: the tile is one bulk tensor copy (map = in as [planes][h][w], box (PITCH, 8, 1)); otherwise per-thread loads.
+template <int SLOT, int R, bool TMA>
 __global__ void __launch_bounds__(256) k_ba_blur_h(const float* __restrict__ in, int w, int h, size_t n,
-                                                    const float* __restrict__ inv, float* __restrict__ out, int vec) {
+                                                    const float* __restrict__ inv, float* __restrict__ out, int vec,
+                                                    const __grid_constant__ CUtensorMap map) {
     constexpr int RUP = (R + 3) & ~3;
     constexpr int PITCH = 128 + 2 * RUP;
-    __shared__ __align__(16) float s[8 * PITCH];
+    __shared__ __align__(128) float s[8 * PITCH];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int x0 = blockIdx.x * 128, y0 = blockIdx.y * 8;
     const float* p = in + (size_t)blockIdx.z * n;
     float* o = out + (size_t)blockIdx.z * n;
-    load_tile<0, PITCH / 4, 8, 256>(s, PITCH, p, w, h, x0 - RUP, y0, vec != 0);
-    __syncthreads();
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(&s_bar, 8 * PITCH * 4);
+            tma_load_3d(s, &map, x0 - RUP, y0, (int)blockIdx.z, &s_bar);
+        }
+        __syncthreads();   // barrier initialised before anyone polls it
+        mbar_wait(&s_bar, 0);
+    } else {
+        load_tile<0, PITCH / 4, 8, 256>(s, PITCH, p, w, h, x0 - RUP, y0, vec != 0);
+        __syncthreads();
+    }
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int y = y0 + ty, x = x0 + tx * 4;
     if (y >= h || x >= w) return;
@@ -264,30 +278,51 @@ CE_DEVINL f32x2 baw2(int t) {
 // planes of an image go through one block; plane c+1 is staged with cp.async while plane c is computed.
 // EPI 0: out[pl] = blurred plane (grid.z counts plane groups of NPL)
 // EPI 1 (NPL = 3): LF epilogue -- lf = blurred xyb; mf_pre = xyb - lf; lf scaled (XybLowFreqToVals)
-template <int SLOT, int R, int NPL, int EPI>
+template <int SLOT, int R, int NPL, int EPI, bool TMA>
 __global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in, int w, int h, size_t n,
                                                     const float* __restrict__ inv, float* __restrict__ out,
-                                                    const float* __restrict__ xyb, float* __restrict__ mf_pre) {
+                                                    const float* __restrict__ xyb, float* __restrict__ mf_pre,
+                                                    const __grid_constant__ CUtensorMap map) {
     constexpr int ROWS = 64 + 2 * R;
-    __shared__ __align__(16) float s[2][ROWS * 32];
+    __shared__ __align__(128) float s[2][ROWS * 32];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 64;
     const int cp = threadIdx.x & 15, g = threadIdx.x >> 4;   // 16 column pairs x 16 groups of 4 rows
     const int x = x0 + 2 * cp;
     const size_t base = (size_t)blockIdx.z * NPL * n;
     const bool vec = (w & 3) == 0;
     float res[NPL][4][2];
-    load_tile_async<8, ROWS, 256>(s[0], 32, in + base, w, h, x0, y0 - R, vec);
-    cp_async_commit();
-#pragma unroll
-    for (int c = 0; c < NPL; c++) {
-        if (c + 1 < NPL) {
-            load_tile_async<8, ROWS, 256>(s[(c + 1) & 1], 32, in + base + (size_t)(c + 1) * n, w, h, x0, y0 - R, vec);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+    auto tma_issue = [&](int c) {   // thread 0: plane c -> buffer c & 1 (map = in as [planes][h][w], box (32, ROWS, 1))
+        mbar_expect_tx(&s_bar[c & 1], ROWS * 32 * 4);
+        tma_load_3d(s[c & 1], &map, x0, y0 - R, (int)(blockIdx.z * NPL + c), &s_bar[c & 1]);
+    };
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            mbar_fence_init();
+            tma_issue(0);
+            if (NPL > 1) tma_issue(1);
         }
         __syncthreads();
+    } else {
+        load_tile_async<8, ROWS, 256>(s[0], 32, in + base, w, h, x0, y0 - R, vec);
+        cp_async_commit();
+    }
+#pragma unroll
+    for (int c = 0; c < NPL; c++) {
+        if (TMA) {
+            mbar_wait(&s_bar[c & 1], (unsigned)(c >> 1) & 1u);
+        } else {
+            if (c + 1 < NPL) {
+                load_tile_async<8, ROWS, 256>(s[(c + 1) & 1], 32, in + base + (size_t)(c + 1) * n, w, h, x0, y0 - R, vec);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+        }
         const float* sc = s[c & 1];
         f32x2 v[4 + 2 * R];
 #pragma unroll
@@ -304,7 +339,9 @@ __global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in,
             res[c][k][0] = lo * iy;
             res[c][k][1] = hi * iy;
         }
+        if (TMA && c + 2 < NPL) fence_proxy_async();
         __syncthreads();   // plane c's buffer is refilled two planes later
+        if (TMA && c + 2 < NPL && threadIdx.x == 0) tma_issue(c + 2);
     }
     if (x >= w) return;
     const bool two = x + 1 < w;
@@ -342,15 +379,17 @@ __global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in,
 //                   out_c = mask input m [img][n] = DiffPrecompute(combine(hf, uhf))
 #define B2_TW 64
 #define B2_TH 32
-template <int SLOT, int R, int NPL, int EPI>
+template <int SLOT, int R, int NPL, int EPI, bool TMA>
 __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in, int w, int h, size_t n,
                                                     const float* __restrict__ inv_x, const float* __restrict__ inv_y,
                                                     float* __restrict__ out_a, float* __restrict__ out_b,
-                                                    float* __restrict__ out_c) {
+                                                    float* __restrict__ out_c, const __grid_constant__ CUtensorMap map) {
     constexpr int RUP = (R + 3) & ~3;
     constexpr int PITCH = B2_TW + 2 * RUP;
     constexpr int ROWS = B2_TH + 2 * R;
-    __shared__ __align__(16) float s_in2[2][ROWS * PITCH];   // plane c+1 is staged with cp.async while plane c is computed
+    constexpr int TILE = (ROWS * PITCH + 31) & ~31;   // 128-byte multiple so both buffers are valid TMA destinations
+    __shared__ __align__(128) float s_in2[2][TILE];   // plane c+1 is staged (TMA / cp.async) while plane c is computed
+    __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ __align__(16) float s_h[ROWS * B2_TW];
     const int x0 = blockIdx.x * B2_TW, y0 = blockIdx.y * B2_TH;
     const size_t img = blockIdx.z;
@@ -359,11 +398,28 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
     const int cp = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int x = x0 + 2 * cp;
     float res[NPL][4][2], ctr[NPL][4][2];
-    load_tile_async<PITCH / 4, ROWS, 256>(s_in2[0], PITCH, in + (img * NPL) * n, w, h, x0 - RUP, y0 - R, vec);
-    cp_async_commit();
+    auto tma_issue = [&](int c) {   // thread 0: plane c -> buffer c & 1 (map = in as [planes][h][w], box (PITCH, ROWS, 1))
+        mbar_expect_tx(&s_bar[c & 1], ROWS * PITCH * 4);
+        tma_load_3d(s_in2[c & 1], &map, x0 - RUP, y0 - R, (int)(img * NPL + c), &s_bar[c & 1]);
+    };
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            mbar_fence_init();
+            tma_issue(0);
+            if (NPL > 1) tma_issue(1);
+        }
+        __syncthreads();
+    } else {
+        load_tile_async<PITCH / 4, ROWS, 256>(s_in2[0], PITCH, in + (img * NPL) * n, w, h, x0 - RUP, y0 - R, vec);
+        cp_async_commit();
+    }
 #pragma unroll
     for (int c = 0; c < NPL; c++) {
-        if (c + 1 < NPL) {
+        if (TMA) {
+            mbar_wait(&s_bar[c & 1], (unsigned)(c >> 1) & 1u);
+        } else if (c + 1 < NPL) {
             load_tile_async<PITCH / 4, ROWS, 256>(s_in2[(c + 1) & 1], PITCH, in + (img * NPL + c + 1) * n, w, h, x0 - RUP, y0 - R, vec);
             cp_async_commit();
             cp_async_wait<1>();
@@ -399,7 +455,9 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
                 ctr[c][k][0] = t.x; ctr[c][k][1] = t.y;
             }
         }
+        if (TMA && c + 2 < NPL) fence_proxy_async();   // the ctr loads above may still be in flight
         __syncthreads();
+        if (TMA && c + 2 < NPL && threadIdx.x == 0) tma_issue(c + 2);   // everyone is done with buffer c & 1
         f32x2 v[4 + 2 * R];
 #pragma unroll
         for (int q = 0; q < 4 + 2 * R; q++) v[q] = *reinterpret_cast<const f32x2*>(&s_h[(g * 4 + q) * B2_TW + 2 * cp]);
@@ -749,6 +807,7 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
         const float* se = buf + 3 * MT_BAND_FLOATS + oy * MT_TW + 4 * g;
         const float4 a = *reinterpret_cast<const float4*>(se), q = *reinterpret_cast<const float4*>(se + MT_TH * MT_TW);
         const float4 m = *reinterpret_cast<const float4*>(se + 2 * MT_TH * MT_TW), o4 = *reinterpret_cast<const float4*>(se + 3 * MT_TH * MT_TW);
+        if (TMA) fence_proxy_async();
         __syncthreads();   // everyone is done reading buffer t & 1
         issue(t + 2);
         const float hv0[4] = {a.x, a.y, a.z, a.w}, hv1[4] = {q.x, q.y, q.z, q.w};
@@ -1101,19 +1160,47 @@ static void ba_psycho_level(Context& c, const float* lin, size_t NI, size_t w, s
     if (dbg_opsin) CE_CUDA(cudaMemcpyAsync(dbg_opsin, L.xyb, 3 * n * 4, cudaMemcpyDeviceToDevice, c.stream));
     {
         dim3 gh(cdiv(w, 128), cdiv(h, 8), (unsigned)(NI * 3));
-        CE_LAUNCH(c, "k_ba_blur_h<R16>", (double)NI * n * 24,
-                  k_ba_blur_h<0, 16><<<gh, 256, 0, c.stream>>>(L.xyb, (int)w, (int)h, n, L.tables.inv_x[0], L.tmp, vec));
+        CUtensorMap mh, mv;
+        memset(&mh, 0, sizeof(mh));
+        memset(&mv, 0, sizeof(mv));
+        const bool tma = tma_enabled(2) && tma_plane_map(&mh, L.xyb, w, h, NI * 3, 128 + 2 * 16, 8, 1) && tma_plane_map(&mv, L.tmp, w, h, NI * 3, 32, 64 + 2 * 16, 1);
+        if (tma)
+            CE_LAUNCH(c, "k_ba_blur_h<R16>", (double)NI * n * 24,
+                      k_ba_blur_h<0, 16, true><<<gh, 256, 0, c.stream>>>(L.xyb, (int)w, (int)h, n, L.tables.inv_x[0], L.tmp, vec, mh));
+        else
+            CE_LAUNCH(c, "k_ba_blur_h<R16>", (double)NI * n * 24,
+                      k_ba_blur_h<0, 16, false><<<gh, 256, 0, c.stream>>>(L.xyb, (int)w, (int)h, n, L.tables.inv_x[0], L.tmp, vec, mh));
         dim3 gv(cdiv(w, 32), cdiv(h, 64), (unsigned)NI);
-        CE_LAUNCH(c, "k_ba_blur_v<R16>+lf", (double)NI * n * 48,
-                  k_ba_blur_v<0, 16, 3, 1><<<gv, 256, 0, c.stream>>>(L.tmp, (int)w, (int)h, n, L.tables.inv_y[0], L.lf, L.xyb, L.mf_pre));
+        if (tma)
+            CE_LAUNCH(c, "k_ba_blur_v<R16>+lf", (double)NI * n * 48,
+                      k_ba_blur_v<0, 16, 3, 1, true><<<gv, 256, 0, c.stream>>>(L.tmp, (int)w, (int)h, n, L.tables.inv_y[0], L.lf, L.xyb, L.mf_pre, mv));
+        else
+            CE_LAUNCH(c, "k_ba_blur_v<R16>+lf", (double)NI * n * 48,
+                      k_ba_blur_v<0, 16, 3, 1, false><<<gv, 256, 0, c.stream>>>(L.tmp, (int)w, (int)h, n, L.tables.inv_y[0], L.lf, L.xyb, L.mf_pre, mv));
     }
     dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), (unsigned)NI);
-    CE_LAUNCH(c, "k_ba_blur2d<R7>+hf_split", (double)NI * n * 32,
-              k_ba_blur2d<1, 7, 3, 2><<<g2, 256, 0, c.stream>>>(L.mf_pre, (int)w, (int)h, n, L.tables.inv_x[1], L.tables.inv_y[1], L.mf,
-                                                              L.hf_pre, nullptr));
-    CE_LAUNCH(c, "k_ba_blur2d<R3>+uhf_split", (double)NI * n * 28,
-              k_ba_blur2d<2, 3, 2, 3><<<g2, 256, 0, c.stream>>>(L.hf_pre, (int)w, (int)h, n, L.tables.inv_x[2], L.tables.inv_y[2], L.hf,
-                                                              L.uhf, L.m));
+    {
+        CUtensorMap m7, m3;
+        memset(&m7, 0, sizeof(m7));
+        memset(&m3, 0, sizeof(m3));
+        const bool tma = tma_enabled(3) && tma_plane_map(&m7, L.mf_pre, w, h, NI * 3, B2_TW + 16, B2_TH + 14, 1) &&
+                         tma_plane_map(&m3, L.hf_pre, w, h, NI * 2, B2_TW + 8, B2_TH + 6, 1);
+        if (tma) {
+            CE_LAUNCH(c, "k_ba_blur2d<R7>+hf_split", (double)NI * n * 32,
+                      k_ba_blur2d<1, 7, 3, 2, true><<<g2, 256, 0, c.stream>>>(L.mf_pre, (int)w, (int)h, n, L.tables.inv_x[1], L.tables.inv_y[1], L.mf,
+                                                                            L.hf_pre, nullptr, m7));
+            CE_LAUNCH(c, "k_ba_blur2d<R3>+uhf_split", (double)NI * n * 28,
+                      k_ba_blur2d<2, 3, 2, 3, true><<<g2, 256, 0, c.stream>>>(L.hf_pre, (int)w, (int)h, n, L.tables.inv_x[2], L.tables.inv_y[2], L.hf,
+                                                                            L.uhf, L.m, m3));
+        } else {
+            CE_LAUNCH(c, "k_ba_blur2d<R7>+hf_split", (double)NI * n * 32,
+                      k_ba_blur2d<1, 7, 3, 2, false><<<g2, 256, 0, c.stream>>>(L.mf_pre, (int)w, (int)h, n, L.tables.inv_x[1], L.tables.inv_y[1], L.mf,
+                                                                             L.hf_pre, nullptr, m7));
+            CE_LAUNCH(c, "k_ba_blur2d<R3>+uhf_split", (double)NI * n * 28,
+                      k_ba_blur2d<2, 3, 2, 3, false><<<g2, 256, 0, c.stream>>>(L.hf_pre, (int)w, (int)h, n, L.tables.inv_x[2], L.tables.inv_y[2], L.hf,
+                                                                             L.uhf, L.m, m3));
+        }
+    }
     CE_CUDA(cudaGetLastError());
 }
 
@@ -1128,9 +1215,16 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
     ba_psycho_level(c, lin, NI, w, h, intensity, L, nullptr);
     {
         dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), (unsigned)NI);
-        CE_LAUNCH(c, "k_ba_blur2d<R6>", (double)NI * n * 8,
-                  k_ba_blur2d<3, 6, 1, 0><<<g2, 256, 0, c.stream>>>(L.m, (int)w, (int)h, n, L.tables.inv_x[3], L.tables.inv_y[3], L.bl,
-                                                                  nullptr, nullptr));
+        CUtensorMap m6;
+        memset(&m6, 0, sizeof(m6));
+        if (tma_enabled(3) && tma_plane_map(&m6, L.m, w, h, NI, B2_TW + 16, B2_TH + 12, 1))
+            CE_LAUNCH(c, "k_ba_blur2d<R6>", (double)NI * n * 8,
+                      k_ba_blur2d<3, 6, 1, 0, true><<<g2, 256, 0, c.stream>>>(L.m, (int)w, (int)h, n, L.tables.inv_x[3], L.tables.inv_y[3], L.bl,
+                                                                            nullptr, nullptr, m6));
+        else
+            CE_LAUNCH(c, "k_ba_blur2d<R6>", (double)NI * n * 8,
+                      k_ba_blur2d<3, 6, 1, 0, false><<<g2, 256, 0, c.stream>>>(L.m, (int)w, (int)h, n, L.tables.inv_x[3], L.tables.inv_y[3], L.bl,
+                                                                             nullptr, nullptr, m6));
     }
     {
         MaltaParams2 mp;
@@ -1145,7 +1239,7 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
         dim3 grid(cdiv(w, MT_TW), cdiv(cdiv(h, MT_TH), MT_NT), (unsigned)(2 * B));
         MaltaMaps maps;
         memset(&maps, 0, sizeof(maps));
-        const bool tma = tma_plane_map(&maps.diff, L.mdiff, w, h, B * 6, MT_P, MT_ROWS, 1) &&
+        const bool tma = tma_enabled(0) && tma_plane_map(&maps.diff, L.mdiff, w, h, B * 6, MT_P, MT_ROWS, 1) &&
                          tma_plane_map(&maps.hf, L.hf, w, h, NI * 2, MT_TW, MT_TH, 1) &&
                          tma_plane_map(&maps.mf, L.mf, w, h, NI * 3, MT_TW, MT_TH, 1);
         if (tma)
@@ -1244,20 +1338,41 @@ void butteraugli_debug_blur(Context& c, const float* in, size_t w, size_t h, flo
         CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_opsin<false><<<grid, 256, 0, c.stream>>>(in, (int)w, (int)h, n, 0.0f, out, vec));
     } else if (fabsf(sigma - kSigmas[0]) < 1e-5f) {
         dim3 gh(cdiv(w, 128), cdiv(h, 8), 1);
-        CE_LAUNCH(c, "k_ba_blur_h<R16>", (double)n * 8,
-                  k_ba_blur_h<0, 16><<<gh, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[0], L.tmp, vec));
         dim3 gv(cdiv(w, 32), cdiv(h, 64), 1);
-        CE_LAUNCH(c, "k_ba_blur_v<R16>", (double)n * 8,
-                  k_ba_blur_v<0, 16, 1, 0><<<gv, 256, 0, c.stream>>>(L.tmp, (int)w, (int)h, n, L.tables.inv_y[0], out, nullptr, nullptr));
-    } else if (fabsf(sigma - kSigmas[1]) < 1e-5f) {
-        CE_LAUNCH(c, "k_ba_blur2d<R7>", (double)n * 8,
-                  k_ba_blur2d<1, 7, 1, 0><<<g2, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[1], L.tables.inv_y[1], out, nullptr, nullptr));
-    } else if (fabsf(sigma - kSigmas[2]) < 1e-5f) {
-        CE_LAUNCH(c, "k_ba_blur2d<R3>", (double)n * 8,
-                  k_ba_blur2d<2, 3, 1, 0><<<g2, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[2], L.tables.inv_y[2], out, nullptr, nullptr));
-    } else if (fabsf(sigma - kSigmas[3]) < 1e-5f) {
-        CE_LAUNCH(c, "k_ba_blur2d<R6>", (double)n * 8,
-                  k_ba_blur2d<3, 6, 1, 0><<<g2, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[3], L.tables.inv_y[3], out, nullptr, nullptr));
+        CUtensorMap mh, mv;
+        memset(&mh, 0, sizeof(mh));
+        memset(&mv, 0, sizeof(mv));
+        // the same staging path (TMA when the width allows it) as the production launches
+        if (tma_plane_map(&mh, in, w, h, 1, 128 + 2 * 16, 8, 1) && tma_plane_map(&mv, L.tmp, w, h, 1, 32, 64 + 2 * 16, 1)) {
+            CE_LAUNCH(c, "k_ba_blur_h<R16>", (double)n * 8,
+                      k_ba_blur_h<0, 16, true><<<gh, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[0], L.tmp, vec, mh));
+            CE_LAUNCH(c, "k_ba_blur_v<R16>", (double)n * 8,
+                      k_ba_blur_v<0, 16, 1, 0, true><<<gv, 256, 0, c.stream>>>(L.tmp, (int)w, (int)h, n, L.tables.inv_y[0], out, nullptr, nullptr, mv));
+        } else {
+            CE_LAUNCH(c, "k_ba_blur_h<R16>", (double)n * 8,
+                      k_ba_blur_h<0, 16, false><<<gh, 256, 0, c.stream>>>(in, (int)w, (int)h, n, L.tables.inv_x[0], L.tmp, vec, mh));
+            CE_LAUNCH(c, "k_ba_blur_v<R16>", (double)n * 8,
+                      k_ba_blur_v<0, 16, 1, 0, false><<<gv, 256, 0, c.stream>>>(L.tmp, (int)w, (int)h, n, L.tables.inv_y[0], out, nullptr, nullptr, mv));
+        }
+    } else if (fabsf(sigma - kSigmas[1]) < 1e-5f || fabsf(sigma - kSigmas[2]) < 1e-5f || fabsf(sigma - kSigmas[3]) < 1e-5f) {
+        const int slot = fabsf(sigma - kSigmas[1]) < 1e-5f ? 1 : fabsf(sigma - kSigmas[2]) < 1e-5f ? 2 : 3;
+        const int R = kRadii[slot], RUP = (R + 3) & ~3;
+        CUtensorMap m;
+        memset(&m, 0, sizeof(m));
+        const bool tma = tma_plane_map(&m, in, w, h, 1, B2_TW + 2 * RUP, B2_TH + 2 * R, 1);
+        const float* ix = L.tables.inv_x[slot];
+        const float* iy = L.tables.inv_y[slot];
+#define BLUR2D_DBG(S, RR)                                                                                                         \
+    do {                                                                                                                          \
+        if (tma) CE_LAUNCH(c, "k_ba_blur2d<dbg>", (double)n * 8,                                                                  \
+                           k_ba_blur2d<S, RR, 1, 0, true><<<g2, 256, 0, c.stream>>>(in, (int)w, (int)h, n, ix, iy, out, nullptr, nullptr, m));  \
+        else CE_LAUNCH(c, "k_ba_blur2d<dbg>", (double)n * 8,                                                                      \
+                       k_ba_blur2d<S, RR, 1, 0, false><<<g2, 256, 0, c.stream>>>(in, (int)w, (int)h, n, ix, iy, out, nullptr, nullptr, m)); \
+    } while (0)
+        if (slot == 1) BLUR2D_DBG(1, 7);
+        else if (slot == 2) BLUR2D_DBG(2, 3);
+        else BLUR2D_DBG(3, 6);
+#undef BLUR2D_DBG
     } else {
         throw CudaError("unsupported sigma");
     }

@@ -419,8 +419,12 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
         for (int half = 0; half < 2; half++) {
             const int t = t0 + half;
             if (t < nbatch) {   // block-uniform
-                if (TMA) mbar_wait(&s_bar[t & (VP_SLOTS - 1)], (unsigned)(t / VP_SLOTS) & 1u);
-                else cp_async_wait<1>();
+                if (TMA) {
+                    mbar_wait(&s_bar[t & (VP_SLOTS - 1)], (unsigned)(t / VP_SLOTS) & 1u);
+                    fence_proxy_async();   // this thread's reads of slot (t-2) % 4 precede its TMA refill below
+                } else {
+                    cp_async_wait<1>();
+                }
                 __syncthreads();   // batch t landed; s_v of batch t-1 complete; slot (t-2) % 4 free
                 issue(t + 2);
                 const float* in = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS + p * VP_BATCH * VP_COLS + lane;
@@ -532,7 +536,7 @@ int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t
             VpassMaps mr, mp;
             memset(&mr, 0, sizeof(mr));
             memset(&mp, 0, sizeof(mp));
-            const bool tma = tma_plane_map(&mr.hb, hbr, cw, ch, R * 6, VP_COLS, VP_BATCH, 2) &&
+            const bool tma = tma_enabled(1) && tma_plane_map(&mr.hb, hbr, cw, ch, R * 6, VP_COLS, VP_BATCH, 2) &&
                              tma_plane_map(&mp.hb, hbp, cw, ch, B * 9, VP_COLS, VP_BATCH, 3) &&
                              tma_plane_map(&mp.xyb, xyb, cw, ch, NI * 3, VP_COLS, VP_BATCH, 1) &&
                              tma_plane_map(&mp.vr, vref, cw, ch, R * 6, VP_COLS, VP_BATCH, 2);
@@ -556,7 +560,7 @@ int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t
                       k_s2_hpass<S2_ALL><<<gh, 160, S2Mode<S2_ALL>::HP_SMEM, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, vecf));
             VpassMaps ma;
             memset(&ma, 0, sizeof(ma));
-            const bool tma = tma_plane_map(&ma.hb, hb, cw, ch, B * 15, VP_COLS, VP_BATCH, 5) &&
+            const bool tma = tma_enabled(1) && tma_plane_map(&ma.hb, hb, cw, ch, B * 15, VP_COLS, VP_BATCH, 5) &&
                              tma_plane_map(&ma.xyb, xyb, cw, ch, NI * 3, VP_COLS, VP_BATCH, 1);
             if (tma)
                 CE_LAUNCH(c, "k_s2_vpass", (double)B * 3 * 7 * n * 4,

@@ -532,3 +532,23 @@ def test_many_tiny_pairs_and_workspace_limits(gpu, O):
         assert tiny.calculate_psnr(big[:192], big[:192], 8, 8) == float("inf")
     finally:
         tiny.close()
+
+
+def test_repeated_runs_are_bit_identical_with_all_metrics_sharing_the_sms(gpu):
+    """Race detector for the asynchronously staged tiles (TMA / cp.async refills of shared-memory buffers): the three
+    perceptual metrics run on separate streams, so their kernels share SMs and the load/store queues are congested.
+    A bulk copy that overtakes a pending shared-memory load showed up as a Butteraugli score that changed in ~1 of 3
+    runs at this size before the proxy fences were added."""
+    from codec_eval_b200.metrics import MetricConfig
+
+    w, h = 3840, 2160
+    ref = G(9, w, h)
+    pairs = [(ref, cheap_distort(ref, 50 + 7 * i, seed=i), w, h) for i in range(2)]
+    cfg = MetricConfig.all()
+    first = None
+    for rep in range(20):
+        out = gpu.evaluate_batch_raw(pairs, cfg)
+        cur = [(o.status, o.sse, o.dssim, o.ssimulacra2, o.butteraugli, o.butteraugli_pnorm3) for o in out[:2]]
+        if first is None:
+            first = cur
+        assert cur == first, (rep, cur, first)
