@@ -19,7 +19,14 @@ def bench_name(k):
     m = {"k_ds_stream<0>": "k_ds_stats<ref>", "k_ds_stream<1>": "k_ds_stats<pair>", "k_ds_blur2s": "k_ds_blur2",
          "k_s2_hpass<0>": "k_s2_hpass", "k_s2_hpass<1>": "k_s2_hpass<ref>", "k_s2_hpass<2>": "k_s2_hpass<pair>",
          "k_s2_vpass<0>": "k_s2_vpass", "k_s2_vpass<1>": "k_s2_vpass<ref>", "k_s2_vpass<2>": "k_s2_vpass<pair>",
-         "k_ba_combine4": "k_ba_combine", "k_jpg_ycc<0>": "k_jpg_ycc", "k_jpg_ycc<2>": "k_jpg_ycc", "k_jpg_rgb<0>": "k_jpg_rgb", "k_jpg_rgb<2>": "k_jpg_rgb", "k_ba_blur_h<0, 16>": "k_ba_blur_h<R16>",
+         "k_ba_combine4": "k_ba_combine", "k_ba_malta<1>": "k_ba_malta", "k_ba_malta<0>": "k_ba_malta",
+         "k_s2_vpass<0, 1>": "k_s2_vpass", "k_s2_vpass<1, 1>": "k_s2_vpass<ref>", "k_s2_vpass<2, 1>": "k_s2_vpass<pair>",
+         "k_s2_vpass<0, 0>": "k_s2_vpass", "k_s2_vpass<1, 0>": "k_s2_vpass<ref>", "k_s2_vpass<2, 0>": "k_s2_vpass<pair>",
+         "k_ba_blur_h<0, 16, 1>": "k_ba_blur_h<R16>", "k_ba_blur_h<0, 16, 0>": "k_ba_blur_h<R16>",
+         "k_ba_blur_v<0, 16, 3, 1, 1>": "k_ba_blur_v<R16>+lf", "k_ba_blur_v<0, 16, 3, 1, 0>": "k_ba_blur_v<R16>+lf",
+         "k_ba_blur2d<1, 7, 3, 2, 1>": "k_ba_blur2d<R7>+hf_split", "k_ba_blur2d<2, 3, 2, 3, 1>": "k_ba_blur2d<R3>+uhf_split",
+         "k_ba_blur2d<3, 6, 1, 0, 1>": "k_ba_blur2d<R6>", "k_ba_blur2d<1, 7, 3, 2, 0>": "k_ba_blur2d<R7>+hf_split",
+         "k_ba_blur2d<2, 3, 2, 3, 0>": "k_ba_blur2d<R3>+uhf_split", "k_ba_blur2d<3, 6, 1, 0, 0>": "k_ba_blur2d<R6>", "k_jpg_ycc<0>": "k_jpg_ycc", "k_jpg_ycc<2>": "k_jpg_ycc", "k_jpg_rgb<0>": "k_jpg_rgb", "k_jpg_rgb<2>": "k_jpg_rgb", "k_ba_blur_h<0, 16>": "k_ba_blur_h<R16>",
          "k_ba_blur_v<0, 16, 3, 1>": "k_ba_blur_v<R16>+lf", "k_ba_blur2d<1, 7, 3, 2>": "k_ba_blur2d<R7>+hf_split",
          "k_ba_blur2d<2, 3, 2, 3>": "k_ba_blur2d<R3>+uhf_split", "k_ba_blur2d<3, 6, 1, 0>": "k_ba_blur2d<R6>",
          "k_ba_opsin<1>": "k_ba_opsin", "k_ba_malta_diff<1>": "k_ba_malta_diff", "k_ba_malta_diff<0>": "k_ba_malta_diff"}
