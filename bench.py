@@ -337,9 +337,9 @@ def main():
             except Exception:
                 traffic = None
         # what ncu says binds the kernels that are not HBM bound (profiles/README.md)
-        issue_bound = {"k_ba_malta": "FP32 issue (16 oriented line sums per pixel and band, ~235 fp32 instructions per pixel-channel after sharing sub-sums), not HBM",
+        issue_bound = {"k_ba_malta": "FP32 issue (16 oriented line sums per pixel and band, ~235 fp32 instructions per pixel-channel after sharing sub-sums; tiles staged by TMA), not HBM: 73 % issue-active",
                        "k_ds_stats<pair>": "FP32 issue (un-fused 3x3 mul+add chains kept for bit parity with dssim-core, 11 instructions per 3x3), not HBM",
-                       "k_s2_vpass<pair>": "FP32 issue (three recurrences + SSIM / edge terms per pixel), not HBM",
+                       "k_s2_vpass<pair>": "FP32 issue (three recurrences + SSIM / edge terms per pixel; rows staged by TMA), not HBM: 80 % issue-active",
                        "k_s2_vpass": "FP32 issue (five recurrences + SSIM / edge terms per pixel), not HBM"}
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "binding_resource": issue_bound.get(name, "HBM"),
