@@ -434,15 +434,18 @@ bool tma_enabled(int group) {   // CE_TMA_MASK (debugging): bit per kernel group
     }
     return (mask & (1 << group)) != 0;
 }
-bool tma_plane_map(CUtensorMap* m, const float* base, size_t w, size_t h, size_t nplanes, unsigned bw, unsigned bh, unsigned bz) {
+bool tma_plane_map(CUtensorMap* m, const float* base, size_t w, size_t h, size_t nplanes, unsigned bw, unsigned bh, unsigned bz,
+                   bool swizzle128) {
     EncodeTiledFn enc = tma_encoder();
     if (!enc || (w & 3) || nplanes == 0 || !base) return false;
+    if (swizzle128 && bw * 4 > 128) return false;   // the swizzle span is the box row
     const cuuint64_t dims[3] = {w, h, nplanes};
     const cuuint64_t strides[2] = {w * 4, w * h * 4};
     const cuuint32_t box[3] = {bw, bh, bz};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 }  // namespace ce
 

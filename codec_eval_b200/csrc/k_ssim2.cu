@@ -105,6 +105,7 @@ template <int MODE> struct S2Mode {
     static constexpr int NW = MODE == S2_ALL ? 5 : MODE == S2_REF ? 2 : 3;     // products = warps per block
     static constexpr int NIN = MODE == S2_REF ? 1 : 2;                          // image planes staged by the row pass
     static constexpr int HP_SMEM = (HP_SLOTS * NIN + NW) * HP_ROWS * HP_PITCH * 4;
+    static constexpr int HP_SMEM_TMA = (2 * NIN * 2 * 32 * 32 + NW * HP_ROWS * HP_PITCH) * 4;   // HP_SLOTS_TMA = 2
 };
 
 // grid (ceil(h/32), 3*units); block NW warps (product) x 32 lanes (row); unit = pair (S2_ALL, S2_PAIR) or distinct
@@ -117,15 +118,24 @@ template <int MODE> struct S2Mode {
 // k*HP_COLS-4 .. ; the first four steps are the upstream warm-up (n = -4 .. -1), and
 // ceil((w+4)/HP_COLS) chunks reach the last column.  Each warp writes out the plane it produced.
 // hb: [unit][3][NW][n].
-template <int MODE>
+// TMA variant: a chunk of one plane is two 32-column x 32-row boxes written with the 128-byte swizzle (4 KB each,
+// no padding): lane = row r reads its 16-byte group j at chunk j ^ (r & 7), conflict free.  Plane stride in a slot =
+// HP_TPLANE floats.
+#define HP_TPLANE (2 * 32 * 32)
+#define HP_SLOTS_TMA 2
+template <int MODE, bool TMA>
 __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float* __restrict__ xyb, size_t R,
                                                                      const int* __restrict__ ridx, float* __restrict__ hb,
-                                                                     int w, int h, size_t n, int vec) {
+                                                                     int w, int h, size_t n, int vec,
+                                                                     const __grid_constant__ CUtensorMap map) {
     constexpr int NW = S2Mode<MODE>::NW, NIN = S2Mode<MODE>::NIN, NT = NW * 32;
-    extern __shared__ __align__(16) float s_dyn[];   // opt-in dynamic shared memory (> 48 KB)
+    constexpr int PLANE = TMA ? HP_TPLANE : HP_ROWS * HP_PITCH;     // floats per staged plane
+    constexpr int SLOTS = TMA ? HP_SLOTS_TMA : HP_SLOTS;            // ring depth
+    extern __shared__ __align__(1024) float s_dyn[];   // opt-in dynamic shared memory (> 48 KB)
+    __shared__ __align__(8) unsigned long long s_bar[HP_SLOTS_TMA];
     float* s_in = s_dyn;
     const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
-    float* so = s_dyn + HP_SLOTS * NIN * HP_ROWS * HP_PITCH + p * (HP_ROWS * HP_PITCH);
+    float* so = s_dyn + SLOTS * NIN * PLANE + p * (HP_ROWS * HP_PITCH);
     const size_t u = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
     const int row0 = blockIdx.x * HP_ROWS;
@@ -136,14 +146,28 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float*
     // product roles: plane of the first / second factor, and whether there is a second factor
     int offA, offB;
     bool mul;
-    if (MODE == S2_ALL) { offA = (p == 1 || p == 3) ? HP_ROWS * HP_PITCH : 0; offB = (p >= 3) ? HP_ROWS * HP_PITCH : 0; mul = p >= 2; }
+    if (MODE == S2_ALL) { offA = (p == 1 || p == 3) ? PLANE : 0; offB = (p >= 3) ? PLANE : 0; mul = p >= 2; }
     else if (MODE == S2_REF) { offA = 0; offB = 0; mul = p == 1; }
-    else { offA = (p == 2) ? 0 : HP_ROWS * HP_PITCH; offB = HP_ROWS * HP_PITCH; mul = p >= 1; }
+    else { offA = (p == 2) ? 0 : PLANE; offB = PLANE; mul = p >= 1; }
+    const size_t pl1 = (MODE == S2_REF ? u : (size_t)ridx[u]) * 3 + c, pl2 = (R + u) * 3 + c;   // planes of the xyb tensor
 
     auto issue = [&](int k) {
+        if (TMA) {
+            if (threadIdx.x == 0 && k < nchunks) {
+                float* slot = s_in + (k % SLOTS) * NIN * PLANE;
+                unsigned long long* bar = &s_bar[k % SLOTS];
+                mbar_expect_tx(bar, NIN * PLANE * 4);
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    tma_load_3d(slot + half * 1024, &map, k * HP_COLS + 32 * half, row0, (int)pl1, bar);
+                    if (NIN == 2) tma_load_3d(slot + PLANE + half * 1024, &map, k * HP_COLS + 32 * half, row0, (int)pl2, bar);
+                }
+            }
+            return;
+        }
         if (k < nchunks) {
             constexpr int ITEMS = NIN * HP_ROWS * HP_C4;
-            float* slot = s_in + (k % HP_SLOTS) * NIN * HP_ROWS * HP_PITCH;
+            float* slot = s_in + (k % SLOTS) * NIN * PLANE;
 #pragma unroll
             for (int it = 0; it < (ITEMS + NT - 1) / NT; it++) {
                 const int e = (int)threadIdx.x + it * NT;
@@ -167,24 +191,42 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float*
         }
         cp_async_commit();
     };
+    if (TMA) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < SLOTS; i++) mbar_init(&s_bar[i], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
     issue(0);
-    if (HP_SLOTS >= 3) issue(1);
+    if (SLOTS >= 3) issue(1);
     RGState st = {0, 0, 0, 0, 0, 0};
     // products of the previous 16 columns: Q0 = c-16..c-13, Q1 = c-12..c-9, Q2 = c-8..c-5, Q3 = c-4..c-1
     float Q0[4] = {0, 0, 0, 0}, Q1[4] = {0, 0, 0, 0}, Q2[4] = {0, 0, 0, 0}, Q3[4] = {0, 0, 0, 0};
     for (int k = 0; k < nchunks; k++) {
-        if (HP_SLOTS >= 3) cp_async_wait<1>(); else cp_async_wait<0>();
+        if (TMA) {
+            mbar_wait(&s_bar[k % SLOTS], (unsigned)(k / SLOTS) & 1u);
+            fence_proxy_async();   // this thread's reads of slot (k-1) % HP_SLOTS precede its refill below
+        } else if (SLOTS >= 3) {
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();   // chunk k visible to all; every warp is past its reads of slot (k-1) % HP_SLOTS
-        issue(k + HP_SLOTS - 1);      // -> slot (k-1) % HP_SLOTS
-        const float* a = s_in + ((k % HP_SLOTS) * NIN * HP_ROWS + lane) * HP_PITCH;
+        issue(k + SLOTS - 1);      // -> slot (k-1) % SLOTS
+        // lane = row: padded rows (cp.async) or 128-byte rows with the TMA swizzle
+        const float* a = TMA ? s_in + (k % SLOTS) * NIN * PLANE + lane * 32 : s_in + ((k % SLOTS) * NIN * HP_ROWS + lane) * HP_PITCH;
+        const int sw = (lane & 7) << 2;   // swizzle: float offset of 16-byte group j is (4 j) ^ sw
 #pragma unroll 1
         for (int m0 = 0; m0 < HP_C4; m0 += 4) {
 #pragma unroll
             for (int mm = 0; mm < 4; mm++) {
                 const int m = m0 + mm;
-                float4 g4 = *reinterpret_cast<const float4*>(a + offA + 4 * m);
+                const int off = TMA ? ((m >> 3) * 1024 + (((m & 7) << 2) ^ sw)) : 4 * m;
+                float4 g4 = *reinterpret_cast<const float4*>(a + offA + off);
                 if (mul) {
-                    const float4 v = *reinterpret_cast<const float4*>(a + offB + 4 * m);
+                    const float4 v = *reinterpret_cast<const float4*>(a + offB + off);
                     g4.x *= v.x; g4.y *= v.y; g4.z *= v.z; g4.w *= v.w;
                 }
                 // steps n = c-4+j: right = in[n+4] = g4[j]; left = in[n-6] = column c-10+j
@@ -473,9 +515,12 @@ __global__ void k_s2_reduce(const double* __restrict__ partials, int nblk, size_
 
 void ssim2_init(Context& c) {
     CE_CUDA(cudaMemcpyToSymbol(c_rg, &c.rg, sizeof(RGaussCoef), 0, cudaMemcpyHostToDevice));
-    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_ALL>::HP_SMEM));
-    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_REF>::HP_SMEM));
-    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_PAIR>::HP_SMEM));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_ALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_ALL>::HP_SMEM));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_REF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_REF>::HP_SMEM));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_PAIR>::HP_SMEM));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_ALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_ALL>::HP_SMEM_TMA));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_REF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_REF>::HP_SMEM_TMA));
+    CE_CUDA(cudaFuncSetAttribute(k_s2_hpass<S2_PAIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Mode<S2_PAIR>::HP_SMEM_TMA));
 }
 
 size_t ssim2_workspace_per_pair(size_t w, size_t h) {
@@ -531,8 +576,15 @@ int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t
         if (split) {
             dim3 ghr(cdiv(ch, HP_ROWS), (unsigned)(R * 3)), ghp(cdiv(ch, HP_ROWS), (unsigned)(B * 3));
             dim3 gvr(nblk, (unsigned)(R * 3)), gvp(nblk, (unsigned)(B * 3));
-            CE_LAUNCH(c, "k_s2_hpass<ref>", (double)R * 3 * 3 * n * 4,
-                      k_s2_hpass<S2_REF><<<ghr, 64, S2Mode<S2_REF>::HP_SMEM, c.stream>>>(xyb, R, ridx, hbr, (int)cw, (int)ch, n, vecf));
+            CUtensorMap mx;
+            memset(&mx, 0, sizeof(mx));
+            const bool htma = tma_enabled(4) && tma_plane_map(&mx, xyb, cw, ch, NI * 3, 32, HP_ROWS, 1, true);
+            if (htma)
+                CE_LAUNCH(c, "k_s2_hpass<ref>", (double)R * 3 * 3 * n * 4,
+                          k_s2_hpass<S2_REF, true><<<ghr, 64, S2Mode<S2_REF>::HP_SMEM_TMA, c.stream>>>(xyb, R, ridx, hbr, (int)cw, (int)ch, n, vecf, mx));
+            else
+                CE_LAUNCH(c, "k_s2_hpass<ref>", (double)R * 3 * 3 * n * 4,
+                          k_s2_hpass<S2_REF, false><<<ghr, 64, S2Mode<S2_REF>::HP_SMEM, c.stream>>>(xyb, R, ridx, hbr, (int)cw, (int)ch, n, vecf, mx));
             VpassMaps mr, mp;
             memset(&mr, 0, sizeof(mr));
             memset(&mp, 0, sizeof(mp));
@@ -546,8 +598,12 @@ int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t
             else
                 CE_LAUNCH(c, "k_s2_vpass<ref>", (double)R * 3 * 4 * n * 4,
                           k_s2_vpass<S2_REF, false><<<gvr, 64, 0, c.stream>>>(xyb, R, ridx, hbr, vref, (int)cw, (int)ch, n, nullptr, nullptr, vecf, mr));
-            CE_LAUNCH(c, "k_s2_hpass<pair>", (double)B * 3 * 5 * n * 4,
-                      k_s2_hpass<S2_PAIR><<<ghp, 96, S2Mode<S2_PAIR>::HP_SMEM, c.stream>>>(xyb, R, ridx, hbp, (int)cw, (int)ch, n, vecf));
+            if (htma)
+                CE_LAUNCH(c, "k_s2_hpass<pair>", (double)B * 3 * 5 * n * 4,
+                          k_s2_hpass<S2_PAIR, true><<<ghp, 96, S2Mode<S2_PAIR>::HP_SMEM_TMA, c.stream>>>(xyb, R, ridx, hbp, (int)cw, (int)ch, n, vecf, mx));
+            else
+                CE_LAUNCH(c, "k_s2_hpass<pair>", (double)B * 3 * 5 * n * 4,
+                          k_s2_hpass<S2_PAIR, false><<<ghp, 96, S2Mode<S2_PAIR>::HP_SMEM, c.stream>>>(xyb, R, ridx, hbp, (int)cw, (int)ch, n, vecf, mx));
             if (tma)
                 CE_LAUNCH(c, "k_s2_vpass<pair>", (double)B * 3 * 7 * n * 4,
                           k_s2_vpass<S2_PAIR, true><<<gvp, 96, 0, c.stream>>>(xyb, R, ridx, hbp, vref, (int)cw, (int)ch, n, partials, dbg, vecf, mp));
@@ -556,8 +612,14 @@ int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t
                           k_s2_vpass<S2_PAIR, false><<<gvp, 96, 0, c.stream>>>(xyb, R, ridx, hbp, vref, (int)cw, (int)ch, n, partials, dbg, vecf, mp));
         } else {
             dim3 gh(cdiv(ch, HP_ROWS), (unsigned)(B * 3)), gv(nblk, (unsigned)(B * 3));
-            CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4,
-                      k_s2_hpass<S2_ALL><<<gh, 160, S2Mode<S2_ALL>::HP_SMEM, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, vecf));
+            CUtensorMap mx;
+            memset(&mx, 0, sizeof(mx));
+            if (tma_enabled(4) && tma_plane_map(&mx, xyb, cw, ch, NI * 3, 32, HP_ROWS, 1, true))
+                CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4,
+                          k_s2_hpass<S2_ALL, true><<<gh, 160, S2Mode<S2_ALL>::HP_SMEM_TMA, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, vecf, mx));
+            else
+                CE_LAUNCH(c, "k_s2_hpass", (double)B * 3 * 7 * n * 4,
+                          k_s2_hpass<S2_ALL, false><<<gh, 160, S2Mode<S2_ALL>::HP_SMEM, c.stream>>>(xyb, R, ridx, hb, (int)cw, (int)ch, n, vecf, mx));
             VpassMaps ma;
             memset(&ma, 0, sizeof(ma));
             const bool tma = tma_enabled(1) && tma_plane_map(&ma.hb, hb, cw, ch, B * 15, VP_COLS, VP_BATCH, 5) &&
