@@ -516,8 +516,17 @@ __global__ void __launch_bounds__(256) k_ds_mad(const float* __restrict__ map, s
     const double a = avg[b];
     const float* m = map + b * n;
     double acc = 0.0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        acc += fabs(a - (double)m[i]);
+    if ((n & 3) == 0) {   // 128-bit loads (the map of pair b starts at a multiple of n floats, 16-byte aligned)
+        const float4* m4 = reinterpret_cast<const float4*>(m);
+        const size_t n4 = n >> 2;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 v = m4[i];
+            acc += (fabs(a - (double)v.x) + fabs(a - (double)v.y)) + (fabs(a - (double)v.z) + fabs(a - (double)v.w));
+        }
+    } else {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+            acc += fabs(a - (double)m[i]);
+    }
     double a1[1] = {acc};
     block_sum<1>(a1, scratch);
     if (threadIdx.x == 0) partial[b * gridDim.x + blockIdx.x] = a1[0];
