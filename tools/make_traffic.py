@@ -20,6 +20,8 @@ def bench_name(k):
          "k_s2_hpass<0>": "k_s2_hpass", "k_s2_hpass<1>": "k_s2_hpass<ref>", "k_s2_hpass<2>": "k_s2_hpass<pair>",
          "k_s2_vpass<0>": "k_s2_vpass", "k_s2_vpass<1>": "k_s2_vpass<ref>", "k_s2_vpass<2>": "k_s2_vpass<pair>",
          "k_ba_combine4": "k_ba_combine", "k_ba_malta<1>": "k_ba_malta", "k_ba_malta<0>": "k_ba_malta",
+         "k_s2_hpass<0, 1>": "k_s2_hpass", "k_s2_hpass<1, 1>": "k_s2_hpass<ref>", "k_s2_hpass<2, 1>": "k_s2_hpass<pair>",
+         "k_s2_hpass<0, 0>": "k_s2_hpass", "k_s2_hpass<1, 0>": "k_s2_hpass<ref>", "k_s2_hpass<2, 0>": "k_s2_hpass<pair>",
          "k_s2_vpass<0, 1>": "k_s2_vpass", "k_s2_vpass<1, 1>": "k_s2_vpass<ref>", "k_s2_vpass<2, 1>": "k_s2_vpass<pair>",
          "k_s2_vpass<0, 0>": "k_s2_vpass", "k_s2_vpass<1, 0>": "k_s2_vpass<ref>", "k_s2_vpass<2, 0>": "k_s2_vpass<pair>",
          "k_ba_blur_h<0, 16, 1>": "k_ba_blur_h<R16>", "k_ba_blur_h<0, 16, 0>": "k_ba_blur_h<R16>",
