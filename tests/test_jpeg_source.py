@@ -138,3 +138,26 @@ def test_sweep_argument_errors(gpu):
     with pytest.raises(AssertionError):
         gpu.jpeg_roundtrip(r, 16, 16, 50, 1)
     assert gpu.evaluate_jpeg_sweep([], 16, 16, [50], MetricConfig.fast()) == []
+
+
+@pytest.mark.gpu
+def test_sweep_with_a_small_workspace_sub_batches_and_matches(gpu):
+    """A context whose workspace holds only a few pairs must cut the sweep into chunks / sub-batches and still return
+    the same bits; 4:4:4 as well as 4:2:0."""
+    from codec_eval_b200.metrics import GpuMetrics, MetricConfig
+
+    w, h, qs = 256, 192, [30, 60, 80, 95]
+    refs = [G(70 + i, w, h) for i in range(6)]
+    cfg = MetricConfig.all()
+    for ss in (2, 0):
+        big = gpu.evaluate_jpeg_sweep_raw(refs, w, h, qs, cfg, subsampling=ss)
+        with GpuMetrics(0, workspace_bytes=96 << 20) as small:
+            out = small.evaluate_jpeg_sweep_raw(refs, w, h, qs, cfg, subsampling=ss)
+        for i in range(len(refs) * len(qs)):
+            a, b = big[i], out[i]
+            assert (a.status, a.sse, a.dssim, a.ssimulacra2, a.butteraugli, a.butteraugli_pnorm3) == \
+                   (b.status, b.sse, b.dssim, b.ssimulacra2, b.butteraugli, b.butteraugli_pnorm3), (ss, i)
+    # monotone in quality for every reference (PSNR of a JPEG round trip)
+    for r in range(len(refs)):
+        p = [big[r * len(qs) + k].psnr for k in range(len(qs))]
+        assert p == sorted(p), p
