@@ -1,9 +1,9 @@
-"""Second, independent restatement of SSIMULACRA2 and DSSIM in numpy ("two independent restatements
+"""Second, independent restatement of SSIMULACRA2, DSSIM and Butteraugli in numpy ("two independent restatements
 ... so that a transcription slip in one shows up as a disagreement").  TEST INFRASTRUCTURE ONLY.
 
-Written from the algorithm statements in SURVEY.md Appendix A.3 / A.4 (the published upstream algorithms: libjxl
-tools/ssimulacra2.cc == rust-av ssimulacra2 == fast-ssim2; kornelski dssim-core), vectorised over whole planes, not
-from oracle/ce_oracle.c.  tests/test_oracle.py::test_two_restatements_agree compares the two on seeded pairs.
+Written from the algorithm statements in SURVEY.md Appendix A.3 / A.4 / A.5 (the published upstream algorithms: libjxl
+tools/ssimulacra2.cc == rust-av ssimulacra2 == fast-ssim2; kornelski dssim-core; libjxl butteraugli.cc), vectorised
+over whole planes, not from oracle/ce_oracle.c.  tests/test_oracle.py::test_two_restatements_agree compares the two on seeded pairs.
 PARITY against the real crates stays UNPINNED (they are not vendored): agreement of two
 restatements of the same text catches transcription slips, not misreadings of upstream.
 
@@ -266,3 +266,207 @@ def dssim(ref_u8: np.ndarray, dist_u8: np.ndarray) -> float:
         scores.append(1.0 - np.abs(a - m).sum() / m.size)
     ssim = sum(sc * w for sc, w in zip(scores, _DS_W)) / sum(_DS_W[:len(scores)])
     return 1.0 / max(ssim, 2.220446049250313e-16) - 1.0
+
+
+# ------------------------------------------------------------------ Butteraugli (A.5)
+_MALTA_HF = [
+    [(0, i) for i in range(-4, 5)], [(i, 0) for i in range(-4, 5)],
+    [(i, i) for i in range(-3, 4)], [(i, -i) for i in range(-3, 4)],
+    [(-4, 1), (-3, 1), (-2, 1), (-1, 0), (0, 0), (1, 0), (2, -1), (3, -1), (4, -1)],
+    [(-4, -1), (-3, -1), (-2, -1), (-1, 0), (0, 0), (1, 0), (2, 1), (3, 1), (4, 1)],
+    [(-1, -4), (-1, -3), (-1, -2), (0, -1), (0, 0), (0, 1), (1, 2), (1, 3), (1, 4)],
+    [(1, -4), (1, -3), (1, -2), (0, -1), (0, 0), (0, 1), (-1, 2), (-1, 3), (-1, 4)],
+    [(-3, -2), (-2, -1), (-1, -1), (0, 0), (1, 1), (2, 1), (3, 2)], [(-3, 2), (-2, 1), (-1, 1), (0, 0), (1, -1), (2, -1), (3, -2)],
+    [(-2, -3), (-1, -2), (-1, -1), (0, 0), (1, 1), (1, 2), (2, 3)], [(-2, 3), (-1, 2), (-1, 1), (0, 0), (1, -1), (1, -2), (2, -3)],
+    [(2, -4), (2, -3), (1, -2), (1, -1), (0, 0), (0, 1), (-1, 2), (-1, 3)],
+    [(-2, -4), (-2, -3), (-1, -2), (-1, -1), (0, 0), (0, 1), (1, 2), (1, 3)],
+    [(-4, -2), (-3, -2), (-2, -1), (-1, -1), (0, 0), (1, 0), (2, 1), (3, 1)],
+    [(-4, 2), (-3, 2), (-2, 1), (-1, 1), (0, 0), (1, 0), (2, -1), (3, -1)]]
+_MALTA_LF = [
+    [(0, -4), (0, -2), (0, 0), (0, 2), (0, 4)], [(-4, 0), (-2, 0), (0, 0), (2, 0), (4, 0)],
+    [(-3, -3), (-2, -2), (0, 0), (2, 2), (3, 3)], [(-3, 3), (-2, 2), (0, 0), (2, -2), (3, -3)],
+    [(-4, 1), (-2, 1), (0, 0), (2, -1), (4, -1)], [(-4, -1), (-2, -1), (0, 0), (2, 1), (4, 1)],
+    [(-1, -4), (-1, -2), (0, 0), (1, 2), (1, 4)], [(1, -4), (1, -2), (0, 0), (-1, 2), (-1, 4)],
+    [(-3, -2), (-2, -1), (0, 0), (2, 1), (3, 2)], [(-3, 2), (-2, 1), (0, 0), (2, -1), (3, -2)],
+    [(-2, -3), (-1, -2), (0, 0), (1, 2), (2, 3)], [(-2, 3), (-1, 2), (0, 0), (1, -2), (2, -3)],
+    [(2, -4), (1, -2), (0, 0), (-1, 2), (-2, 4)], [(-2, -4), (-1, -2), (0, 0), (1, 2), (2, 4)],
+    [(-4, -2), (-2, -1), (0, 0), (2, 1), (4, 2)], [(-4, 2), (-2, 1), (0, 0), (2, -1), (4, -2)]]
+
+
+def _ba_blur(p: np.ndarray, sigma: float) -> np.ndarray:
+    """A.5.0: truncated Gaussian, separable; borders renormalised by the in-range taps; sigma 1.2 = mirror-padded 5 taps."""
+    diff = max(1, int(2.25 * abs(sigma)))
+    wts = np.array([math.exp(-(i * i) / (2.0 * sigma * sigma)) for i in range(-diff, diff + 1)]).astype(np.float32).astype(np.float64)
+
+    def line(a):   # along the last axis
+        n = a.shape[-1]
+        a64 = a.astype(np.float64)
+        if diff == 2:
+            wn = (wts.astype(np.float32) * (F(1.0) / wts.astype(np.float32).sum(dtype=np.float32))).astype(np.float64)
+            q = np.pad(a64, [(0, 0)] * (a.ndim - 1) + [(2, 2)], mode="symmetric")
+            out = sum(wn[t] * q[..., t:t + n] for t in range(5))
+            return out.astype(np.float32)
+        q = np.pad(a64, [(0, 0)] * (a.ndim - 1) + [(diff, diff)])
+        ones = np.pad(np.ones(n), (diff, diff))
+        num = sum(wts[t] * q[..., t:t + n] for t in range(2 * diff + 1))
+        den = sum(wts[t] * ones[t:t + n] for t in range(2 * diff + 1))
+        return (num / den).astype(np.float32)
+
+    hpass = line(p)
+    return np.ascontiguousarray(line(np.ascontiguousarray(hpass.T)).T)
+
+
+def _opsin_abs(r, g, b):
+    o0 = F(0.29956550340058319) * r + F(0.63373087833825936) * g + F(0.077705617820981968) * b + F(1.7557483643287353)
+    o1 = F(0.22158691104574774) * r + F(0.69391388044116142) * g + F(0.0987313588422) * b + F(1.7557483643287353)
+    o2 = F(0.02) * r + F(0.02) * g + F(0.20480129041026129) * b + F(12.226454707163354)
+    return o0, o1, o2
+
+
+def _gamma(v):
+    return (19.245013259874995 * np.log(np.maximum(v, 0).astype(np.float64) + 9.9710635769299145) - 23.16046239805755).astype(np.float32)
+
+
+def _remove_range(v, w):
+    return np.where(v > w, v - w, np.where(v < -w, v + w, F(0))).astype(np.float32)
+
+
+def _amplify_range(v, w):
+    return np.where(v > w, v + w, np.where(v < -w, v - w, v + v)).astype(np.float32)
+
+
+def _max_clamp(v, m):
+    k = F(0.724216145665)
+    return np.where(v >= m, (v - m) * k + m, np.where(v < -m, (v + m) * k - m, v)).astype(np.float32)
+
+
+def _ba_psycho(lin: np.ndarray, intensity: float):
+    """linear rgb [3,h,w] (0..1) -> dict of frequency bands (A.5.1-3) and the mask input (A.5.6)."""
+    rgb = [c * F(intensity) for c in lin]
+    blurred = [_ba_blur(c, 1.2) for c in rgb]
+    pre = [np.maximum(o, F(1e-4)) for o in _opsin_abs(*blurred)]
+    sens = [np.maximum(_gamma(p) / p, F(1e-4)) for p in pre]
+    cur = [o * s for o, s in zip(_opsin_abs(*rgb), sens)]
+    cur = [np.maximum(cur[0], F(1.7557483643287353)), np.maximum(cur[1], F(1.7557483643287353)), np.maximum(cur[2], F(12.226454707163354))]
+    xyb = [cur[0] - cur[1], cur[0] + cur[1], cur[2]]
+    lf = [_ba_blur(c, 7.15593339443) for c in xyb]
+    mf = [c - l for c, l in zip(xyb, lf)]
+    mfb = [_ba_blur(c, 3.22489901262) for c in mf]
+    hf = [mf[0] - mfb[0], mf[1] - mfb[1]]
+    mfo = [_remove_range(mfb[0], F(0.29)), _amplify_range(mfb[1], F(0.1)), mfb[2]]
+    hf[0] = hf[0] * (F(0.653020556257) + F(46.0) * F(1 - 0.653020556257) / (F(46.0) + hf[1] * hf[1]))
+    hfb = [_ba_blur(c, 1.56416327805) for c in hf]
+    uhf_x = _remove_range(hf[0] - hfb[0], F(0.04))
+    hf_x = _remove_range(hfb[0], F(1.5))
+    hh = _max_clamp(hfb[1], F(28.4691806922))
+    u = _max_clamp(hf[1] - hh, F(5.19175294647))
+    uhf_y = F(2.69313763794) * u
+    hf_y = _amplify_range(F(2.155) * hh, F(0.132))
+    lfb = lf[2] + F(-0.362267051518) * lf[1]
+    lfo = [lf[0] * F(33.832837186260), lf[1] * F(14.458268100570), lfb * F(49.87984651440)]
+    m = np.sqrt(((uhf_x + hf_x) * F(2.5)) ** 2 + (uhf_y * F(0.4) + hf_y * F(0.4)) ** 2)
+    bb = F(6.19424080439) * F(12.61050594197)
+    pm = np.sqrt(F(6.19424080439) * np.abs(m) + bb) - np.sqrt(bb)
+    return {"lf": lfo, "mf": mfo, "hf": [hf_x, hf_y], "uhf": [uhf_x, uhf_y], "bl": _ba_blur(pm.astype(np.float32), 2.7)}
+
+
+def _malta(l0, l1, w0gt1, w0lt1, norm1, lf_patterns):
+    length, mulli = 3.75, (0.611612573796 if lf_patterns else 0.39905817637)
+    wpre0 = mulli * math.sqrt(0.5 * w0gt1) / (2 * length + 1)
+    wpre1 = mulli * math.sqrt(0.33 * w0lt1) / (2 * length + 1)
+    n20, n21, n1 = F(wpre0 * norm1), F(wpre1 * norm1), F(norm1)
+    absval = F(0.5) * (np.abs(l0) + np.abs(l1))
+    d = n20 / (n1 + absval) * (l0 - l1)
+    s2 = n21 / (n1 + absval)
+    small, big = F(0.55) * np.abs(l0), F(1.05) * np.abs(l0)
+    neg = l0 < 0
+    d = np.where(neg & (l1 > -small), d - s2 * (l1 + small), d)
+    d = np.where(neg & ~(l1 > -small) & (l1 < -big), d + s2 * (-l1 - big), d)
+    d = np.where(~neg & (l1 < small), d + s2 * (small - l1), d)
+    d = np.where(~neg & ~(l1 < small) & (l1 > big), d - s2 * (l1 - big), d)
+    d = d.astype(np.float32)
+    h, w = d.shape
+    q = np.pad(d.astype(np.float64), 4)
+    acc = np.zeros((h, w))
+    for pat in (_MALTA_LF if lf_patterns else _MALTA_HF):
+        s = sum(q[4 + dy:4 + dy + h, 4 + dx:4 + dx + w] for dy, dx in pat)
+        acc += s * s
+    return acc.astype(np.float32)
+
+
+def _l2_asym(a, b, w0gt1, w0lt1):
+    vw0, vw1 = F(0.8 * w0gt1), F(0.8 * w0lt1)
+    t = vw0 * (a - b) ** 2
+    small, big = F(0.4) * np.abs(a), np.abs(a)
+    neg = a < 0
+    v = np.where(neg, np.where(b > -small, b + small, np.where(b < -big, -b - big, F(0))),
+                 np.where(b < small, small - b, np.where(b > big, b - big, F(0))))
+    return (t + vw1 * v * v).astype(np.float32)
+
+
+def _fuzzy_erosion(bl):
+    h, w = bl.shape
+    inf = np.float32(np.inf)
+    q = np.pad(bl, 3, constant_values=inf)
+    cands = [bl, F(2.0) * bl, F(2.0) * bl]
+    for dy in (-3, 0, 3):
+        for dx in (-3, 0, 3):
+            if dy or dx:
+                cands.append(q[3 + dy:3 + dy + h, 3 + dx:3 + dx + w])
+    st = np.sort(np.stack(cands), axis=0)
+    return (F(0.45) * st[0] + F(0.3) * st[1] + F(0.25) * st[2]).astype(np.float32)
+
+
+def _ba_diffmap(l1, l2, intensity, hf_asym=1.0, xmul=1.0):
+    p0, p1 = _ba_psycho(l1, intensity), _ba_psycho(l2, intensity)
+    ac = [np.zeros_like(l1[0]) for _ in range(3)]
+    sq = math.sqrt(hf_asym)
+    ac[1] += _malta(p0["uhf"][1], p1["uhf"][1], 1.10039032555 * hf_asym, 1.10039032555 / hf_asym, 71.7800275169, False)
+    ac[0] += _malta(p0["uhf"][0], p1["uhf"][0], 173.5 * hf_asym, 173.5 / hf_asym, 5.0, False)
+    ac[1] += _malta(p0["hf"][1], p1["hf"][1], 18.7237414387 * sq, 18.7237414387 / sq, 4498534.45232, True)
+    ac[0] += _malta(p0["hf"][0], p1["hf"][0], 6923.99476109 * sq, 6923.99476109 / sq, 8051.15833247, True)
+    ac[1] += _malta(p0["mf"][1], p1["mf"][1], 37.0819870399, 37.0819870399, 130262059.556, True)
+    ac[0] += _malta(p0["mf"][0], p1["mf"][0], 8246.75321353, 8246.75321353, 1009002.70582, True)
+    wmul = [400.0, 1.50815703118, 0, 2150.0, 10.6195433239, 16.2176043152, 29.2353797994, 0.844626970982, 0.703646627719]
+    for c in range(2):
+        ac[c] += _l2_asym(p0["hf"][c], p1["hf"][c], wmul[c] * hf_asym, wmul[c] / hf_asym)
+    dc = []
+    for c in range(3):
+        ac[c] += F(wmul[3 + c]) * (p0["mf"][c] - p1["mf"][c]) ** 2
+        dc.append(F(wmul[6 + c]) * (p0["lf"][c] - p1["lf"][c]) ** 2)
+    mask = _fuzzy_erosion(p0["bl"])
+    ac[1] += F(10.0) * (p0["bl"] - p1["bl"]) ** 2
+    gs = F(1.0 / 17.83)
+    mask_y = (gs * (F(1.0) + F(2.5485944793) / (F(0.451936922203) * mask + F(0.829591754942)))) ** 2
+    mask_dc = (gs * (F(1.0) + F(0.505054525019) / (F(3.87449418804) * mask + F(0.20025578522)))) ** 2
+    return np.sqrt(mask_dc * (F(xmul) * dc[0] + dc[1] + dc[2]) + mask_y * (F(xmul) * ac[0] + ac[1] + ac[2])).astype(np.float32)
+
+
+def _ba_subsample(lin):
+    _, h, w = lin.shape
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    out = np.zeros((3, oh, ow), np.float32)
+    for dy in range(2):
+        for dx in range(2):
+            part = lin[:, dy::2, dx::2]
+            out[:, :part.shape[1], :part.shape[2]] += F(0.25) * part
+    if w & 1:
+        out[:, :, -1] *= F(2.0)
+    if h & 1:
+        out[:, -1, :] *= F(2.0)
+    return out
+
+
+def butteraugli(ref_u8: np.ndarray, dist_u8: np.ndarray, intensity: float = 80.0):
+    """[h,w,3] uint8 pair -> (max of the diffmap, libjxl 3-norm) (A.5)."""
+    l1, l2 = srgb8_to_linear(ref_u8), srgb8_to_linear(dist_u8)
+    dm = _ba_diffmap(l1, l2, intensity)
+    _, h, w = l1.shape
+    if (w + 1) // 2 >= 8 and (h + 1) // 2 >= 8:
+        ds = _ba_diffmap(_ba_subsample(l1), _ba_subsample(l2), intensity)
+        up = ds[np.arange(h)[:, None] // 2, np.arange(w)[None, :] // 2]
+        dm = dm * F(1.0 - 0.3 * 0.5) + F(0.5) * up
+    d = dm.astype(np.float64)
+    n = d.size
+    pn = ((d ** 3).sum() / n) ** (1 / 3) + ((d ** 6).sum() / n) ** (1 / 6) + ((d ** 12).sum() / n) ** (1 / 12)
+    return float(dm.max()), pn / 3.0

@@ -208,3 +208,12 @@ def test_two_restatements_agree(O):
                 N._cbrtf = rounded
     same = G(1, 40, 40)
     assert N.ssimulacra2(same, same) == 100.0 and N.dssim(same, same) == 0.0
+    # Butteraugli (Appendix A.5): float64-accumulated blurs and an exact log in numpy vs fp32 fused chains and
+    # FastLog2f in C => agreement to ~1e-6 relative; a wrong constant or tap would show at the percent level
+    for w, h, q in cases + [(256, 256, 80)]:
+        r = G(w + h, w, h)
+        d = J(r, q, 2)
+        mx, pn = N.butteraugli(r, d)
+        emx, epn = O.butteraugli(r, d, w, h)
+        assert abs(mx - emx) <= 2e-5 * emx and abs(pn - epn) <= 2e-5 * epn, (w, h, q, mx, emx, pn, epn)
+    assert N.butteraugli(same, same) == (0.0, 0.0)
