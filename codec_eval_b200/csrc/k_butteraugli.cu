@@ -133,18 +133,48 @@ CE_DEVINL float blur5(float l2, float l1, float c, float r1, float r2) {
 
 // OPSIN = true : lin [NI][3][n] -> xyb [NI][3][n] (blur + OpsinDynamicsImage), grid.z = image
 // OPSIN = false: one plane per grid.z, out = blurred plane (stage test entry)
-template <bool OPSIN>
+// TMA: the NPL plane tiles arrive as one bulk tensor copy (box OP_P x OP_ROWS x NPL, zeros outside the image); tiles on
+// the image border then overwrite their out-of-image entries with the mirrored in-image values (Separable5's rule).
+template <bool OPSIN, bool TMA>
 __global__ void __launch_bounds__(256) k_ba_opsin(const float* __restrict__ lin, int w, int h, size_t n, float intensity,
-                                                   float* __restrict__ out, int vec) {
+                                                   float* __restrict__ out, int vec, const __grid_constant__ CUtensorMap map) {
     constexpr int NPL = OPSIN ? 3 : 1;
-    __shared__ __align__(16) float s_in[NPL][OP_ROWS * OP_P];
+    __shared__ __align__(128) float s_in[NPL][OP_ROWS * OP_P];
     __shared__ __align__(16) float s_h[NPL][OP_ROWS * OP_TW];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int x0 = blockIdx.x * OP_TW, y0 = blockIdx.y * OP_TH;
     const float* src = lin + (size_t)blockIdx.z * NPL * n;
     float* dst = out + (size_t)blockIdx.z * NPL * n;
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(&s_bar, NPL * OP_ROWS * OP_P * 4);
+            tma_load_3d(&s_in[0][0], &map, x0 - 4, y0 - 2, (int)(blockIdx.z * NPL), &s_bar);
+        }
+        __syncthreads();
+        mbar_wait(&s_bar, 0);
+        const bool border = x0 - 4 < 0 || x0 - 4 + OP_P > w || y0 - 2 < 0 || y0 - 2 + OP_ROWS > h;   // block-uniform
+        if (border) {
+            for (int e = threadIdx.x; e < OP_ROWS * OP_P; e += 256) {
+                const int r = e / OP_P, cx = e - r * OP_P;
+                const int x = x0 - 4 + cx, y = y0 - 2 + r;
+                if (x < 0 || x >= w || y < 0 || y >= h) {
+                    const int mx = mirror(x, w), my = mirror(y, h);
+                    const int tr = my - (y0 - 2), tc = mx - (x0 - 4);
+                    const bool in_tile = tr >= 0 && tr < OP_ROWS && tc >= 0 && tc < OP_P;
 #pragma unroll
-    for (int c = 0; c < NPL; c++) load_tile<1, OP_P / 4, OP_ROWS, 256>(s_in[c], OP_P, src + (size_t)c * n, w, h, x0 - 4, y0 - 2, vec != 0);
-    __syncthreads();
+                    for (int c = 0; c < NPL; c++)
+                        s_in[c][e] = in_tile ? s_in[c][tr * OP_P + tc] : src[(size_t)c * n + (size_t)my * w + mx];
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < NPL; c++) load_tile<1, OP_P / 4, OP_ROWS, 256>(s_in[c], OP_P, src + (size_t)c * n, w, h, x0 - 4, y0 - 2, vec != 0);
+        __syncthreads();
+    }
     // horizontal pass: (row, 4-column group) items
     for (int e = threadIdx.x; e < OP_ROWS * (OP_TW / 4); e += 256) {
         const int r = e >> 4, g = e & 15;
@@ -1154,8 +1184,14 @@ static void ba_psycho_level(Context& c, const float* lin, size_t NI, size_t w, s
     check_grid_z(NI * 3);
     {
         dim3 grid(cdiv(w, OP_TW), cdiv(h, OP_TH), (unsigned)NI);
-        CE_LAUNCH(c, "k_ba_opsin", (double)NI * n * 24,
-                  k_ba_opsin<true><<<grid, 256, 0, c.stream>>>(lin, (int)w, (int)h, n, intensity, L.xyb, vec));
+        CUtensorMap mo;
+        memset(&mo, 0, sizeof(mo));
+        if (tma_enabled(5) && tma_plane_map(&mo, lin, w, h, NI * 3, OP_P, OP_ROWS, 3))
+            CE_LAUNCH(c, "k_ba_opsin", (double)NI * n * 24,
+                      k_ba_opsin<true, true><<<grid, 256, 0, c.stream>>>(lin, (int)w, (int)h, n, intensity, L.xyb, vec, mo));
+        else
+            CE_LAUNCH(c, "k_ba_opsin", (double)NI * n * 24,
+                      k_ba_opsin<true, false><<<grid, 256, 0, c.stream>>>(lin, (int)w, (int)h, n, intensity, L.xyb, vec, mo));
     }
     if (dbg_opsin) CE_CUDA(cudaMemcpyAsync(dbg_opsin, L.xyb, 3 * n * 4, cudaMemcpyDeviceToDevice, c.stream));
     {
@@ -1335,7 +1371,12 @@ void butteraugli_debug_blur(Context& c, const float* in, size_t w, size_t h, flo
     dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), 1);
     if (fabsf(sigma - 1.2f) < 1e-6f) {
         dim3 grid(cdiv(w, OP_TW), cdiv(h, OP_TH), 1);
-        CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_opsin<false><<<grid, 256, 0, c.stream>>>(in, (int)w, (int)h, n, 0.0f, out, vec));
+        CUtensorMap m5;
+        memset(&m5, 0, sizeof(m5));
+        if (tma_plane_map(&m5, in, w, h, 1, OP_P, OP_ROWS, 1))
+            CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_opsin<false, true><<<grid, 256, 0, c.stream>>>(in, (int)w, (int)h, n, 0.0f, out, vec, m5));
+        else
+            CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_opsin<false, false><<<grid, 256, 0, c.stream>>>(in, (int)w, (int)h, n, 0.0f, out, vec, m5));
     } else if (fabsf(sigma - kSigmas[0]) < 1e-5f) {
         dim3 gh(cdiv(w, 128), cdiv(h, 8), 1);
         dim3 gv(cdiv(w, 32), cdiv(h, 64), 1);
