@@ -12,6 +12,8 @@
 //                  channel-averaged SSIM map written once + fp64 partial of its sum    [FP32-issue bound]
 //   k_ds_mean    : fixed-order reduce -> sum(map), avg = max(mean,0)^(0.5^scale)
 //   k_ds_mad     : sum |avg - map_i| in fp64 -> block partials; k_ds_mad_reduce fixes the order
+#include <cuda.h>
+
 #include "ce_common.cuh"
 #include "ce_internal.h"
 
@@ -85,16 +87,47 @@ __global__ void __launch_bounds__(256) k_ds_down(const float* __restrict__ in, i
 // grid (tiles_x, tiles_y, NI): blockIdx.z = image; chroma [NI][2][n] -> img[(z*3) + 1 + {0,1}].
 // Both planes of a 64x16 tile (+ halo 2, clamped) are staged; each pass evaluates 4 positions per thread
 // from 128-bit shared loads.
+// TMA: both plane tiles arrive as one bulk tensor copy (box DS_IW x DS_IH x 2, zeros outside the image); tiles on the
+// image border then overwrite their out-of-image entries with the nearest in-image value (clamp-replicate).
+template <bool TMA>
 __global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chroma, int w, int h, size_t n,
-                                                   float* __restrict__ img) {
-    __shared__ __align__(16) float s_ab[2][DS_IH * DS_IW];
+                                                   float* __restrict__ img, const __grid_constant__ CUtensorMap map) {
+    __shared__ __align__(128) float s_ab[2][DS_IH * DS_IW];
     __shared__ __align__(16) float s_f[2][DS_FH * DS_FW];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int x0 = blockIdx.x * DS_TW, y0 = blockIdx.y * DS_TH;
     const size_t z = blockIdx.z;
     const bool vec = (w & 3) == 0;
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(&s_bar, 2 * DS_IH * DS_IW * 4);
+            tma_load_3d(&s_ab[0][0], &map, x0 - 4, y0 - 2, (int)(z * 2), &s_bar);
+        }
+        __syncthreads();
+        mbar_wait(&s_bar, 0);
+        const bool border = x0 - 4 < 0 || x0 - 4 + DS_IW > w || y0 - 2 < 0 || y0 - 2 + DS_IH > h;   // block-uniform
+        if (border) {
+            for (int e = threadIdx.x; e < DS_IH * DS_IW; e += 256) {
+                const int r = e / DS_IW, cx = e - r * DS_IW;
+                const int x = x0 - 4 + cx, y = y0 - 2 + r;
+                if (x < 0 || x >= w || y < 0 || y >= h) {
+                    const int mx = min(max(x, 0), w - 1), my = min(max(y, 0), h - 1);
+                    const int tr = my - (y0 - 2), tc = mx - (x0 - 4);
+                    const bool in_tile = tr >= 0 && tr < DS_IH && tc >= 0 && tc < DS_IW;
 #pragma unroll
-    for (int pl = 0; pl < 2; pl++) load_tile<2, DS_IW / 4, DS_IH, 256>(s_ab[pl], DS_IW, chroma + (z * 2 + pl) * n, w, h, x0 - 4, y0 - 2, vec);
-    __syncthreads();
+                    for (int pl = 0; pl < 2; pl++)
+                        s_ab[pl][e] = in_tile ? s_ab[pl][tr * DS_IW + tc] : chroma[(z * 2 + pl) * n + (size_t)my * w + mx];
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) load_tile<2, DS_IW / 4, DS_IH, 256>(s_ab[pl], DS_IW, chroma + (z * 2 + pl) * n, w, h, x0 - 4, y0 - 2, vec);
+        __syncthreads();
+    }
     // first 3x3 pass over the positions the second pass needs
     for (int e = threadIdx.x; e < 2 * DS_FH * DS_FG; e += 256) {
         const int pl = e / (DS_FH * DS_FG), r = e - pl * (DS_FH * DS_FG);
@@ -612,7 +645,12 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
         }
         {
             dim3 grid(cdiv(cw, DS_TW), cdiv(ch, DS_TH), (unsigned)NI);
-            CE_LAUNCH(c, "k_ds_blur2", (double)NI * n * 16, k_ds_blur2<<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img));
+            CUtensorMap mc;
+            memset(&mc, 0, sizeof(mc));
+            if (tma_enabled(6) && tma_plane_map(&mc, chroma, cw, ch, NI * 2, DS_IW, DS_IH, 2))
+                CE_LAUNCH(c, "k_ds_blur2", (double)NI * n * 16, k_ds_blur2<true><<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img, mc));
+            else
+                CE_LAUNCH(c, "k_ds_blur2", (double)NI * n * 16, k_ds_blur2<false><<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img, mc));
         }
         // row strips: 64 rows per warp, fewer when the launch would not fill the machine
         int rows = 64;
