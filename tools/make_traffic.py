@@ -19,6 +19,7 @@ def bench_name(k):
     m = {"k_ds_stream<0>": "k_ds_stats<ref>", "k_ds_stream<1>": "k_ds_stats<pair>", "k_ds_blur2s": "k_ds_blur2",
          "k_s2_hpass<0>": "k_s2_hpass", "k_s2_hpass<1>": "k_s2_hpass<ref>", "k_s2_hpass<2>": "k_s2_hpass<pair>",
          "k_s2_vpass<0>": "k_s2_vpass", "k_s2_vpass<1>": "k_s2_vpass<ref>", "k_s2_vpass<2>": "k_s2_vpass<pair>",
+         "k_ba_opsin<1, 1>": "k_ba_opsin", "k_ba_opsin<1, 0>": "k_ba_opsin", "k_ds_blur2<1>": "k_ds_blur2", "k_ds_blur2<0>": "k_ds_blur2",
          "k_ba_combine4": "k_ba_combine", "k_ba_malta<1>": "k_ba_malta", "k_ba_malta<0>": "k_ba_malta",
          "k_s2_hpass<0, 1>": "k_s2_hpass", "k_s2_hpass<1, 1>": "k_s2_hpass<ref>", "k_s2_hpass<2, 1>": "k_s2_hpass<pair>",
          "k_s2_hpass<0, 0>": "k_s2_hpass", "k_s2_hpass<1, 0>": "k_s2_hpass<ref>", "k_s2_hpass<2, 0>": "k_s2_hpass<pair>",
