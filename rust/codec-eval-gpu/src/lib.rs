@@ -93,3 +93,43 @@ pub fn evaluate_image_batched(gpu: &mut GpuMetrics, reference_rgb: &[u8], decode
     let pairs: Vec<(&[u8], &[u8], u32, u32)> = decoded_rgb.iter().map(|d| (reference_rgb, d.as_slice(), width, height)).collect();
     gpu.evaluate_batch(&pairs, cfg).into_iter().collect()      // first per-pair error, like the `?` chain today
 }
+
+impl GpuMetrics {
+    /// `transform_to_srgb` (src/metrics/icc.rs:69-103) for matrix/TRC profiles on the device; `None` = ColorProfile::Srgb.
+    /// `Err(MetricCalculation{metric:"ICC"})` for profiles the device path does not cover (the caller falls back to moxcms).
+    pub fn transform_to_srgb(&mut self, rgb: &[u8], width: usize, height: usize, icc: Option<&[u8]>) -> Result<Vec<u8>> {
+        let mut out = vec![0u8; rgb.len()];
+        let (p, n) = icc.map_or((std::ptr::null(), 0), |d| (d.as_ptr(), d.len()));
+        let st = unsafe { sys::ce_transform_to_srgb(self.ctx, rgb.as_ptr(), rgb.len(), width, height, p, n, out.as_mut_ptr()) };
+        match st {
+            sys::CE_OK => Ok(out),
+            _ => Err(Error::MetricCalculation { metric: "ICC".into(), reason: self.last_error() }),
+        }
+    }
+
+    /// codec-iter's per-image quality sweep (crates/codec-iter/src/eval.rs:153-200) for baseline JPEG with the decoded
+    /// images generated on the device (bit-exact with libjpeg-turbo): `out[r][k]` = metrics of `refs[r]` against its own
+    /// JPEG(`qualities[k]`) round trip.  Only the references are uploaded.  `subsampling`: 0 = 4:4:4, 2 = 4:2:0.
+    pub fn evaluate_jpeg_sweep(&mut self, refs: &[&[u8]], width: u32, height: u32, qualities: &[i32], subsampling: i32,
+                               cfg: &MetricConfig) -> Result<Vec<Vec<MetricResult>>> {
+        let ptrs: Vec<*const u8> = refs.iter().map(|r| r.as_ptr()).collect();
+        let c_cfg = sys::ce_metric_config {
+            dssim: cfg.dssim as u8, ssimulacra2: cfg.ssimulacra2 as u8, butteraugli: cfg.butteraugli as u8,
+            psnr: cfg.psnr as u8, xyb_roundtrip: cfg.xyb_roundtrip as u8,
+        };
+        let mut out = vec![sys::ce_result::default(); refs.len() * qualities.len()];
+        let st = unsafe {
+            sys::ce_evaluate_jpeg_sweep(self.ctx, ptrs.as_ptr(), refs.len(), width, height, qualities.as_ptr(), qualities.len(),
+                                        subsampling, &c_cfg, 80.0, out.as_mut_ptr())
+        };
+        if st != sys::CE_OK {
+            return Err(Error::MetricCalculation { metric: "GPU".into(), reason: self.last_error() });
+        }
+        Ok(out.chunks(qualities.len().max(1)).map(|row| row.iter().map(|r| MetricResult {
+            dssim: (r.valid & 1 != 0).then_some(r.dssim),
+            ssimulacra2: (r.valid & 2 != 0).then_some(r.ssimulacra2),
+            butteraugli: (r.valid & 4 != 0).then_some(r.butteraugli),
+            psnr: (r.valid & 8 != 0).then_some(r.psnr),
+        }).collect()).collect())
+    }
+}
