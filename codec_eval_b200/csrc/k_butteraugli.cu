@@ -13,12 +13,17 @@
 //   k_ba_blur2d<HF> : sigma-1.56 H+V + UHF split + mask precompute                             hf_pre -> hf, uhf, m
 //   k_ba_blur2d<NONE>: sigma-2.7 H+V of the mask input                                         m -> bl
 //   k_ba_malta   : Malta filters, 3 bands x {X,Y}: diffs staged in smem, 9x12 register window per
-//                  thread (4 pixels), 16 oriented line sums each, + L2 diffs                    -> ac
+//                  thread (4 pixels), 16 oriented line sums each (built from shared sub-sums),
+//                  + L2 diffs                                                                   -> ac
 //   k_ba_combine : fuzzy erosion, mask, DC/AC combine                                          -> diffmap
 // then the half-resolution diffmap is supersample-added and max / sum d^3,d^6,d^12 reduced in
 // fp64 (warp shuffles -> block partials -> fixed order).
 // Blurs use zero padding + per-coordinate 1/sum(in-range taps) tables (the renormalised
-// borders of libjxl's ConvolveBorderColumn); tile loads are 128-bit where the row pitch allows.
+// borders of libjxl's ConvolveBorderColumn).  Tiles are staged by TMA (cp.async.bulk.tensor.3d, one
+// box per plane group, out-of-image elements zero-filled by the copy engine, completion on an
+// mbarrier) when the row pitch is a multiple of 16 bytes; otherwise by 128-/32-bit loads.  Every
+// consumer thread issues fence.proxy.async before the barrier that precedes a refill of a slot it
+// has read with ordinary shared loads.
 #include <cuda.h>
 
 #include "ce_common.cuh"

@@ -3,11 +3,13 @@
 //
 // Per scale (6 scales, ceil-halving with clamp on LINEAR rgb):
 //   k_s2_xyb_down : linear(s) -> positive-XYB(s) planes + linear(s+1)        [HBM-bound, pointwise]
-//   k_s2_hpass    : recursive Gaussian along x of {i1,i2,i1^2,i2^2,i1*i2};   [rows staged in smem by cp.async]
-//                   lane = row, warp = product, 32x32 tiles double-buffered through shared memory,
-//                   128-bit shared / global accesses
+//   k_s2_hpass    : recursive Gaussian along x of {i1,i2,i1^2,i2^2,i1*i2};   [rows staged in smem by TMA]
+//                   lane = row, warp = product, 32-row x 64-column input slots double-buffered
+//                   through shared memory (TMA boxes with the 128-byte swizzle so lane = row reads
+//                   are conflict-free; cp.async + padded pitch when the row pitch is not 16 B aligned)
 //   k_s2_vpass    : column-parallel recurrence along y (lane = column, warp = product, 10-row
-//                   register delay line) fused with the SSIM / edge-artifact / detail-loss maps
+//                   register delay line, 5-row slots staged by TMA) fused with the SSIM /
+//                   edge-artifact / detail-loss maps
 //                   and L1/L4 pooling in fp64 (warp shuffles -> per-block partials)
 //   k_s2_reduce   : fixed-order sum of the block partials -> 18 sums per (pair, scale)
 // The recurrence is the exact operation sequence of the upstream code so the
