@@ -31,6 +31,12 @@ pub const CE_ERR_INVALID_ARGUMENT: c_int = 3;
 pub const CE_ERR_CUDA: c_int = 4;
 pub const CE_ERR_OUT_OF_MEMORY: c_int = 5;
 
+// ce_result.valid bits  <->  Some(..) in MetricResult
+pub const CE_VALID_DSSIM: u32 = 1;
+pub const CE_VALID_SSIMULACRA2: u32 = 2;
+pub const CE_VALID_BUTTERAUGLI: u32 = 4;
+pub const CE_VALID_PSNR: u32 = 8;
+
 #[link(name = "ce_gpu")]
 extern "C" {
     pub fn ce_ctx_create(out: *mut *mut ce_ctx, device: c_int, workspace_bytes: usize) -> c_int;

@@ -56,10 +56,10 @@ impl GpuMetrics {
         }
         out.iter().zip(pairs).map(|(r, p)| match r.status {
             sys::CE_OK => Ok(MetricResult {
-                dssim: (r.valid & 1 != 0).then_some(r.dssim),
-                ssimulacra2: (r.valid & 2 != 0).then_some(r.ssimulacra2),
-                butteraugli: (r.valid & 4 != 0).then_some(r.butteraugli),
-                psnr: (r.valid & 8 != 0).then_some(r.psnr),
+                dssim: (r.valid & sys::CE_VALID_DSSIM != 0).then_some(r.dssim),
+                ssimulacra2: (r.valid & sys::CE_VALID_SSIMULACRA2 != 0).then_some(r.ssimulacra2),
+                butteraugli: (r.valid & sys::CE_VALID_BUTTERAUGLI != 0).then_some(r.butteraugli),
+                psnr: (r.valid & sys::CE_VALID_PSNR != 0).then_some(r.psnr),
             }),
             sys::CE_ERR_DIMENSION_MISMATCH => Err(Error::DimensionMismatch {        // src/metrics/ssimulacra2.rs:65-70
                 expected: (p.2 as usize, p.3 as usize),
@@ -126,10 +126,10 @@ impl GpuMetrics {
             return Err(Error::MetricCalculation { metric: "GPU".into(), reason: self.last_error() });
         }
         Ok(out.chunks(qualities.len().max(1)).map(|row| row.iter().map(|r| MetricResult {
-            dssim: (r.valid & 1 != 0).then_some(r.dssim),
-            ssimulacra2: (r.valid & 2 != 0).then_some(r.ssimulacra2),
-            butteraugli: (r.valid & 4 != 0).then_some(r.butteraugli),
-            psnr: (r.valid & 8 != 0).then_some(r.psnr),
+            dssim: (r.valid & sys::CE_VALID_DSSIM != 0).then_some(r.dssim),
+            ssimulacra2: (r.valid & sys::CE_VALID_SSIMULACRA2 != 0).then_some(r.ssimulacra2),
+            butteraugli: (r.valid & sys::CE_VALID_BUTTERAUGLI != 0).then_some(r.butteraugli),
+            psnr: (r.valid & sys::CE_VALID_PSNR != 0).then_some(r.psnr),
         }).collect()).collect())
     }
 }

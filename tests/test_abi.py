@@ -89,3 +89,90 @@ def test_metric_config_presets():
     assert MetricConfig.ssimulacra2_only().with_xyb_roundtrip().xyb_roundtrip
     r = MetricResult(dssim=0.0005)
     assert r.perception_level().code() == "MAR" and r.perception_level_ssimulacra2() is None
+
+
+# ---- the Rust -sys crate cannot be compiled in this image; check it textually ----
+_C2R = {"int": "c_int", "size_t": "usize", "float": "f32", "double": "f64", "uint32_t": "u32", "uint64_t": "u64",
+        "uint8_t": "u8", "char": "c_char", "void": "c_void", "int32_t": "i32"}
+
+
+def _c_type_to_rust(decl, is_param=True):
+    """'const uint8_t* const* dists' -> '*const *const u8' (parameter name dropped)."""
+    decl = re.sub(r"\s+", " ", decl).strip()
+    if is_param:
+        decl = re.sub(r"\b\w+$", "", decl).strip()
+    toks = re.findall(r"const|\*|\w+", decl)
+    toks = [t for t in toks if t != "struct"]
+    base = [t for t in toks if t not in ("const", "*")][0]
+    out = _C2R.get(base, base)
+    # pointer levels left to right; a level is const if 'const' qualifies the pointee it points at
+    pointee_const = "const" in toks[: toks.index("*")] if "*" in toks else False
+    i = 0
+    while i < len(toks):
+        if toks[i] == "*":
+            out = ("*const " if pointee_const else "*mut ") + out
+            pointee_const = i + 1 < len(toks) and toks[i + 1] == "const"
+        i += 1
+    return out
+
+
+def _strip_c_comments(src):
+    return re.sub(r"//[^\n]*", "", re.sub(r"/\*.*?\*/", "", src, flags=re.S))
+
+
+def test_rust_sys_crate_matches_header():
+    h = _strip_c_comments(open(os.path.join(ROOT, "include", "ce_gpu.h")).read())
+    r = re.sub(r"//[^\n]*", "", open(os.path.join(ROOT, "rust", "ce-gpu-sys", "src", "lib.rs")).read())
+    c_funcs = {}
+    for m in re.finditer(r"CE_API\s+([\w\s\*]+?)\b(ce_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S):
+        ret, name, args = m.groups()
+        args = [] if args.strip() in ("", "void") else [a.strip() for a in args.split(",")]
+        c_funcs[name] = (ret.strip(), args)
+    r_funcs = {}
+    for m in re.finditer(r"pub fn (ce_\w+)\s*\(([^;]*?)\)\s*(?:->\s*([^;]+?))?\s*;", r, flags=re.S):
+        name, args, ret = m.groups()
+        r_funcs[name] = (ret, [a.strip() for a in args.split(",") if a.strip()])
+    assert len(r_funcs) >= 25
+    norm = lambda s: s.replace(" ", "")
+    for name, (ret, args) in r_funcs.items():
+        assert name in c_funcs, name
+        c_ret, c_args = c_funcs[name]
+        assert len(c_args) == len(args), name
+        for ca, ra in zip(c_args, args):
+            assert norm(_c_type_to_rust(ca)) == norm(ra.split(":", 1)[1]), (name, ca, ra)
+        want = _c_type_to_rust(c_ret, is_param=False)
+        assert norm(ret or "c_void") == norm(want), (name, c_ret, ret)
+    # everything a caller of the path needs is bound; only the debug taps and the profiler stay C-only
+    unbound = set(c_funcs) - set(r_funcs)
+    assert all(n.startswith(("ce_debug_", "ce_profile_")) for n in unbound), unbound
+
+    # #[repr(C)] structs: same field order and widths as the header
+    def c_fields(struct):
+        body = re.search(r"typedef struct\s*\{([^}]*)\}\s*%s\s*;" % struct, h, flags=re.S).group(1)
+        out = []
+        for f in body.split(";"):
+            if not f.strip():
+                continue
+            first, *more = [d.strip() for d in f.split(",")]  # 'size_t ref_len, dist_len' -> one entry per name
+            ty = _c_type_to_rust(first)
+            out.append((ty, re.search(r"(\w+)$", first).group(1)))
+            out += [(ty, n) for n in more]
+        return out
+
+    def r_fields(struct):
+        body = re.search(r"pub struct %s\s*\{(.*?)\}" % struct, r, flags=re.S).group(1)
+        return [(norm(f.split(":", 1)[1]), f.split(":", 1)[0].replace("pub", "").strip())
+                for f in body.split(",") if f.strip()]
+
+    for s in ("ce_metric_config", "ce_result", "ce_pair"):
+        cf, rf = c_fields(s), r_fields(s)
+        assert [{"ref": "reference"}.get(n, n) for _, n in cf] == [n for _, n in rf], s  # `ref` is a Rust keyword
+        assert [norm(t) for t, _ in cf] == [t for t, _ in rf], s
+
+    # status codes and validity bits carry the same values on both sides (and in the ctypes mirror)
+    c_consts = {k: int(v) for k, v in re.findall(r"\b(CE_(?:OK|ERR_\w+))\s*=\s*(\d+)", h)}
+    c_consts.update({k: int(v) for k, v in re.findall(r"#define\s+(CE_VALID_\w+)\s+(\d+)u", h)})
+    r_consts = {k: int(v) for k, v in re.findall(r"pub const (CE_\w+)\s*:\s*\w+\s*=\s*(\d+)\s*;", r)}
+    assert len(c_consts) >= 10
+    for k, v in c_consts.items():
+        assert r_consts.get(k) == v, k
