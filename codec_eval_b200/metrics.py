@@ -160,6 +160,36 @@ class MetricResult:  # src/metrics/mod.rs:139-149 (+ raw SSE and the 3-norm the 
         return None if self.butteraugli is None else PerceptionLevel.from_butteraugli(self.butteraugli)
 
 
+class ColorProfile:
+    """src/metrics/icc.rs:31-56: `ColorProfile::Srgb` (no transform) or `ColorProfile::Icc(bytes)`."""
+
+    __slots__ = ("icc",)
+
+    def __init__(self, icc: Optional[bytes] = None):
+        self.icc = bytes(icc) if icc else None
+
+    Srgb: "ColorProfile"  # set below
+
+    @staticmethod
+    def Icc(data: bytes) -> "ColorProfile":
+        p = ColorProfile()
+        p.icc = bytes(data)  # kept even if empty, like the Rust variant
+        return p
+
+    def is_srgb(self) -> bool:  # icc.rs:43-45
+        return self.icc is None
+
+    @staticmethod
+    def from_icc_bytes(icc: Optional[bytes]) -> "ColorProfile":  # icc.rs:49-54: None / empty -> Srgb
+        return ColorProfile.Icc(icc) if icc else ColorProfile()
+
+    def __repr__(self) -> str:
+        return "Srgb" if self.icc is None else f"Icc({len(self.icc)} bytes)"
+
+
+ColorProfile.Srgb = ColorProfile()
+
+
 def _result_from_c(r: _lib.CeResult) -> MetricResult:
     v = r.valid
     return MetricResult(
@@ -399,6 +429,45 @@ class GpuMetrics:
         self._raise(st, "ICC")
         return out
 
+    def transform_profile_to_srgb(self, rgb, profile: ColorProfile) -> np.ndarray:
+        """`transform_to_srgb(rgb, &ColorProfile)` (src/metrics/icc.rs:69-103): no dimensions in the signature -- the
+        transform is per pixel, so the buffer goes down as one row.  Srgb returns a copy (icc.rs:73)."""
+        d = _as_u8(rgb)
+        if profile.is_srgb():
+            return d.copy()
+        if not profile.icc:  # ColorProfile::Icc(vec![]) does not parse (icc.rs:77-81)
+            raise MetricCalculation("ICC", "Failed to parse ICC profile: empty profile")
+        if d.size % 3:
+            raise MetricCalculation("ICC", f"Failed to apply ICC transform: {d.size} bytes is not a whole number of RGB8 pixels")
+        if d.size == 0:
+            return d.copy()
+        out = np.empty(d.size, np.uint8)
+        st = self._L.ce_transform_to_srgb(self._h, d.ctypes.data, d.size, d.size // 3, 1, profile.icc, len(profile.icc),
+                                          out.ctypes.data)
+        self._raise(st, "ICC")
+        return out
+
+    def prepare_for_comparison(self, reference, reference_profile: ColorProfile, test, test_profile: ColorProfile):
+        """src/metrics/icc.rs:121-130: both images to sRGB, reference first (so its error wins)."""
+        return (self.transform_profile_to_srgb(reference, reference_profile),
+                self.transform_profile_to_srgb(test, test_profile))
+
+    def calculate_ssimulacra2_icc(self, reference, reference_profile, test, test_profile, width: int, height: int) -> float:
+        """src/metrics/ssimulacra2.rs:135-147: ICC transform first, then the plain function (which validates sizes)."""
+        r, t = self.prepare_for_comparison(reference, reference_profile, test, test_profile)
+        return self.calculate_ssimulacra2(r, t, width, height)
+
+    def calculate_butteraugli_icc(self, reference, reference_profile, test, test_profile, width: int, height: int) -> float:
+        """src/metrics/butteraugli.rs:150-162."""
+        r, t = self.prepare_for_comparison(reference, reference_profile, test, test_profile)
+        return self.calculate_butteraugli(r, t, width, height)
+
+    def calculate_dssim_icc(self, reference, reference_profile, test, test_profile, width: int, height: int,
+                            viewing=None) -> float:
+        """src/metrics/dssim.rs:158-174: transform, rgb8_to_dssim_image x2, calculate_dssim (fused on the device)."""
+        r, t = self.prepare_for_comparison(reference, reference_profile, test, test_profile)
+        return self.calculate_dssim_rgb8(r, t, width, height)
+
     # -- on-device distortion source (SURVEY.md 8(f) rank 2; the step before the metric path in codec-iter's run_eval,
     #    crates/codec-iter/src/eval.rs:153-172)
     def jpeg_roundtrip(self, rgb, width: int, height: int, quality: int, subsampling: int = 2) -> np.ndarray:
@@ -538,3 +607,23 @@ def rgba8_to_dssim_image(data, width, height) -> np.ndarray:
 
 def xyb_roundtrip(rgb, width, height) -> np.ndarray:
     return default_context().xyb_roundtrip(rgb, width, height)
+
+
+def transform_to_srgb(rgb, profile: ColorProfile) -> np.ndarray:
+    return default_context().transform_profile_to_srgb(rgb, profile)
+
+
+def prepare_for_comparison(reference, reference_profile, test, test_profile):
+    return default_context().prepare_for_comparison(reference, reference_profile, test, test_profile)
+
+
+def calculate_ssimulacra2_icc(reference, reference_profile, test, test_profile, width, height) -> float:
+    return default_context().calculate_ssimulacra2_icc(reference, reference_profile, test, test_profile, width, height)
+
+
+def calculate_butteraugli_icc(reference, reference_profile, test, test_profile, width, height) -> float:
+    return default_context().calculate_butteraugli_icc(reference, reference_profile, test, test_profile, width, height)
+
+
+def calculate_dssim_icc(reference, reference_profile, test, test_profile, width, height, viewing=None) -> float:
+    return default_context().calculate_dssim_icc(reference, reference_profile, test, test_profile, width, height, viewing)

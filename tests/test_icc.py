@@ -120,3 +120,91 @@ def test_image_data_to_rgb8_srgb_applies_the_profile(gpu):
     # a wide-gamut source pushed into sRGB changes the metric input: the scores differ from the untagged ones
     a = gpu.calculate_ssimulacra2(img, tagged.to_rgb8_srgb(gpu), 64, 48)
     assert a < 100.0
+
+
+# ---- the *_icc metric variants (src/metrics/{ssimulacra2.rs:135-147, butteraugli.rs:150-162, dssim.rs:158-174}) are host
+# wiring over entries the GPU tests above already cover: check the wiring on the CPU with a recording stand-in for the
+# C library (no compute; the product class itself still refuses to start without a GPU)
+class _FakeLib:
+    def __init__(self):
+        self.calls = []
+
+    def ce_transform_to_srgb(self, h, src, n, w, hgt, icc, icc_len, dst):
+        import ctypes as C
+
+        self.calls.append(("icc", n, w, hgt, bytes(icc), icc_len))
+        buf = (C.c_ubyte * n).from_address(src)
+        out = (C.c_ubyte * n).from_address(dst)
+        for i in range(n):
+            out[i] = 255 - buf[i]  # a recognisable stand-in transform
+        return 0
+
+    def _metric(self, name, r, rn, t, tn, w, h, out):
+        import ctypes as C
+
+        a = np.frombuffer((C.c_ubyte * rn).from_address(r), np.uint8).astype(np.int64)
+        b = np.frombuffer((C.c_ubyte * tn).from_address(t), np.uint8).astype(np.int64)
+        self.calls.append((name, w, h))
+        out._obj.value = float(np.abs(a - b).sum())
+        return 0
+
+    def ce_ssimulacra2(self, h, r, rn, t, tn, w, hh, out):
+        return self._metric("ssim2", r, rn, t, tn, w, hh, out)
+
+    def ce_dssim_rgb8(self, h, r, rn, t, tn, w, hh, out):
+        return self._metric("dssim", r, rn, t, tn, w, hh, out)
+
+    def ce_butteraugli(self, h, r, rn, t, tn, w, hh, intensity, out, pn):
+        return self._metric("ba", r, rn, t, tn, w, hh, out)
+
+
+def _fake_ctx():
+    from codec_eval_b200.metrics import GpuMetrics
+
+    ctx = object.__new__(GpuMetrics)
+    ctx._L, ctx._h = _FakeLib(), None
+    return ctx
+
+
+def test_color_profile_mirrors_the_reference_enum():
+    from codec_eval_b200.metrics import ColorProfile
+
+    assert ColorProfile.Srgb.is_srgb() and ColorProfile().is_srgb()
+    assert not ColorProfile.Icc(b"\x01\x02").is_srgb()
+    # icc.rs:49-54 and its tests (:139-154): None and empty bytes mean sRGB
+    assert ColorProfile.from_icc_bytes(None).is_srgb() and ColorProfile.from_icc_bytes(b"").is_srgb()
+    assert not ColorProfile.from_icc_bytes(b"\x00" * 4).is_srgb()
+
+
+def test_icc_variants_transform_each_side_then_call_the_plain_metric():
+    from codec_eval_b200.metrics import ColorProfile, MetricCalculation
+
+    ctx = _fake_ctx()
+    rng = np.random.default_rng(5)
+    w, h = 6, 4
+    ref = rng.integers(0, 256, w * h * 3, dtype=np.uint8)
+    tst = rng.integers(0, 256, w * h * 3, dtype=np.uint8)
+    prof = ColorProfile.Icc(b"PROFILE")
+
+    # sRGB on both sides: no transform call, buffers passed through (icc.rs:73)
+    r, t = ctx.prepare_for_comparison(ref, ColorProfile.Srgb, tst, ColorProfile.Srgb)
+    assert np.array_equal(r, ref) and np.array_equal(t, tst) and r is not ref and ctx._L.calls == []
+
+    # only the side that carries a profile is transformed, as one row of len/3 pixels
+    want = float(np.abs(ref.astype(np.int64) - (255 - tst.astype(np.int64))).sum())
+    for name, fn in (("ssim2", ctx.calculate_ssimulacra2_icc), ("ba", ctx.calculate_butteraugli_icc),
+                     ("dssim", ctx.calculate_dssim_icc)):
+        ctx._L.calls.clear()
+        got = fn(ref, ColorProfile.Srgb, tst, prof, w, h)
+        assert got == want, name
+        assert ctx._L.calls == [("icc", ref.size, w * h, 1, b"PROFILE", 7), (name, w, h)]
+    ctx._L.calls.clear()
+    ctx.calculate_ssimulacra2_icc(ref, prof, tst, prof, w, h)
+    assert [c[0] for c in ctx._L.calls] == ["icc", "icc", "ssim2"]  # reference first (icc.rs:127-128)
+
+    # an empty Icc(..) and a ragged buffer are ICC errors, raised before the metric's own validation
+    for bad_args in ((ref, ColorProfile.Icc(b""), tst, ColorProfile.Srgb), (ref[:-1], prof, tst, ColorProfile.Srgb)):
+        ctx._L.calls.clear()
+        with pytest.raises(MetricCalculation) as e:
+            ctx.calculate_butteraugli_icc(*bad_args, w, h)
+        assert e.value.metric == "ICC" and ctx._L.calls == []
