@@ -176,3 +176,33 @@ def test_rust_sys_crate_matches_header():
     assert len(c_consts) >= 10
     for k, v in c_consts.items():
         assert r_consts.get(k) == v, k
+
+
+def test_host_mirror_covers_the_reference_metrics_api():
+    """Every public item of the reference's `metrics` module (docs/public-api/codec-eval.txt:386-458) has a
+    same-named counterpart in codec_eval_b200.metrics (free functions also as GpuMetrics methods)."""
+    from codec_eval_b200 import metrics as M
+
+    free_functions = [
+        "calculate_psnr", "calculate_ssimulacra2", "calculate_ssimulacra2_icc", "calculate_butteraugli",
+        "calculate_butteraugli_icc", "calculate_butteraugli_with_intensity", "calculate_dssim", "calculate_dssim_icc",
+        "rgb8_to_dssim_image", "rgba8_to_dssim_image", "xyb_roundtrip", "prepare_for_comparison", "transform_to_srgb",
+    ]
+    for f in free_functions:
+        assert callable(getattr(M, f)), f
+        method = "transform_profile_to_srgb" if f == "transform_to_srgb" else f  # the method of that name takes w, h
+        assert callable(getattr(M.GpuMetrics, method)), f
+    for cls, members in {
+        "MetricConfig": ["all", "fast", "perceptual", "perceptual_xyb", "ssimulacra2_only", "with_xyb_roundtrip"],
+        "MetricResult": ["perception_level", "perception_level_butteraugli", "perception_level_ssimulacra2"],
+        "PerceptionLevel": ["code", "from_butteraugli", "from_dssim", "from_ssimulacra2", "max_butteraugli", "max_dssim",
+                            "min_ssimulacra2", "Imperceptible", "Marginal", "Subtle", "Noticeable", "Degraded"],
+        "ColorProfile": ["Srgb", "Icc", "from_icc_bytes", "is_srgb"],
+        "GpuReference": ["compare", "compare_many"],  # Ssimulacra2Reference::{new, compare} (prelude.rs:85)
+    }.items():
+        for m in members:
+            assert hasattr(getattr(M, cls), m), (cls, m)
+    for field in ("dssim", "ssimulacra2", "butteraugli", "psnr", "xyb_roundtrip"):
+        assert field in M.MetricConfig.__dataclass_fields__
+    for field in ("dssim", "ssimulacra2", "butteraugli", "psnr"):
+        assert field in M.MetricResult.__dataclass_fields__
