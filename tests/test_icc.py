@@ -122,6 +122,33 @@ def test_image_data_to_rgb8_srgb_applies_the_profile(gpu):
     assert a < 100.0
 
 
+@pytest.mark.gpu
+def test_icc_metric_variants_on_gpu(gpu):
+    """calculate_*_icc == the plain metric on the transformed buffers; profiles on one or both sides; sRGB = plain."""
+    from codec_eval_b200.metrics import ColorProfile, MetricCalculation
+    from codec_eval_b200.synth import J
+
+    w, h = 96, 64
+    ref = G(21, w, h)
+    dist = J(ref, 70, 2)
+    p3, adobe = ColorProfile.Icc(P.display_p3()), ColorProfile.from_icc_bytes(P.adobe_rgb())
+    srgb = ColorProfile.Srgb
+    r_p3 = IO.transform_to_srgb(ref, p3.icc)
+    d_ad = IO.transform_to_srgb(dist, adobe.icc)
+    assert np.array_equal(gpu.transform_profile_to_srgb(ref, p3).reshape(h, w, 3), r_p3)
+    pr, pt = gpu.prepare_for_comparison(ref, p3, dist, adobe)
+    assert np.array_equal(pr.reshape(h, w, 3), r_p3) and np.array_equal(pt.reshape(h, w, 3), d_ad)
+    assert gpu.calculate_ssimulacra2_icc(ref, srgb, dist, srgb, w, h) == gpu.calculate_ssimulacra2(ref, dist, w, h)
+    assert gpu.calculate_ssimulacra2_icc(ref, p3, dist, adobe, w, h) == gpu.calculate_ssimulacra2(r_p3, d_ad, w, h)
+    assert gpu.calculate_butteraugli_icc(ref, srgb, dist, adobe, w, h) == gpu.calculate_butteraugli(ref, d_ad, w, h)
+    assert gpu.calculate_dssim_icc(ref, p3, dist, srgb, w, h) == gpu.calculate_dssim_rgb8(r_p3, dist, w, h)
+    # same profile on both sides of identical images: still identical after the transform
+    assert gpu.calculate_ssimulacra2_icc(ref, p3, ref, p3, w, h) == 100.0
+    with pytest.raises(MetricCalculation) as e:
+        gpu.calculate_dssim_icc(ref, ColorProfile.Icc(b"\0" * 200), dist, srgb, w, h)
+    assert e.value.metric == "ICC"
+
+
 # ---- the *_icc metric variants (src/metrics/{ssimulacra2.rs:135-147, butteraugli.rs:150-162, dssim.rs:158-174}) are host
 # wiring over entries the GPU tests above already cover: check the wiring on the CPU with a recording stand-in for the
 # C library (no compute; the product class itself still refuses to start without a GPU)
