@@ -217,3 +217,35 @@ def test_two_restatements_agree(O):
         emx, epn = O.butteraugli(r, d, w, h)
         assert abs(mx - emx) <= 2e-5 * emx and abs(pn - epn) <= 2e-5 * epn, (w, h, q, mx, emx, pn, epn)
     assert N.butteraugli(same, same) == (0.0, 0.0)
+
+
+def _fnv1a64(data: bytes) -> int:
+    h = 0xCBF29CE484222325
+    for b in data:
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def test_reference_scores_pin_the_oracle(O):
+    """The pin that is still missing: tests/golden/reference_scores.json holds the outputs of the
+    real codec-eval functions for the golden pairs, produced by rust/pin-parity on a machine with a Rust toolchain.
+    While that file is absent parity with the three crates is UNPINNED and this test skips; once it is committed the
+    oracle must meet the contract tolerances (and the GPU tests, which compare against the oracle, inherit the pin)."""
+    import json
+
+    path = os.path.join(os.path.dirname(GOLD), "reference_scores.json")
+    if not os.path.exists(path):
+        pytest.skip("parity unpinned: no tests/golden/reference_scores.json (run rust/pin-parity to create it)")
+    z = np.load(GOLD)
+    for row in json.load(open(path))["cases"]:
+        k, w, h = row["case"], row["width"], row["height"]
+        r, d = z[f"ref{k}"], z[f"dist{k}"]
+        assert r.shape == (h, w, 3)
+        assert O.psnr(r, d, w, h) == pytest.approx(row["psnr"], rel=1e-12)
+        assert abs(O.ssimulacra2(r, d, w, h) - row["ssimulacra2"]) <= 0.01
+        assert abs(O.dssim(r, d, w, h) - row["dssim"]) <= 1e-4 * row["dssim"]
+        assert abs(O.butteraugli(r, d, w, h)[0] - row["butteraugli"]) <= 1e-3 * row["butteraugli"]
+        assert abs(O.butteraugli(r, d, w, h, 250.0)[0] - row["butteraugli_250"]) <= 1e-3 * row["butteraugli_250"]
+        rt = O.xyb_roundtrip(r, w, h)
+        assert "%016x" % _fnv1a64(np.asarray(rt, np.uint8).tobytes()) == row["xyb_roundtrip_fnv1a64"]
+        assert abs(O.ssimulacra2(np.asarray(rt).reshape(h, w, 3), d, w, h) - row["ssimulacra2_xyb_ref"]) <= 0.01
