@@ -106,3 +106,39 @@ def test_result_bytes_roundtrip():
     b = bytes_to_results(results_to_bytes(a, 3))
     assert bytes(C.string_at(C.addressof(a), 3 * 56)) == bytes(C.string_at(C.addressof(b), 3 * 56))
     assert results_to_bytes(a, 0).shape == (0, 56)
+
+
+def test_partition_properties_on_random_batches():
+    """Properties that hold for any batch: every pair is assigned exactly once, a reference's pairs stay together,
+    the assignment does not depend on who computes it, and the load obeys the greedy (largest-first) bound
+    max_load <= mean_load + largest_group."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from codec_eval_b200.shard import partition_pairs
+
+    batches = st.lists(st.tuples(st.integers(0, 12), st.sampled_from([64 * 64, 512 * 512, 768 * 512, 3840 * 2160])),
+                       min_size=0, max_size=60)
+
+    @settings(max_examples=150, deadline=None)
+    @given(batches, st.integers(1, 8))
+    def check(batch, world):
+        ref_ids = [b[0] for b in batch]
+        px = [b[1] for b in batch]
+        shards = partition_pairs(ref_ids, px, world)
+        assert len(shards) == world
+        assert sorted(i for s in shards for i in s) == list(range(len(batch)))
+        owner = {}
+        for r, s in enumerate(shards):
+            assert s == sorted(s)
+            for i in s:
+                assert owner.setdefault(ref_ids[i], r) == r
+        assert shards == partition_pairs(list(ref_ids), list(px), world)
+        if batch:
+            group = {}
+            for g, p in batch:
+                group[g] = group.get(g, 0) + p
+            loads = [sum(px[i] for i in s) for s in shards]
+            assert max(loads) <= sum(px) / world + max(group.values())
+
+    check()
