@@ -249,3 +249,31 @@ def test_reference_scores_pin_the_oracle(O):
         rt = O.xyb_roundtrip(r, w, h)
         assert "%016x" % _fnv1a64(np.asarray(rt, np.uint8).tobytes()) == row["xyb_roundtrip_fnv1a64"]
         assert abs(O.ssimulacra2(np.asarray(rt).reshape(h, w, 3), d, w, h) - row["ssimulacra2_xyb_ref"]) <= 0.01
+
+
+def test_plausibility_on_a_photograph(O):
+    """NOT a parity pin -- a guard against gross constant errors (SURVEY A.7 grade-B items).  On a real photograph
+    (scikit-learn's bundled china.jpg) compressed by libjpeg-turbo 4:2:0 the three metrics must land where the
+    reference's own tables put such encodes: its PerceptionLevel boundaries (src/metrics/mod.rs:189-232) line the metrics
+    up as DSSIM 0.0003 / SSIMULACRA2 90 / Butteraugli 1.0 (imperceptible) ... 0.0015 / 70 / 3.0 (subtle), and its README
+    calibration (mozjpeg 4:2:0 on CID22: SSIMULACRA2 65.1 and Butteraugli 4.38 at ~0.7 bpp) ties SSIMULACRA2 ~65 to
+    Butteraugli ~3-5.  Measured with this oracle: q95 87.3 / 0.00026 / 1.12, q75 70.1 / 0.0024 / 2.80, q30 42.5 / 0.0099 / 4.34."""
+    sk = pytest.importorskip("sklearn.datasets")
+    from codec_eval_b200.synth import J
+
+    img = np.ascontiguousarray(sk.load_sample_image("china.jpg"))
+    h, w, _ = img.shape
+    bands = {  # quality: (ssimulacra2 lo, hi), (dssim lo, hi), (butteraugli lo, hi)
+        95: ((80.0, 95.0), (1e-4, 8e-4), (0.5, 2.5)),
+        75: ((60.0, 80.0), (1e-3, 4e-3), (1.5, 4.5)),
+        30: ((25.0, 55.0), (4e-3, 2e-2), (3.0, 8.0)),
+    }
+    prev = None
+    for q in (95, 75, 30):
+        d = J(img, q, 2)
+        got = (O.ssimulacra2(img, d, w, h), O.dssim(img, d, w, h), O.butteraugli(img, d, w, h)[0])
+        for v, (lo, hi) in zip(got, bands[q]):
+            assert lo <= v <= hi, (q, got)
+        if prev:
+            assert got[0] < prev[0] and got[1] > prev[1] and got[2] > prev[2]
+        prev = got
