@@ -1,0 +1,44 @@
+"""CPU test of bench.py's reference arm (`--impl reference`): the one bench leg that runs without a GPU.  It times the
+CPU oracle port on a bounded sample of the same workload and must print exactly one JSON line with the contract's keys.
+Under torchrun only rank 0 runs it; the other ranks exit 0 silently."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra_env=None):
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    env.update(extra_env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                          capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+
+
+def test_reference_arm_prints_one_contract_line():
+    p = _run()
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["metric"] == "mpix_pairs_per_sec_all_metrics" and d["unit"] == "MPix-pairs/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["steps"] == 1 and d["warmup"] >= 3          # the timing rules ask for at least 3 warm-up steps
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # value and ms_per_step describe the same measurement: sample MPix / time
+    assert d["ms_per_step"] > 0
+
+
+def test_reference_arm_on_a_non_zero_rank_is_silent():
+    p = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert p.returncode == 0 and p.stdout.strip() == ""
