@@ -42,3 +42,22 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_on_a_non_zero_rank_is_silent():
     p = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_committed_gpu_lines_carry_the_contract_keys():
+    """The bench lines committed under profiles/ (what DESIGN.md and profiles/README.md quote) have the full contract:
+    roofline of the dominant kernel against the measured peak, cpu_baseline, e2e with real copies, launches, clocks."""
+    for name, n in (("r1_v47_bench.json", 1), ("r1_v45_bench.json", 1), ("r1_v47_bench_2gpu.json", 2), ("r1_v47_bench_4gpu.json", 4)):
+        d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["metric"] == "mpix_pairs_per_sec_all_metrics"
+        assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] > 0 and d["warmup"] >= 3
+        r = d["roofline"]
+        assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(r)
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        e = d["e2e"]
+        assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+        c = d["clocks"]
+        assert c["sm_mhz"] > 0 and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+        assert "workload" in d["config"]
+        if n == 1:
+            assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
