@@ -207,6 +207,36 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+def single_pair_latency(ctx, reps: int = 20):
+    """BASELINE.json configs[0]: ONE 512x512 pair (G(0), JPEG q80 4:2:0) through the single-pair entries, in the order
+    EvalSession::calculate_metrics calls them (src/eval/session.rs:437-497: PSNR, DSSIM, SSIMULACRA2), from pageable
+    host buffers, synchronous -- wall-clock latency per call, median of `reps`."""
+    from codec_eval_b200.synth import G, J
+
+    w = h = 512
+    ref = G(0, w, h)
+    dist = J(ref, 80, 2)
+    calls = [("psnr", lambda: ctx.calculate_psnr(ref, dist, w, h)), ("dssim", lambda: ctx.calculate_dssim_rgb8(ref, dist, w, h)),
+             ("ssimulacra2", lambda: ctx.calculate_ssimulacra2(ref, dist, w, h))]
+    times = {k: [] for k, _ in calls}
+    total = []
+    for it in range(reps + 3):
+        t_all = 0.0
+        for k, fn in calls:
+            t0 = time.perf_counter()
+            fn()
+            dt = (time.perf_counter() - t0) * 1e3
+            t_all += dt
+            if it >= 3:
+                times[k].append(dt)
+        if it >= 3:
+            total.append(t_all)
+    med = lambda v: float(sorted(v)[len(v) // 2])
+    return {"workload": "configs[0]: 1 pair 512x512, PSNR + DSSIM + SSIMULACRA2, single-pair C-ABI entries, pageable host buffers",
+            "ms_per_pair": med(total), "ms": {k: med(v) for k, v in times.items()}, "reps": reps,
+            "mpix_pairs_per_sec": w * h / 1e6 / (med(total) / 1e3)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -411,6 +441,14 @@ def main():
                  "what": "ce_evaluate_jpeg_sweep: host references -> on-device baseline-JPEG round trips (bit-exact with "
                          "libjpeg-turbo) -> all four metrics"}
 
+    # ---- configs[0] beside it: single-pair call latency (an extra: it must never take the headline line down)
+    single = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        try:
+            single = single_pair_latency(ctx)
+        except Exception as e:
+            single = {"error": repr(e)[:300]}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -432,7 +470,7 @@ def main():
                        "references": f"{n_ref} distinct references, {n // max(n_ref, 1)} distortions each; reference-side work is done once per distinct reference (the reference's Ssimulacra2Reference reuse, generalised)",
                        "l2": f"no explicit flush: {(n + n_ref) * img_bytes / 1e6:.0f} MB of inputs and >1 GB of fp32 intermediates per step exceed the 126 MB L2",
                        "parallelism": f"pairs sharded over {world} rank(s), NCCL all_gather of 56 B/pair results"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sweep_e2e": sweep, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sweep_e2e": sweep, "single_pair": single, "gpu_launches": launches, "clocks": clocks,
             "per_metric": per_metric, "kernels": kernels, "sanity": sanity,
         }
         emit(line)

@@ -61,3 +61,33 @@ def test_committed_gpu_lines_carry_the_contract_keys():
         assert "workload" in d["config"]
         if n == 1:
             assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_single_pair_latency_leg_with_a_stand_in_context():
+    """The configs[0] leg of bench.py is host logic over three already-tested single-pair entries: run it against a
+    recording stand-in (no GPU here) so a slip in it cannot surface for the first time on the GPU box."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Ctx:
+        def __init__(self):
+            self.calls = []
+
+        def calculate_psnr(self, r, t, w, h):
+            self.calls.append(("psnr", r.shape, t.shape, w, h))
+            return 30.0
+
+        def calculate_dssim_rgb8(self, r, t, w, h):
+            self.calls.append(("dssim", r.shape, t.shape, w, h))
+            return 0.001
+
+        def calculate_ssimulacra2(self, r, t, w, h):
+            self.calls.append(("ssimulacra2", r.shape, t.shape, w, h))
+            return 70.0
+
+    c = Ctx()
+    out = bench.single_pair_latency(c, reps=4)
+    assert [k[0] for k in c.calls[:3]] == ["psnr", "dssim", "ssimulacra2"]      # the order of calculate_metrics
+    assert len(c.calls) == 3 * (4 + 3) and c.calls[0][1:] == ((512, 512, 3), (512, 512, 3), 512, 512)
+    assert set(out["ms"]) == {"psnr", "dssim", "ssimulacra2"} and out["reps"] == 4
+    assert out["ms_per_pair"] >= 0 and out["mpix_pairs_per_sec"] > 0 and "configs[0]" in out["workload"]
