@@ -57,7 +57,7 @@ def test_no_product_code_touches_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in txt.lower() or f == "synth.py", (dirpath, f)
+                assert "oracle" not in txt.lower(), (dirpath, f)
 
 
 # ---- src/metrics/mod.rs:337-397
