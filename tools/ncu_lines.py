@@ -1,21 +1,59 @@
 #!/usr/bin/env python
-"""Executed warp-instructions per CUDA source line for one kernel: python tools/ncu_lines.py rep kernel_regex [top]"""
-import csv, subprocess, sys
-out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'source', '--csv', '--print-source', 'cuda,sass', '--kernel-name', 'regex:' + sys.argv[2]],
-                     capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hi = [i for i, r in enumerate(rows) if 'Line No' in r and 'Instructions Executed' in r]
-lines = []
-for t, start in enumerate(hi):
-    h = rows[start]
-    ie, ln, src, smp = h.index('Instructions Executed'), h.index('Line No'), h.index('Source'), h.index('# Samples')
-    end = hi[t + 1] if t + 1 < len(hi) else len(rows)
-    for r in rows[start + 1:end]:
-        if len(r) > ie and r[ln] not in ('', '-'):
-            try: lines.append((int(r[ie]), int(r[smp]) if r[smp].isdigit() else 0, f"{t}:{r[ln]}", r[src].strip()))
-            except ValueError: pass
-tot = sum(x[0] for x in lines); ts = sum(x[1] for x in lines)
-print('total warp-instr (this launch)', tot)
+"""Executed warp-instructions per CUDA source line of one kernel, from an .ncu-rep captured with --import-source on
+(read here, no GPU).  Optionally only one SASS opcode (e.g. where do the MOVs come from):
+
+  python tools/ncu_lines.py rep kernel_substring [top] [opcode]
+  python tools/ncu_lines.py gpurun_out/prof_v47_ds.ncu-rep "k_ds_stream<(int)1>" 25 MOV
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+rep, fn_sub = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-for n, s, l, t in sorted(lines, reverse=True)[:top]:
-    print(f'{100*n/tot:5.1f}% instr {100*s/max(ts,1):5.1f}% samples  L{l:>6s}  {t[:120]}')
+opname = sys.argv[4] if len(sys.argv) > 4 else None
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass'], capture_output=True, text=True).stdout
+cur_file = hdr = cur_line = None
+active = False
+first_fn = None
+sel, tot = collections.Counter(), collections.Counter()
+for r in csv.reader(out.splitlines()):
+    if not r:
+        continue
+    if r[0] == 'File Path':
+        cur_file = r[1].split('/')[-1]
+        continue
+    if r[0] == 'Function Name':
+        # the report lists every profiled launch; keep the first launch of the first matching function
+        if fn_sub in r[1] and first_fn in (None, r[1]):
+            first_fn = r[1]
+            active = True
+        else:
+            active = False
+        continue
+    if r[0] == 'Line No':
+        hdr = r
+        continue
+    if not active or hdr is None:
+        continue
+    if r[0] not in ('', '-'):
+        cur_line = (cur_file, r[0], r[1].strip()[:100])
+        continue
+    sass = r[3].strip()
+    if sass in ('...', '-', ''):
+        continue
+    try:
+        n = int(r[hdr.index('Instructions Executed')])
+    except ValueError:
+        continue
+    t = sass.split()
+    op = (t[1] if t[0].startswith('@') else t[0]).split('.')[0]
+    tot[cur_line] += n
+    if opname is None or op == opname:
+        sel[cur_line] += n
+T, A = sum(tot.values()), sum(sel.values())
+print(first_fn)
+print(f'warp-instructions {T}' + (f'; {opname} {A} = {100 * A / max(T, 1):.1f} %' if opname else ''))
+for k, v in sel.most_common(top):
+    print(f'{100 * v / max(T, 1):5.2f}%  {k[0]}:{k[1]}  {k[2]}')
