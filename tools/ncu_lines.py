@@ -2,7 +2,7 @@
 """Executed warp-instructions per CUDA source line of one kernel, from an .ncu-rep captured with --import-source on
 (read here, no GPU).  Optionally only one SASS opcode (e.g. where do the MOVs come from):
 
-  python tools/ncu_lines.py rep kernel_substring [top] [opcode]
+  python tools/ncu_lines.py rep kernel_substring [top] [opcode|-] [samples]     ('samples': rank lines by stall samples)
   python tools/ncu_lines.py gpurun_out/prof_v47_ds.ncu-rep "k_ds_stream<(int)1>" 25 MOV
 """
 import collections
@@ -12,7 +12,8 @@ import sys
 
 rep, fn_sub = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-opname = sys.argv[4] if len(sys.argv) > 4 else None
+opname = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != '-' else None
+by_samples = len(sys.argv) > 5 and sys.argv[5] == 'samples'
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass'], capture_output=True, text=True).stdout
 cur_file = hdr = cur_line = None
 active = False
@@ -44,7 +45,7 @@ for r in csv.reader(out.splitlines()):
     if sass in ('...', '-', ''):
         continue
     try:
-        n = int(r[hdr.index('Instructions Executed')])
+        n = int(r[hdr.index('# Samples' if by_samples else 'Instructions Executed')])
     except ValueError:
         continue
     t = sass.split()
@@ -54,6 +55,6 @@ for r in csv.reader(out.splitlines()):
         sel[cur_line] += n
 T, A = sum(tot.values()), sum(sel.values())
 print(first_fn)
-print(f'warp-instructions {T}' + (f'; {opname} {A} = {100 * A / max(T, 1):.1f} %' if opname else ''))
+print(('stall samples ' if by_samples else 'warp-instructions ') + f'{T}' + (f'; {opname} {A} = {100 * A / max(T, 1):.1f} %' if opname else ''))
 for k, v in sel.most_common(top):
     print(f'{100 * v / max(T, 1):5.2f}%  {k[0]}:{k[1]}  {k[2]}')
