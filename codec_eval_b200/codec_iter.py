@@ -63,6 +63,8 @@ def decode_ppm(data: bytes) -> np.ndarray:
     if tokens[0] != b"P6":
         raise ValueError(f"not a binary PPM (magic {tokens[0]!r})")
     w, h, maxval = int(tokens[1]), int(tokens[2]), int(tokens[3])
+    if w <= 0 or h <= 0:
+        raise ValueError(f"bad PPM dimensions {w}x{h}")
     if not 0 < maxval <= 255:
         raise ValueError("only 8-bit PPM is supported")
     pos += 1  # the single whitespace byte after maxval

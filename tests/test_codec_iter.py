@@ -134,3 +134,27 @@ def test_on_device_sweep_equals_the_real_codec_sweep(gpu, tmp_path):
     rows = ci.compare_with_baseline(host.points, ci.load_baseline(str(tmp_path), "jpeg"))
     assert all(r.delta_bpp == 0.0 and r.delta_ssim2 == 0.0 for r in rows)
     json.loads(b.to_json())
+
+
+def test_ppm_decoder_on_arbitrary_images_and_damaged_files():
+    """encode -> decode is the identity for any 8-bit RGB image; a damaged file raises ValueError, never anything else."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    ci = _ci()
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 17), st.integers(1, 13), st.integers(0, 2**32 - 1))
+    def roundtrip(w, h, seed):
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        data = ci.encode_ppm(img)
+        assert np.array_equal(ci.decode_ppm(data), img)
+        assert np.array_equal(ci.decode_ppm(data.replace(b"P6\n", b"P6 # made by a test\n\t", 1)), img)
+        for cut in (3, len(data) // 2, len(data) - 1):
+            with pytest.raises(ValueError):
+                ci.decode_ppm(data[:cut])
+
+    roundtrip()
+    for bad in (b"", b"P6", b"P6\n0 4\n255\n", b"P6\n-2 4\n255\n" + b"\0" * 24, b"P6\nx y\n255\n", b"P6\n2 2\n0\n" + b"\0" * 12):
+        with pytest.raises(ValueError):
+            ci.decode_ppm(bad)
