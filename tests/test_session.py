@@ -115,6 +115,11 @@ def test_image_data_and_config_defaults():
     cr = CodecResult("t", "1", 80.0, 1000, 0.5, 0.1, None, MetricResult(), None)
     assert abs(cr.compression_ratio(10000) - 10.0) < 1e-3                                            # report.rs:262-279
     assert CorpusReport("c").codec_ids() == []
+    s = EvalSession(c, metrics=object())                                                             # session.rs:630-637
+    assert s.codec_count() == 0
+    s.add_codec("test", "1.0", lambda image, req: bytes(100))
+    assert s.codec_count() == 1
+    assert (rep.name, rep.width, rep.height) == ("test.png", 1920, 1080)
 
 
 @pytest.mark.gpu
