@@ -38,7 +38,8 @@ class CeResult(C.Structure):
 EXPORTS = [
     "ce_ctx_create", "ce_ctx_destroy", "ce_ctx_set_stream", "ce_last_error", "ce_launch_count", "ce_version",
     "ce_profile_enable", "ce_profile_reset", "ce_profile_report",
-    "ce_evaluate_batch", "ce_evaluate_batch_device", "ce_evaluate_batch_device_grouped", "ce_psnr", "ce_ssimulacra2", "ce_butteraugli", "ce_dssim_rgb8",
+    "ce_host_register", "ce_host_unregister", "ce_host_alloc", "ce_host_free",
+    "ce_sub_batch_capacity", "ce_evaluate_batch", "ce_evaluate_batch_device", "ce_evaluate_batch_device_grouped", "ce_psnr", "ce_ssimulacra2", "ce_butteraugli", "ce_dssim_rgb8",
     "ce_dssim_rgbaf32", "ce_rgb8_to_dssim_image", "ce_rgba8_to_dssim_image", "ce_xyb_roundtrip",
     "ce_reference_create", "ce_reference_compare", "ce_reference_compare_many", "ce_reference_destroy",
     "ce_jpeg_roundtrip", "ce_jpeg_roundtrip_device", "ce_evaluate_jpeg_sweep", "ce_transform_to_srgb",
@@ -49,16 +50,57 @@ EXPORTS = [
 _lib = None
 
 
+def source_hash() -> str:
+    """sha256/16 over csrc/* and include/ce_gpu.h (names and contents, sorted) -- what build.py stamps into
+    ce_version().  Empty string when the sources are not beside the package (a binary-only install)."""
+    import hashlib
+
+    csrc = os.path.join(_HERE, "csrc")
+    header = os.path.join(_HERE, "..", "include", "ce_gpu.h")
+    if not os.path.isdir(csrc) or not os.path.exists(header):
+        return ""
+    hh = hashlib.sha256()
+    for path in sorted(os.path.join(csrc, f) for f in os.listdir(csrc)) + [header]:
+        hh.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as f:
+            hh.update(f.read())
+    return hh.hexdigest()[:16]
+
+
+def _check_source_hash(version: str):
+    """A library built from other sources than the ones beside it must not be taken for them."""
+    want = source_hash()
+    if not want or os.environ.get("CE_ALLOW_STALE_LIB") == "1":
+        return
+    got = version.rsplit("src:", 1)[-1] if "src:" in version else "unhashed"
+    if got != want:
+        raise RuntimeError(f"{LIB_PATH} was built from sources with hash {got}, the tree has {want}: rebuild with "
+                           "`python -m codec_eval_b200.build` (or __graft_entry__.build())")
+
+
 def load():
     """Load libce_gpu.so and declare prototypes.  Raises if the CUDA library has not been built."""
     global _lib
     if _lib is not None:
         return _lib
+    if os.environ.get("CE_ALLOW_STALE_LIB") != "1" and os.path.isdir(os.path.join(_HERE, "csrc")):
+        # the library must be the build of the sources beside it: rebuild when it is missing or stale (nvcc is part of
+        # the image on both the CPU and the GPU box); without nvcc this raises -- there is no CPU fallback
+        from . import build as _build
+
+        try:
+            _build.ensure_built()
+        except Exception as e:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(f"{LIB_PATH} is missing and could not be built: {e}. codec_eval_b200 has no CPU fallback.")
+            # a stale library is refused by _check_source_hash below
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m codec_eval_b200.build` "
             "(nvcc, sm_100a). codec_eval_b200 has no CPU fallback.")
     L = C.CDLL(LIB_PATH)
+    L.ce_version.restype = C.c_char_p
+    _check_source_hash(L.ce_version().decode())
     vp, sz, u8p = C.c_void_p, C.c_size_t, C.c_void_p
     f64p, f32p = C.POINTER(C.c_double), C.c_void_p
     cfgp, resp = C.POINTER(CeMetricConfig), C.POINTER(CeResult)
@@ -75,6 +117,12 @@ def load():
     L.ce_profile_reset.argtypes = [vp]
     L.ce_profile_report.argtypes = [vp, C.c_char_p, sz]
     L.ce_profile_report.restype = sz
+    L.ce_host_register.argtypes = [vp, vp, sz]
+    L.ce_host_unregister.argtypes = [vp, vp]
+    L.ce_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.ce_host_free.argtypes = [vp, vp]
+    L.ce_host_free.restype = None
+    L.ce_sub_batch_capacity.argtypes = [vp, cfgp, C.c_uint32, C.c_uint32, C.POINTER(sz)]
     L.ce_evaluate_batch.argtypes = [vp, C.POINTER(CePair), sz, cfgp, C.c_float, resp]
     L.ce_evaluate_batch_device.argtypes = [vp, vp, vp, sz, C.c_uint32, C.c_uint32, cfgp, C.c_float, resp]
     L.ce_evaluate_batch_device_grouped.argtypes = [vp, vp, sz, vp, sz, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, cfgp,

@@ -21,23 +21,41 @@ FLAGS = [
 ]
 
 
-def needs_build() -> bool:
+def built_hash() -> str:
+    """The source hash stamped into the existing library's ce_version() ('' if there is none / it cannot be read)."""
     if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ce_gpu.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+        return ""
+    try:   # a child process: a stale library must not stay mapped in this one
+        out = subprocess.run([sys.executable, "-c",
+                              "import ctypes,sys; L=ctypes.CDLL(sys.argv[1]); L.ce_version.restype=ctypes.c_char_p; "
+                              "print(L.ce_version().decode())", OUT], capture_output=True, text=True, timeout=120)
+        v = out.stdout.strip()
+        return v.rsplit("src:", 1)[-1] if "src:" in v else ""
+    except Exception:
+        return ""
+
+
+def needs_build() -> bool:
+    """True unless the library on disk was built from exactly the sources in the tree (content hash, not mtime)."""
+    from . import _lib
+
+    return built_hash() != _lib.source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
+    if not os.path.exists(NVCC):
+        raise RuntimeError(f"{NVCC} not found: libce_gpu.so cannot be (re)built here and codec_eval_b200 has no CPU fallback")
+    from . import _lib
+
+    stamp = ["-DCE_SOURCE_HASH=\"" + _lib.source_hash() + "\""]
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [NVCC] + [f for f in FLAGS if f not in ("-shared",)] + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [NVCC] + [f for f in FLAGS if f not in ("-shared",)] + stamp + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
@@ -51,7 +69,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc build failed")
-    subprocess.check_call([NVCC] + FLAGS + objs + ["-o", OUT])
+    tmp = OUT + f".{os.getpid()}.tmp"
+    subprocess.check_call([NVCC] + FLAGS + objs + ["-o", tmp])
+    os.replace(tmp, OUT)
+    return OUT
+
+
+def ensure_built(verbose: bool = False) -> str:
+    """Build unless the library on disk already carries the hash of the sources in the tree.  Safe to call from several
+    ranks at once (one builds under a file lock, the others wait and find it fresh)."""
+    import fcntl
+
+    if not needs_build():
+        return OUT
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if needs_build():
+                sys.stderr.write("codec_eval_b200: libce_gpu.so does not match the sources in the tree -- rebuilding (nvcc, sm_100a)\n")
+                build(force=True, verbose=verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return OUT
 
 

@@ -17,7 +17,8 @@ struct ce_ctx {
 };
 
 struct ce_ref {
-    ce_ctx* owner;
+    ce_ctx* owner;   // identity check only (ce_reference_compare*); never dereferenced by ce_reference_destroy
+    int device;      // so the handle can be destroyed after its context
     uint8_t* d_ref;  // device RGB8 (already XYB-round-tripped if the config asked for it)
     size_t width, height;
     ce_metric_config cfg;
@@ -68,7 +69,7 @@ void Context::ensure_idx(size_t count) {
     idx_cap = cap;
 }
 
-void Context::prof_begin(const char* name, double bytes) {
+void Context::prof_begin(const char* name, double bytes, double bytes_per_pair) {
     launches++;
     if (!prof.enabled) return;
     auto it = prof.index.find(name);
@@ -82,6 +83,7 @@ void Context::prof_begin(const char* name, double bytes) {
     } else idx = it->second;
     prof.stats[idx].launches++;
     prof.stats[idx].bytes += bytes;
+    prof.stats[idx].bytes_pp += bytes_per_pair;
     auto get = [&]() {
         cudaEvent_t e;
         if (!prof.pool.empty()) { e = prof.pool.back(); prof.pool.pop_back(); }
@@ -254,158 +256,206 @@ struct DebugOut {
     float* ba_diffmap = nullptr; // device pointer
 };
 
-static size_t per_pair_bytes(const ce_metric_config& cfg, size_t w, size_t h) {
+// workspace bytes of one pair: `forked` = the three perceptual metrics overlap on separate streams, so their
+// workspaces coexist; otherwise they run back to back and share one region (each *_run releases what it took)
+static size_t per_pair_bytes(const ce_metric_config& cfg, size_t w, size_t h, bool forked) {
     size_t n = w * h;
     size_t bytes = 1024;
     if (cfg.xyb_roundtrip) bytes += n * 3 + 256;
     bool perceptual = cfg.dssim || cfg.ssimulacra2 || cfg.butteraugli;
     if (perceptual) bytes += 2 * 3 * n * 4 + 512;
-    // the metrics run concurrently on separate streams, so their workspaces coexist
-    size_t m = 0;
-    if (cfg.dssim) m += dssim_workspace_per_pair(w, h);
-    if (cfg.ssimulacra2) m += ssim2_workspace_per_pair(w, h);
-    if (cfg.butteraugli) m += butteraugli_workspace_per_pair(w, h);
-    return bytes + m;
+    size_t sum = 0, mx = 0;
+    auto add = [&](size_t b) { sum += b; mx = std::max(mx, b); };
+    if (cfg.dssim) add(dssim_workspace_per_pair(w, h));
+    if (cfg.ssimulacra2) add(ssim2_workspace_per_pair(w, h));
+    if (cfg.butteraugli) add(butteraugli_workspace_per_pair(w, h));
+    return bytes + (forked ? sum : mx);
 }
 
-// d_ref: n_ref device images, d_dist: n device images (tight RGB8, w x h).  Pair i compares reference
-// ref_of[i] (host array; nullptr = identity, n_ref == n) with distorted image i.  Reference-side work of a
-// sub-batch is done once per distinct reference (fast_ssim2's Ssimulacra2Reference reuse,
-// crates/codec-iter/src/eval.rs:138-149, generalised to all metrics).
-static void run_device_batch(Context& c, const uint8_t* d_ref, size_t n_ref, const uint8_t* d_dist, size_t n,
-                             const uint32_t* ref_of, size_t w, size_t h, const ce_metric_config& cfg, float intensity,
-                             ce_result* out, const DebugOut* dbg) {
-    const size_t npix = w * h, img_bytes = npix * 3;
-    const bool small = (w < 8 || h < 8);
-    const bool perceptual = cfg.dssim || cfg.ssimulacra2 || cfg.butteraugli;
-    const size_t ppb = per_pair_bytes(cfg, w, h);
-    const size_t fixed = 1 << 20;
-    if (c.arena.cap < ppb + fixed) throw OomError("workspace too small for one pair of this size");
-    size_t Bmax = (c.arena.cap - fixed) / ppb;
-    Bmax = std::min<size_t>(Bmax, 10000);   // keeps every grid.z (up to 3 planes x 2 images per pair) under 65535
-    // raw per-pair device results: sse(1 u64) + s2 sums(108) + ds(10) + ba(4) doubles
-    const size_t raw_doubles = 1 + 108 + 10 + 4;
-    std::vector<int> local_of(ref_of ? n_ref : 0, -1);
-    for (size_t p0 = 0; p0 < n; p0 += Bmax) {
-        const size_t B = std::min(Bmax, n - p0);
-        c.arena.reset();
-        c.ensure_results(B * raw_doubles * 8);
-        // ---- index tables of the sub-batch: ridx[B] local reference of each pair, uniq[R] global reference
-        // image of each local one, gref[B] global reference image of each pair
-        c.ensure_idx(3 * B);
-        int* h_ridx = c.h_idx;
-        int* h_uniq = c.h_idx + B;
-        int* h_gref = c.h_idx + 2 * B;
-        size_t R = 0;
-        if (ref_of) {
-            for (size_t i = 0; i < B; i++) {
-                const uint32_t g = ref_of[p0 + i];
-                if (local_of[g] < 0) { local_of[g] = (int)R; h_uniq[R++] = (int)g; }
-                h_ridx[i] = local_of[g];
-                h_gref[i] = (int)g;
-            }
-            for (size_t r = 0; r < R; r++) local_of[h_uniq[r]] = -1;
-        } else {
-            R = B;
-            for (size_t i = 0; i < B; i++) { h_ridx[i] = (int)i; h_uniq[i] = (int)(p0 + i); h_gref[i] = (int)(p0 + i); }
-        }
-        CE_CUDA(cudaMemcpyAsync(c.d_idx, c.h_idx, 3 * B * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-        const int* d_ridx = c.d_idx;
-        const int* d_uniq = c.d_idx + B;
-        const int* d_gref = c.d_idx + 2 * B;
-        bool contiguous = true;
-        for (size_t r = 1; r < R; r++) contiguous = contiguous && h_uniq[r] == h_uniq[r - 1] + 1;
+static const size_t kArenaFixed = 1 << 20;
+static const size_t kRawDoubles = 1 + 108 + 10 + 4;   // per pair: sse (u64), SSIMULACRA2 sums, DSSIM sums, Butteraugli
 
-        double* d_raw = reinterpret_cast<double*>(c.d_results);
-        unsigned long long* d_sse = reinterpret_cast<unsigned long long*>(d_raw);
-        double* d_s2 = d_raw + B;
-        double* d_ds = d_s2 + B * 108;
-        double* d_ba = d_ds + B * 10;
-        const uint8_t* dist = d_dist + p0 * img_bytes;
-        // reference images of this sub-batch: (ref_base, ref_src) with ref_src a device index array or
-        // nullptr for "image r of ref_base"; (ref_base, sse_idx) the same per pair
-        const uint8_t* ref_base = d_ref;
-        const int* ref_src = d_uniq;
-        const int* sse_idx = d_gref;
-        if (contiguous) { ref_base = d_ref + (size_t)h_uniq[0] * img_bytes; ref_src = nullptr; sse_idx = d_ridx; }
-        if (cfg.xyb_roundtrip) {  // distinct references only, before every metric (src/eval/session.rs:447-456)
-            uint8_t* rt = c.arena.alloc<uint8_t>(R * img_bytes);
-            for (size_t r = 0; r < R;) {   // one launch per run of consecutive source images
-                size_t e = r + 1;
-                while (e < R && h_uniq[e] == h_uniq[e - 1] + 1) e++;
-                launch_xyb_roundtrip(c, d_ref + (size_t)h_uniq[r] * img_bytes, (e - r) * npix, rt + r * img_bytes);
-                r = e;
-            }
-            ref_base = rt; ref_src = nullptr; sse_idx = d_ridx;
+// most pairs of this size one sub-batch can hold (metrics back to back)
+static size_t sub_batch_capacity(Context& c, const ce_metric_config& cfg, size_t w, size_t h) {
+    const size_t ppb = per_pair_bytes(cfg, w, h, false);
+    if (c.arena.cap < ppb + kArenaFixed) throw OomError("workspace too small for one pair of this size");
+    // 10000 keeps every grid.z (up to 3 planes x 2 images per pair) under 65535
+    return std::min<size_t>((c.arena.cap - kArenaFixed) / ppb, 10000);
+}
+
+static bool fork_metrics(const Context& c, const ce_metric_config& cfg, size_t B, size_t w, size_t h) {
+    if (c.prof.enabled || c.fork_mode == 0) return false;
+    if ((int)(cfg.dssim != 0) + (int)(cfg.ssimulacra2 != 0) + (int)(cfg.butteraugli != 0) < 2) return false;
+    if (c.fork_mode < 0 && B * w * h > Context::FORK_MAX_PIXELS) return false;
+    return B * per_pair_bytes(cfg, w, h, true) + kArenaFixed <= c.arena.cap;
+}
+
+// One sub-batch in flight: launch_sub_batch queues every kernel and the result copy on c.stream and returns without
+// waiting; finish_sub_batch waits for it and evaluates the scores on the host.  Between the two the caller may
+// stage the next chunk's host->device copies (ce_evaluate_batch), which is what lets a blocking copy from pageable
+// memory overlap the kernels of the previous chunk.
+struct SubBatch {
+    size_t p0 = 0, B = 0;
+    int s2_ns = 0, ds_ns = 0;
+    bool small = false;
+};
+
+// d_ref: n_ref device images, d_dist: device images (tight RGB8, w x h).  Pair p0 + i compares reference
+// ref_of[p0 + i] (host array; nullptr = identity) with distorted image p0 + i.  Reference-side work of a
+// sub-batch is done once per distinct reference (fast_ssim2's Ssimulacra2Reference reuse,
+// crates/codec-iter/src/eval.rs:138-149, generalised to all metrics).  local_of: scratch of n_ref ints, all -1.
+static SubBatch launch_sub_batch(Context& c, const uint8_t* d_ref, const uint8_t* d_dist, const uint32_t* ref_of,
+                                 std::vector<int>& local_of, size_t p0, size_t B, size_t w, size_t h,
+                                 const ce_metric_config& cfg, float intensity, const DebugOut* dbg) {
+    const size_t npix = w * h, img_bytes = npix * 3;
+    SubBatch sb;
+    sb.p0 = p0;
+    sb.B = B;
+    sb.small = (w < 8 || h < 8);
+    const bool small = sb.small;
+    const bool perceptual = cfg.dssim || cfg.ssimulacra2 || cfg.butteraugli;
+    c.arena.reset();
+    c.ensure_results(B * kRawDoubles * 8);
+    // ---- index tables of the sub-batch: ridx[B] local reference of each pair, uniq[R] global reference
+    // image of each local one, gref[B] global reference image of each pair
+    c.ensure_idx(3 * B);
+    int* h_ridx = c.h_idx;
+    int* h_uniq = c.h_idx + B;
+    int* h_gref = c.h_idx + 2 * B;
+    size_t R = 0;
+    if (ref_of) {
+        for (size_t i = 0; i < B; i++) {
+            const uint32_t g = ref_of[p0 + i];
+            if (local_of[g] < 0) { local_of[g] = (int)R; h_uniq[R++] = (int)g; }
+            h_ridx[i] = local_of[g];
+            h_gref[i] = (int)g;
         }
-        if (cfg.psnr) launch_sse(c, ref_base, sse_idx, dist, B, img_bytes, d_sse);
-        int s2_ns = 0, ds_ns = 0;
-        if (perceptual) {
-            const size_t NI = R + B;
-            float* lin = c.arena.alloc<float>(NI * 3 * npix);
-            launch_srgb8_to_linear(c, ref_base, ref_src, R, npix, lin);
-            launch_srgb8_to_linear(c, dist, nullptr, B, npix, lin + R * 3 * npix);
-            // fork: DSSIM and SSIMULACRA2 on the side streams, Butteraugli on the main one.  Each metric keeps
-            // its arena region (no release between them) because their kernels overlap in time.
-            const bool fork = c.concurrent && !c.prof.enabled;
-            cudaStream_t main_stream = c.stream;
-            if (fork) CE_CUDA(cudaEventRecord(c.ev_fork, main_stream));
-            int used = 0;
-            auto on_side = [&](auto&& fn) {
-                if (!fork) { fn(); return; }
-                cudaStream_t s = c.side[used];
-                CE_CUDA(cudaStreamWaitEvent(s, c.ev_fork, 0));
-                c.stream = s;
-                c.arena.high = c.arena.off;
-                try { fn(); } catch (...) { c.stream = main_stream; throw; }
-                c.arena.off = c.arena.high;   // keep the metric's workspace reserved until the join
-                c.stream = main_stream;
-                CE_CUDA(cudaEventRecord(c.ev_join[used], s));
-                used++;
-            };
-            if (cfg.dssim) on_side([&] { ds_ns = dssim_run(c, lin, nullptr, R, d_ridx, B, w, h, d_ds, dbg ? dbg->ds_map0 : nullptr); });
-            if (cfg.ssimulacra2 && !small) on_side([&] { s2_ns = ssim2_run(c, lin, R, d_ridx, B, w, h, d_s2, dbg ? dbg->s2_planes : nullptr); });
+        for (size_t r = 0; r < R; r++) local_of[h_uniq[r]] = -1;
+    } else {
+        R = B;
+        for (size_t i = 0; i < B; i++) { h_ridx[i] = (int)i; h_uniq[i] = (int)(p0 + i); h_gref[i] = (int)(p0 + i); }
+    }
+    CE_CUDA(cudaMemcpyAsync(c.d_idx, c.h_idx, 3 * B * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    const int* d_ridx = c.d_idx;
+    const int* d_uniq = c.d_idx + B;
+    const int* d_gref = c.d_idx + 2 * B;
+    bool contiguous = true;
+    for (size_t r = 1; r < R; r++) contiguous = contiguous && h_uniq[r] == h_uniq[r - 1] + 1;
+
+    double* d_raw = reinterpret_cast<double*>(c.d_results);
+    unsigned long long* d_sse = reinterpret_cast<unsigned long long*>(d_raw);
+    double* d_s2 = d_raw + B;
+    double* d_ds = d_s2 + B * 108;
+    double* d_ba = d_ds + B * 10;
+    const uint8_t* dist = d_dist + p0 * img_bytes;
+    // reference images of this sub-batch: (ref_base, ref_src) with ref_src a device index array or
+    // nullptr for "image r of ref_base"; (ref_base, sse_idx) the same per pair
+    const uint8_t* ref_base = d_ref;
+    const int* ref_src = d_uniq;
+    const int* sse_idx = d_gref;
+    if (contiguous) { ref_base = d_ref + (size_t)h_uniq[0] * img_bytes; ref_src = nullptr; sse_idx = d_ridx; }
+    if (cfg.xyb_roundtrip) {  // distinct references only, before every metric (src/eval/session.rs:447-456)
+        uint8_t* rt = c.arena.alloc<uint8_t>(R * img_bytes);
+        for (size_t r = 0; r < R;) {   // one launch per run of consecutive source images
+            size_t e = r + 1;
+            while (e < R && h_uniq[e] == h_uniq[e - 1] + 1) e++;
+            launch_xyb_roundtrip(c, d_ref + (size_t)h_uniq[r] * img_bytes, (e - r) * npix, rt + r * img_bytes);
+            r = e;
+        }
+        ref_base = rt; ref_src = nullptr; sse_idx = d_ridx;
+    }
+    if (cfg.psnr) launch_sse(c, ref_base, sse_idx, dist, B, img_bytes, d_sse, R);
+    if (perceptual) {
+        const size_t NI = R + B;
+        float* lin = c.arena.alloc<float>(NI * 3 * npix);
+        launch_srgb8_to_linear(c, ref_base, ref_src, R, npix, lin);
+        launch_srgb8_to_linear(c, dist, nullptr, B, npix, lin + R * 3 * npix);
+        // fork (small sub-batches only): DSSIM and SSIMULACRA2 on the side streams, Butteraugli on the main one.
+        // Each forked metric keeps its arena region (no release between them) because their kernels overlap in time.
+        const bool fork = fork_metrics(c, cfg, B, w, h);
+        cudaStream_t main_stream = c.stream;
+        if (fork) CE_CUDA(cudaEventRecord(c.ev_fork, main_stream));
+        int used = 0;
+        auto on_side = [&](auto&& fn) {
+            if (!fork) { fn(); return; }
+            cudaStream_t s = c.side[used];
+            CE_CUDA(cudaStreamWaitEvent(s, c.ev_fork, 0));
+            c.stream = s;
+            c.arena.high = c.arena.off;
+            try { fn(); } catch (...) { c.stream = main_stream; throw; }
+            c.arena.off = c.arena.high;   // keep the metric's workspace reserved until the join
+            c.stream = main_stream;
+            CE_CUDA(cudaEventRecord(c.ev_join[used], s));
+            used++;
+        };
+        try {
+            if (cfg.dssim) on_side([&] { sb.ds_ns = dssim_run(c, lin, nullptr, R, d_ridx, B, w, h, d_ds, dbg ? dbg->ds_map0 : nullptr); });
+            if (cfg.ssimulacra2 && !small) on_side([&] { sb.s2_ns = ssim2_run(c, lin, R, d_ridx, B, w, h, d_s2, dbg ? dbg->s2_planes : nullptr); });
             if (cfg.butteraugli && !small) butteraugli_run(c, lin, R, d_ridx, B, w, h, intensity, d_ba, dbg ? dbg->ba_diffmap : nullptr);
             for (int i = 0; i < used; i++) CE_CUDA(cudaStreamWaitEvent(main_stream, c.ev_join[i], 0));
+        } catch (...) {
+            // kernels already queued on the side streams still use the arena: nothing may reset it before they end
+            if (fork) { cudaStreamSynchronize(c.side[0]); cudaStreamSynchronize(c.side[1]); }
+            cudaStreamSynchronize(main_stream);
+            throw;
         }
-        CE_CUDA(cudaMemcpyAsync(c.h_pinned, d_raw, B * raw_doubles * 8, cudaMemcpyDeviceToHost, c.stream));
-        CE_CUDA(cudaStreamSynchronize(c.stream));
-        c.prof_collect();
-        const double* h_raw = reinterpret_cast<const double*>(c.h_pinned);
-        const uint64_t* h_sse = reinterpret_cast<const uint64_t*>(h_raw);
-        const double* h_s2 = h_raw + B;
-        const double* h_ds = h_s2 + B * 108;
-        const double* h_ba = h_ds + B * 10;
-        for (size_t i = 0; i < B; i++) {
-            ce_result& r = out[p0 + i];
-            memset(&r, 0, sizeof(r));
-            // reference order: psnr, dssim, ssimulacra2, butteraugli; first failure ends the pair
-            if (cfg.psnr) {
-                r.sse = h_sse[i];
-                r.psnr = finalize_psnr(r.sse, w, h);
-                r.valid |= CE_VALID_PSNR;
-            }
-            if (cfg.dssim) {
-                r.dssim = finalize_dssim(h_ds + i * 10, ds_ns, w, h, (dbg && i == 0) ? dbg->ds_scores : nullptr);
-                if (dbg && dbg->ds_nscales) *dbg->ds_nscales = ds_ns;
-                r.valid |= CE_VALID_DSSIM;
-            }
-            if (cfg.ssimulacra2) {
-                if (small) { r.status = CE_ERR_METRIC_CALCULATION; continue; }
-                r.ssimulacra2 = finalize_ssim2(h_s2 + i * 108, s2_ns, w, h);
-                if (dbg && i == 0 && dbg->s2_sums) memcpy(dbg->s2_sums, h_s2, sizeof(double) * 18 * (size_t)s2_ns);
-                if (dbg && dbg->s2_nscales) *dbg->s2_nscales = s2_ns;
-                r.valid |= CE_VALID_SSIMULACRA2;
-            }
-            if (cfg.butteraugli) {
-                if (small) { r.status = CE_ERR_METRIC_CALCULATION; continue; }
-                finalize_butteraugli(h_ba + i * 4, w, h, &r.butteraugli, &r.butteraugli_pnorm3);
-                r.valid |= CE_VALID_BUTTERAUGLI;
-            }
+    }
+    CE_CUDA(cudaMemcpyAsync(c.h_pinned, d_raw, B * kRawDoubles * 8, cudaMemcpyDeviceToHost, c.stream));
+    return sb;
+}
+
+static void finish_sub_batch(Context& c, const SubBatch& sb, size_t w, size_t h, const ce_metric_config& cfg, ce_result* out,
+                             const DebugOut* dbg) {
+    CE_CUDA(cudaStreamSynchronize(c.stream));
+    c.prof_collect();
+    const size_t B = sb.B;
+    const bool small = sb.small;
+    const double* h_raw = reinterpret_cast<const double*>(c.h_pinned);
+    const uint64_t* h_sse = reinterpret_cast<const uint64_t*>(h_raw);
+    const double* h_s2 = h_raw + B;
+    const double* h_ds = h_s2 + B * 108;
+    const double* h_ba = h_ds + B * 10;
+    for (size_t i = 0; i < B; i++) {
+        ce_result& r = out[sb.p0 + i];
+        memset(&r, 0, sizeof(r));
+        // reference order: psnr, dssim, ssimulacra2, butteraugli; first failure ends the pair
+        if (cfg.psnr) {
+            r.sse = h_sse[i];
+            r.psnr = finalize_psnr(r.sse, w, h);
+            r.valid |= CE_VALID_PSNR;
+        }
+        if (cfg.dssim) {
+            r.dssim = finalize_dssim(h_ds + i * 10, sb.ds_ns, w, h, (dbg && i == 0) ? dbg->ds_scores : nullptr);
+            if (dbg && dbg->ds_nscales) *dbg->ds_nscales = sb.ds_ns;
+            r.valid |= CE_VALID_DSSIM;
+        }
+        if (cfg.ssimulacra2) {
+            if (small) { r.status = CE_ERR_METRIC_CALCULATION; continue; }
+            r.ssimulacra2 = finalize_ssim2(h_s2 + i * 108, sb.s2_ns, w, h);
+            if (dbg && i == 0 && dbg->s2_sums) memcpy(dbg->s2_sums, h_s2, sizeof(double) * 18 * (size_t)sb.s2_ns);
+            if (dbg && dbg->s2_nscales) *dbg->s2_nscales = sb.s2_ns;
+            r.valid |= CE_VALID_SSIMULACRA2;
+        }
+        if (cfg.butteraugli) {
+            if (small) { r.status = CE_ERR_METRIC_CALCULATION; continue; }
+            finalize_butteraugli(h_ba + i * 4, w, h, &r.butteraugli, &r.butteraugli_pnorm3);
+            r.valid |= CE_VALID_BUTTERAUGLI;
         }
     }
     if (small && (cfg.ssimulacra2 || cfg.butteraugli))
         c.last_error = cfg.ssimulacra2 ? "SSIMULACRA2: images must be at least 8x8 pixels" : "Butteraugli: images must be at least 8x8 pixels";
+}
+
+static void run_device_batch(Context& c, const uint8_t* d_ref, size_t n_ref, const uint8_t* d_dist, size_t n,
+                             const uint32_t* ref_of, size_t w, size_t h, const ce_metric_config& cfg, float intensity,
+                             ce_result* out, const DebugOut* dbg) {
+    const size_t Bmax = sub_batch_capacity(c, cfg, w, h);
+    std::vector<int> local_of(ref_of ? n_ref : 0, -1);
+    for (size_t p0 = 0; p0 < n; p0 += Bmax) {
+        const size_t B = std::min(Bmax, n - p0);
+        SubBatch sb = launch_sub_batch(c, d_ref, d_dist, ref_of, local_of, p0, B, w, h, cfg, intensity, dbg);
+        finish_sub_batch(c, sb, w, h, cfg, out, dbg);
+    }
 }
 
 // ------------------------------------------------------------------ TMA descriptors
@@ -466,7 +516,47 @@ bool tma_plane_map(CUtensorMap* m, const float* base, size_t w, size_t h, size_t
 
 extern "C" {
 
-CE_API const char* ce_version(void) { return "ce_gpu 0.1.0 (sm_100a)"; }
+#ifndef CE_SOURCE_HASH
+#define CE_SOURCE_HASH "unhashed"
+#endif
+// "... src:<sha256/16 of csrc/* + include/ce_gpu.h>": codec_eval_b200.build stamps it, _lib.load() compares it with the
+// sources beside the library, so a stale binary cannot be taken for the committed code.
+CE_API const char* ce_version(void) { return "ce_gpu 0.2.0 (sm_100a) src:" CE_SOURCE_HASH; }
+
+// ---- pinned host memory for the callers' image buffers (opt-in) ---------------------------------------
+CE_API int ce_host_register(ce_ctx* ctx, void* ptr, size_t bytes) {
+    if (!ctx || !ptr || !bytes) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        CE_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    })
+    return CE_OK;
+}
+CE_API int ce_host_unregister(ce_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        CE_CUDA(cudaHostUnregister(ptr));
+    })
+    return CE_OK;
+}
+CE_API int ce_host_alloc(ce_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out || !bytes) return CE_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    Context& c = ctx->c;
+    CE_TRY(c, {
+        CE_CUDA(cudaSetDevice(c.device));
+        CE_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    })
+    return CE_OK;
+}
+CE_API void ce_host_free(ce_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) return;
+    cudaSetDevice(ctx->c.device);
+    cudaFreeHost(ptr);
+}
 
 CE_API int ce_ctx_create(ce_ctx** out, int device, size_t workspace_bytes) {
     if (!out) return CE_ERR_INVALID_ARGUMENT;
@@ -494,6 +584,7 @@ CE_API int ce_ctx_create(ce_ctx** out, int device, size_t workspace_bytes) {
         Context& c = ctx->c;
         c.device = device;
         c.sm_count = prop.multiProcessorCount;
+        if (const char* e = getenv("CE_FORK")) c.fork_mode = atoi(e) > 0 ? 1 : (atoi(e) == 0 ? 0 : -1);
         CE_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
         c.stream = c.own_stream;
         for (int i = 0; i < 2; i++) {
@@ -572,7 +663,7 @@ CE_API int ce_profile_enable(ce_ctx* ctx, int enable) {
 }
 CE_API int ce_profile_reset(ce_ctx* ctx) {
     if (!ctx) return CE_ERR_INVALID_ARGUMENT;
-    for (auto& k : ctx->c.prof.stats) { k.launches = 0; k.ms = 0.0; k.bytes = 0.0; }
+    for (auto& k : ctx->c.prof.stats) { k.launches = 0; k.ms = 0.0; k.bytes = 0.0; k.bytes_pp = 0.0; }
     return CE_OK;
 }
 CE_API size_t ce_profile_report(ce_ctx* ctx, char* buf, size_t cap) {
@@ -581,7 +672,8 @@ CE_API size_t ce_profile_report(ce_ctx* ctx, char* buf, size_t cap) {
     char line[512];
     for (auto& k : ctx->c.prof.stats) {
         if (!k.launches) continue;
-        snprintf(line, sizeof(line), "%s\t%llu\t%.6f\t%.0f\n", k.name.c_str(), (unsigned long long)k.launches, k.ms, k.bytes);
+        snprintf(line, sizeof(line), "%s\t%llu\t%.6f\t%.0f\t%.0f\n", k.name.c_str(), (unsigned long long)k.launches, k.ms, k.bytes,
+                 k.bytes_pp);
         out += line;
     }
     if (buf && cap) {
@@ -590,6 +682,13 @@ CE_API size_t ce_profile_report(ce_ctx* ctx, char* buf, size_t cap) {
         buf[n] = 0;
     }
     return out.size();
+}
+
+CE_API int ce_sub_batch_capacity(ce_ctx* ctx, const ce_metric_config* cfg, uint32_t width, uint32_t height, size_t* pairs) {
+    if (!ctx || !cfg || !pairs || width == 0 || height == 0) return CE_ERR_INVALID_ARGUMENT;
+    Context& c = ctx->c;
+    CE_TRY(c, { *pairs = sub_batch_capacity(c, *cfg, width, height); })
+    return CE_OK;
 }
 
 CE_API int ce_evaluate_batch_device(ce_ctx* ctx, const uint8_t* d_ref, const uint8_t* d_dist, size_t n, uint32_t width,
@@ -665,34 +764,39 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
         size_t k0 = 0, B = 0, Ru = 0;
         std::vector<uint32_t> ref_of;
     } st[2];
+    // Two pairs share a reference image when their `ref` pointer AND their `ref_id` are equal (evaluate_image compares
+    // one reference with every codec x quality output, src/eval/session.rs:375-431): it is uploaded and pre-processed once.
+    auto same_ref = [&](size_t a, size_t b) { return pairs[a].ref == pairs[b].ref && pairs[a].ref_id == pairs[b].ref_id; };
     for (auto& g : groups) {
         const size_t w = g.first.first, h = g.first.second, img_bytes = w * h * 3;
         const std::vector<size_t>& idx = g.second;
-        // The group is cut into up to 4 chunks (at most 2 GiB of distorted input each): chunk k+1 is copied to the
-        // device on the copy stream while chunk k computes.  Only the first chunk's copy is exposed, so it is the
-        // small one (1/12 of the group); boundaries do not split a run of pairs that share a reference buffer.
+        // The group is cut into chunks of at most one sub-batch (what the workspace holds, and at most 2 GiB of
+        // distorted input): chunk k+1 is copied to the device on the copy stream while chunk k computes.  Only the first
+        // chunk's copy is exposed, so it is the small one (1/12 of the group); boundaries prefer the end of a run of
+        // pairs that share a reference.
         size_t max_chunks = 4;
         if (const char* e = getenv("CE_HOST_CHUNKS")) max_chunks = std::max<size_t>(1, (size_t)atoi(e));
-        const size_t cap = std::max<size_t>(1, ((size_t)2 << 30) / std::max<size_t>(img_bytes, 1));
+        const size_t cap = std::min<size_t>(sub_batch_capacity(c, cfg, w, h), std::max<size_t>(1, ((size_t)2 << 30) / std::max<size_t>(img_bytes, 1)));
         std::vector<size_t> bounds(1, 0);
         {
             const size_t total = idx.size();
             size_t want = std::min<size_t>(max_chunks, (total + 7) / 8);
             want = std::max<size_t>(want, (total + cap - 1) / cap);
             auto snap = [&](size_t b) {   // move a boundary to the end of the current same-reference run
-                while (b > 0 && b < total && pairs[idx[b]].ref == pairs[idx[b - 1]].ref) b++;
+                while (b > 0 && b < total && same_ref(idx[b], idx[b - 1])) b++;
                 return b;
             };
             if (want > 1) {
-                const size_t first = snap(std::max<size_t>(1, total / 12));
+                const size_t first = snap(std::max<size_t>(1, std::min(cap, total / 12)));
                 if (first < total) bounds.push_back(first);
-                const size_t start = bounds.back(), rest = total - start, parts = want - 1;
+                const size_t start = bounds.back(), rest = total - start;
+                const size_t parts = std::max<size_t>(want - 1, (rest + cap - 1) / cap);
                 for (size_t k = 1; k < parts; k++) {
                     const size_t b = snap(start + rest * k / parts);
                     if (b > bounds.back() && b < total) bounds.push_back(b);
                 }
             }
-            // enforce the size cap
+            // enforce the size cap (a snapped boundary may have overshot it)
             std::vector<size_t> capped(1, 0);
             for (size_t k = 1; k <= bounds.size(); k++) {
                 const size_t end = k < bounds.size() ? bounds[k] : total;
@@ -707,15 +811,14 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
             Staged& s = st[ci & 1];
             s.k0 = bounds[ci];
             s.B = bounds[ci + 1] - bounds[ci];
-            // distinct reference buffers of the chunk (same host pointer == same image: evaluate_image compares one
-            // reference with every codec x quality output, src/eval/session.rs:375-431) are uploaded once
-            std::map<const uint8_t*, uint32_t> seen;
+            std::map<std::pair<const uint8_t*, uint32_t>, uint32_t> seen;
             std::vector<const uint8_t*> urefs;
             s.ref_of.resize(s.B);
             for (size_t k = 0; k < s.B; k++) {
                 const ce_pair& p = pairs[idx[s.k0 + k]];
-                auto it = seen.find(p.ref);
-                if (it == seen.end()) { it = seen.emplace(p.ref, (uint32_t)urefs.size()).first; urefs.push_back(p.ref); }
+                const auto key = std::make_pair(p.ref, p.ref_id);
+                auto it = seen.find(key);
+                if (it == seen.end()) { it = seen.emplace(key, (uint32_t)urefs.size()).first; urefs.push_back(p.ref); }
                 s.ref_of[k] = it->second;
             }
             s.Ru = urefs.size();
@@ -729,19 +832,26 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
                                         c.copy_stream));
             CE_CUDA(cudaEventRecord(c.ev_copy[ci & 1], c.copy_stream));
         };
+        std::vector<int> local_of;
         try {
             stage(0);
             for (size_t ci = 0; ci < nchunks; ci++) {
-                if (ci + 1 < nchunks) stage(ci + 1);   // its slot was last read by chunk ci-1, which has completed
                 Staged& s = st[ci & 1];
                 CE_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy[ci & 1], 0));
                 tmp.resize(s.B);
-                run_device_batch(c, c.d_stage[ci & 1], s.Ru, c.d_stage[ci & 1] + s.Ru * img_bytes, s.B, s.ref_of.data(), w, h,
-                                 cfg, intensity, tmp.data(), dbg);
+                local_of.assign(s.Ru, -1);
+                // queue chunk ci, THEN stage chunk ci+1: a copy from pageable memory blocks this thread until the driver
+                // has moved the bytes, and that time now runs under the kernels of chunk ci (pinned or registered buffers
+                // return at once either way).  Slot (ci+1)&1 was last read by chunk ci-1, which has completed.
+                SubBatch sb = launch_sub_batch(c, c.d_stage[ci & 1], c.d_stage[ci & 1] + s.Ru * img_bytes, s.ref_of.data(), local_of, 0,
+                                               s.B, w, h, cfg, intensity, dbg);
+                if (ci + 1 < nchunks) stage(ci + 1);
+                finish_sub_batch(c, sb, w, h, cfg, tmp.data(), dbg);
                 for (size_t k = 0; k < s.B; k++) out[idx[s.k0 + k]] = tmp[k];
             }
         } catch (...) {
             cudaStreamSynchronize(c.copy_stream);   // no copy may outlive the caller's buffers
+            cudaStreamSynchronize(c.stream);
             throw;
         }
     }
@@ -1081,10 +1191,10 @@ CE_API int ce_reference_create(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, 
         return CE_ERR_METRIC_CALCULATION;
     }
     ce_ref* r = nullptr;
-    CE_TRY(c, {
+    try {
         CE_CUDA(cudaSetDevice(c.device));
         r = new ce_ref();
-        r->owner = ctx; r->width = width; r->height = height; r->cfg = *cfg; r->d_ref = nullptr;
+        r->owner = ctx; r->device = c.device; r->width = width; r->height = height; r->cfg = *cfg; r->d_ref = nullptr;
         CE_CUDA(cudaMalloc(&r->d_ref, ref_len));
         if (cfg->xyb_roundtrip) {
             c.arena.reset();
@@ -1097,7 +1207,15 @@ CE_API int ce_reference_create(ce_ctx* ctx, const uint8_t* ref, size_t ref_len, 
         CE_CUDA(cudaStreamSynchronize(c.stream));
         r->cfg.xyb_roundtrip = 0;  // already applied
         *out = r;
-    })
+    } catch (const std::exception& e) {   // nothing of a half-built handle may leak
+        c.last_error = e.what();
+        if (r) {
+            cudaStreamSynchronize(c.stream);
+            if (r->d_ref) cudaFree(r->d_ref);
+            delete r;
+        }
+        return dynamic_cast<const OomError*>(&e) ? CE_ERR_OUT_OF_MEMORY : CE_ERR_CUDA;
+    }
     return CE_OK;
 }
 
@@ -1144,8 +1262,8 @@ CE_API int ce_reference_compare(ce_ctx* ctx, ce_ref* ref, const uint8_t* dist, s
 
 CE_API void ce_reference_destroy(ce_ref* ref) {
     if (!ref) return;
-    if (ref->d_ref) {
-        cudaSetDevice(ref->owner->c.device);
+    if (ref->d_ref) {   // the owning context may already be gone: only the handle's own fields are used
+        cudaSetDevice(ref->device);
         cudaFree(ref->d_ref);
     }
     delete ref;

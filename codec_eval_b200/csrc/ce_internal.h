@@ -66,7 +66,9 @@ struct KernelStat {
     std::string name;
     uint64_t launches = 0;
     double ms = 0.0;      // summed device time of the timed launches
-    double bytes = 0.0;   // summed ALGORITHMIC bytes (distinct inputs read once + outputs written once)
+    double bytes = 0.0;   // summed ALGORITHMIC bytes: each distinct input element once + each output element once
+                          // (planes of a reference shared by several pairs count once per reference)
+    double bytes_pp = 0.0;  // the same with shared reference planes charged once per PAIR (the no-reuse figure)
 };
 struct Profiler {
     bool enabled = false;
@@ -105,14 +107,19 @@ struct Context {
     std::map<uint64_t, float*> ba_inv_cache;  // Butteraugli border-renormalisation tables
     int sm_count = 148;
 
-    // the three perceptual metrics of a sub-batch run concurrently on the main stream + two side streams
-    // (disabled while the per-kernel profiler is on, so its event pairs bracket one kernel each)
+    // Small sub-batches (a single pair, a handful of thumbnails) cannot fill 148 SMs with one metric's kernels, so
+    // there the three perceptual metrics run concurrently on the main stream + two side streams.  Large sub-batches
+    // run the metrics back to back on the main stream (measured round 1: 17.26 ms forked vs 17.09 ms serialised on
+    // the 192-pair batch) and reuse one workspace region, which doubles the pairs per sub-batch.
+    // fork_mode: -1 = auto (fork when the sub-batch has at most FORK_MAX_PIXELS pixel-pairs), 0 = never, 1 = always
+    // (env CE_FORK).  Never while the per-kernel profiler is on, so its event pairs bracket one kernel each.
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    bool concurrent = true;
+    int fork_mode = -1;
+    static constexpr size_t FORK_MAX_PIXELS = (size_t)4 << 20;
 
     Profiler prof;
-    void prof_begin(const char* name, double bytes);
+    void prof_begin(const char* name, double bytes, double bytes_per_pair);
     void prof_end();
     void prof_collect();   // call after the stream is synchronised
     void ensure_input(size_t bytes);
@@ -122,11 +129,18 @@ struct Context {
 };
 
 // every kernel launch of the library goes through this: counts it, and (when profiling) brackets it with events
-#define CE_LAUNCH(ctx, name, bytes, ...)            \
-    do {                                            \
-        (ctx).prof_begin(name, (double)(bytes));    \
-        __VA_ARGS__;                                \
-        (ctx).prof_end();                           \
+#define CE_LAUNCH(ctx, name, bytes, ...)                           \
+    do {                                                           \
+        (ctx).prof_begin(name, (double)(bytes), (double)(bytes));  \
+        __VA_ARGS__;                                               \
+        (ctx).prof_end();                                          \
+    } while (0)
+// pair kernels that read planes of a shared reference: bytes = distinct elements, bytes_pp = charged per pair
+#define CE_LAUNCH_SHARED(ctx, name, bytes, bytes_pp, ...)             \
+    do {                                                              \
+        (ctx).prof_begin(name, (double)(bytes), (double)(bytes_pp));  \
+        __VA_ARGS__;                                                  \
+        (ctx).prof_end();                                             \
     } while (0)
 
 // TMA descriptor of fp32 planes [nplanes][h][w] as a rank-3 tensor with box (bw, bh, bz) and zero fill outside
@@ -146,8 +160,9 @@ inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 void launch_srgb8_to_linear(Context& c, const uint8_t* d_rgb, const int* src_index, size_t n_img, size_t npix, float* d_planes);
 // exact integer SSE per pair: d_sse[n] (zeroed inside)
 // ref_index (device, nullable): pair i compares reference image ref_index[i] (identity when null)
+// n_distinct_ref: distinct reference images behind ref_index (byte accounting only; 0 = n)
 void launch_sse(Context& c, const uint8_t* d_ref, const int* ref_index, const uint8_t* d_dist, size_t n, size_t bytes_per_img,
-                unsigned long long* d_sse);
+                unsigned long long* d_sse, size_t n_distinct_ref = 0);
 void launch_xyb_roundtrip(Context& c, const uint8_t* d_rgb, size_t npix_total, uint8_t* d_out);
 void launch_rgb8_to_rgba_linear(Context& c, const uint8_t* d_in, size_t npix, int in_channels, float* d_out);
 void launch_rgba_to_planar(Context& c, const float* d_rgba, size_t w, size_t h, size_t stride, float* d_planes3, float* d_alpha);

@@ -1272,10 +1272,10 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
         mp.ch[0] = make_malta_params(0, hf_asym);
         mp.ch[1] = make_malta_params(1, hf_asym);
         if (n % 4 == 0)
-            CE_LAUNCH(c, "k_ba_malta_diff", (double)B * n * 72,
+            CE_LAUNCH_SHARED(c, "k_ba_malta_diff", ((double)B * 48 + (double)R * 24) * n, (double)B * n * 72,
                       k_ba_malta_diff<true><<<ew_blocks(c, B * 2 * (n / 4)), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
         else
-            CE_LAUNCH(c, "k_ba_malta_diff", (double)B * n * 72,
+            CE_LAUNCH_SHARED(c, "k_ba_malta_diff", ((double)B * 48 + (double)R * 24) * n, (double)B * n * 72,
                       k_ba_malta_diff<false><<<ew_blocks(c, B * 2 * n), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
         dim3 grid(cdiv(w, MT_TW), cdiv(cdiv(h, MT_TH), MT_NT), (unsigned)(2 * B));
         MaltaMaps maps;
@@ -1284,18 +1284,18 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
                          tma_plane_map(&maps.hf, L.hf, w, h, NI * 2, MT_TW, MT_TH, 1) &&
                          tma_plane_map(&maps.mf, L.mf, w, h, NI * 3, MT_TW, MT_TH, 1);
         if (tma)
-            CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
+            CE_LAUNCH_SHARED(c, "k_ba_malta", ((double)B * 48 + (double)R * 16) * n, (double)B * n * 64,
                       k_ba_malta<true><<<grid, 256, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));
         else   // widths that are not a multiple of 4 cannot be described by a tensor map (16-byte row stride): cp.async tiles
-            CE_LAUNCH(c, "k_ba_malta", (double)B * n * 48,
+            CE_LAUNCH_SHARED(c, "k_ba_malta", ((double)B * 48 + (double)R * 16) * n, (double)B * n * 64,
                       k_ba_malta<false><<<grid, 256, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));
     }
     if (w % 4 == 0)
-        CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,
+        CE_LAUNCH_SHARED(c, "k_ba_combine", ((double)B * 32 + (double)R * 20) * n, (double)B * n * 52,
                   k_ba_combine4<<<ew_blocks(c, B * (n / 4)), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul,
                                                                                 diffmap));
     else
-        CE_LAUNCH(c, "k_ba_combine", (double)B * n * 52,
+        CE_LAUNCH_SHARED(c, "k_ba_combine", ((double)B * 32 + (double)R * 20) * n, (double)B * n * 52,
                   k_ba_combine<<<ew_blocks(c, B * n), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul, diffmap));
     CE_CUDA(cudaGetLastError());
     c.arena.release(mark);

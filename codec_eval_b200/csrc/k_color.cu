@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(256) k_sse_scalar(const uint8_t* __restrict__ 
 }
 
 void launch_sse(Context& c, const uint8_t* d_ref, const int* ref_index, const uint8_t* d_dist, size_t n, size_t bytes_per_img,
-                unsigned long long* d_sse) {
+                unsigned long long* d_sse, size_t n_distinct_ref) {
     if (n == 0) return;
+    if (n_distinct_ref == 0 || n_distinct_ref > n) n_distinct_ref = n;
     CE_CUDA(cudaMemsetAsync(d_sse, 0, n * sizeof(unsigned long long), c.stream));
     if (bytes_per_img == 0) return;
     // each thread should see >= 4 vectors; cap chunks so that grid ~ a few waves
@@ -185,11 +186,13 @@ void launch_sse(Context& c, const uint8_t* d_ref, const int* ref_index, const ui
         // the vector kernel needs every ref / dist image pair to share its offset modulo 16
         bool same_align = ((reinterpret_cast<uintptr_t>(d_ref) ^ reinterpret_cast<uintptr_t>(d_dist)) & 15) == 0 &&
                           (bytes_per_img % 16 == 0 || !ref_index);
+        const double nr = (double)std::min<size_t>(np, n_distinct_ref);   // distinct references behind this launch
         if (same_align)
-            CE_LAUNCH(c, "k_sse", (double)np * (2 * bytes_per_img + 8), k_sse<<<grid, 256, 0, c.stream>>>(r, ri, d, bytes_per_img, d_sse + p0));
+            CE_LAUNCH_SHARED(c, "k_sse", (np + nr) * bytes_per_img + np * 8.0, (double)np * (2 * bytes_per_img + 8),
+                             k_sse<<<grid, 256, 0, c.stream>>>(r, ri, d, bytes_per_img, d_sse + p0));
         else
-            CE_LAUNCH(c, "k_sse_scalar", (double)np * (2 * bytes_per_img + 8),
-                      k_sse_scalar<<<grid, 256, 0, c.stream>>>(r, ri, d, bytes_per_img, d_sse + p0));
+            CE_LAUNCH_SHARED(c, "k_sse_scalar", (np + nr) * bytes_per_img + np * 8.0, (double)np * (2 * bytes_per_img + 8),
+                             k_sse_scalar<<<grid, 256, 0, c.stream>>>(r, ri, d, bytes_per_img, d_sse + p0));
     }
     CE_CUDA(cudaGetLastError());
 }

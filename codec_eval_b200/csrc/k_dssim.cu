@@ -667,7 +667,8 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
             dim3 grid(sx, sy, nb);
-            CE_LAUNCH(c, "k_ds_stats<pair>", (double)nb * n * 52,
+            // per pair: ch2 (12 B) + map out (4 B); per distinct reference: ch1 (12 B) + its statistics (24 B)
+            CE_LAUNCH_SHARED(c, "k_ds_stats<pair>", ((double)nb * 16 + (double)std::min<size_t>(R, nb) * 36) * n, (double)nb * n * 52,
                       k_ds_stream<1><<<grid, 32, 0, c.stream>>>(img, R + b0, ridx + b0, (int)cw, (int)ch, n, rows, refstat,
                                                                  map + b0 * n, partial + b0 * ntiles));
         }

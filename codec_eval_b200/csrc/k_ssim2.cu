@@ -601,16 +601,16 @@ int ssim2_run(Context& c, const float* lin_in, size_t R, const int* ridx, size_t
                 CE_LAUNCH(c, "k_s2_vpass<ref>", (double)R * 3 * 4 * n * 4,
                           k_s2_vpass<S2_REF, false><<<gvr, 64, 0, c.stream>>>(xyb, R, ridx, hbr, vref, (int)cw, (int)ch, n, nullptr, nullptr, vecf, mr));
             if (htma)
-                CE_LAUNCH(c, "k_s2_hpass<pair>", (double)B * 3 * 5 * n * 4,
+                CE_LAUNCH_SHARED(c, "k_s2_hpass<pair>", (double)(B * 4 + R) * 3 * n * 4, (double)B * 3 * 5 * n * 4,
                           k_s2_hpass<S2_PAIR, true><<<ghp, 96, S2Mode<S2_PAIR>::HP_SMEM_TMA, c.stream>>>(xyb, R, ridx, hbp, (int)cw, (int)ch, n, vecf, mx));
             else
-                CE_LAUNCH(c, "k_s2_hpass<pair>", (double)B * 3 * 5 * n * 4,
+                CE_LAUNCH_SHARED(c, "k_s2_hpass<pair>", (double)(B * 4 + R) * 3 * n * 4, (double)B * 3 * 5 * n * 4,
                           k_s2_hpass<S2_PAIR, false><<<ghp, 96, S2Mode<S2_PAIR>::HP_SMEM, c.stream>>>(xyb, R, ridx, hbp, (int)cw, (int)ch, n, vecf, mx));
             if (tma)
-                CE_LAUNCH(c, "k_s2_vpass<pair>", (double)B * 3 * 7 * n * 4,
+                CE_LAUNCH_SHARED(c, "k_s2_vpass<pair>", (double)(B * 4 + R * 3) * 3 * n * 4, (double)B * 3 * 7 * n * 4,
                           k_s2_vpass<S2_PAIR, true><<<gvp, 96, 0, c.stream>>>(xyb, R, ridx, hbp, vref, (int)cw, (int)ch, n, partials, dbg, vecf, mp));
             else
-                CE_LAUNCH(c, "k_s2_vpass<pair>", (double)B * 3 * 7 * n * 4,
+                CE_LAUNCH_SHARED(c, "k_s2_vpass<pair>", (double)(B * 4 + R * 3) * 3 * n * 4, (double)B * 3 * 7 * n * 4,
                           k_s2_vpass<S2_PAIR, false><<<gvp, 96, 0, c.stream>>>(xyb, R, ridx, hbp, vref, (int)cw, (int)ch, n, partials, dbg, vecf, mp));
         } else {
             dim3 gh(cdiv(ch, HP_ROWS), (unsigned)(B * 3)), gv(nblk, (unsigned)(B * 3));

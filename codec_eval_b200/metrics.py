@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import weakref
 import math
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -222,9 +223,12 @@ class GpuMetrics:
             raise CudaError(f"ce_ctx_create failed ({st}): {self._L.ce_last_error(None).decode()}")
         self._h = h
         self.device = device
+        self._refs = weakref.WeakSet()   # live GpuReference handles: closed with the context
 
     def close(self):
         if getattr(self, "_h", None):
+            for r in list(getattr(self, "_refs", ())):
+                r.close()
             self._L.ce_ctx_destroy(self._h)
             self._h = None
 
@@ -262,8 +266,8 @@ class GpuMetrics:
         self._L.ce_profile_report(self._h, buf, n + 1)
         rows = {}
         for line in buf.value.decode().splitlines():
-            name, launches, ms, nbytes = line.split("\t")
-            rows[name] = {"launches": int(launches), "ms": float(ms), "bytes": float(nbytes)}
+            name, launches, ms, nbytes, nbytes_pp = line.split("\t")
+            rows[name] = {"launches": int(launches), "ms": float(ms), "bytes": float(nbytes), "bytes_per_pair": float(nbytes_pp)}
         return rows
 
     def _raise(self, st: int, metric: str, expected=None, actual=None):
@@ -365,16 +369,37 @@ class GpuMetrics:
         n = len(pairs)
         arr = (_lib.CePair * max(n, 1))()
         keep = []
+        ref_ids = {}   # pairs that hand over the same reference buffer share a ref_id (= one upload, one pre-processing)
         for i, (r, t, w, h) in enumerate(pairs):
             r, t = _as_u8(r), _as_u8(t)
             keep.append((r, t))
-            arr[i] = _lib.CePair(r.ctypes.data, t.ctypes.data, r.size, t.size, w, h, i, 0)
+            rid = ref_ids.setdefault(r.ctypes.data, len(ref_ids))
+            arr[i] = _lib.CePair(r.ctypes.data, t.ctypes.data, r.size, t.size, w, h, rid, 0)
+        return self.evaluate_pair_table(arr, n, config, intensity_target)
+
+    def evaluate_pair_table(self, table, n: int, config: MetricConfig, intensity_target: float = 80.0):
+        """A prebuilt ce_pair[n] table (host pointers the caller keeps alive) -> ce_result[n]."""
         out = (_lib.CeResult * max(n, 1))()
         cfg = config._c()
-        st = self._L.ce_evaluate_batch(self._h, arr, n, C.byref(cfg), intensity_target, out)
+        st = self._L.ce_evaluate_batch(self._h, table, n, C.byref(cfg), intensity_target, out)
         if st != _lib.CE_OK:
             self._raise(st, "batch")
         return out
+
+    @staticmethod
+    def _failing_metric(config: MetricConfig, width: int, height: int) -> str:
+        """Name for Error::MetricCalculation.metric of a failed pair: the first enabled metric, in calculate_metrics'
+        order (src/eval/session.rs:437-497), that can fail for these dimensions."""
+        small = width < 8 or height < 8
+        if small and config.ssimulacra2:
+            return "SSIMULACRA2"
+        if small and config.butteraugli:
+            return "Butteraugli"
+        for flag, name in ((config.psnr, "PSNR"), (config.dssim, "DSSIM"), (config.ssimulacra2, "SSIMULACRA2"),
+                           (config.butteraugli, "Butteraugli")):
+            if flag:
+                return name
+        return "batch"
 
     def evaluate_batch(self, pairs, config: MetricConfig, intensity_target: float = 80.0) -> List[MetricResult]:
         """Batched calculate_metrics (src/eval/session.rs:437-497).  Raises the first per-pair error,
@@ -384,10 +409,27 @@ class GpuMetrics:
         for i, (r, t, w, h) in enumerate(pairs):
             if out[i].status != _lib.CE_OK:
                 tsz = np.asarray(t).size
-                self._raise(out[i].status, "SSIMULACRA2" if config.ssimulacra2 else "Butteraugli", (w, h),
-                            (tsz // 3 // max(h, 1), h))
+                self._raise(out[i].status, self._failing_metric(config, w, h), (w, h), (tsz // 3 // max(h, 1), h))
             res.append(_result_from_c(out[i]))
         return res
+
+    def sub_batch_capacity(self, config: MetricConfig, width: int, height: int) -> int:
+        """Pairs of this size one sub-batch holds in the workspace (ce_sub_batch_capacity)."""
+        out = C.c_size_t()
+        cfg = config._c()
+        self._raise(self._L.ce_sub_batch_capacity(self._h, C.byref(cfg), width, height, C.byref(out)), "batch")
+        return int(out.value)
+
+    # -- pinned host memory (opt-in; include/ce_gpu.h "pinned host memory")
+    def host_register(self, array: np.ndarray) -> None:
+        """Page-lock an existing contiguous array (cudaHostRegister) so its copies run asynchronously at PCIe rate."""
+        a = np.asarray(array)
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("host_register needs a C-contiguous array")
+        self._raise(self._L.ce_host_register(self._h, C.c_void_p(a.ctypes.data), a.nbytes), "host_register")
+
+    def host_unregister(self, array: np.ndarray) -> None:
+        self._raise(self._L.ce_host_unregister(self._h, C.c_void_p(np.asarray(array).ctypes.data)), "host_unregister")
 
     def evaluate_batch_device(self, d_ref: int, d_dist: int, n: int, width: int, height: int, config: MetricConfig,
                               intensity_target: float = 80.0):
@@ -517,7 +559,7 @@ class GpuMetrics:
             for k in range(n_q):
                 o = out[r * n_q + k]
                 if o.status != _lib.CE_OK:
-                    self._raise(o.status, "SSIMULACRA2" if config.ssimulacra2 else "Butteraugli", (width, height), (width, height))
+                    self._raise(o.status, self._failing_metric(config, width, height), (width, height), (width, height))
                 row.append(_result_from_c(o))
             table.append(row)
         return table
@@ -529,12 +571,14 @@ class GpuReference:
 
     def __init__(self, ctx: GpuMetrics, reference, width: int, height: int, config: MetricConfig):
         self._ctx = ctx
+        self._config = config
         r = _as_u8(reference)
         h = C.c_void_p()
         cfg = config._c()
         st = ctx._L.ce_reference_create(ctx._h, r.ctypes.data, r.size, width, height, C.byref(cfg), C.byref(h))
         ctx._raise(st, "SSIMULACRA2")
         self._h, self.width, self.height = h, width, height
+        ctx._refs.add(self)
 
     def compare(self, test, intensity_target: float = 80.0) -> MetricResult:
         return self.compare_many([test], intensity_target)[0]
@@ -549,7 +593,7 @@ class GpuReference:
         self._ctx._raise(st, "batch")
         res = []
         for i in range(n):
-            self._ctx._raise(out[i].status, "SSIMULACRA2", (self.width, self.height),
+            self._ctx._raise(out[i].status, self._ctx._failing_metric(self._config, self.width, self.height), (self.width, self.height),
                              (ts[i].size // 3 // max(self.height, 1), self.height))
             res.append(_result_from_c(out[i]))
         return res

@@ -15,6 +15,7 @@ from __future__ import annotations
 import csv
 import datetime as _dt
 import json
+import math
 import os
 import time
 from dataclasses import dataclass, field
@@ -114,10 +115,17 @@ class CodecResult:
             "codec_id": self.codec_id, "codec_version": self.codec_version, "quality": float(self.quality),
             "file_size": self.file_size, "bits_per_pixel": self.bits_per_pixel,
             "encode_time": int(self.encode_time * 1000), "decode_time": None if self.decode_time is None else int(self.decode_time * 1000),
-            "metrics": {"dssim": m.dssim, "ssimulacra2": m.ssimulacra2, "butteraugli": m.butteraugli, "psnr": m.psnr},
+            # serde_json writes a non-finite f64 as null (PSNR of identical images is +inf, src/metrics/mod.rs:326-328);
+            # Python's bare `Infinity` token is not JSON and the reference's reader rejects it
+            "metrics": {"dssim": _json_f64(m.dssim), "ssimulacra2": _json_f64(m.ssimulacra2),
+                        "butteraugli": _json_f64(m.butteraugli), "psnr": _json_f64(m.psnr)},
             "perception": None if self.perception is None else self.perception.name,
             "cached_path": self.cached_path, "codec_params": dict(self.codec_params),
         }
+
+
+def _json_f64(v: Optional[float]) -> Optional[float]:
+    return None if v is None or not math.isfinite(v) else v
 
 
 def _now() -> str:
@@ -311,12 +319,12 @@ class EvalSession:
     def write_image_report(self, report: ImageReport) -> None:
         os.makedirs(self.config.report_dir, exist_ok=True)
         with open(os.path.join(self.config.report_dir, f"{report.name}.json"), "w") as f:
-            json.dump(report.to_json(), f, indent=2)
+            json.dump(report.to_json(), f, indent=2, allow_nan=False)
 
     def write_corpus_report(self, report: CorpusReport) -> None:
         os.makedirs(self.config.report_dir, exist_ok=True)
         with open(os.path.join(self.config.report_dir, f"{report.name}.json"), "w") as f:
-            json.dump(report.to_json(), f, indent=2)
+            json.dump(report.to_json(), f, indent=2, allow_nan=False)
         self.write_csv_summary(report, os.path.join(self.config.report_dir, f"{report.name}.csv"))
 
     @staticmethod

@@ -88,15 +88,76 @@ def gather_results(local_rows: np.ndarray, shards: List[List[int]], device=None)
     return table
 
 
-def evaluate_sharded(ctx, pairs: Sequence[Tuple[np.ndarray, np.ndarray, int, int]], ref_ids: Sequence[int], config,
-                     intensity_target: float = 80.0, device=None):
-    """Each rank evaluates its shard on its own GPU context `ctx`; returns ce_result[n_total] on every rank."""
+def _world_rank():
     import torch.distributed as dist
 
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def evaluate_sharded(ctx, pairs: Sequence[Tuple[np.ndarray, np.ndarray, int, int]], ref_ids: Sequence[int], config,
+                     intensity_target: float = 80.0, device=None):
+    """Each rank evaluates its shard on its own GPU context `ctx`; returns ce_result[n_total] on every rank.
+    Host pairs of any mix of sizes (ce_evaluate_batch groups them by size)."""
+    world, rank = _world_rank()
     shards = partition_pairs(ref_ids, [p[2] * p[3] for p in pairs], world)
     mine = [pairs[i] for i in shards[rank]]
     out = ctx.evaluate_batch_raw(mine, config, intensity_target)
     rows = results_to_bytes(out, len(mine))
     return bytes_to_results(gather_results(rows, shards, device=device))
+
+
+def evaluate_sharded_table(ctx, shards: List[List[int]], table, config, intensity_target: float = 80.0, device=None):
+    """Same, for a caller that already holds its shard as a ce_pair table (host pointers it keeps alive): `table` is
+    ce_pair[len(shards[rank])] in the order of shards[rank].  Returns the uint8 [n_total, 56] result table."""
+    world, rank = _world_rank()
+    n = len(shards[rank])
+    out = ctx.evaluate_pair_table(table, n, config, intensity_target)
+    return gather_results(results_to_bytes(out, n), shards, device=device)
+
+
+def evaluate_sharded_resident(ctx, shards: List[List[int]], d_ref: int, n_ref: int, d_dist: int, ref_index, width: int,
+                              height: int, config, intensity_target: float = 80.0, device=None):
+    """Same, for a shard that is already resident in this rank's HBM (what an on-device decoder produces): n_ref
+    reference images at d_ref, len(shards[rank]) distorted images at d_dist (raw device pointers, tight RGB8,
+    uniform size), pair i compares reference ref_index[i].  Returns the uint8 [n_total, 56] result table."""
+    world, rank = _world_rank()
+    n = len(shards[rank])
+    out = ctx.evaluate_batch_device_grouped(d_ref, n_ref, d_dist, n, ref_index, width, height, config, intensity_target)
+    return gather_results(results_to_bytes(out, n), shards, device=device)
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Before a rank allocates its pinned staging memory: restrict the process to the CPUs of its GPU's NUMA node
+    (intersected with the CPUs it is allowed to use), so page-locked buffers are first-touched next to the PCIe root
+    the copies go through.  Best effort -- containers often expose one node only; returns what it did."""
+    import os
+
+    info = {"bound": False}
+    try:
+        import torch
+
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(f"{base}/numa_node") as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(f"{base}/local_cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                if not part:
+                    continue
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info["local_cpus"] = len(cpus)
+        info["allowed_cpus"] = len(allowed)
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+            info["cpus"] = len(use)
+    except Exception as e:   # no sysfs entry, no permission: run unbound
+        info["error"] = repr(e)[:120]
+    return info

@@ -20,6 +20,18 @@ def G(seed: int, w: int, h: int) -> np.ndarray:
     return np.clip(v, 0, 255).astype(np.uint8)
 
 
+def G_many(seeds, w: int, h: int) -> np.ndarray:
+    """[len(seeds), h, w, 3] uint8, image k bit-identical to G(seeds[k], w, h): the deterministic pattern is formed once,
+    only the noise differs per seed."""
+    y, x, c = np.meshgrid(np.arange(h), np.arange(w), np.arange(3), indexing="ij")
+    base = 128.0 + 90.0 * np.sin(x / 23.0 + c) * np.cos(y / 31.0 - c) + 40.0 * (((x // 32) + (y // 32)) & 1)
+    out = np.empty((len(seeds), h, w, 3), np.uint8)
+    for k, seed in enumerate(seeds):
+        v = base + np.random.default_rng(int(seed)).normal(0.0, 6.0, size=(h, w, 3))
+        out[k] = np.clip(v, 0, 255).astype(np.uint8)
+    return out
+
+
 def J(img: np.ndarray, quality: int, subsampling: int = 2) -> np.ndarray:
     """Pillow JPEG round trip; subsampling 2 = 4:2:0, 0 = 4:4:4."""
     from PIL import Image

@@ -49,7 +49,10 @@ typedef struct {
  * (src/metrics/ssimulacra2.rs:41-44).  ref_len/dist_len are the slice lengths
  * the Rust caller holds (they drive the same validation, in the same order,
  * as ssimulacra2.rs:65-82).  ref_id groups pairs that share a reference
- * (evaluate_image's codecs x quality_levels, src/eval/session.rs:375-431). */
+ * (evaluate_image's codecs x quality_levels, src/eval/session.rs:375-431):
+ * pairs of one call whose `ref` pointer AND `ref_id` are both equal are
+ * treated as one reference image, uploaded and pre-processed once.  Give
+ * every pair its own ref_id (or its own buffer) to switch that off. */
 typedef struct {
     const uint8_t* ref;
     const uint8_t* dist;
@@ -88,10 +91,27 @@ CE_API int ce_ctx_set_stream(ce_ctx* ctx, void* cuda_stream);
 CE_API const char* ce_last_error(const ce_ctx* ctx);
 /* number of this library's kernels launched on ctx since creation */
 CE_API uint64_t ce_launch_count(const ce_ctx* ctx);
+/* "ce_gpu <version> (sm_100a) src:<hash>": the hash covers csrc/ and this header as they were when the
+ * library was built (codec_eval_b200/build.py); the Python loader refuses a library whose hash differs
+ * from the sources beside it. */
 CE_API const char* ce_version(void);
+
+/* ---- pinned host memory (opt-in) -------------------------------------- */
+/* The Rust caller holds decoded images in pageable Vec<u8> (src/eval/session.rs:394).  ce_evaluate_batch
+ * accepts those as they are -- the copy of chunk k+1 then blocks the calling thread under the kernels of
+ * chunk k -- but page-locked buffers copy at full PCIe rate and fully asynchronously.  Two ways to opt in:
+ * register an existing allocation (cudaHostRegister; the decode buffers of a session, once), or let the
+ * library allocate a pinned ring the decoder writes into. */
+CE_API int ce_host_register(ce_ctx* ctx, void* ptr, size_t bytes);
+CE_API int ce_host_unregister(ce_ctx* ctx, void* ptr);
+CE_API int ce_host_alloc(ce_ctx* ctx, size_t bytes, void** out);
+CE_API void ce_host_free(ce_ctx* ctx, void* ptr);
 /* opt-in per-kernel CUDA-event timing on the context's stream (bench.py's roofline evidence).
- * report: one line per kernel "name\tlaunches\tmilliseconds\talgorithmic_bytes\n"; returns the
- * length needed.  Durations are collected when a batch call synchronises. */
+ * report: one line per kernel "name\tlaunches\tmilliseconds\talgorithmic_bytes\tbytes_per_pair\n"; returns
+ * the length needed.  algorithmic_bytes counts each distinct input element and each output element once
+ * (planes of a reference shared by several pairs once per reference); bytes_per_pair charges those shared
+ * planes once per pair (the figure for batches without reference reuse).  Durations are collected when a
+ * batch call synchronises. */
 CE_API int ce_profile_enable(ce_ctx* ctx, int enable);
 CE_API int ce_profile_reset(ce_ctx* ctx);
 CE_API size_t ce_profile_report(ce_ctx* ctx, char* buf, size_t cap);
@@ -106,6 +126,11 @@ CE_API size_t ce_profile_report(ce_ctx* ctx, char* buf, size_t cap);
  * the return value is CE_OK unless the call itself could not run. */
 CE_API int ce_evaluate_batch(ce_ctx* ctx, const ce_pair* pairs, size_t n, const ce_metric_config* cfg,
                              float intensity_target, ce_result* out);
+
+/* How many pairs of this size and metric set one sub-batch holds in the context's workspace (larger batches
+ * are processed as several sub-batches; callers that stream a corpus can size their calls to a multiple of it).
+ * CE_ERR_OUT_OF_MEMORY when not even one pair fits. */
+CE_API int ce_sub_batch_capacity(ce_ctx* ctx, const ce_metric_config* cfg, uint32_t width, uint32_t height, size_t* pairs);
 
 /* Same computation for a uniform-size batch already resident in device memory:
  * d_ref / d_dist hold n tightly packed RGB8 images of width x height (the

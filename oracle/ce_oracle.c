@@ -110,8 +110,11 @@ CEO_API double ceo_psnr_from_sse(uint64_t sse, size_t w, size_t h) {
  * ulp from the correctly rounded value for ~11% of inputs).  The oracle
  * pins the platform-independent definition: the correctly rounded result,
  * obtained by evaluating in double and rounding once. */
-static inline float cr_cbrtf(float v) { return (float)cbrt((double)v); }
-static inline float cr_powf(float v, float e) { return (float)pow((double)v, (double)e); }
+/* g_xyb_libm (tests only, ceo_xyb_roundtrip_libm): call this platform's cbrtf / powf instead -- what the Rust
+ * reference itself executes on a glibc host -- so a test can count how many output bytes the choice moves. */
+static __thread int g_xyb_libm = 0;
+static inline float cr_cbrtf(float v) { return g_xyb_libm ? cbrtf(v) : (float)cbrt((double)v); }
+static inline float cr_powf(float v, float e) { return g_xyb_libm ? powf(v, e) : (float)pow((double)v, (double)e); }
 
 static const float XYB_M[9] = {0.30f, 0.622f, 0.078f, 0.23f, 0.692f, 0.078f,
                                0.24342269f, 0.20476744f, 0.55180987f};  /* xyb.rs:33-43 */
@@ -183,6 +186,13 @@ CEO_API void ceo_xyb_roundtrip(const uint8_t* rgb, size_t w, size_t h, uint8_t* 
     }
 }
 
+/* the same round trip through the platform libm's cbrtf / powf (src/metrics/xyb.rs:60-100 as Rust runs it on glibc) */
+CEO_API void ceo_xyb_roundtrip_libm(const uint8_t* rgb, size_t w, size_t h, uint8_t* out) {
+    g_xyb_libm = 1;
+    ceo_xyb_roundtrip(rgb, w, h, out);
+    g_xyb_libm = 0;
+}
+
 /* ------------------------------------------------------------------ */
 /* helpers: planar fp32 images                                         */
 /* ------------------------------------------------------------------ */
@@ -206,25 +216,25 @@ static void rgb8_to_linear_planes(const uint8_t* rgb, size_t n, float* r, float*
 /*     == fast-ssim2 0.8.0; call site src/metrics/ssimulacra2.rs:96)   */
 /* ------------------------------------------------------------------ */
 
-/* Division-free fp32 cube root for x > 0 (normal): two Newton steps on
- * y = x^(-1/3) from a bit-level seed, r = x*y*y, one correction step.
- * Max error 0.77 ulp over [0.0035, 1.2] (the range of the opsin mix).
- * The CUDA path executes the same operation sequence. */
+/* Cube root of the opsin mix.  fast-ssim2 0.8.0 depends on yuvxyb 0.5.0 and yuvxyb-math 0.1.1 (Cargo.lock:410-421,
+ * 1310-1330), the crates rust-av's `ssimulacra2` takes its linear RGB -> XYB conversion from (CHANGELOG.md:43:
+ * "identical results").  Their cbrtf is the FreeBSD msun / musl s_cbrtf.c algorithm without the special cases: a
+ * bit-level seed, then two Halley steps t <- t (2x + t^3) / (x + 2 t^3) in double ("to 16 bits", "to 47 bits"),
+ * rounded once to float.  Checked exhaustively over every float in [0.0035, 1.3] (71,370,277 values): the result is
+ * the correctly rounded cube root for all of them.  (Round 1 used a cheaper 0.77-ulp fp32 sequence of its own here;
+ * that differed from this in 9 % of the values and moved the score by up to 0.016 at 768x512 / q90.)
+ * The CUDA path reaches the same value with an fp32 sequence whose last Newton step uses an error-free residual
+ * (ce_common.cuh cbrt_pos: differs from this in 349 of the 71,370,277 values, by one ulp). */
 static inline float ce_cbrtf(float x) {
-    uint32_t i = 0x54a2fa8cu - asu(x) / 3u;
-    float y = asf(i);
-    float c = x * 0.33333334f;
-    float t = y * y;
-    float u = c * y;
-    y = y * fmaf(-u, t, 1.3333334f);
-    t = y * y;
-    u = c * y;
-    y = y * fmaf(-u, t, 1.3333334f);
-    t = y * y;
-    float r = x * t;
-    float e = fmaf(r * r, r, -x);
-    r = fmaf(-(e * 0.33333334f), t, r);
-    return r;
+    const uint32_t B1 = 709958130u; /* (127 - 127.0/3 - 0.03306235651) * 2^23 */
+    uint32_t hx = (asu(x) & 0x7fffffffu) / 3u + B1;
+    double t = (double)asf((asu(x) & 0x80000000u) | hx);
+    const double xd = (double)x;
+    double r = t * t * t;
+    t = t * (xd + xd + r) / (xd + r + r);
+    r = t * t * t;
+    t = t * (xd + xd + r) / (xd + r + r);
+    return (float)t;
 }
 
 CEO_API float ceo_cbrtf(float x) { return ce_cbrtf(x); }

@@ -54,6 +54,7 @@ def lib():
         L.ceo_psnr_from_sse.restype = C.c_double
         L.ceo_psnr_from_sse.argtypes = [C.c_uint64, sz, sz]
         L.ceo_xyb_roundtrip.argtypes = [u8p, sz, sz, u8p]
+        L.ceo_xyb_roundtrip_libm.argtypes = [u8p, sz, sz, u8p]
         L.ceo_ssimulacra2.argtypes = [u8p, u8p, sz, sz, f64p]
         L.ceo_ssimulacra2_ex.argtypes = [u8p, u8p, sz, sz, f64p, f64p, C.POINTER(C.c_int)]
         L.ceo_ssimulacra2_scale0_planes.argtypes = [u8p, u8p, sz, sz, f32p]
@@ -132,6 +133,15 @@ def xyb_roundtrip(rgb, w, h) -> np.ndarray:
     assert r.size == w * h * 3
     out = np.empty(w * h * 3, np.uint8)
     lib().ceo_xyb_roundtrip(rp, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out
+
+
+def xyb_roundtrip_libm(rgb, w, h) -> np.ndarray:
+    """xyb_roundtrip with this platform's cbrtf / powf (what Rust's f32::cbrt / f32::powf call on a glibc host)."""
+    r, rp = _u8(rgb)
+    assert r.size == w * h * 3
+    out = np.empty(w * h * 3, np.uint8)
+    lib().ceo_xyb_roundtrip_libm(rp, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8)))
     return out
 
 

@@ -45,6 +45,13 @@ extern "C" {
     pub fn ce_last_error(ctx: *const ce_ctx) -> *const c_char;
     pub fn ce_launch_count(ctx: *const ce_ctx) -> u64;
     pub fn ce_version() -> *const c_char;
+    // ---- pinned host memory (opt-in): register the session's decode buffers once, or allocate a pinned ring ----
+    pub fn ce_host_register(ctx: *mut ce_ctx, ptr: *mut c_void, bytes: usize) -> c_int;
+    pub fn ce_host_unregister(ctx: *mut ce_ctx, ptr: *mut c_void) -> c_int;
+    pub fn ce_host_alloc(ctx: *mut ce_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn ce_host_free(ctx: *mut ce_ctx, ptr: *mut c_void);
+    pub fn ce_sub_batch_capacity(ctx: *mut ce_ctx, cfg: *const ce_metric_config, width: u32, height: u32,
+                                 pairs: *mut usize) -> c_int;
     pub fn ce_evaluate_batch(ctx: *mut ce_ctx, pairs: *const ce_pair, n: usize, cfg: *const ce_metric_config,
                              intensity_target: f32, out: *mut ce_result) -> c_int;
     pub fn ce_evaluate_batch_device_grouped(ctx: *mut ce_ctx, d_ref: *const u8, n_ref: usize, d_dist: *const u8, n: usize,

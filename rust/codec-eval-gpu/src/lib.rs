@@ -40,9 +40,14 @@ impl GpuMetrics {
     /// Batched `calculate_metrics` (src/eval/session.rs:437-497).  Pairs that borrow the same reference slice are
     /// grouped inside the library: the reference is uploaded and pre-processed once.
     pub fn evaluate_batch(&mut self, pairs: &[(&[u8], &[u8], u32, u32)], cfg: &MetricConfig) -> Vec<Result<MetricResult>> {
-        let c_pairs: Vec<sys::ce_pair> = pairs.iter().enumerate().map(|(i, (r, t, w, h))| sys::ce_pair {
-            reference: r.as_ptr(), dist: t.as_ptr(), ref_len: r.len(), dist_len: t.len(),
-            width: *w, height: *h, ref_id: i as u32, reserved: 0,
+        // pairs that borrow the same reference slice get the same ref_id: the library treats equal (pointer, ref_id)
+        // as ONE reference image
+        let mut ids: std::collections::HashMap<*const u8, u32> = std::collections::HashMap::new();
+        let c_pairs: Vec<sys::ce_pair> = pairs.iter().map(|(r, t, w, h)| {
+            let next = ids.len() as u32;
+            let ref_id = *ids.entry(r.as_ptr()).or_insert(next);
+            sys::ce_pair { reference: r.as_ptr(), dist: t.as_ptr(), ref_len: r.len(), dist_len: t.len(),
+                           width: *w, height: *h, ref_id, reserved: 0 }
         }).collect();
         let c_cfg = sys::ce_metric_config {
             dssim: cfg.dssim as u8, ssimulacra2: cfg.ssimulacra2 as u8, butteraugli: cfg.butteraugli as u8,
@@ -81,6 +86,91 @@ impl GpuMetrics {
     }
 }
 
+impl GpuMetrics {
+    /// `calculate_psnr` (src/metrics/mod.rs:312-331): asserts on the lengths like the reference, exact integer SSE on
+    /// the device, `f64::INFINITY` for identical images.
+    pub fn calculate_psnr(&mut self, reference: &[u8], test: &[u8], width: usize, height: usize) -> f64 {
+        assert_eq!(reference.len(), test.len());
+        assert_eq!(reference.len(), width * height * 3);
+        let (mut psnr, mut sse) = (0.0f64, 0u64);
+        let st = unsafe { sys::ce_psnr(self.ctx, reference.as_ptr(), reference.len(), test.as_ptr(), test.len(), width, height, &mut psnr, &mut sse) };
+        assert_eq!(st, sys::CE_OK, "ce_psnr: {}", self.last_error());
+        psnr
+    }
+
+    /// `rgb8_to_dssim_image` x2 + `calculate_dssim` (src/metrics/dssim.rs:102-114,40-71) as EvalSession calls them
+    /// (src/eval/session.rs:467-476), fused on the device.
+    pub fn calculate_dssim_rgb8(&mut self, reference: &[u8], test: &[u8], width: usize, height: usize) -> Result<f64> {
+        let mut d = 0.0f64;
+        let st = unsafe { sys::ce_dssim_rgb8(self.ctx, reference.as_ptr(), reference.len(), test.as_ptr(), test.len(), width, height, &mut d) };
+        self.status_to_result(st, "DSSIM", d, width, height, test.len())
+    }
+
+    /// `calculate_dssim` (src/metrics/dssim.rs:40-71) on linear RGBA f32 images (`ImgVec<RGBA<f32>>` as flat
+    /// `[r, g, b, a]` floats; strides in pixels).
+    pub fn calculate_dssim(&mut self, reference: &[f32], ref_size: (usize, usize), ref_stride: usize, test: &[f32],
+                           test_size: (usize, usize), test_stride: usize) -> Result<f64> {
+        if ref_size != test_size {                                       // src/metrics/dssim.rs:45-50
+            return Err(Error::DimensionMismatch { expected: ref_size, actual: test_size });
+        }
+        let need = |stride: usize, (w, h): (usize, usize)| if h == 0 { 0 } else { (stride * (h - 1) + w) * 4 };
+        if ref_stride < ref_size.0 || test_stride < test_size.0 || reference.len() < need(ref_stride, ref_size)
+            || test.len() < need(test_stride, test_size) {
+            return Err(Error::MetricCalculation { metric: "DSSIM".into(), reason: "Failed to create reference image".into() });
+        }
+        let mut d = 0.0f64;
+        let st = unsafe {
+            sys::ce_dssim_rgbaf32(self.ctx, reference.as_ptr(), ref_size.0, ref_size.1, ref_stride, test.as_ptr(), test_size.0,
+                                  test_size.1, test_stride, &mut d)
+        };
+        self.status_to_result(st, "DSSIM", d, ref_size.0, ref_size.1, test_size.0 * test_size.1 * 3)
+    }
+
+    /// `calculate_butteraugli` (src/metrics/butteraugli.rs:45-81): intensity target 80 nits.
+    pub fn calculate_butteraugli(&mut self, reference: &[u8], test: &[u8], width: usize, height: usize) -> Result<f64> {
+        self.calculate_butteraugli_with_intensity(reference, test, width, height, 80.0)
+    }
+
+    /// `calculate_butteraugli_with_intensity` (src/metrics/butteraugli.rs:99-136).
+    pub fn calculate_butteraugli_with_intensity(&mut self, reference: &[u8], test: &[u8], width: usize, height: usize,
+                                                intensity_target: f32) -> Result<f64> {
+        let mut score = 0.0f64;
+        let st = unsafe {
+            sys::ce_butteraugli(self.ctx, reference.as_ptr(), reference.len(), test.as_ptr(), test.len(), width, height,
+                                intensity_target, &mut score, std::ptr::null_mut())
+        };
+        self.status_to_result(st, "Butteraugli", score, width, height, test.len())
+    }
+
+    /// `xyb_roundtrip` (src/metrics/xyb.rs:225-253).
+    pub fn xyb_roundtrip(&mut self, rgb: &[u8], width: usize, height: usize) -> Vec<u8> {
+        assert_eq!(rgb.len(), width * height * 3, "Buffer size mismatch");
+        let mut out = vec![0u8; rgb.len()];
+        let st = unsafe { sys::ce_xyb_roundtrip(self.ctx, rgb.as_ptr(), rgb.len(), width, height, out.as_mut_ptr()) };
+        assert_eq!(st, sys::CE_OK, "ce_xyb_roundtrip: {}", self.last_error());
+        out
+    }
+
+    /// Page-lock a decode buffer the session keeps (cudaHostRegister): its copies then run asynchronously at PCIe rate.
+    /// The slice must stay allocated (and not be reallocated) until `host_unregister`.
+    pub fn host_register(&mut self, buf: &mut [u8]) -> Result<()> {
+        let st = unsafe { sys::ce_host_register(self.ctx, buf.as_mut_ptr() as *mut std::ffi::c_void, buf.len()) };
+        self.status_to_result(st, "GPU", (), 0, 0, 0)
+    }
+    pub fn host_unregister(&mut self, buf: &mut [u8]) -> Result<()> {
+        let st = unsafe { sys::ce_host_unregister(self.ctx, buf.as_mut_ptr() as *mut std::ffi::c_void) };
+        self.status_to_result(st, "GPU", (), 0, 0, 0)
+    }
+
+    fn status_to_result<T>(&self, st: i32, metric: &str, value: T, width: usize, height: usize, test_len: usize) -> Result<T> {
+        match st {
+            sys::CE_OK => Ok(value),
+            sys::CE_ERR_DIMENSION_MISMATCH => Err(Error::DimensionMismatch { expected: (width, height), actual: (test_len / 3 / height.max(1), height) }),
+            _ => Err(Error::MetricCalculation { metric: metric.into(), reason: self.last_error() }),
+        }
+    }
+}
+
 impl Drop for GpuMetrics {
     fn drop(&mut self) { unsafe { sys::ce_ctx_destroy(self.ctx) } }
 }
@@ -112,6 +202,17 @@ impl GpuMetrics {
     /// JPEG(`qualities[k]`) round trip.  Only the references are uploaded.  `subsampling`: 0 = 4:4:4, 2 = 4:2:0.
     pub fn evaluate_jpeg_sweep(&mut self, refs: &[&[u8]], width: u32, height: u32, qualities: &[i32], subsampling: i32,
                                cfg: &MetricConfig) -> Result<Vec<Vec<MetricResult>>> {
+        // the C side reads width*height*3 bytes from every pointer: a short slice must never reach it
+        let need = (width as usize).checked_mul(height as usize).and_then(|n| n.checked_mul(3));
+        for r in refs {
+            if need != Some(r.len()) {
+                return Err(Error::DimensionMismatch { expected: (width as usize, height as usize),
+                                                      actual: (r.len() / 3 / (height as usize).max(1), height as usize) });
+            }
+        }
+        if qualities.len() > 32 {
+            return Err(Error::MetricCalculation { metric: "JPEG".into(), reason: "at most 32 quality levels per call".into() });
+        }
         let ptrs: Vec<*const u8> = refs.iter().map(|r| r.as_ptr()).collect();
         let c_cfg = sys::ce_metric_config {
             dssim: cfg.dssim as u8, ssimulacra2: cfg.ssimulacra2 as u8, butteraugli: cfg.butteraugli as u8,

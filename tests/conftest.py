@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The library under test must be the build of the sources in the tree (content hash in ce_version()): rebuild a
+    stale one before any test maps it (dlopen would keep serving the old mapping to the whole session)."""
+    from codec_eval_b200 import build
+
+    try:
+        build.ensure_built()
+    except Exception as e:   # no nvcc: the tests that load the library then fail loudly on their own
+        sys.stderr.write(f"conftest: could not (re)build libce_gpu.so: {e}\n")
+
+
 @pytest.fixture(scope="session")
 def O():
     """The CPU oracle (test infrastructure)."""

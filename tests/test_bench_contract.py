@@ -32,6 +32,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["steps"] == 1 and d["warmup"] >= 3          # the timing rules ask for at least 3 warm-up steps
     assert "workload" in d["config"] and "model" not in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.corpus_config(1) and d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -85,9 +89,33 @@ def test_single_pair_latency_leg_with_a_stand_in_context():
             self.calls.append(("ssimulacra2", r.shape, t.shape, w, h))
             return 70.0
 
+        def evaluate_batch(self, pairs, cfg):
+            self.calls.append(("batch", len(pairs), cfg.psnr and cfg.dssim and cfg.ssimulacra2 and not cfg.butteraugli))
+            return [None]
+
     c = Ctx()
     out = bench.single_pair_latency(c, reps=4)
-    assert [k[0] for k in c.calls[:3]] == ["psnr", "dssim", "ssimulacra2"]      # the order of calculate_metrics
-    assert len(c.calls) == 3 * (4 + 3) and c.calls[0][1:] == ((512, 512, 3), (512, 512, 3), 512, 512)
-    assert set(out["ms"]) == {"psnr", "dssim", "ssimulacra2"} and out["reps"] == 4
-    assert out["ms_per_pair"] >= 0 and out["mpix_pairs_per_sec"] > 0 and "configs[0]" in out["workload"]
+    assert [k[0] for k in c.calls[:4]] == ["psnr", "dssim", "ssimulacra2", "batch"]      # the order of calculate_metrics
+    assert len(c.calls) == 4 * (4 + 3) and c.calls[0][1:] == ((512, 512, 3), (512, 512, 3), 512, 512)
+    assert c.calls[3] == ("batch", 1, True)
+    assert out["reps"] == 4 and out["ms_psnr"] >= 0 and out["ms_dssim"] >= 0 and out["ms_ssimulacra2"] >= 0
+    assert out["ms_per_pair"] >= 0 and out["ms_one_batch_call"] >= 0 and out["mpix_pairs_per_sec"] > 0 and "cfg1" in out["what"]
+
+
+def test_both_arms_describe_the_same_config():
+    """The driver compares the two arms' `config` dicts: they come from one function, and the corpus layout the GPU arm
+    shards is the one the CPU arm samples (group-major, quality-minor; ragged shards at 8 ranks)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    c1, c8 = bench.corpus_config(1), bench.corpus_config(8)
+    assert c1["pairs"] == 10000 and c1["width"] == c1["height"] == 1024 and "cfg5" in c1["workload"]
+    assert {k: v for k, v in c1.items() if k != "parallelism"} == {k: v for k, v in c8.items() if k != "parallelism"}
+    assert all(len(str(v)) <= 120 for v in c1.values())      # the driver's record truncates longer strings
+    for world in (1, 2, 8):
+        ref_ids, shards = bench.corpus_layout(world)
+        assert sorted(i for s in shards for i in s) == list(range(10000))
+        assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 8
+        for s in shards:                                       # a reference group never straddles two ranks
+            assert len(s) % 8 == 0 and len({int(ref_ids[i]) for i in s}) == len(s) // 8
+    assert len({len(s) for s in bench.corpus_layout(8)[1]}) == 2       # 1250 groups over 8 ranks: 157 / 156 -> ragged

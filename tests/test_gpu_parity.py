@@ -539,16 +539,160 @@ def test_repeated_runs_are_bit_identical_with_all_metrics_sharing_the_sms(gpu):
     perceptual metrics run on separate streams, so their kernels share SMs and the load/store queues are congested.
     A bulk copy that overtakes a pending shared-memory load showed up as a Butteraugli score that changed in ~1 of 3
     runs at this size before the proxy fences were added."""
-    from codec_eval_b200.metrics import MetricConfig
+    from codec_eval_b200.metrics import GpuMetrics, MetricConfig
 
     w, h = 3840, 2160
     ref = G(9, w, h)
     pairs = [(ref, cheap_distort(ref, 50 + 7 * i, seed=i), w, h) for i in range(2)]
     cfg = MetricConfig.all()
-    first = None
-    for rep in range(20):
-        out = gpu.evaluate_batch_raw(pairs, cfg)
-        cur = [(o.status, o.sse, o.dssim, o.ssimulacra2, o.butteraugli, o.butteraugli_pnorm3) for o in out[:2]]
-        if first is None:
-            first = cur
-        assert cur == first, (rep, cur, first)
+    serial = gpu.evaluate_batch_raw(pairs, cfg)        # 16.6 MPix-pairs: above the fork threshold, metrics back to back
+    want = [(o.status, o.sse, o.dssim, o.ssimulacra2, o.butteraugli, o.butteraugli_pnorm3) for o in serial[:2]]
+    os.environ["CE_FORK"] = "1"                        # read at context creation: always fork
+    try:
+        forked = GpuMetrics(0, workspace_bytes=12 << 30)
+    finally:
+        del os.environ["CE_FORK"]
+    try:
+        for rep in range(20):
+            out = forked.evaluate_batch_raw(pairs, cfg)
+            cur = [(o.status, o.sse, o.dssim, o.ssimulacra2, o.butteraugli, o.butteraugli_pnorm3) for o in out[:2]]
+            assert cur == want, (rep, cur, want)       # and forked == serial, bit for bit
+    finally:
+        forked.close()
+
+
+# ------------------------------------------------------------------ JPEG-distorted full sizes (what the bench times)
+@pytest.mark.parametrize("w,h,q,ss", [(768, 512, 75, 2), (768, 512, 90, 0), (1024, 1024, 50, 2), (1024, 1024, 95, 2),
+                                      (3840, 2160, 85, 2)])
+def test_jpeg_distorted_full_sizes_all_metrics_vs_oracle(gpu, O, w, h, q, ss):
+    """BASELINE.json's shapes with the distortion the benchmark uses (baseline JPEG, 4:2:0 and 4:4:4, low and high
+    quality) rather than the codec-free stand-in: all four metrics, 4K included, at the contract tolerances."""
+    from codec_eval_b200.metrics import MetricConfig
+
+    ref = G(w + q, w, h)
+    dist = O.jpeg_roundtrip(ref, w, h, q, ss)
+    assert np.array_equal(gpu.jpeg_roundtrip(ref, w, h, q, ss), dist)      # the on-device source makes the same image
+    r = gpu.evaluate_batch([(ref, dist, w, h)], MetricConfig.all())[0]
+    e = O.evaluate_batch(ref[None], dist[None], w, h, 15, threads=0)[0]
+    assert r.sse == e.sse and r.psnr == e.psnr
+    assert abs(r.ssimulacra2 - e.ssimulacra2) < S2_TOL, (r.ssimulacra2, e.ssimulacra2)
+    assert rel(r.dssim, e.dssim) < DS_RTOL, (r.dssim, e.dssim)
+    assert rel(r.butteraugli, e.butteraugli) < BA_RTOL and rel(r.butteraugli_pnorm3, e.butteraugli_pnorm3) < BA_RTOL
+    print(f"{w}x{h} q{q}: d_ssim2 {abs(r.ssimulacra2 - e.ssimulacra2):.2e} rel_dssim {rel(r.dssim, e.dssim):.2e} "
+          f"rel_ba {rel(r.butteraugli, e.butteraugli):.2e}")
+
+
+def test_ssim2_xyb_planes_follow_the_reference_cube_root(gpu, O):
+    """The XYB planes of the GPU path against the oracle's (whose cbrtf restates yuvxyb-math's, i.e. is correctly
+    rounded): the device's fp32-only sequence may differ by one ulp in ~5 values per million, never more."""
+    w, h = 512, 512
+    ref = G(77, w, h)
+    dist = O.jpeg_roundtrip(ref, w, h, 90, 0)
+    got = np.empty((3, 7, h, w), np.float32)
+    import ctypes as C
+
+    st = gpu._L.ce_debug_ssim2_scale0_planes(gpu._h, ref.ctypes.data, dist.ctypes.data, w, h, got.ctypes.data)
+    assert st == 0
+    exp = O.ssimulacra2_scale0_planes(ref, dist, w, h)
+    for c in range(3):
+        for k in (0, 1):     # i1, i2: pointwise colour conversion only
+            a, b = got[c, k], np.asarray(exp)[c, k]
+            assert np.abs(a - b).max() <= 2.4e-7 * 2, (c, k)         # <= 1 ulp of values < 2
+            assert (a != b).mean() < 1e-4, (c, k, (a != b).mean())
+
+
+# ------------------------------------------------------------------ host-side pipeline of ce_evaluate_batch
+def test_reference_sharing_needs_equal_pointer_and_ref_id(gpu):
+    """ce_pair.ref_id: pairs share a reference when pointer AND ref_id are equal; a different ref_id on the same buffer
+    only switches the sharing off (two uploads) -- the scores are the same bits either way."""
+    import ctypes as C
+
+    from codec_eval_b200 import _lib
+    from codec_eval_b200.metrics import MetricConfig
+
+    w, h = 160, 96
+    ref = G(3, w, h)
+    dists = [cheap_distort(ref, q, seed=q) for q in (30, 55, 80, 95)]
+    n = len(dists)
+    cfg = MetricConfig.all()
+
+    def run(ids):
+        tab = (_lib.CePair * n)()
+        for i, d in enumerate(dists):
+            tab[i] = _lib.CePair(ref.ctypes.data, d.ctypes.data, ref.size, d.size, w, h, ids[i], 0)
+        l0 = gpu.launch_count()
+        out = gpu.evaluate_pair_table(tab, n, cfg)
+        return [(o.status, o.sse, o.dssim, o.ssimulacra2, o.butteraugli, o.butteraugli_pnorm3) for o in out[:n]], gpu.launch_count() - l0
+
+    shared, l_shared = run([7, 7, 7, 7])
+    apart, l_apart = run([0, 1, 2, 3])
+    mixed, _ = run([0, 0, 5, 5])
+    assert shared == apart == mixed
+    assert all(s[0] == 0 for s in shared)
+
+
+def test_pageable_registered_and_chunked_host_batches_agree(gpu, O):
+    """The same host batch from pageable arrays, from arrays page-locked with ce_host_register, and through a context
+    whose workspace holds only a few pairs (many chunks: launch chunk k, stage chunk k+1, finish chunk k): identical
+    results in submission order."""
+    from codec_eval_b200.metrics import GpuMetrics, MetricConfig
+
+    w, h = 192, 128
+    refs = [G(40 + i, w, h) for i in range(5)]
+    pairs = []
+    for i, r in enumerate(refs):
+        for q in (35, 60, 85):
+            pairs.append((r, cheap_distort(r, q, seed=i * 7 + q), w, h))
+    cfg = MetricConfig.all()
+    key = lambda o: (o.status, o.valid, o.sse, o.dssim, o.ssimulacra2, o.butteraugli, o.butteraugli_pnorm3)
+    base = [key(o) for o in gpu.evaluate_batch_raw(pairs, cfg)[:len(pairs)]]
+    small = GpuMetrics(0, workspace_bytes=48 << 20)
+    try:
+        cap = small.sub_batch_capacity(cfg, w, h)
+        assert 1 <= cap < len(pairs)                                        # several chunks
+        assert [key(o) for o in small.evaluate_batch_raw(pairs, cfg)[:len(pairs)]] == base
+        big = np.ascontiguousarray(np.stack([p[1] for p in pairs]))       # one allocation, page-locked in place
+        small.host_register(big)
+        try:
+            reg = [(p[0], big[i], w, h) for i, p in enumerate(pairs)]
+            assert [key(o) for o in small.evaluate_batch_raw(reg, cfg)[:len(pairs)]] == base
+        finally:
+            small.host_unregister(big)
+    finally:
+        small.close()
+    assert base[4][2] == O.sse(pairs[4][0], pairs[4][1])
+    assert gpu.sub_batch_capacity(cfg, w, h) > cap
+
+
+def test_reference_handle_outlives_its_context():
+    """ce_reference_destroy after ce_ctx_destroy (Python: `with GpuMetrics() as g: ref = GpuReference(g, ...)` and the
+    handle's finaliser later) must not touch the freed context."""
+    from codec_eval_b200.metrics import GpuMetrics, GpuReference, MetricConfig
+
+    w, h = 64, 48
+    ref = G(1, w, h)
+    with GpuMetrics(0, workspace_bytes=256 << 20) as g:
+        handle = GpuReference(g, ref, w, h, MetricConfig.ssimulacra2_only())
+        assert handle.compare(ref).ssimulacra2 == 100.0
+        raw = handle._h
+    assert handle._h is None           # closed with its context
+    # and the C entry itself tolerates the other order
+    g2 = GpuMetrics(0, workspace_bytes=256 << 20)
+    h2 = GpuReference(g2, ref, w, h, MetricConfig.ssimulacra2_only())
+    keep, h2._h = h2._h, None          # detach from the wrapper so that closing the context does not close it
+    g2._refs.clear()
+    L = g2._L
+    g2.close()
+    L.ce_reference_destroy(keep)
+
+
+def test_failing_pair_is_named_after_the_metric_that_failed(gpu):
+    from codec_eval_b200.metrics import MetricCalculation, MetricConfig
+
+    tiny = np.zeros((4, 4, 3), np.uint8)
+    with pytest.raises(MetricCalculation) as e:
+        gpu.evaluate_batch([(tiny, tiny, 4, 4)], MetricConfig(butteraugli=True, psnr=True))
+    assert e.value.metric == "Butteraugli"
+    with pytest.raises(MetricCalculation) as e:
+        gpu.evaluate_batch([(tiny, tiny, 4, 4)], MetricConfig.all())
+    assert e.value.metric == "SSIMULACRA2"

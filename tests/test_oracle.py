@@ -158,8 +158,8 @@ def test_rgauss_is_9tap_fir(O):
 
 def test_fast_log2_and_cbrt_accuracy(O):
     xs = np.linspace(0.004, 1.2, 20001, dtype=np.float32)
-    c = np.array([O.lib().ceo_cbrtf(float(x)) for x in xs[::20]])
-    assert np.abs(c / np.cbrt(xs[::20].astype(np.float64)) - 1).max() < 2e-7
+    c = np.array([O.lib().ceo_cbrtf(float(x)) for x in xs], np.float32)
+    assert np.array_equal(c, np.cbrt(xs.astype(np.float64)).astype(np.float32))     # correctly rounded, like yuvxyb-math's
     ys = np.geomspace(1e-3, 1e4, 2000).astype(np.float32)
     l2 = np.array([O.lib().ceo_ba_fast_log2f(float(y)) for y in ys])
     assert np.abs(l2 - np.log2(ys.astype(np.float64))).max() < 2e-5
@@ -177,35 +177,21 @@ def test_batch_matches_single(O):
 
 def test_two_restatements_agree(O):
     """the C oracle and an independent numpy restatement written from Appendix A.3 / A.4
-    (oracle/np_restatement.py) must give the same numbers.  DSSIM agrees to the last bit of the pooled sums.
-    SSIMULACRA2 agrees to 1e-9 once both use the same cube root; with numpy's correctly rounded cbrt instead of the
-    oracle's 0.77-ulp Newton cbrt (1-ulp differences in ~8 % of the values) the score moves by up to ~0.012 on images
-    this small -- the size of the 0.01 contract tolerance, i.e. parity with the real crate hinges on its cbrt."""
-    import ctypes as C
-
+    (oracle/np_restatement.py) must give the same numbers.  DSSIM agrees to the last bit of the pooled sums;
+    SSIMULACRA2 to 1e-9 -- both now take the cube root the reference's dependency takes (yuvxyb-math's cbrtf, which is
+    the correctly rounded one: the C oracle restates its double-precision Halley steps, numpy rounds np.cbrt in float64
+    once).  Round 1's own 0.77-ulp fp32 cbrt moved the score by 0.0003 ... 0.016 against this one, more than the 0.01
+    contract at 768x512 / q90, which is why it was replaced."""
     from codec_eval_b200.synth import G, J
     from oracle import np_restatement as N
 
-    L = O.lib()
     cases = [(64, 48, 60), (160, 96, 85), (100, 100, 40), (77, 35, 70), (9, 33, 50)]
-    rounded = N._cbrtf
-
-    def oracle_cbrt(x):
-        x = np.asarray(x, np.float32)
-        return np.array([L.ceo_cbrtf(float(v)) if v > 0 else 0.0 for v in x.reshape(-1)], np.float32).reshape(x.shape)
-
     for w, h, q in cases:
         r = G(w + h, w, h)
         d = J(r, q, 2)
         e_ds, e_s2 = O.dssim(r, d, w, h), O.ssimulacra2(r, d, w, h)
         assert abs(N.dssim(r, d) - e_ds) <= 1e-9 * e_ds, (w, h, q)
-        assert abs(N.ssimulacra2(r, d) - e_s2) < 0.02, (w, h, q)
-        if w * h <= 64 * 48:
-            try:
-                N._cbrtf = oracle_cbrt
-                assert abs(N.ssimulacra2(r, d) - e_s2) < 1e-9, (w, h, q)
-            finally:
-                N._cbrtf = rounded
+        assert abs(N.ssimulacra2(r, d) - e_s2) < 1e-9, (w, h, q)
     same = G(1, 40, 40)
     assert N.ssimulacra2(same, same) == 100.0 and N.dssim(same, same) == 0.0
     # Butteraugli (Appendix A.5): float64-accumulated blurs and an exact log in numpy vs fp32 fused chains and
@@ -277,3 +263,50 @@ def test_plausibility_on_a_photograph(O):
         if prev:
             assert got[0] < prev[0] and got[1] > prev[1] and got[2] > prev[2]
         prev = got
+
+
+def test_two_restatements_agree_at_kodak_size(O):
+    """The same cross-check at a BASELINE size (768x512, JPEG q75 4:2:0 and q90 4:4:4), not only on thumbnails: the
+    numpy restatement (np.cbrt in float64 rounded once, float64 blurs for Butteraugli, exact log) and the C oracle
+    (yuvxyb-math's cbrtf restated, fp32 chains, FastLog2f) give the same SSIMULACRA2 and DSSIM to 1e-9 and the same
+    Butteraugli to 2e-5 relative."""
+    from codec_eval_b200.synth import G, J
+    from oracle import np_restatement as N
+
+    w, h = 768, 512
+    r = G(3, w, h)
+    for q, ss in ((75, 2), (90, 0)):
+        d = J(r, q, ss)
+        e_ds, e_s2 = O.dssim(r, d, w, h), O.ssimulacra2(r, d, w, h)
+        emx, epn = O.butteraugli(r, d, w, h)
+        assert abs(N.dssim(r, d) - e_ds) <= 1e-9 * e_ds
+        assert abs(N.ssimulacra2(r, d) - e_s2) < 1e-9
+        mx, pn = N.butteraugli(r, d)
+        assert abs(mx - emx) <= 2e-5 * emx and abs(pn - epn) <= 2e-5 * epn
+
+
+def test_xyb_roundtrip_libm_choice_moves_few_bytes(O):
+    """The oracle pins xyb_roundtrip (src/metrics/xyb.rs:60-100,225-253) to correctly rounded cbrt / pow; the Rust
+    reference calls the platform libm (glibc cbrtf is off by one ulp for ~11 % of inputs).  Quantified over a lattice of
+    the whole RGB cube: the choice changes about 2 bytes in 100,000 (1102 of 50.3 M over all 2^24 colours).  Where it
+    does, a value sat on a rounding boundary of the 8-bit XYB quantiser (xyb.rs:192-199) and one level of X moves the
+    decoded colour by up to ~22 code values -- so byte-exactness against the crate is a property of the libm, not of the
+    algorithm, and the GPU kernel follows the oracle's platform-independent definition."""
+    g = np.arange(256, dtype=np.uint8)
+    total = flips = worst = 0
+    for r in range(0, 256, 5):
+        cube = np.stack(np.meshgrid(np.array([r], np.uint8), g, g, indexing="ij"), -1).reshape(-1, 3)
+        a = O.xyb_roundtrip(cube, cube.shape[0], 1)
+        b = O.xyb_roundtrip_libm(cube, cube.shape[0], 1)
+        d = np.abs(a.astype(int) - b.astype(int))
+        flips += int((d > 0).sum())
+        total += d.size
+        worst = max(worst, int(d.max()))
+    assert total == 52 * 65536 * 3
+    assert flips / total < 1e-4, (flips, total)
+    assert worst <= 40
+    # the reference's own three tests (xyb.rs:260-301) hold for either choice
+    grey = np.full((4, 4, 3), 128, np.uint8)
+    for fn in (O.xyb_roundtrip, O.xyb_roundtrip_libm):
+        out = fn(grey, 4, 4).reshape(-1, 3).astype(int)
+        assert np.abs(out - 128).max() <= 3

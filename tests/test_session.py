@@ -163,3 +163,18 @@ def test_session_on_gpu_matches_direct_calls(gpu, tmp_path):
     assert_perception_level(pat, pat, PerceptionLevel.Imperceptible, gpu)
     with pytest.raises(QualityBelowThreshold):
         assert_perception_level(pat, bad, PerceptionLevel.Imperceptible, gpu)
+
+
+def test_identical_images_serialise_psnr_as_null_like_serde_json():
+    """PSNR of a lossless result is +inf (src/metrics/mod.rs:326-328).  serde_json writes non-finite f64 as null; a bare
+    `Infinity` token is not JSON and the reference's reader rejects it."""
+    import json
+    import math
+
+    from codec_eval_b200.metrics import MetricResult
+    from codec_eval_b200.session import CodecResult
+
+    r = CodecResult("png", "1.0", 100.0, 1234, 8.0, 0.01, None,
+                    MetricResult(dssim=0.0, ssimulacra2=100.0, butteraugli=0.0, psnr=math.inf), None)
+    text = json.dumps(r.to_json(), allow_nan=False)
+    assert "Infinity" not in text and json.loads(text)["metrics"] == {"dssim": 0.0, "ssimulacra2": 100.0, "butteraugli": 0.0, "psnr": None}

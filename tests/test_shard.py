@@ -72,6 +72,46 @@ def _worker(rank, world, port, q):
             ok &= res[i].sse == exp[i].sse and res[i].ssimulacra2 == exp[i].ssimulacra2
             ok &= res[i].dssim == exp[i].dssim and res[i].butteraugli == exp[i].butteraugli
             ok &= res[i].psnr == exp[i].psnr and res[i].valid == 15
+        # the three sharded entries, over a stand-in context that answers for whatever shard it is handed
+        from codec_eval_b200.shard import evaluate_sharded, evaluate_sharded_resident, evaluate_sharded_table
+
+        class Ctx:
+            def __init__(self):
+                self.seen = []
+
+            def evaluate_batch_raw(self, pairs, config, intensity_target=80.0):
+                self.seen.append(("raw", [int(p[0][0]) for p in pairs]))
+                return _fake_rows([int(p[0][0]) for p in pairs])      # pair i carries its index in its first byte
+
+            def evaluate_pair_table(self, table, n, config, intensity_target=80.0):
+                self.seen.append(("table", n))
+                return _fake_rows([int(table[k]) for k in range(n)])
+
+            def evaluate_batch_device_grouped(self, d_ref, n_ref, d_dist, n, ref_index, w, h, config, intensity_target=80.0):
+                self.seen.append(("resident", n, n_ref, list(ref_index)))
+                return _fake_rows(list(range(d_dist, d_dist + n)))
+
+        fake = Ctx()
+        pairs = [(np.full(3, i, np.uint8), np.full(3, i, np.uint8), int(np.sqrt(px[i])), int(np.sqrt(px[i]))) for i in range(len(ref_ids))]
+        for r3 in (bytes_to_results(np.asarray(t)) if not hasattr(t, "_length_") else t for t in (
+                evaluate_sharded(fake, pairs, ref_ids, None),
+                evaluate_sharded_table(fake, shards, mine, None))):
+            for i in range(len(ref_ids)):
+                ok &= r3[i].sse == exp[i].sse and r3[i].butteraugli == exp[i].butteraugli
+        ok &= fake.seen[0] == ("raw", mine) and fake.seen[1] == ("table", len(mine))
+        # resident: a uniform batch of 9 pairs / 3 references; rank r's shard starts at "device pointer" shards2[r][0]
+        rid2 = [0, 0, 0, 1, 1, 1, 2, 2, 2]
+        shards2 = partition_pairs(rid2, [100] * 9, world)
+        mine2 = shards2[rank]
+        local_refs = sorted({rid2[i] for i in mine2})
+        t2 = evaluate_sharded_resident(fake, shards2, 0, len(local_refs), mine2[0] if mine2 else 0,
+                                       [local_refs.index(rid2[i]) for i in mine2], 10, 10, None)
+        r2 = bytes_to_results(t2)
+        exp2 = _fake_rows(list(range(9)))
+        contiguous = all(s2 == list(range(s2[0], s2[0] + len(s2))) for s2 in shards2 if s2)
+        if contiguous:
+            for i in range(9):
+                ok &= r2[i].sse == exp2[i].sse
         q.put((rank, bool(ok), [len(s) for s in shards]))
     finally:
         dist.destroy_process_group()
