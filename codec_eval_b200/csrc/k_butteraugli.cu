@@ -573,12 +573,13 @@ struct BlurTables {
 #define MT_TH 16
 #define MT_P (MT_TW + 8)
 #define MT_ROWS (MT_TH + 8)
-#define D(dy, dx) win[(dy) + 4][(dx) + 4 + K]
+#define MT_WIN_ROWS 10   // a thread's register window: its 2 output rows + 4 rows of halo above and below
+#define D(dy, dx) win[(dy) + 4 + J][(dx) + 4 + K]
 // The 16 line sums of a pixel share sub-sums (the centre triples of the four principal directions, the pairs
 // next to the centre of the "knight" lines); they are formed once per pixel.  Mathematically the upstream sums;
 // the association differs, i.e. ~1e-7 relative per sum.
-template <int K>
-CE_DEVINL float malta_hf(const float (&win)[9][12]) {  // pixel K of the thread's 4; window rows -4..4, cols -4..7
+template <int K, int J>
+CE_DEVINL float malta_hf(const float (&win)[MT_WIN_ROWS][12]) {  // pixel (row J, column K) of the thread's 2 x 4; window rows -4..5, cols -4..7
     const float c = D(0,0);
     const float V3 = (D(-1,0) + c) + D(1,0), H3 = (D(0,-1) + c) + D(0,1);
     const float D3 = (D(-1,-1) + c) + D(1,1), A3 = (D(-1,1) + c) + D(1,-1);
@@ -620,8 +621,8 @@ CE_DEVINL float malta_hf(const float (&win)[9][12]) {  // pixel K of the thread'
     acc = __fmaf_rn(t, t, acc);
     return acc;
 }
-template <int K>
-CE_DEVINL float malta_lf(const float (&win)[9][12]) {
+template <int K, int J>
+CE_DEVINL float malta_lf(const float (&win)[MT_WIN_ROWS][12]) {
     const float c = D(0,0);
     const float Ia = (c + D(-2,-1)) + D(2,1), Ib = (c + D(-2,1)) + D(2,-1);
     const float Ic = (c + D(-1,-2)) + D(1,2), Id = (c + D(-1,2)) + D(1,-2);
@@ -736,12 +737,15 @@ __global__ void __launch_bounds__(256) k_ba_malta_diff(const float* __restrict__
 }
 
 // grid (tiles_x, ceil(tiles_y / MT_NT), 2B): blockIdx.z = b*2 + C.  diff: [B][2][3][n]; hf: [NI][2][n]; mf: [NI][3][n];
-// ac out: [B][2][n] plane C.  A block walks down MT_NT vertically adjacent 64x16 tiles.  Per tile the three band
-// tiles (+ halo 4, zero outside the image) and the four pointwise inputs of the L2 terms are staged with cp.async
-// into one of two buffers, so the loads of tile t+1 run under the arithmetic of tile t.  Each thread pulls the
-// 9x12 window of its 4 pixels into registers (27 LDS.128 per band) and evaluates the 16 oriented line sums per
-// pixel from there.
+// ac out: [B][2][n] plane C.  A block of 128 threads walks down MT_NT vertically adjacent 64x16 tiles.  Per tile the
+// three band tiles (+ halo 4, zero outside the image) and the four pointwise inputs of the L2 terms are staged by TMA
+// (cp.async for widths TMA cannot describe) into one of two buffers, so the loads of tile t+1 run under the arithmetic
+// of tile t.  A thread owns 4 x 2 pixels: it pulls their 10x12 window into registers (30 LDS.128 per band for 8
+// pixels; round 1's 4 x 1 layout needed 27 for 4 pixels and was bound by shared-memory bandwidth: 81 LDS.128 = 324
+// shared-memory cycles per warp and band set against 234 cycles of FP32 issue) and evaluates the 16 oriented line sums
+// of each pixel from there.
 #define MT_NT 4
+#define MT_THREADS 128
 #define MT_BAND_FLOATS (MT_ROWS * MT_P)
 #define MT_BUF_FLOATS (3 * MT_BAND_FLOATS + 4 * MT_TH * MT_TW)
 #define MT_SMEM (2 * MT_BUF_FLOATS * 4)
@@ -751,11 +755,11 @@ struct MaltaMaps {   // TMA descriptors (used by the TMA variant only): planes a
     CUtensorMap mf;     // [NI*3 planes][h][w]
 };
 template <bool TMA>
-__global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ diff, const float* __restrict__ hf,
-                                                      const float* __restrict__ mf, int w, int h, size_t n, size_t R,
-                                                      const int* __restrict__ ridx,
-                                                      const __grid_constant__ MaltaParams2 prm2,
-                                                      const __grid_constant__ MaltaMaps maps, float* __restrict__ ac) {
+__global__ void __launch_bounds__(MT_THREADS, 3) k_ba_malta(const float* __restrict__ diff, const float* __restrict__ hf,
+                                                             const float* __restrict__ mf, int w, int h, size_t n, size_t R,
+                                                             const int* __restrict__ ridx,
+                                                             const __grid_constant__ MaltaParams2 prm2,
+                                                             const __grid_constant__ MaltaMaps maps, float* __restrict__ ac) {
     extern __shared__ __align__(128) float s_mt[];   // [2 buffers][3 band tiles | hf0 hf1 mf0 mf1 tiles]
     __shared__ __align__(8) unsigned long long s_bar[2];
     const size_t b = blockIdx.z >> 1;
@@ -764,7 +768,7 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
     const int tx0 = blockIdx.x * MT_TW;
     const int tiles_y = (h + MT_TH - 1) / MT_TH;
     const int t_begin = blockIdx.y * MT_NT, nt = min(MT_NT, tiles_y - t_begin);
-    const int g = threadIdx.x & 15, oy = threadIdx.x >> 4;
+    const int g = threadIdx.x & 15, oy = (threadIdx.x >> 4) * 2;   // columns 4g .. 4g+3, rows oy and oy+1 of the tile
     const bool vec = (w & 3) == 0;
     const size_t im0 = (size_t)ridx[b], im1 = R + b;
     const float* e_src[4] = {hf + (im0 * 2 + C) * n, hf + (im1 * 2 + C) * n, mf + (im0 * 3 + C) * n, mf + (im1 * 3 + C) * n};
@@ -792,11 +796,12 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
             const int ty0 = (t_begin + t) * MT_TH;
 #pragma unroll
             for (int bd = 0; bd < 3; bd++)
-                load_tile_async<MT_P / 4, MT_ROWS, 256>(buf + bd * MT_BAND_FLOATS, MT_P, diff + ((size_t)blockIdx.z * 3 + bd) * n, w, h,
-                                                        tx0 - 4, ty0 - 4, vec);
+                load_tile_async<MT_P / 4, MT_ROWS, MT_THREADS>(buf + bd * MT_BAND_FLOATS, MT_P, diff + ((size_t)blockIdx.z * 3 + bd) * n,
+                                                               w, h, tx0 - 4, ty0 - 4, vec);
 #pragma unroll
             for (int e = 0; e < 4; e++)
-                load_tile_async<MT_TW / 4, MT_TH, 256>(buf + 3 * MT_BAND_FLOATS + e * MT_TH * MT_TW, MT_TW, e_src[e], w, h, tx0, ty0, vec);
+                load_tile_async<MT_TW / 4, MT_TH, MT_THREADS>(buf + 3 * MT_BAND_FLOATS + e * MT_TH * MT_TW, MT_TW, e_src[e], w, h, tx0,
+                                                              ty0, vec);
         }
         cp_async_commit();
     };
@@ -820,13 +825,13 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
         }
         const float* buf = s_mt + (t & 1) * MT_BUF_FLOATS;
         const int y = (t_begin + t) * MT_TH + oy;
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float acc[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
 #pragma unroll
         for (int bd = 0; bd < 3; bd++) {
-            float win[9][12];
+            float win[MT_WIN_ROWS][12];
             const float* sb = buf + bd * MT_BAND_FLOATS;
 #pragma unroll
-            for (int r = 0; r < 9; r++) {
+            for (int r = 0; r < MT_WIN_ROWS; r++) {
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
                     const float4 f = *reinterpret_cast<const float4*>(&sb[(oy + r) * MT_P + 4 * g + 4 * q]);
@@ -834,47 +839,56 @@ __global__ void __launch_bounds__(256, 2) k_ba_malta(const float* __restrict__ d
                 }
             }
             if (bd == 0) {
-                acc[0] += malta_hf<0>(win); acc[1] += malta_hf<1>(win); acc[2] += malta_hf<2>(win); acc[3] += malta_hf<3>(win);
+                acc[0][0] += malta_hf<0, 0>(win); acc[0][1] += malta_hf<1, 0>(win); acc[0][2] += malta_hf<2, 0>(win); acc[0][3] += malta_hf<3, 0>(win);
+                acc[1][0] += malta_hf<0, 1>(win); acc[1][1] += malta_hf<1, 1>(win); acc[1][2] += malta_hf<2, 1>(win); acc[1][3] += malta_hf<3, 1>(win);
             } else {
-                acc[0] += malta_lf<0>(win); acc[1] += malta_lf<1>(win); acc[2] += malta_lf<2>(win); acc[3] += malta_lf<3>(win);
+                acc[0][0] += malta_lf<0, 0>(win); acc[0][1] += malta_lf<1, 0>(win); acc[0][2] += malta_lf<2, 0>(win); acc[0][3] += malta_lf<3, 0>(win);
+                acc[1][0] += malta_lf<0, 1>(win); acc[1][1] += malta_lf<1, 1>(win); acc[1][2] += malta_lf<2, 1>(win); acc[1][3] += malta_lf<3, 1>(win);
             }
         }
-        const float* se = buf + 3 * MT_BAND_FLOATS + oy * MT_TW + 4 * g;
-        const float4 a = *reinterpret_cast<const float4*>(se), q = *reinterpret_cast<const float4*>(se + MT_TH * MT_TW);
-        const float4 m = *reinterpret_cast<const float4*>(se + 2 * MT_TH * MT_TW), o4 = *reinterpret_cast<const float4*>(se + 3 * MT_TH * MT_TW);
+        float4 pw[2][4];   // hf(ref), hf(dist), mf(ref), mf(dist) of the thread's two rows
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const float* se = buf + 3 * MT_BAND_FLOATS + (oy + j) * MT_TW + 4 * g;
+#pragma unroll
+            for (int e = 0; e < 4; e++) pw[j][e] = *reinterpret_cast<const float4*>(se + e * MT_TH * MT_TW);
+        }
         if (TMA) fence_proxy_async();
         __syncthreads();   // everyone is done reading buffer t & 1
         issue(t + 2);
-        const float hv0[4] = {a.x, a.y, a.z, a.w}, hv1[4] = {q.x, q.y, q.z, q.w};
-        const float mv0[4] = {m.x, m.y, m.z, m.w}, mv1[4] = {o4.x, o4.y, o4.z, o4.w};
-        float tot[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            // the three L2 products, added after the Malta sums in the upstream order
-            const float v0 = hv0[k], v1 = hv1[k];
-            const float df = v0 - v1;
-            const float l2a = df * df;
-            const float fabs0 = fabsf(v0);
-            const float too_small = 0.4f * fabs0, too_big = fabs0;
-            const float if_neg = v1 > -too_small ? v1 + too_small : (v1 < -too_big ? -v1 - too_big : 0.0f);
-            const float if_pos = v1 < too_small ? too_small - v1 : (v1 > too_big ? v1 - too_big : 0.0f);
-            const float v = v0 < 0.0f ? if_neg : if_pos;
-            const float l2b = v * v;
-            const float dm = mv0[k] - mv1[k];
-            const float l2c = dm * dm;
-            float total = acc[k];
-            total = __fmaf_rn(l2a, prm.l2_hf_gt, total);   // L2DiffAsymmetric on hf
-            total = __fmaf_rn(prm.l2_hf_lt, l2b, total);
-            total = __fmaf_rn(l2c, prm.l2_mf, total);      // L2Diff on mf
-            tot[k] = total;
-        }
-        if (y < h && x < w) {
-            float* o = ac + (b * 2 + C) * n + (size_t)y * w + x;
-            if (vec) *reinterpret_cast<float4*>(o) = make_float4(tot[0], tot[1], tot[2], tot[3]);
-            else {
+        for (int j = 0; j < 2; j++) {
+            const float hv0[4] = {pw[j][0].x, pw[j][0].y, pw[j][0].z, pw[j][0].w}, hv1[4] = {pw[j][1].x, pw[j][1].y, pw[j][1].z, pw[j][1].w};
+            const float mv0[4] = {pw[j][2].x, pw[j][2].y, pw[j][2].z, pw[j][2].w}, mv1[4] = {pw[j][3].x, pw[j][3].y, pw[j][3].z, pw[j][3].w};
+            float tot[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (x + k < w) o[k] = tot[k];
+            for (int k = 0; k < 4; k++) {
+                // the three L2 products, added after the Malta sums in the upstream order
+                const float v0 = hv0[k], v1 = hv1[k];
+                const float df = v0 - v1;
+                const float l2a = df * df;
+                const float fabs0 = fabsf(v0);
+                const float too_small = 0.4f * fabs0, too_big = fabs0;
+                const float if_neg = v1 > -too_small ? v1 + too_small : (v1 < -too_big ? -v1 - too_big : 0.0f);
+                const float if_pos = v1 < too_small ? too_small - v1 : (v1 > too_big ? v1 - too_big : 0.0f);
+                const float v = v0 < 0.0f ? if_neg : if_pos;
+                const float l2b = v * v;
+                const float dm = mv0[k] - mv1[k];
+                const float l2c = dm * dm;
+                float total = acc[j][k];
+                total = __fmaf_rn(l2a, prm.l2_hf_gt, total);   // L2DiffAsymmetric on hf
+                total = __fmaf_rn(prm.l2_hf_lt, l2b, total);
+                total = __fmaf_rn(l2c, prm.l2_mf, total);      // L2Diff on mf
+                tot[k] = total;
+            }
+            if (y + j < h && x < w) {
+                float* o = ac + (b * 2 + C) * n + (size_t)(y + j) * w + x;
+                if (vec) *reinterpret_cast<float4*>(o) = make_float4(tot[0], tot[1], tot[2], tot[3]);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (x + k < w) o[k] = tot[k];
+                }
             }
         }
     }
@@ -1285,10 +1299,10 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
                          tma_plane_map(&maps.mf, L.mf, w, h, NI * 3, MT_TW, MT_TH, 1);
         if (tma)
             CE_LAUNCH_SHARED(c, "k_ba_malta", ((double)B * 48 + (double)R * 16) * n, (double)B * n * 64,
-                      k_ba_malta<true><<<grid, 256, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));
+                      k_ba_malta<true><<<grid, MT_THREADS, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));
         else   // widths that are not a multiple of 4 cannot be described by a tensor map (16-byte row stride): cp.async tiles
             CE_LAUNCH_SHARED(c, "k_ba_malta", ((double)B * 48 + (double)R * 16) * n, (double)B * n * 64,
-                      k_ba_malta<false><<<grid, 256, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));
+                      k_ba_malta<false><<<grid, MT_THREADS, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));
     }
     if (w % 4 == 0)
         CE_LAUNCH_SHARED(c, "k_ba_combine", ((double)B * 32 + (double)R * 20) * n, (double)B * n * 52,
