@@ -524,12 +524,34 @@ def main():
         def step_e2e():
             return shard.evaluate_sharded_table(ctx, shards, tab, all_cfg, device=dev)
 
+        # what the platform gives every rank when all ranks copy at once (pinned -> device, 256 MB x 8): the end-to-end
+        # leg cannot beat resident unless this exceeds the rate the shard needs
+        probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        probe_d.copy_(probe_h, non_blocking=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(8):
+            probe_d.copy_(probe_h, non_blocking=True)
+        p1.record(stream)
+        torch.cuda.synchronize()
+        h2d_gbs = 8 * (256 << 20) / (p0.elapsed_time(p1) / 1e3) / 1e9
+        if world > 1:
+            t = torch.tensor([h2d_gbs], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            h2d_gbs = float(t.item())
+        del probe_h, probe_d
         e2e_ms, e2e_table = timed(step_e2e, args.steps, 2)
         e2e_val = mpix_total * args.steps / (e2e_ms / 1e3)
         same = bool(np.array_equal(e2e_table, table))
         e2e = {"value": e2e_val, "unit": "MPix-pairs/s", "h2d_bytes_per_step": (n_total + CORPUS["groups"]) * img_bytes,
                "d2h_bytes_per_step": n_total * (1 + 108 + 10 + 4) * 8, "ms_per_step": e2e_ms / args.steps,
-               "host_memory": "pinned", "results_identical_to_resident": same}
+               "host_memory": "pinned", "results_identical_to_resident": same,
+               "h2d_gbs_per_gpu_all_ranks_copying": round(h2d_gbs, 2),
+               "h2d_gbs_per_gpu_needed_to_match_resident": round((n_local + n_ref_local) * img_bytes / (ms / args.steps / 1e3) / 1e9, 2)}
         log(f"[rank {rank}] e2e pinned: {e2e_val:.0f} MPix-pairs/s")
         if not args.no_secondary:
             # what the Rust caller holds today: pageable Vec<u8> (src/eval/session.rs:394)
@@ -589,8 +611,12 @@ def main():
             v3, ms3, _ = quick(step3, 15 * 12 * w3 * h3 / 1e6)
             for hd in handles:
                 hd.close()
+            # the same 180 pairs handed over in ONE ce_evaluate_batch call (what the batched run_eval twin does)
+            pairs3 = [(refs3[i], d3[i, k], w3, h3) for i in range(15) for k in range(12)]
+            v3b, ms3b, _ = quick(lambda: ctx.evaluate_batch_raw(pairs3, s2cfg), 15 * 12 * w3 * h3 / 1e6)
             other["cfg3"] = {"what": "cfg3: 15 refs 512x512 x 12 distortions, SSIMULACRA2 only via ce_reference_compare_many, host dists",
-                             "mpix_pairs_per_sec": round(v3, 1), "ms_per_step": round(ms3, 3)}
+                             "mpix_pairs_per_sec": round(v3, 1), "ms_per_step": round(ms3, 3),
+                             "one_batch_call_mpix_pairs_per_sec": round(v3b, 1), "one_batch_call_ms": round(ms3b, 3)}
         except Exception as e:
             other["cfg3"] = {"error": repr(e)[:200]}
         try:    # cfg4: 256 pairs 3840x2160, Butteraugli + DSSIM only, every pair its own reference (no reuse)

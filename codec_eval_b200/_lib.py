@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libce_gpu.so")
+# CE_LIB_PATH: an experiment build made with `python -m codec_eval_b200.build --out <path> -D...` (A/B runs only)
+LIB_PATH = os.environ.get("CE_LIB_PATH") or os.path.join(_HERE, "libce_gpu.so")
+_EXPERIMENT = bool(os.environ.get("CE_LIB_PATH"))
 
 CE_OK = 0
 CE_ERR_DIMENSION_MISMATCH = 1
@@ -72,6 +74,8 @@ def _check_source_hash(version: str):
     want = source_hash()
     if not want or os.environ.get("CE_ALLOW_STALE_LIB") == "1":
         return
+    if _EXPERIMENT:   # same sources, other -D flags: "src:<hash>+<flags>"
+        version = version.split("+", 1)[0]
     got = version.rsplit("src:", 1)[-1] if "src:" in version else "unhashed"
     if got != want:
         raise RuntimeError(f"{LIB_PATH} was built from sources with hash {got}, the tree has {want}: rebuild with "
@@ -83,7 +87,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if os.environ.get("CE_ALLOW_STALE_LIB") != "1" and os.path.isdir(os.path.join(_HERE, "csrc")):
+    if not _EXPERIMENT and os.environ.get("CE_ALLOW_STALE_LIB") != "1" and os.path.isdir(os.path.join(_HERE, "csrc")):
         # the library must be the build of the sources beside it: rebuild when it is missing or stale (nvcc is part of
         # the image on both the CPU and the GPU box); without nvcc this raises -- there is no CPU fallback
         from . import build as _build

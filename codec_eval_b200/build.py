@@ -42,37 +42,40 @@ def needs_build() -> bool:
     return built_hash() != _lib.source_hash()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = None, extra: list = None) -> str:
+    """out / extra: an experiment build (other -D flags) written elsewhere; load it with CE_LIB_PATH=<out>."""
+    if out is None and not force and not needs_build():
         return OUT
     if not os.path.exists(NVCC):
         raise RuntimeError(f"{NVCC} not found: libce_gpu.so cannot be (re)built here and codec_eval_b200 has no CPU fallback")
     from . import _lib
 
-    stamp = ["-DCE_SOURCE_HASH=\"" + _lib.source_hash() + "\""]
+    stamp = ["-DCE_SOURCE_HASH=\"" + _lib.source_hash() + ("+" + ",".join(extra) if extra else "") + "\""] + list(extra or [])
+    tag = ("_" + "".join(ch if ch.isalnum() else "_" for ch in ",".join(extra))) if extra else ""
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = os.path.join(HERE, "build", s.replace(".cu", tag + ".o"))
         cmd = [NVCC] + [f for f in FLAGS if f not in ("-shared",)] + stamp + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     failed = False
     for s, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0:
             failed = True
-            sys.stderr.write(f"nvcc failed on {s}:\n{out}\n")
-        elif verbose or out.strip():
-            sys.stderr.write(out)
+            sys.stderr.write(f"nvcc failed on {s}:\n{log}\n")
+        elif verbose or log.strip():
+            sys.stderr.write(log)
     if failed:
         raise RuntimeError("nvcc build failed")
-    tmp = OUT + f".{os.getpid()}.tmp"
+    dst = out or OUT
+    tmp = dst + f".{os.getpid()}.tmp"
     subprocess.check_call([NVCC] + FLAGS + objs + ["-o", tmp])
-    os.replace(tmp, OUT)
-    return OUT
+    os.replace(tmp, dst)
+    return dst
 
 
 def ensure_built(verbose: bool = False) -> str:
@@ -95,4 +98,6 @@ def ensure_built(verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    _extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out, extra=_extra))

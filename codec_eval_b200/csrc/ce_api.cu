@@ -43,6 +43,25 @@ void Context::ensure_stage(int slot, size_t bytes) {
     CE_CUDA(cudaMalloc(&d_stage[slot], bytes));
     d_stage_bytes[slot] = bytes;
 }
+void Context::ensure_host_stage(int slot, size_t bytes) {
+    if (bytes <= h_stage_bytes[slot]) return;
+    if (h_stage[slot]) CE_CUDA(cudaFreeHost(h_stage[slot]));
+    h_stage[slot] = nullptr;
+    h_stage_bytes[slot] = 0;
+    CE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_stage[slot]), bytes, cudaHostAllocDefault));
+    h_stage_bytes[slot] = bytes;
+}
+
+// true when the driver would have to bounce this host pointer (plain malloc / Vec<u8> memory)
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 void Context::ensure_results(size_t bytes) {
     if (bytes <= h_pinned_bytes) return;
     if (h_pinned) CE_CUDA(cudaFreeHost(h_pinned));
@@ -642,6 +661,7 @@ CE_API void ce_ctx_destroy(ce_ctx* ctx) {
     for (int i = 0; i < 2; i++) {
         if (c.ev_copy[i]) cudaEventDestroy(c.ev_copy[i]);
         if (c.d_stage[i]) cudaFree(c.d_stage[i]);
+        if (c.h_stage[i]) cudaFreeHost(c.h_stage[i]);
     }
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     delete ctx;
@@ -766,6 +786,9 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
     } st[2];
     // Two pairs share a reference image when their `ref` pointer AND their `ref_id` are equal (evaluate_image compares
     // one reference with every codec x quality output, src/eval/session.rs:375-431): it is uploaded and pre-processed once.
+    unsigned staging_threads = 4;   // CE_STAGING_THREADS=0 leaves pageable memory to the driver's own bounce path
+    if (const char* e = getenv("CE_STAGING_THREADS")) staging_threads = (unsigned)std::max(0, atoi(e));
+    staging_threads = std::min<unsigned>(staging_threads, std::max(1u, std::thread::hardware_concurrency()));
     auto same_ref = [&](size_t a, size_t b) { return pairs[a].ref == pairs[b].ref && pairs[a].ref_id == pairs[b].ref_id; };
     for (auto& g : groups) {
         const size_t w = g.first.first, h = g.first.second, img_bytes = w * h * 3;
@@ -822,14 +845,37 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
                 s.ref_of[k] = it->second;
             }
             s.Ru = urefs.size();
-            c.ensure_stage((int)(ci & 1), (s.Ru + s.B) * img_bytes);
+            const size_t slot_bytes = (s.Ru + s.B) * img_bytes;
+            c.ensure_stage((int)(ci & 1), slot_bytes);
             uint8_t* d_ref = c.d_stage[ci & 1];
             uint8_t* d_dist = d_ref + s.Ru * img_bytes;
-            for (size_t r = 0; r < s.Ru; r++)
-                CE_CUDA(cudaMemcpyAsync(d_ref + r * img_bytes, urefs[r], img_bytes, cudaMemcpyHostToDevice, c.copy_stream));
-            for (size_t k = 0; k < s.B; k++)
-                CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, pairs[idx[s.k0 + k]].dist, img_bytes, cudaMemcpyHostToDevice,
-                                        c.copy_stream));
+            // Pageable caller memory (what the Rust side holds today, src/eval/session.rs:394) in a chunk worth the
+            // trouble: gather the images into the slot's pinned twin with a few memcpy threads, then ONE asynchronous
+            // copy.  (The previous user of this pinned slot, chunk ci-2, has completed: its copy was awaited by the
+            // compute stream before chunk ci-2 ran, and chunk ci-2 has been finished.)
+            bool bounce = slot_bytes >= ((size_t)8 << 20) && staging_threads > 0;
+            if (bounce) {
+                bounce = is_pageable(pairs[idx[s.k0]].dist) || is_pageable(urefs[0]);
+                for (size_t k = 1; bounce == false && k < s.B; k += 16) bounce = is_pageable(pairs[idx[s.k0 + k]].dist);
+            }
+            if (bounce) {
+                c.ensure_host_stage((int)(ci & 1), slot_bytes);
+                c.copy_pool.start(staging_threads);
+                uint8_t* hs = c.h_stage[ci & 1];
+                const size_t Ru = s.Ru, k0 = s.k0;
+                const std::function<void(size_t)> job = [&](size_t i) {
+                    const uint8_t* src = i < Ru ? urefs[i] : pairs[idx[k0 + (i - Ru)]].dist;
+                    memcpy(hs + i * img_bytes, src, img_bytes);
+                };
+                c.copy_pool.run(s.Ru + s.B, job);
+                CE_CUDA(cudaMemcpyAsync(d_ref, hs, slot_bytes, cudaMemcpyHostToDevice, c.copy_stream));
+            } else {
+                for (size_t r = 0; r < s.Ru; r++)
+                    CE_CUDA(cudaMemcpyAsync(d_ref + r * img_bytes, urefs[r], img_bytes, cudaMemcpyHostToDevice, c.copy_stream));
+                for (size_t k = 0; k < s.B; k++)
+                    CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, pairs[idx[s.k0 + k]].dist, img_bytes, cudaMemcpyHostToDevice,
+                                            c.copy_stream));
+            }
             CE_CUDA(cudaEventRecord(c.ev_copy[ci & 1], c.copy_stream));
         };
         std::vector<int> local_of;

@@ -6,12 +6,17 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <vector>
 
 #include "../../include/ce_gpu.h"
+#include "ce_copy_pool.h"
 
 namespace ce {
 
@@ -96,6 +101,9 @@ struct Context {
     // double-buffered staging of ce_evaluate_batch: chunk k+1 is copied on copy_stream while chunk k computes
     uint8_t* d_stage[2] = {nullptr, nullptr};
     size_t d_stage_bytes[2] = {0, 0};
+    uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned twins of d_stage, used only for pageable caller memory
+    size_t h_stage_bytes[2] = {0, 0};
+    CopyPool copy_pool;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     int* h_idx = nullptr;         // pinned + device index staging (reference index tables of a sub-batch)
@@ -124,6 +132,7 @@ struct Context {
     void prof_collect();   // call after the stream is synchronised
     void ensure_input(size_t bytes);
     void ensure_stage(int slot, size_t bytes);
+    void ensure_host_stage(int slot, size_t bytes);
     void ensure_results(size_t bytes);
     void ensure_idx(size_t count);
 };

@@ -107,7 +107,7 @@ template <int MODE> struct S2Mode {
     static constexpr int NW = MODE == S2_ALL ? 5 : MODE == S2_REF ? 2 : 3;     // products = warps per block
     static constexpr int NIN = MODE == S2_REF ? 1 : 2;                          // image planes staged by the row pass
     static constexpr int HP_SMEM = (HP_SLOTS * NIN + NW) * HP_ROWS * HP_PITCH * 4;
-    static constexpr int HP_SMEM_TMA = (2 * NIN * 2 * 32 * 32 + NW * HP_ROWS * HP_PITCH) * 4;   // HP_SLOTS_TMA = 2
+    static constexpr int HP_SMEM_TMA = (2 * NIN * (HP_COLS / 32) * 32 * 32 + NW * HP_ROWS * HP_PITCH) * 4;   // HP_SLOTS_TMA = 2
 };
 
 // grid (ceil(h/32), 3*units); block NW warps (product) x 32 lanes (row); unit = pair (S2_ALL, S2_PAIR) or distinct
@@ -123,7 +123,7 @@ template <int MODE> struct S2Mode {
 // TMA variant: a chunk of one plane is two 32-column x 32-row boxes written with the 128-byte swizzle (4 KB each,
 // no padding): lane = row r reads its 16-byte group j at chunk j ^ (r & 7), conflict free.  Plane stride in a slot =
 // HP_TPLANE floats.
-#define HP_TPLANE (2 * 32 * 32)
+#define HP_TPLANE ((HP_COLS / 32) * 32 * 32)
 #define HP_SLOTS_TMA 2
 template <int MODE, bool TMA>
 __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float* __restrict__ xyb, size_t R,
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float*
                 unsigned long long* bar = &s_bar[k % SLOTS];
                 mbar_expect_tx(bar, NIN * PLANE * 4);
 #pragma unroll
-                for (int half = 0; half < 2; half++) {
+                for (int half = 0; half < HP_COLS / 32; half++) {
                     tma_load_3d(slot + half * 1024, &map, k * HP_COLS + 32 * half, row0, (int)pl1, bar);
                     if (NIN == 2) tma_load_3d(slot + PLANE + half * 1024, &map, k * HP_COLS + 32 * half, row0, (int)pl2, bar);
                 }
@@ -390,6 +390,10 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
         cp_async_commit();
     };
 
+    // Pooling in fp64: a sum of fp32 terms in fp64 is exact at these counts and magnitudes, so the pooled sums -- and
+    // with them the score -- do not depend on how rows are dealt over warps, i.e. on the launch mode or the batch a
+    // pair travels in (test_full_size_1024: the same pair alone and inside a shared-reference batch gives the same
+    // bits).  fp32 partials flushed every few rows were measured 4 % faster on this kernel and rejected for that.
     double acc[6] = {0, 0, 0, 0, 0, 0};
     // SSIM / edge terms of row r of batch t (blurred values in s_v[t & 1], image-space rows in slot t % VP_SLOTS)
     auto map_row = [&](int t, int r) {
