@@ -62,17 +62,20 @@ static bool is_pageable(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
+// results of a sub-batch: one device buffer, TWO pinned halves (slot 0 / 1) so that the host can still be evaluating
+// the scores of sub-batch k while sub-batch k+1's copy lands (h_results(slot))
 void Context::ensure_results(size_t bytes) {
-    if (bytes <= h_pinned_bytes) return;
+    if (bytes <= d_results_bytes) return;
     if (h_pinned) CE_CUDA(cudaFreeHost(h_pinned));
     if (d_results) CE_CUDA(cudaFree(d_results));
     h_pinned = nullptr;
     d_results = nullptr;
     h_pinned_bytes = d_results_bytes = 0;
-    size_t cap = std::max<size_t>(bytes, 1 << 20);
-    CE_CUDA(cudaMallocHost(&h_pinned, cap));
+    size_t cap = (std::max<size_t>(bytes, 1 << 20) + 255) & ~size_t(255);
+    CE_CUDA(cudaMallocHost(&h_pinned, 2 * cap));
     CE_CUDA(cudaMalloc(&d_results, cap));
-    h_pinned_bytes = d_results_bytes = cap;
+    h_pinned_bytes = 2 * cap;
+    d_results_bytes = cap;
 }
 
 void Context::ensure_idx(size_t count) {
@@ -316,8 +319,10 @@ static bool fork_metrics(const Context& c, const ce_metric_config& cfg, size_t B
 struct SubBatch {
     size_t p0 = 0, B = 0;
     int s2_ns = 0, ds_ns = 0;
+    int slot = 0;          // pinned result half
     bool small = false;
 };
+static inline char* h_results(Context& c, int slot) { return static_cast<char*>(c.h_pinned) + (size_t)slot * c.d_results_bytes; }
 
 // d_ref: n_ref device images, d_dist: device images (tight RGB8, w x h).  Pair p0 + i compares reference
 // ref_of[p0 + i] (host array; nullptr = identity) with distorted image p0 + i.  Reference-side work of a
@@ -325,16 +330,19 @@ struct SubBatch {
 // crates/codec-iter/src/eval.rs:138-149, generalised to all metrics).  local_of: scratch of n_ref ints, all -1.
 static SubBatch launch_sub_batch(Context& c, const uint8_t* d_ref, const uint8_t* d_dist, const uint32_t* ref_of,
                                  std::vector<int>& local_of, size_t p0, size_t B, size_t w, size_t h,
-                                 const ce_metric_config& cfg, float intensity, const DebugOut* dbg) {
+                                 const ce_metric_config& cfg, float intensity, const DebugOut* dbg, int slot) {
     const size_t npix = w * h, img_bytes = npix * 3;
     SubBatch sb;
     sb.p0 = p0;
     sb.B = B;
     sb.small = (w < 8 || h < 8);
+    sb.slot = slot;
     const bool small = sb.small;
     const bool perceptual = cfg.dssim || cfg.ssimulacra2 || cfg.butteraugli;
     c.arena.reset();
-    c.ensure_results(B * kRawDoubles * 8);
+    // the caller sized the result staging for its largest sub-batch before the first launch: growing it here would
+    // free the pinned half that still holds the previous sub-batch's unread results
+    if (B * kRawDoubles * 8 > c.d_results_bytes) throw CudaError("internal: result staging not sized before launch");
     // ---- index tables of the sub-batch: ridx[B] local reference of each pair, uniq[R] global reference
     // image of each local one, gref[B] global reference image of each pair
     c.ensure_idx(3 * B);
@@ -419,17 +427,23 @@ static SubBatch launch_sub_batch(Context& c, const uint8_t* d_ref, const uint8_t
             throw;
         }
     }
-    CE_CUDA(cudaMemcpyAsync(c.h_pinned, d_raw, B * kRawDoubles * 8, cudaMemcpyDeviceToHost, c.stream));
+    CE_CUDA(cudaMemcpyAsync(h_results(c, slot), d_raw, B * kRawDoubles * 8, cudaMemcpyDeviceToHost, c.stream));
     return sb;
 }
 
-static void finish_sub_batch(Context& c, const SubBatch& sb, size_t w, size_t h, const ce_metric_config& cfg, ce_result* out,
-                             const DebugOut* dbg) {
+// wait for the sub-batch in flight (after this the workspace, the index tables and the device result buffer are free
+// for the next launch; the raw results sit in the sub-batch's pinned half)
+static void wait_sub_batch(Context& c) {
     CE_CUDA(cudaStreamSynchronize(c.stream));
     c.prof_collect();
+}
+
+// host-side score evaluation (fp64) of a sub-batch that has been waited for; may run while the next one computes
+static void finalize_sub_batch(Context& c, const SubBatch& sb, size_t w, size_t h, const ce_metric_config& cfg, ce_result* out,
+                               const DebugOut* dbg) {
     const size_t B = sb.B;
     const bool small = sb.small;
-    const double* h_raw = reinterpret_cast<const double*>(c.h_pinned);
+    const double* h_raw = reinterpret_cast<const double*>(h_results(c, sb.slot));
     const uint64_t* h_sse = reinterpret_cast<const uint64_t*>(h_raw);
     const double* h_s2 = h_raw + B;
     const double* h_ds = h_s2 + B * 108;
@@ -470,10 +484,26 @@ static void run_device_batch(Context& c, const uint8_t* d_ref, size_t n_ref, con
                              ce_result* out, const DebugOut* dbg) {
     const size_t Bmax = sub_batch_capacity(c, cfg, w, h);
     std::vector<int> local_of(ref_of ? n_ref : 0, -1);
-    for (size_t p0 = 0; p0 < n; p0 += Bmax) {
-        const size_t B = std::min(Bmax, n - p0);
-        SubBatch sb = launch_sub_batch(c, d_ref, d_dist, ref_of, local_of, p0, B, w, h, cfg, intensity, dbg);
-        finish_sub_batch(c, sb, w, h, cfg, out, dbg);
+    if (n == 0) return;
+    c.ensure_results(std::min(Bmax, n) * kRawDoubles * 8);
+    // launch k+1 as soon as k has drained, THEN evaluate k's scores on the host: the fp64 finalisation (108-term
+    // polynomial, roots and pow per pair: ~0.5 ms per 262-pair sub-batch) runs under the next sub-batch's kernels
+    int slot = 0;
+    try {
+        SubBatch cur = launch_sub_batch(c, d_ref, d_dist, ref_of, local_of, 0, std::min(Bmax, n), w, h, cfg, intensity, dbg, slot);
+        for (size_t p0 = 0; p0 < n; p0 += Bmax) {
+            wait_sub_batch(c);
+            const SubBatch done = cur;
+            const size_t q0 = p0 + Bmax;
+            if (q0 < n) {
+                slot ^= 1;
+                cur = launch_sub_batch(c, d_ref, d_dist, ref_of, local_of, q0, std::min(Bmax, n - q0), w, h, cfg, intensity, dbg, slot);
+            }
+            finalize_sub_batch(c, done, w, h, cfg, out, dbg);
+        }
+    } catch (...) {
+        cudaStreamSynchronize(c.stream);   // nothing of a failed call may still be running when the next one resets the workspace
+        throw;
     }
 }
 
@@ -795,31 +825,37 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
         const std::vector<size_t>& idx = g.second;
         // The group is cut into chunks of at most one sub-batch (what the workspace holds, and at most 2 GiB of
         // distorted input): chunk k+1 is copied to the device on the copy stream while chunk k computes.  Only the first
-        // chunk's copy is exposed, so it is the small one (1/12 of the group); boundaries prefer the end of a run of
-        // pairs that share a reference.
-        size_t max_chunks = 4;
-        if (const char* e = getenv("CE_HOST_CHUNKS")) max_chunks = std::max<size_t>(1, (size_t)atoi(e));
+        // chunk's copy is exposed, so the chunks ramp up -- 1/12 of the group (at most 1/8 of a sub-batch), then three
+        // times the previous one until the cap -- which keeps every later copy shorter than the compute it hides under.
+        // Boundaries prefer the end of a run of pairs that share a reference.  CE_HOST_CHUNKS=1 disables the cutting.
+        size_t max_chunks = 0;
+        if (const char* e = getenv("CE_HOST_CHUNKS")) max_chunks = (size_t)std::max(0, atoi(e));
         const size_t cap = std::min<size_t>(sub_batch_capacity(c, cfg, w, h), std::max<size_t>(1, ((size_t)2 << 30) / std::max<size_t>(img_bytes, 1)));
         std::vector<size_t> bounds(1, 0);
         {
             const size_t total = idx.size();
-            size_t want = std::min<size_t>(max_chunks, (total + 7) / 8);
-            want = std::max<size_t>(want, (total + cap - 1) / cap);
             auto snap = [&](size_t b) {   // move a boundary to the end of the current same-reference run
                 while (b > 0 && b < total && same_ref(idx[b], idx[b - 1])) b++;
                 return b;
             };
-            if (want > 1) {
-                const size_t first = snap(std::max<size_t>(1, std::min(cap, total / 12)));
-                if (first < total) bounds.push_back(first);
-                const size_t start = bounds.back(), rest = total - start;
-                const size_t parts = std::max<size_t>(want - 1, (rest + cap - 1) / cap);
-                for (size_t k = 1; k < parts; k++) {
-                    const size_t b = snap(start + rest * k / parts);
-                    if (b > bounds.back() && b < total) bounds.push_back(b);
+            if (total >= 16 && max_chunks != 1) {
+                size_t size = std::max<size_t>(1, std::min(std::max<size_t>(1, cap / 8), total / 12));
+                auto snap_down = [&](size_t from, size_t b) {   // the last run boundary in (from, b], or b if there is none
+                    size_t d = b;
+                    while (d > from && d < total && same_ref(idx[d], idx[d - 1])) d--;
+                    return d > from ? d : b;
+                };
+                for (size_t b = 0;;) {
+                    const size_t from = b;
+                    b = snap(from + size);
+                    if (b - from > cap) b = snap_down(from, from + cap);
+                    if (b >= total) break;
+                    bounds.push_back(b);
+                    size = std::min(cap, size * 3);
+                    if (total - b <= size + size / 4) break;   // no tiny tail chunk: the rest goes as one
                 }
             }
-            // enforce the size cap (a snapped boundary may have overshot it)
+            // enforce the size cap (a snapped boundary, or the tail, may have overshot it)
             std::vector<size_t> capped(1, 0);
             for (size_t k = 1; k <= bounds.size(); k++) {
                 const size_t end = k < bounds.size() ? bounds[k] : total;
@@ -879,21 +915,35 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
             CE_CUDA(cudaEventRecord(c.ev_copy[ci & 1], c.copy_stream));
         };
         std::vector<int> local_of;
+        {
+            size_t largest = 0;
+            for (size_t ci = 0; ci < nchunks; ci++) largest = std::max(largest, bounds[ci + 1] - bounds[ci]);
+            c.ensure_results(largest * kRawDoubles * 8);
+        }
+        auto launch = [&](size_t ci) {
+            Staged& s = st[ci & 1];
+            CE_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy[ci & 1], 0));
+            local_of.assign(s.Ru, -1);
+            return launch_sub_batch(c, c.d_stage[ci & 1], c.d_stage[ci & 1] + s.Ru * img_bytes, s.ref_of.data(), local_of, 0, s.B, w, h,
+                                    cfg, intensity, dbg, (int)(ci & 1));
+        };
         try {
+            // Per chunk: [chunk ci is computing] stage ci+1 -> wait for ci -> launch ci+1 -> evaluate ci's scores.
+            // Staging after the launch matters for pageable memory: gathering it (or the driver's own blocking copy)
+            // holds this thread, and that time runs under the kernels of chunk ci.  Staging slot (ci+1)&1 was last
+            // read by chunk ci-1, which has completed.  The host-side score evaluation of ci runs under chunk ci+1.
             stage(0);
+            SubBatch cur = launch(0);
             for (size_t ci = 0; ci < nchunks; ci++) {
-                Staged& s = st[ci & 1];
-                CE_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy[ci & 1], 0));
-                tmp.resize(s.B);
-                local_of.assign(s.Ru, -1);
-                // queue chunk ci, THEN stage chunk ci+1: a copy from pageable memory blocks this thread until the driver
-                // has moved the bytes, and that time now runs under the kernels of chunk ci (pinned or registered buffers
-                // return at once either way).  Slot (ci+1)&1 was last read by chunk ci-1, which has completed.
-                SubBatch sb = launch_sub_batch(c, c.d_stage[ci & 1], c.d_stage[ci & 1] + s.Ru * img_bytes, s.ref_of.data(), local_of, 0,
-                                               s.B, w, h, cfg, intensity, dbg);
+                const Staged& s = st[ci & 1];
+                const size_t k0 = s.k0, B = s.B;
                 if (ci + 1 < nchunks) stage(ci + 1);
-                finish_sub_batch(c, sb, w, h, cfg, tmp.data(), dbg);
-                for (size_t k = 0; k < s.B; k++) out[idx[s.k0 + k]] = tmp[k];
+                wait_sub_batch(c);
+                const SubBatch done = cur;
+                if (ci + 1 < nchunks) cur = launch(ci + 1);
+                tmp.resize(B);
+                finalize_sub_batch(c, done, w, h, cfg, tmp.data(), dbg);
+                for (size_t k = 0; k < B; k++) out[idx[k0 + k]] = tmp[k];
             }
         } catch (...) {
             cudaStreamSynchronize(c.copy_stream);   // no copy may outlive the caller's buffers
