@@ -269,6 +269,15 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float*
     }
 }
 
+// Tried in round 2 and dropped (measurements on the 192-pair batch, block version above = 1.39 ms):
+//   * 32-column chunks (HP_COLS 32: 30 KB per block, 7 blocks / SM instead of 3): 1.89 ms -- twice the block barriers
+//     and half-length inner loops cost more than the occupancy gives;
+//   * one warp per row band running all three products (nine independent chains per thread, no block barrier, 24 KB
+//     per warp): 2.57 ms with a coalescing output stage, 4.16 ms storing each lane's float4 straight to global memory
+//     (32 distinct lines per store instruction).  ncu: 8 warps / SM, 17 % issue-active, the stalls are the shared-memory
+//     loads at the head of every 4-column group (short scoreboard 4.8 per issue) and the wait for the next chunk -- one
+//     warp cannot hide them, three warps sharing a barrier can.
+
 // ------------------------------------------------------------------ vertical pass + maps
 #define VP_COLS 32
 #define VP_BATCH 5

@@ -3,12 +3,12 @@
 
 Input: the CSV log of
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
-      --log-file gpurun_out/launches_raw.csv python bench.py --groups 131 --steps 1 --warmup 3 --no-cpu-baseline \
-      --no-secondary --no-e2e
+      --log-file gpurun_out/launches_raw.csv python bench.py --groups 131 --ncu
 (1048 pairs = 4 sub-batches of 262, the sub-batch size of the full 10,000-pair corpus, so per-launch figures carry
-over).  The run holds 5 identical passes (3 warm-up, 1 timed, 1 per-kernel pass); the LAST pass is kept.
+over).  The run holds PASSES identical passes (--ncu: 1 warm-up + 1; a plain `--steps 1 --warmup 3` run: 5); the LAST
+pass is kept.
 
-  python tools/launch_table.py gpurun_out/launches_raw.csv r2_final [pairs_in_run=1048] [pairs_full=10000]
+  python tools/launch_table.py gpurun_out/launches_raw.csv r2_final [pairs_in_run=1048] [pairs_full=10000] [passes=2]
 
 Writes profiles/<tag>_launches.csv (one row per launch of one pass), prints the per-kernel share table, and records in
 profiles/ncu_traffic.json: DRAM bytes per launch per kernel (keyed like bench.py's kernel table; `roofline.traffic`),
@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 raw, tag = sys.argv[1], sys.argv[2]
 pairs_run = int(sys.argv[3]) if len(sys.argv) > 3 else 1048
 pairs_full = int(sys.argv[4]) if len(sys.argv) > 4 else 10000
-PASSES = 5
+PASSES = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 
 NAMES = {"k_ds_stream<0>": "k_ds_stats<ref>", "k_ds_stream<1>": "k_ds_stats<pair>", "k_ds_blur2<1>": "k_ds_blur2",
          "k_ds_blur2<0>": "k_ds_blur2", "k_ba_combine4": "k_ba_combine", "k_ba_malta<1>": "k_ba_malta", "k_ba_malta<0>": "k_ba_malta",
