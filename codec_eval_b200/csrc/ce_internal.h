@@ -155,7 +155,7 @@ struct Context {
 // TMA descriptor of fp32 planes [nplanes][h][w] as a rank-3 tensor with box (bw, bh, bz) and zero fill outside
 // (cuTensorMapEncodeTiled through the runtime's driver entry point; libcuda is not linked).  False when the shape
 // cannot be described (w % 4 != 0: the row stride must be a multiple of 16 bytes) -- callers then use cp.async tiles.
-bool tma_enabled(int group);   // 0 Malta, 1 SSIMULACRA2 column pass, 2 wide blur, 3 fused 2-D blurs, 4 SSIMULACRA2 row pass, 5 opsin, 6 DSSIM chroma blur
+bool tma_enabled(int group);   // 0 Malta, 1 SSIMULACRA2 column pass, 2 wide blur, 3 fused 2-D blurs, 4 SSIMULACRA2 row pass, 5 opsin, 6 DSSIM chroma blur, 7 DSSIM statistics rows
 // swizzle128: 128-byte swizzle (box rows of exactly 128 bytes; the destination must be 1024-byte aligned): 16-byte chunk j
 // of box row r lands at chunk j ^ (r & 7), which makes lane = row accesses bank-conflict free without padding.
 bool tma_plane_map(CUtensorMap* m, const float* base, size_t w, size_t h, size_t nplanes, unsigned bw, unsigned bh, unsigned bz,

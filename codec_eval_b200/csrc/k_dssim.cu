@@ -181,6 +181,10 @@ __global__ void __launch_bounds__(256) k_ds_blur2(const float* __restrict__ chro
 #define DSS_OUT 60
 #define DSS_PITCH 68     // floats per staged plane row: 2 pad + 64 window columns + 2 pad
 #define DSS_SLOTS 4      // ring depth (three rows in flight ahead of the one being consumed)
+// slot layout (floats): the three plane groups start on 128-byte boundaries so that each can be the destination of one
+// TMA box (68 columns x 1 row x planes):  [ch1 x3 | pad][ch2 x3 | pad][reference statistics x6 | pad]
+#define DSS_OFF_P2 224   // 3 * 68 = 204 floats -> 224 (896 B)
+#define DSS_OFF_ST 448   // (1792 B)
 
 // two-row window of one quantity: a[par] = A(r-2), a[par ^ 1] = A(r-1) for the tick parity par, b = B(r-1).
 // Pushing writes the new A over the oldest one, so with the tick loop unrolled by two no register moves remain.
@@ -207,7 +211,7 @@ template <int MODE>
 struct DsStream {
     static constexpr int NQ = MODE == 0 ? 2 : 3;
     static constexpr int NPL = MODE == 0 ? 3 : 12;   // staged planes per tick: inputs (+ the reference statistics)
-    static constexpr int SLOT = NPL * DSS_PITCH;
+    static constexpr int SLOT = MODE == 0 ? 224 : 864;   // floats per slot (896 B / 3456 B: multiples of 128 B)
     static constexpr unsigned FULL = 0xffffffffu;
 
     DsWin s1[3][NQ], s2[3][NQ];
@@ -275,7 +279,7 @@ struct DsStream {
                     in[0][0] = am; in[0][1] = a12.x; in[0][2] = a12.y; in[0][3] = a3;
                     in[1][0] = am * am; in[1][1] = a12.x * a12.x; in[1][2] = a12.y * a12.y; in[1][3] = a3 * a3;
                 } else {
-                    const float* pb = sl + (3 + c) * DSS_PITCH;
+                    const float* pb = sl + DSS_OFF_P2 + c * DSS_PITCH;
                     const float bm = pb[0], b3 = pb[3];
                     const float2 b12 = *reinterpret_cast<const float2*>(pb + 1);
                     in[0][0] = bm; in[0][1] = b12.x; in[0][2] = b12.y; in[0][3] = b3;
@@ -323,8 +327,8 @@ struct DsStream {
             if (MODE == 0) {
                 if (emit) store_ref(ref_row + (size_t)c * 2 * n, n, o);
             } else {
-                const float2 mu = *reinterpret_cast<const float2*>(sl + (6 + 2 * c) * DSS_PITCH + 1);
-                const float2 ee = *reinterpret_cast<const float2*>(sl + (7 + 2 * c) * DSS_PITCH + 1);
+                const float2 mu = *reinterpret_cast<const float2*>(sl + DSS_OFF_ST + (2 * c) * DSS_PITCH + 1);
+                const float2 ee = *reinterpret_cast<const float2*>(sl + DSS_OFF_ST + (2 * c + 1) * DSS_PITCH + 1);
                 const float rmu[2] = {mu.x, mu.y}, re[2] = {ee.x, ee.y};
                 terms(c, o, rmu, re);
             }
@@ -341,26 +345,40 @@ struct DsStream {
 };
 
 // grid (column strips, row strips, units); block = one warp; unit = distinct reference (MODE 0) or pair (MODE 1)
-template <int MODE>
+// TMA (strips whose 68-column window lies inside the image, widths TMA can describe): lane 0 arms the slot's mbarrier
+// and issues one bulk tensor copy per plane group of the row; the per-lane cp.async path (12 copies and their 64-bit
+// address arithmetic per lane and row, ~10 % of the instruction stream) remains for the two edge strips, whose columns
+// are clamped, and for odd widths.
+struct DsMaps {
+    CUtensorMap img;   // [NI*3 planes][h][w], box (68, 1, 3)
+    CUtensorMap st;    // reference statistics [R*6 planes][h][w], box (68, 1, 6)
+};
+// Two launches per scale: the interior strips 1 .. s_hi (TMA = true: blockIdx.x + 1) and the edge strips 0 and
+// s_hi+1 .. sx-1 (TMA = false: blockIdx.x == 0 -> strip 0, else s_hi + blockIdx.x), so that each variant carries only
+// its own copy code and the interior one none of the clamping.
+template <int MODE, bool TMA>
 __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ img, size_t R, const int* __restrict__ ridx, int w,
                                                    int h, size_t n, int rows_per_strip, float* __restrict__ refstat,
-                                                   float* __restrict__ map, double* __restrict__ partial) {
+                                                   float* __restrict__ map, double* __restrict__ partial, int sx_total, int s_hi,
+                                                   const __grid_constant__ DsMaps maps) {
     typedef DsStream<MODE> S;
     constexpr int NQ = S::NQ;
-    __shared__ __align__(16) float ring[DSS_SLOTS * S::SLOT];
+    __shared__ __align__(128) float ring[DSS_SLOTS * S::SLOT];
+    __shared__ __align__(8) unsigned long long s_bar[TMA ? DSS_SLOTS : 1];
     S st;
     const int lane = threadIdx.x;
-    const int xw = (int)blockIdx.x * DSS_OUT - 2;   // first column of the warp's 64-column window
+    const int strip = TMA ? 1 + (int)blockIdx.x : (blockIdx.x == 0 ? 0 : s_hi + (int)blockIdx.x);
+    const int xw = strip * DSS_OUT - 2;   // first column of the warp's 64-column window
     const int c0 = xw + 2 * lane;                   // this lane's columns c0, c0 + 1 (may lie outside the image)
     const int ys = (int)blockIdx.y * rows_per_strip, ye = min(ys + rows_per_strip, h);
     const size_t b = blockIdx.z;
     const size_t im1 = MODE == 0 ? b : (size_t)ridx[b];   // reference image
     const size_t im2 = R + b;                             // distorted image (pair mode)
     const int cc0 = min(max(c0, 0), w - 1), cc1 = min(max(c0 + 1, 0), w - 1);
-    const bool allvec = (w & 1) == 0 && xw >= 0 && xw + 63 < w;   // warp-uniform: every lane's pair is inside and 8-B aligned
+    const bool allvec = TMA || ((w & 1) == 0 && xw >= 0 && xw + 63 < w);   // warp-uniform: every lane's pair is inside and 8-B aligned
     st.lane = lane; st.c0 = c0; st.w = w;
-    st.v2ok = (w & 1) == 0 && c0 >= 0 && c0 + 1 < w;
-    st.left_edge = xw < 0; st.right_edge = xw + 63 > w - 1;
+    st.v2ok = TMA || ((w & 1) == 0 && c0 >= 0 && c0 + 1 < w);
+    st.left_edge = !TMA && xw < 0; st.right_edge = !TMA && xw + 63 > w - 1;
     st.rsrc = (w - 1 - xw) >> 1; st.rel = (w - 1 - xw) & 1;   // lane / element holding column w-1
     st.st0 = lane >= 1 && lane <= 30 && c0 < w; st.st1 = lane >= 1 && lane <= 30 && c0 + 1 < w;
     st.acc = 0.0;
@@ -383,7 +401,33 @@ __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ 
     const float* p2 = img + im2 * 3 * n;                 // unused in ref mode
     const float* prs = refstat + im1 * 6 * n;            // pair mode: [3][2][n] statistics of the reference
     float* my = ring + 2 + 2 * lane;                     // this lane's two columns of plane 0, slot 0
+    // TMA strips: the whole 68-column window (pads included) lies inside the image, nothing to clamp
+    constexpr bool tma = TMA;
+    if (tma) {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < DSS_SLOTS; i++) mbar_init(&s_bar[i], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
     auto issue = [&](int k) {
+        if (tma) {
+            if (lane == 0 && k < nin) {
+                float* d = ring + (k & (DSS_SLOTS - 1)) * S::SLOT;
+                unsigned long long* bar = &s_bar[k & (DSS_SLOTS - 1)];
+                const int row = min(max(r_lo - 1 + k, 0), h - 1);
+                const int y = ys + k - kfirst;
+                const bool stats = MODE == 1 && k >= kfirst && y < h;
+                mbar_expect_tx(bar, (MODE == 1 ? 2 : 1) * 3 * DSS_PITCH * 4 + (stats ? 6 * DSS_PITCH * 4 : 0));
+                tma_load_3d(d, &maps.img, xw - 2, row, (int)(im1 * 3), bar);
+                if (MODE == 1) {
+                    tma_load_3d(d + DSS_OFF_P2, &maps.img, xw - 2, row, (int)(im2 * 3), bar);
+                    if (stats) tma_load_3d(d + DSS_OFF_ST, &maps.st, xw - 2, min(max(y, 0), h - 1), (int)(im1 * 6), bar);
+                }
+            }
+            return;
+        }
         if (k < nin) {
             float* d = my + (k & (DSS_SLOTS - 1)) * S::SLOT;
             const size_t ro = (size_t)min(max(r_lo - 1 + k, 0), h - 1) * w;
@@ -394,11 +438,11 @@ __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ 
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     cp_async8(d + c * DSS_PITCH, p1 + c * n + ro + c0);
-                    if (MODE == 1) cp_async8(d + (3 + c) * DSS_PITCH, p2 + c * n + ro + c0);
+                    if (MODE == 1) cp_async8(d + DSS_OFF_P2 + c * DSS_PITCH, p2 + c * n + ro + c0);
                 }
                 if (stats) {
 #pragma unroll
-                    for (int j = 0; j < 6; j++) cp_async8(d + (6 + j) * DSS_PITCH, prs + j * n + so + c0);
+                    for (int j = 0; j < 6; j++) cp_async8(d + DSS_OFF_ST + j * DSS_PITCH, prs + j * n + so + c0);
                 }
             } else {
 #pragma unroll
@@ -406,15 +450,15 @@ __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ 
                     cp_async4(d + c * DSS_PITCH, p1 + c * n + ro + cc0, true);
                     cp_async4(d + c * DSS_PITCH + 1, p1 + c * n + ro + cc1, true);
                     if (MODE == 1) {
-                        cp_async4(d + (3 + c) * DSS_PITCH, p2 + c * n + ro + cc0, true);
-                        cp_async4(d + (3 + c) * DSS_PITCH + 1, p2 + c * n + ro + cc1, true);
+                        cp_async4(d + DSS_OFF_P2 + c * DSS_PITCH, p2 + c * n + ro + cc0, true);
+                        cp_async4(d + DSS_OFF_P2 + c * DSS_PITCH + 1, p2 + c * n + ro + cc1, true);
                     }
                 }
                 if (stats) {
 #pragma unroll
                     for (int j = 0; j < 6; j++) {
-                        cp_async4(d + (6 + j) * DSS_PITCH, prs + j * n + so + cc0, true);
-                        cp_async4(d + (6 + j) * DSS_PITCH + 1, prs + j * n + so + cc1, true);
+                        cp_async4(d + DSS_OFF_ST + j * DSS_PITCH, prs + j * n + so + cc0, true);
+                        cp_async4(d + DSS_OFF_ST + j * DSS_PITCH + 1, prs + j * n + so + cc1, true);
                     }
                 }
             }
@@ -431,7 +475,12 @@ __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ 
         for (int par = 0; par < 2; par++) {
             const int kk = k + par;
             if (kk < nin) {   // warp-uniform
-                cp_async_wait<2>();
+                if (tma) {
+                    mbar_wait(&s_bar[kk & (DSS_SLOTS - 1)], (unsigned)(kk / DSS_SLOTS) & 1u);
+                    fence_proxy_async();   // this lane's reads of slot (kk - 1) & 3 precede its refill below
+                } else {
+                    cp_async_wait<2>();
+                }
                 __syncwarp();   // row kk landed for every lane; every lane is past its reads of slot (kk - 1) & 3
                 issue(kk + 3);
                 const int y = ys + kk - kfirst;
@@ -472,7 +521,7 @@ __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ 
     }
     if (MODE == 0) return;
     const double tot = warp_sum(st.acc);
-    if (lane == 0) partial[(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+    if (lane == 0) partial[(b * gridDim.y + blockIdx.y) * sx_total + strip] = tot;
 }
 
 // ------------------------------------------------------------------ Lab (+ next scale)
@@ -652,25 +701,44 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
             else
                 CE_LAUNCH(c, "k_ds_blur2", (double)NI * n * 16, k_ds_blur2<false><<<grid, 256, 0, c.stream>>>(chroma, (int)cw, (int)ch, n, img, mc));
         }
-        // row strips: 64 rows per warp, fewer when the launch would not fill the machine
+        // row strips: 64 rows per warp (128 measured no faster: the 4 window-filling ticks per strip it saves are offset
+        // by the coarser tail), fewer when the launch would not fill the machine
         int rows = 64;
         while (rows > 16 && (size_t)sx * cdiv(ch, rows) * B < (size_t)c.sm_count * 32) rows /= 2;
         const unsigned sy = cdiv(ch, rows);
         const int ntiles = (int)(sx * sy);
+        DsMaps dm;
+        memset(&dm, 0, sizeof(dm));
+        const bool ds_tma = tma_enabled(7) && cw >= 124 && tma_plane_map(&dm.img, img, cw, ch, NI * 3, DSS_PITCH, 1, 3) &&
+                            tma_plane_map(&dm.st, refstat, cw, ch, R * 6, DSS_PITCH, 1, 6);
+        // strips 1 .. s_hi have their 68-column window (60 s - 4 .. 60 s + 63) inside the image; s_hi = 0: none
+        const int s_hi = ds_tma ? std::min<int>((int)sx - 1, ((int)cw - 64) / DSS_OUT) : 0;
+        const unsigned n_edge = sx - (unsigned)s_hi;   // strip 0 and the strips after s_hi
         {
             int rrows = 64;   // the reference launch has R, not B, images to spread over the machine
             while (rrows > 16 && (size_t)sx * cdiv(ch, rrows) * R < (size_t)c.sm_count * 32) rrows /= 2;
-            dim3 grid(sx, cdiv(ch, rrows), (unsigned)R);
-            CE_LAUNCH(c, "k_ds_stats<ref>", (double)R * n * 36,
-                      k_ds_stream<0><<<grid, 32, 0, c.stream>>>(img, R, nullptr, (int)cw, (int)ch, n, rrows, refstat, nullptr, nullptr));
+            const double bytes = (double)R * n * 36;
+            if (s_hi > 0)
+                CE_LAUNCH(c, "k_ds_stats<ref>", bytes * s_hi / sx,
+                          k_ds_stream<0, true><<<dim3((unsigned)s_hi, cdiv(ch, rrows), (unsigned)R), 32, 0, c.stream>>>(
+                              img, R, nullptr, (int)cw, (int)ch, n, rrows, refstat, nullptr, nullptr, (int)sx, s_hi, dm));
+            CE_LAUNCH(c, "k_ds_stats<ref>", bytes * n_edge / sx,
+                      k_ds_stream<0, false><<<dim3(n_edge, cdiv(ch, rrows), (unsigned)R), 32, 0, c.stream>>>(
+                          img, R, nullptr, (int)cw, (int)ch, n, rrows, refstat, nullptr, nullptr, (int)sx, s_hi, dm));
         }
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
-            dim3 grid(sx, sy, nb);
             // per pair: ch2 (12 B) + map out (4 B); per distinct reference: ch1 (12 B) + its statistics (24 B)
-            CE_LAUNCH_SHARED(c, "k_ds_stats<pair>", ((double)nb * 16 + (double)std::min<size_t>(R, nb) * 36) * n, (double)nb * n * 52,
-                      k_ds_stream<1><<<grid, 32, 0, c.stream>>>(img, R + b0, ridx + b0, (int)cw, (int)ch, n, rows, refstat,
-                                                                 map + b0 * n, partial + b0 * ntiles));
+            const double bytes = ((double)nb * 16 + (double)std::min<size_t>(R, nb) * 36) * n, bytes_pp = (double)nb * n * 52;
+            if (s_hi > 0)
+                CE_LAUNCH_SHARED(c, "k_ds_stats<pair>", bytes * s_hi / sx, bytes_pp * s_hi / sx,
+                                 k_ds_stream<1, true><<<dim3((unsigned)s_hi, sy, nb), 32, 0, c.stream>>>(
+                                     img, R + b0, ridx + b0, (int)cw, (int)ch, n, rows, refstat, map + b0 * n, partial + b0 * ntiles,
+                                     (int)sx, s_hi, dm));
+            CE_LAUNCH_SHARED(c, "k_ds_stats<pair>", bytes * n_edge / sx, bytes_pp * n_edge / sx,
+                             k_ds_stream<1, false><<<dim3(n_edge, sy, nb), 32, 0, c.stream>>>(
+                                 img, R + b0, ridx + b0, (int)cw, (int)ch, n, rows, refstat, map + b0 * n, partial + b0 * ntiles,
+                                 (int)sx, s_hi, dm));
         }
         CE_LAUNCH(c, "k_ds_mean", (double)B * (ntiles + 2) * 8,
                   k_ds_mean<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, ntiles, B, n, s, d_out, avg));
