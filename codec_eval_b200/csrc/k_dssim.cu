@@ -248,8 +248,8 @@ struct DsStream {
         for (int e = 0; e < 2; e++) {
             const float mu1_sq = sm11[e] * third, mu2_sq = sm22[e] * third, mu1_mu2 = sm12[e] * third;
             const float sigma1_sq = ss1[e] * third, sigma2_sq = ss2[e] * third, sigma12 = ss12[e] * third;
-            vv[e] = (__fmaf_rn(2.0f, mu1_mu2, c1) * __fmaf_rn(2.0f, sigma12, c2)) /
-                    (((mu1_sq + mu2_sq) + c1) * ((sigma1_sq + sigma2_sq) + c2));
+            vv[e] = div_rn_normal(__fmaf_rn(2.0f, mu1_mu2, c1) * __fmaf_rn(2.0f, sigma12, c2),
+                                  ((mu1_sq + mu2_sq) + c1) * ((sigma1_sq + sigma2_sq) + c2));
         }
         if (!emit) return;
         if (v2ok && st0) {

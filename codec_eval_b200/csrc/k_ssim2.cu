@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
             const float denom_s = ((s11 - m11) + (s22 - m22)) + 0.0009f;
             // IEEE quotient like upstream (a 2-ulp __fdividef here was measured 4.6 % faster on this kernel, 0.1 % on the
             // step, and moved scores by ~2e-5: not taken)
-            const float d = fmaxf(1.0f - (num_m * num_s) / denom_s, 0.0f);   // NaN -> 0 like !(d > 0)
+            const float d = fmaxf(1.0f - div_rn_normal(num_m * num_s, denom_s), 0.0f);   // NaN -> 0 like !(d > 0)
             const float d2 = d * d;
             acc[0] += (double)d;
             acc[1] += (double)(d2 * d2);
