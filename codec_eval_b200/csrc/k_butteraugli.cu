@@ -556,8 +556,8 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
             const float bias = kMul * kBias;
             const float xd = (ux + hx) * 2.5f;
             const float yd = uy * 0.4f + hy * 0.4f;
-            const float vv = sqrtf(xd * xd + yd * yd);
-            out_c[img * n + i] = sqrtf(kMul * fabsf(vv) + bias) - sqrtf(bias);
+            const float vv = sqrt_rn_nonneg(xd * xd + yd * yd);
+            out_c[img * n + i] = sqrt_rn_nonneg(kMul * fabsf(vv) + bias) - sqrtf(bias);
         }
         }
     }
@@ -708,10 +708,10 @@ __global__ void __launch_bounds__(256) k_ba_malta_diff(const float* __restrict__
                                                         const float* __restrict__ mf, size_t n, size_t B, size_t R,
                                                         const int* __restrict__ ridx,
                                                         const __grid_constant__ MaltaParams2 prm2, float* __restrict__ diff) {
+    // grid (blocks over the plane, 2B): blockIdx.y = b*2 + C (a 1-D grid-stride loop needed a 64-bit division per step)
     const size_t per = VEC ? n / 4 : n;
-    const size_t total = B * 2 * per;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t bc = t / per, q = t - bc * per;
+    const size_t bc = blockIdx.y;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < per; q += (size_t)gridDim.x * blockDim.x) {
         const size_t b = bc >> 1;
         const int C = (int)(bc & 1);
         const size_t i = VEC ? q * 4 : q;
@@ -970,10 +970,10 @@ __global__ void __launch_bounds__(256, 3) k_ba_combine4(const float* __restrict_
                                                       float* __restrict__ diffmap) {
     const int S = 3;
     const int w4 = w >> 2;
-    const size_t per = n >> 2, total = B * per;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = t / per;
-        const int q = (int)(t - b * per);
+    // grid (blocks over the plane, B)
+    const int per = (int)(n >> 2);
+    const size_t b = blockIdx.y;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
         const int y = q / w4, x = (q - y * w4) * 4;
         const int i = y * w + x;
         const size_t i0 = (size_t)ridx[b], i1 = R + b;
@@ -1042,7 +1042,7 @@ __global__ void __launch_bounds__(256, 3) k_ba_combine4(const float* __restrict_
             const float maskval = ba_mask_y(mask), dc_maskval = ba_mask_dc_y(mask);
             const float dsum = ((dc0 * xmul) * dc_maskval + dc1 * dc_maskval) + dc2 * dc_maskval;
             const float asum = ((ac0 * xmul) * maskval + ac1 * maskval) + ac2 * maskval;
-            res[k] = sqrtf(dsum + asum);
+            res[k] = sqrt_rn_nonneg(dsum + asum);
         }
         *reinterpret_cast<float4*>(diffmap + b * n + i) = make_float4(res[0], res[1], res[2], res[3]);
     }
@@ -1175,6 +1175,12 @@ static size_t ba_level_floats_per_pair(size_t n) {
 static unsigned ew_blocks(Context& c, size_t total) {
     return (unsigned)std::min<size_t>(cdiv(total, 256), (size_t)c.sm_count * 32);
 }
+// 2-D variant: grid.y = units (pairs or pair-channels), grid.x = blocks of 256 threads striding over `per` items of a unit,
+// about sm_count * 32 blocks in all
+static dim3 ew_grid2(Context& c, size_t per, size_t units) {
+    const size_t want = std::max<size_t>(1, cdiv((size_t)c.sm_count * 32, units));
+    return dim3((unsigned)std::min<size_t>(cdiv(per, 256), want), (unsigned)units);
+}
 
 static void ba_alloc_level(Context& c, size_t NI, size_t B, size_t w, size_t h, BaLevelBufs& L) {
     const size_t n = w * h;
@@ -1292,10 +1298,10 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
         mp.ch[1] = make_malta_params(1, hf_asym);
         if (n % 4 == 0)
             CE_LAUNCH_SHARED(c, "k_ba_malta_diff", ((double)B * 48 + (double)R * 24) * n, (double)B * n * 72,
-                      k_ba_malta_diff<true><<<ew_blocks(c, B * 2 * (n / 4)), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
+                      k_ba_malta_diff<true><<<ew_grid2(c, n / 4, 2 * B), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
         else
             CE_LAUNCH_SHARED(c, "k_ba_malta_diff", ((double)B * 48 + (double)R * 24) * n, (double)B * n * 72,
-                      k_ba_malta_diff<false><<<ew_blocks(c, B * 2 * n), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
+                      k_ba_malta_diff<false><<<ew_grid2(c, n, 2 * B), 256, 0, c.stream>>>(L.uhf, L.hf, L.mf, n, B, R, ridx, mp, L.mdiff));
         dim3 grid(cdiv(w, MT_TW), cdiv(cdiv(h, MT_TH), MT_NT), (unsigned)(2 * B));
         MaltaMaps maps;
         memset(&maps, 0, sizeof(maps));
@@ -1311,7 +1317,7 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
     }
     if (w % 4 == 0)
         CE_LAUNCH_SHARED(c, "k_ba_combine", ((double)B * 32 + (double)R * 20) * n, (double)B * n * 52,
-                  k_ba_combine4<<<ew_blocks(c, B * (n / 4)), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul,
+                  k_ba_combine4<<<ew_grid2(c, n / 4, B), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul,
                                                                                 diffmap));
     else
         CE_LAUNCH_SHARED(c, "k_ba_combine", ((double)B * 32 + (double)R * 20) * n, (double)B * n * 52,
