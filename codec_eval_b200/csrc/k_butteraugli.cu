@@ -1050,12 +1050,14 @@ __global__ void __launch_bounds__(256, 3) k_ba_combine4(const float* __restrict_
 
 // ---------------------------------------------------------------- multi-resolution
 // SubSample2x on linear planes: [np][n] -> [np][on]; ((a+b)+c)+d)*0.25 with the x2 fix-ups
+// grid (blocks over a plane, planes): 32-bit index arithmetic inside a plane
 __global__ void __launch_bounds__(256) k_ba_subsample(const float* __restrict__ in, int w, int h, size_t n, int ow, int oh,
                                                        size_t on, size_t total, float* __restrict__ out) {
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        size_t pl = t / on, i = t - pl * on;
-        int oy = (int)(i / ow), ox = (int)(i - (size_t)oy * ow);
-        const float* p = in + pl * n;
+    const size_t pl = blockIdx.y;
+    const float* p = in + pl * n;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)on; i += gridDim.x * blockDim.x) {
+        const size_t t = pl * on + i;
+        int oy = (int)(i / (unsigned)ow), ox = (int)(i - (unsigned)oy * (unsigned)ow);
         int x0 = 2 * ox, y0 = 2 * oy;
         bool vx = x0 + 1 < w, vy = y0 + 1 < h;
         float s = 0.0f;
@@ -1348,7 +1350,7 @@ void butteraugli_run(Context& c, const float* lin, size_t R, const int* ridx, si
         sub = c.arena.alloc<float>(B * sn);
         size_t total = NI * 3 * sn;
         CE_LAUNCH(c, "k_ba_subsample", (double)total * 20,
-                  k_ba_subsample<<<ew_blocks(c, total), 256, 0, c.stream>>>(lin, (int)w, (int)h, n, (int)sw, (int)sh, sn, total, slin));
+                  k_ba_subsample<<<ew_grid2(c, sn, total / sn), 256, 0, c.stream>>>(lin, (int)w, (int)h, n, (int)sw, (int)sh, sn, total, slin));
         ba_diffmap_level(c, slin, R, ridx, B, sw, sh, intensity, sub);
     }
     for (size_t b0 = 0; b0 < B; b0 += 32768) {
