@@ -264,7 +264,25 @@ struct DsStream {
     // One tick: consume the staged input row (slot), advance the first pass, push the finished first-pass row into
     // the second pass and form the output row.  Straight-line code: during the first ticks of a strip the windows
     // are still filling and the values are meaningless; only the stores and the pooled sum are predicated (emit).
-    template <int PAR>
+    // TMA-staged edge strips: columns outside the image arrived as zeros; give them the value of the nearest inside
+    // column (clamp-replicate), in registers.  Left edge (window starts at column -4): lane 0 holds columns -3 .. 0,
+    // lane 1 columns -1 .. 2.  Right edge: column w-1 sits in lane rsrc, element rel of its pair.
+    CE_DEVINL void patch_edges(float& vm, float& v0, float& v1, float& v2) const {
+        if (left_edge) {
+            if (lane == 0) { vm = v2; v0 = v2; v1 = v2; }
+            else if (lane == 1) vm = v0;
+        }
+        if (right_edge) {
+            const float ve = __shfl_sync(FULL, rel ? v1 : v0, rsrc);
+            const int e = w - 1;
+            if (c0 - 1 > e) vm = ve;
+            if (c0 > e) v0 = ve;
+            if (c0 + 1 > e) v1 = ve;
+            if (c0 + 2 > e) v2 = ve;
+        }
+    }
+
+    template <int PAR, bool PATCH>
     CE_DEVINL void tick(const float* __restrict__ slot, bool emit, float* __restrict__ ref_row, size_t n,
                         float* __restrict__ map_row) {
         const float* sl = slot + 2 * lane + 1;   // column c0 - 1 of plane 0
@@ -273,15 +291,17 @@ struct DsStream {
             float in[NQ][4];
             {
                 const float* pa = sl + c * DSS_PITCH;
-                const float am = pa[0], a3 = pa[3];
-                const float2 a12 = *reinterpret_cast<const float2*>(pa + 1);
+                float am = pa[0], a3 = pa[3];
+                float2 a12 = *reinterpret_cast<const float2*>(pa + 1);
+                if (PATCH) patch_edges(am, a12.x, a12.y, a3);
                 if (MODE == 0) {
                     in[0][0] = am; in[0][1] = a12.x; in[0][2] = a12.y; in[0][3] = a3;
                     in[1][0] = am * am; in[1][1] = a12.x * a12.x; in[1][2] = a12.y * a12.y; in[1][3] = a3 * a3;
                 } else {
                     const float* pb = sl + DSS_OFF_P2 + c * DSS_PITCH;
-                    const float bm = pb[0], b3 = pb[3];
-                    const float2 b12 = *reinterpret_cast<const float2*>(pb + 1);
+                    float bm = pb[0], b3 = pb[3];
+                    float2 b12 = *reinterpret_cast<const float2*>(pb + 1);
+                    if (PATCH) patch_edges(bm, b12.x, b12.y, b3);
                     in[0][0] = bm; in[0][1] = b12.x; in[0][2] = b12.y; in[0][3] = b3;
                     in[1][0] = bm * bm; in[1][1] = b12.x * b12.x; in[1][2] = b12.y * b12.y; in[1][3] = b3 * b3;
                     in[NQ - 1][0] = am * bm; in[NQ - 1][1] = a12.x * b12.x; in[NQ - 1][2] = a12.y * b12.y; in[NQ - 1][3] = a3 * b3;
@@ -353,10 +373,12 @@ struct DsMaps {
     CUtensorMap img;   // [NI*3 planes][h][w], box (68, 1, 3)
     CUtensorMap st;    // reference statistics [R*6 planes][h][w], box (68, 1, 6)
 };
-// Two launches per scale: the interior strips 1 .. s_hi (TMA = true: blockIdx.x + 1) and the edge strips 0 and
-// s_hi+1 .. sx-1 (TMA = false: blockIdx.x == 0 -> strip 0, else s_hi + blockIdx.x), so that each variant carries only
-// its own copy code and the interior one none of the clamping.
-template <int MODE, bool TMA>
+// Two launches per scale when TMA can describe the planes: the interior strips 1 .. s_hi (EDGE = false: blockIdx.x + 1)
+// and the edge strips 0 and s_hi+1 .. sx-1 (EDGE = true: blockIdx.x == 0 -> strip 0, else s_hi + blockIdx.x), so that
+// the interior variant carries none of the clamping; the edge variant fetches the same boxes (columns outside the image
+// arrive as zeros) and patches the clamped columns in registers.  TMA = false: one launch over all strips with per-lane
+// cp.async copies (odd widths, narrow scales).
+template <int MODE, bool TMA, bool EDGE>
 __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ img, size_t R, const int* __restrict__ ridx, int w,
                                                    int h, size_t n, int rows_per_strip, float* __restrict__ refstat,
                                                    float* __restrict__ map, double* __restrict__ partial, int sx_total, int s_hi,
@@ -367,7 +389,7 @@ __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ 
     __shared__ __align__(8) unsigned long long s_bar[TMA ? DSS_SLOTS : 1];
     S st;
     const int lane = threadIdx.x;
-    const int strip = TMA ? 1 + (int)blockIdx.x : (blockIdx.x == 0 ? 0 : s_hi + (int)blockIdx.x);
+    const int strip = (TMA && !EDGE) ? 1 + (int)blockIdx.x : (blockIdx.x == 0 ? 0 : s_hi + (int)blockIdx.x);
     const int xw = strip * DSS_OUT - 2;   // first column of the warp's 64-column window
     const int c0 = xw + 2 * lane;                   // this lane's columns c0, c0 + 1 (may lie outside the image)
     const int ys = (int)blockIdx.y * rows_per_strip, ye = min(ys + rows_per_strip, h);
@@ -375,10 +397,11 @@ __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ 
     const size_t im1 = MODE == 0 ? b : (size_t)ridx[b];   // reference image
     const size_t im2 = R + b;                             // distorted image (pair mode)
     const int cc0 = min(max(c0, 0), w - 1), cc1 = min(max(c0 + 1, 0), w - 1);
+    constexpr bool INTERIOR = TMA && !EDGE;
     const bool allvec = TMA || ((w & 1) == 0 && xw >= 0 && xw + 63 < w);   // warp-uniform: every lane's pair is inside and 8-B aligned
     st.lane = lane; st.c0 = c0; st.w = w;
-    st.v2ok = TMA || ((w & 1) == 0 && c0 >= 0 && c0 + 1 < w);
-    st.left_edge = !TMA && xw < 0; st.right_edge = !TMA && xw + 63 > w - 1;
+    st.v2ok = INTERIOR || ((w & 1) == 0 && c0 >= 0 && c0 + 1 < w);
+    st.left_edge = !INTERIOR && xw < 0; st.right_edge = !INTERIOR && xw + 63 > w - 1;
     st.rsrc = (w - 1 - xw) >> 1; st.rel = (w - 1 - xw) & 1;   // lane / element holding column w-1
     st.st0 = lane >= 1 && lane <= 30 && c0 < w; st.st1 = lane >= 1 && lane <= 30 && c0 + 1 < w;
     st.acc = 0.0;
@@ -489,7 +512,7 @@ __global__ void __launch_bounds__(32, 12) k_ds_stream(const float* __restrict__ 
         const float* slot = ring + (kk & (DSS_SLOTS - 1)) * S::SLOT;
         float* rr = MODE == 0 ? ref_out + (size_t)max(y, 0) * w : nullptr;
         float* mr = MODE == 1 ? map_out + (size_t)max(y, 0) * w : nullptr;
-        st.template tick<PAR>(slot, emit, rr, n, mr);
+        st.template tick<PAR, TMA && EDGE>(slot, emit, rr, n, mr);
         if (PAR == 0 && kk == 2 && ys == 0) st.dup_top();   // tick 2 (parity 0) pushed first-pass row 0
     };
     int k = 0;
@@ -724,25 +747,36 @@ int dssim_run(Context& c, const float* lin_in, const float* alpha_in, size_t R, 
             const double bytes = (double)R * n * 36;
             if (s_hi > 0)
                 CE_LAUNCH(c, "k_ds_stats<ref>", bytes * s_hi / sx,
-                          k_ds_stream<0, true><<<dim3((unsigned)s_hi, cdiv(ch, rrows), (unsigned)R), 32, 0, c.stream>>>(
+                          k_ds_stream<0, true, false><<<dim3((unsigned)s_hi, cdiv(ch, rrows), (unsigned)R), 32, 0, c.stream>>>(
                               img, R, nullptr, (int)cw, (int)ch, n, rrows, refstat, nullptr, nullptr, (int)sx, s_hi, dm));
-            CE_LAUNCH(c, "k_ds_stats<ref>", bytes * n_edge / sx,
-                      k_ds_stream<0, false><<<dim3(n_edge, cdiv(ch, rrows), (unsigned)R), 32, 0, c.stream>>>(
-                          img, R, nullptr, (int)cw, (int)ch, n, rrows, refstat, nullptr, nullptr, (int)sx, s_hi, dm));
+            if (s_hi > 0)
+                CE_LAUNCH(c, "k_ds_stats<ref>", bytes * n_edge / sx,
+                          k_ds_stream<0, true, true><<<dim3(n_edge, cdiv(ch, rrows), (unsigned)R), 32, 0, c.stream>>>(
+                              img, R, nullptr, (int)cw, (int)ch, n, rrows, refstat, nullptr, nullptr, (int)sx, s_hi, dm));
+            else
+                CE_LAUNCH(c, "k_ds_stats<ref>", bytes,
+                          k_ds_stream<0, false, true><<<dim3(sx, cdiv(ch, rrows), (unsigned)R), 32, 0, c.stream>>>(
+                              img, R, nullptr, (int)cw, (int)ch, n, rrows, refstat, nullptr, nullptr, (int)sx, 0, dm));
         }
         for (size_t b0 = 0; b0 < B; b0 += 32768) {
             unsigned nb = (unsigned)std::min<size_t>(32768, B - b0);
             // per pair: ch2 (12 B) + map out (4 B); per distinct reference: ch1 (12 B) + its statistics (24 B)
             const double bytes = ((double)nb * 16 + (double)std::min<size_t>(R, nb) * 36) * n, bytes_pp = (double)nb * n * 52;
-            if (s_hi > 0)
+            if (s_hi > 0) {
                 CE_LAUNCH_SHARED(c, "k_ds_stats<pair>", bytes * s_hi / sx, bytes_pp * s_hi / sx,
-                                 k_ds_stream<1, true><<<dim3((unsigned)s_hi, sy, nb), 32, 0, c.stream>>>(
+                                 k_ds_stream<1, true, false><<<dim3((unsigned)s_hi, sy, nb), 32, 0, c.stream>>>(
                                      img, R + b0, ridx + b0, (int)cw, (int)ch, n, rows, refstat, map + b0 * n, partial + b0 * ntiles,
                                      (int)sx, s_hi, dm));
-            CE_LAUNCH_SHARED(c, "k_ds_stats<pair>", bytes * n_edge / sx, bytes_pp * n_edge / sx,
-                             k_ds_stream<1, false><<<dim3(n_edge, sy, nb), 32, 0, c.stream>>>(
-                                 img, R + b0, ridx + b0, (int)cw, (int)ch, n, rows, refstat, map + b0 * n, partial + b0 * ntiles,
-                                 (int)sx, s_hi, dm));
+                CE_LAUNCH_SHARED(c, "k_ds_stats<pair>", bytes * n_edge / sx, bytes_pp * n_edge / sx,
+                                 k_ds_stream<1, true, true><<<dim3(n_edge, sy, nb), 32, 0, c.stream>>>(
+                                     img, R + b0, ridx + b0, (int)cw, (int)ch, n, rows, refstat, map + b0 * n, partial + b0 * ntiles,
+                                     (int)sx, s_hi, dm));
+            } else {
+                CE_LAUNCH_SHARED(c, "k_ds_stats<pair>", bytes, bytes_pp,
+                                 k_ds_stream<1, false, true><<<dim3(sx, sy, nb), 32, 0, c.stream>>>(
+                                     img, R + b0, ridx + b0, (int)cw, (int)ch, n, rows, refstat, map + b0 * n, partial + b0 * ntiles,
+                                     (int)sx, 0, dm));
+            }
         }
         CE_LAUNCH(c, "k_ds_mean", (double)B * (ntiles + 2) * 8,
                   k_ds_mean<<<cdiv(B, 128), 128, 0, c.stream>>>(partial, ntiles, B, n, s, d_out, avg));
