@@ -47,6 +47,9 @@ for t in ("0", "1"):
 def bench_name(k):
     k = re.sub(r"^void\s+", "", k).replace("ce::", "")
     base = k.split("(")[0].replace("(int)", "").replace("(bool)", "")
+    m = re.match(r"k_ds_stream<(\d), \d, \d>", base)   # interior / edge / cp.async variants: one name, like bench.py
+    if m:
+        return "k_ds_stats<pair>" if m.group(1) == "1" else "k_ds_stats<ref>"
     return NAMES.get(base, base)
 
 
