@@ -825,8 +825,10 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
         const std::vector<size_t>& idx = g.second;
         // The group is cut into chunks of at most one sub-batch (what the workspace holds, and at most 2 GiB of
         // distorted input): chunk k+1 is copied to the device on the copy stream while chunk k computes.  Only the first
-        // chunk's copy is exposed, so the chunks ramp up -- 1/12 of the group (at most 1/8 of a sub-batch), then three
-        // times the previous one until the cap -- which keeps every later copy shorter than the compute it hides under.
+        // chunk's copy is exposed, so the chunks ramp up -- 1/12 of the group (at most 1/8 of a sub-batch), then 1.5 times
+        // the previous one until the cap.  A copy hides under the previous chunk's compute only while the growth factor
+        // stays below (copy rate) / (compute rate): 55 GB/s against 4.5 pairs/ms allows 3.6 on one GPU, but with eight
+        // ranks sharing the host each gets 23 GB/s and the bound is 1.5 (a factor of 3 stalled 27 ms of a 280 ms step).
         // Boundaries prefer the end of a run of pairs that share a reference.  CE_HOST_CHUNKS=1 disables the cutting.
         size_t max_chunks = 0;
         if (const char* e = getenv("CE_HOST_CHUNKS")) max_chunks = (size_t)std::max(0, atoi(e));
@@ -851,7 +853,7 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
                     if (b - from > cap) b = snap_down(from, from + cap);
                     if (b >= total) break;
                     bounds.push_back(b);
-                    size = std::min(cap, size * 3);
+                    size = std::min(cap, size + (size + 1) / 2);
                     if (total - b <= size + size / 4) break;   // no tiny tail chunk: the rest goes as one
                 }
             }
@@ -906,11 +908,22 @@ static void evaluate_host_pairs(Context& c, const ce_pair* pairs, size_t n, cons
                 c.copy_pool.run(s.Ru + s.B, job);
                 CE_CUDA(cudaMemcpyAsync(d_ref, hs, slot_bytes, cudaMemcpyHostToDevice, c.copy_stream));
             } else {
-                for (size_t r = 0; r < s.Ru; r++)
-                    CE_CUDA(cudaMemcpyAsync(d_ref + r * img_bytes, urefs[r], img_bytes, cudaMemcpyHostToDevice, c.copy_stream));
-                for (size_t k = 0; k < s.B; k++)
-                    CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, pairs[idx[s.k0 + k]].dist, img_bytes, cudaMemcpyHostToDevice,
-                                            c.copy_stream));
+                // one copy per image, except that images which follow one another in host memory (a decoder writing
+                // into one arena, the distortions of a sweep) go as ONE copy: with eight ranks sharing the host's memory
+                // system, 3 MB copies reached 14 GB/s per GPU where 25 MB ones reach 24
+                for (size_t r = 0; r < s.Ru;) {
+                    size_t e = r + 1;
+                    while (e < s.Ru && urefs[e] == urefs[e - 1] + img_bytes) e++;
+                    CE_CUDA(cudaMemcpyAsync(d_ref + r * img_bytes, urefs[r], (e - r) * img_bytes, cudaMemcpyHostToDevice, c.copy_stream));
+                    r = e;
+                }
+                for (size_t k = 0; k < s.B;) {
+                    size_t e = k + 1;
+                    while (e < s.B && pairs[idx[s.k0 + e]].dist == pairs[idx[s.k0 + e - 1]].dist + img_bytes) e++;
+                    CE_CUDA(cudaMemcpyAsync(d_dist + k * img_bytes, pairs[idx[s.k0 + k]].dist, (e - k) * img_bytes,
+                                            cudaMemcpyHostToDevice, c.copy_stream));
+                    k = e;
+                }
             }
             CE_CUDA(cudaEventRecord(c.ev_copy[ci & 1], c.copy_stream));
         };
