@@ -677,7 +677,7 @@ CE_DEVINL float malta_diff(float v0, float v1, const MaltaBand& p) {
     float absval = 0.5f * (fabsf(v0) + fabsf(v1));
     float diff = v0 - v1;
     // upstream divides twice by the same denominator; one IEEE reciprocal serves both scalers here (each product is
-    // within an ulp of the quotient the oracle forms; the diffmap moves by ~1e-7 relative, the contract is 1e-3).
+    // within an ulp of the quotient upstream forms; the diffmap moves by ~1e-7 relative, the contract is 1e-3).
     // The kernel was XU / issue bound on the two divisions (47 % XU pipe): 1.11 -> 1.00 ms on the 192-pair batch.
     const float inv = 1.0f / (p.norm1 + absval);
     float scaler = p.norm2_0gt1 * inv;
