@@ -662,6 +662,7 @@ CE_DEVINL float malta_lf(const float (&win)[MT_WIN_ROWS][12]) {
     return acc;
 }
 #undef D
+#include "malta_sums.inc"
 
 
 struct MaltaBand {
@@ -842,6 +843,7 @@ __global__ void __launch_bounds__(MT_THREADS, 3) k_ba_malta(const float* __restr
                     win[r][4 * q] = f.x; win[r][4 * q + 1] = f.y; win[r][4 * q + 2] = f.z; win[r][4 * q + 3] = f.w;
                 }
             }
+#ifdef CE_MALTA_PER_PIXEL
             if (bd == 0) {
                 acc[0][0] += malta_hf<0, 0>(win); acc[0][1] += malta_hf<1, 0>(win); acc[0][2] += malta_hf<2, 0>(win); acc[0][3] += malta_hf<3, 0>(win);
                 acc[1][0] += malta_hf<0, 1>(win); acc[1][1] += malta_hf<1, 1>(win); acc[1][2] += malta_hf<2, 1>(win); acc[1][3] += malta_hf<3, 1>(win);
@@ -849,6 +851,15 @@ __global__ void __launch_bounds__(MT_THREADS, 3) k_ba_malta(const float* __restr
                 acc[0][0] += malta_lf<0, 0>(win); acc[0][1] += malta_lf<1, 0>(win); acc[0][2] += malta_lf<2, 0>(win); acc[0][3] += malta_lf<3, 0>(win);
                 acc[1][0] += malta_lf<0, 1>(win); acc[1][1] += malta_lf<1, 1>(win); acc[1][2] += malta_lf<2, 1>(win); acc[1][3] += malta_lf<3, 1>(win);
             }
+#else
+            float accb[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};   // a band's squares sum from 0, as upstream
+            if (bd == 0) malta_hf8(win, accb);
+            else malta_lf8(win, accb);
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc[j][k] += accb[j][k];
+#endif
         }
         float4 pw[2][4];   // hf(ref), hf(dist), mf(ref), mf(dist) of the thread's two rows
 #pragma unroll
@@ -913,18 +924,15 @@ CE_DEVINL void store_min3(float v, float& m0, float& m1, float& m2) {
     }
 }
 
-// bl: [NI][n] blurred mask inputs; ac: [B][2][n]; mf, lf: [NI][3][n]; diffmap out [B][n]
-__global__ void __launch_bounds__(256) k_ba_combine(const float* __restrict__ bl, const float* __restrict__ ac,
-                                                     const float* __restrict__ mf, const float* __restrict__ lf, int w, int h,
-                                                     size_t n, size_t B, size_t R, const int* __restrict__ ridx, float xmul,
-                                                     float* __restrict__ diffmap) {
-    const size_t total = B * n;
+// The mask (fuzzy erosion of the REFERENCE's blurred mask input, then MaskY / MaskDcY) does not depend on the distorted
+// image: it is formed once per distinct reference of the launch and the per-pair kernel reads the two factors.
+// bl: [NI][n] blurred mask inputs (references first); mask out: [R][2][n] = {MaskY, MaskDcY}.
+__global__ void __launch_bounds__(256) k_ba_mask(const float* __restrict__ bl, int w, int h, size_t n, float* __restrict__ mask) {
     const int S = 3;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        size_t b = t / n, i = t - b * n;
+    const size_t r = blockIdx.y;
+    const float* from = bl + r * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         int y = (int)(i / w), x = (int)(i - (size_t)y * w);
-        const size_t i0 = (size_t)ridx[b], i1 = R + b;
-        const float* from = bl + i0 * n;
         float m0 = from[i], m1 = 2.0f * m0, m2 = m1;
         if (x >= S) {
             store_min3(from[i - S], m0, m1, m2);
@@ -938,9 +946,76 @@ __global__ void __launch_bounds__(256) k_ba_combine(const float* __restrict__ bl
         }
         if (y >= S) store_min3(from[i - (size_t)S * w], m0, m1, m2);
         if (y < h - S) store_min3(from[i + (size_t)S * w], m0, m1, m2);
-        float mask = (0.45f * m0 + 0.3f * m1) + 0.25f * m2;
+        const float mk = (0.45f * m0 + 0.3f * m1) + 0.25f * m2;
+        mask[(r * 2 + 0) * n + i] = ba_mask_y(mk);
+        mask[(r * 2 + 1) * n + i] = ba_mask_dc_y(mk);
+    }
+}
 
-        float dmk = from[i] - bl[i1 * n + i];
+// sorted insert into the three smallest (m0 <= m1 <= m2), branch free: the values store_min3 leaves
+CE_DEVINL void insert_min3(float v, float& m0, float& m1, float& m2) {
+    const float a = fminf(m0, v), v1 = fmaxf(m0, v);
+    const float b = fminf(m1, v1), v2 = fmaxf(m1, v1);
+    m0 = a; m1 = b; m2 = fminf(m2, v2);
+}
+
+// 4 pixels per thread (w % 4 == 0): the 3x3 stride-3 neighbourhood comes from three aligned 128-bit loads per row
+// (columns x-4 .. x+7); positions outside the image hold +inf, which an insert never selects (the blurred mask input
+// is >= 0, so the start triple {c, 2c, 2c} is sorted).
+__global__ void __launch_bounds__(256) k_ba_mask4(const float* __restrict__ bl, int w, int h, size_t n, float* __restrict__ mask) {
+    const int S = 3;
+    const int w4 = w >> 2;
+    const int per = (int)(n >> 2);
+    const size_t r = blockIdx.y;
+    const float* from = bl + r * n;
+    const float inf = __int_as_float(0x7f800000);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
+        const int y = q / w4, x = (q - y * w4) * 4;
+        const int i = y * w + x;
+        float win[3][12];
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+            const int yy = y + (rr - 1) * S;
+            const bool yok = yy >= 0 && yy < h;
+#pragma unroll
+            for (int c4 = 0; c4 < 3; c4++) {
+                const int xx = x - 4 + 4 * c4;
+                float4 v = make_float4(inf, inf, inf, inf);
+                if (yok && xx >= 0 && xx < w) v = *reinterpret_cast<const float4*>(from + yy * w + xx);
+                win[rr][4 * c4] = v.x; win[rr][4 * c4 + 1] = v.y; win[rr][4 * c4 + 2] = v.z; win[rr][4 * c4 + 3] = v.w;
+            }
+        }
+        float my[4], mdc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = 4 + k;   // centre column in the window
+            float mn0 = win[1][c], mn1 = 2.0f * mn0, mn2 = mn1;
+            insert_min3(win[1][c - S], mn0, mn1, mn2);
+            insert_min3(win[0][c - S], mn0, mn1, mn2);
+            insert_min3(win[2][c - S], mn0, mn1, mn2);
+            insert_min3(win[1][c + S], mn0, mn1, mn2);
+            insert_min3(win[0][c + S], mn0, mn1, mn2);
+            insert_min3(win[2][c + S], mn0, mn1, mn2);
+            insert_min3(win[0][c], mn0, mn1, mn2);
+            insert_min3(win[2][c], mn0, mn1, mn2);
+            const float mk = (0.45f * mn0 + 0.3f * mn1) + 0.25f * mn2;
+            my[k] = ba_mask_y(mk);
+            mdc[k] = ba_mask_dc_y(mk);
+        }
+        *reinterpret_cast<float4*>(mask + (r * 2 + 0) * n + i) = make_float4(my[0], my[1], my[2], my[3]);
+        *reinterpret_cast<float4*>(mask + (r * 2 + 1) * n + i) = make_float4(mdc[0], mdc[1], mdc[2], mdc[3]);
+    }
+}
+
+// bl: [NI][n] blurred mask inputs; mask: [R][2][n]; ac: [B][2][n]; mf, lf: [NI][3][n]; diffmap out [B][n]
+__global__ void __launch_bounds__(256) k_ba_combine(const float* __restrict__ bl, const float* __restrict__ mask,
+                                                     const float* __restrict__ ac, const float* __restrict__ mf,
+                                                     const float* __restrict__ lf, size_t n, size_t B, size_t R,
+                                                     const int* __restrict__ ridx, float xmul, float* __restrict__ diffmap) {
+    const size_t b = blockIdx.y;
+    const size_t i0 = (size_t)ridx[b], i1 = R + b;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float dmk = bl[i0 * n + i] - bl[i1 * n + i];
         float ac0 = ac[(b * 2 + 0) * n + i];
         float ac1 = ac[(b * 2 + 1) * n + i];
         ac1 += (10.0f * dmk) * dmk;
@@ -954,82 +1029,44 @@ __global__ void __launch_bounds__(256) k_ba_combine(const float* __restrict__ bl
         float dc0 = (e0 * e0) * 29.2353797994f;
         float dc1 = (e1 * e1) * 0.844626970982f;
         float dc2 = (e2 * e2) * 0.703646627719f;
-        float maskval = ba_mask_y(mask), dc_maskval = ba_mask_dc_y(mask);
+        float maskval = mask[(i0 * 2 + 0) * n + i], dc_maskval = mask[(i0 * 2 + 1) * n + i];
         float dsum = ((dc0 * xmul) * dc_maskval + dc1 * dc_maskval) + dc2 * dc_maskval;
         float asum = ((ac0 * xmul) * maskval + ac1 * maskval) + ac2 * maskval;
-        diffmap[t] = sqrtf(dsum + asum);
+        diffmap[b * n + i] = sqrtf(dsum + asum);
     }
 }
 
-// 4 pixels per thread (w % 4 == 0): the 3x3 stride-3 neighbourhood of the mask comes from three aligned
-// 128-bit loads per row (columns x-4 .. x+7), everything else from one 128-bit load per plane.
-// 3 blocks / SM at 80 registers; forcing 4 (64 registers) spills 164 bytes and was measured 15 % slower
-__global__ void __launch_bounds__(256, 3) k_ba_combine4(const float* __restrict__ bl, const float* __restrict__ ac,
-                                                      const float* __restrict__ mf, const float* __restrict__ lf, int w, int h,
-                                                      size_t n, size_t B, size_t R, const int* __restrict__ ridx, float xmul,
-                                                      float* __restrict__ diffmap) {
-    const int S = 3;
-    const int w4 = w >> 2;
-    // grid (blocks over the plane, B)
+// 4 pixels per thread (n % 4 == 0): one 128-bit load per plane.  grid (blocks over the plane, B)
+__global__ void __launch_bounds__(256) k_ba_combine4(const float* __restrict__ bl, const float* __restrict__ mask,
+                                                      const float* __restrict__ ac, const float* __restrict__ mf,
+                                                      const float* __restrict__ lf, size_t n, size_t B, size_t R,
+                                                      const int* __restrict__ ridx, float xmul, float* __restrict__ diffmap) {
     const int per = (int)(n >> 2);
     const size_t b = blockIdx.y;
+    const size_t i0 = (size_t)ridx[b], i1 = R + b;
+    auto ld = [](const float* p) { const float4 v = *reinterpret_cast<const float4*>(p); return v; };
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
-        const int y = q / w4, x = (q - y * w4) * 4;
-        const int i = y * w + x;
-        const size_t i0 = (size_t)ridx[b], i1 = R + b;
-        const float* from = bl + i0 * n;
-        // rows y-3, y, y+3, columns x-4 .. x+7 (values outside the image are never selected)
-        float win[3][12];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            const int yy = y + (r - 1) * S;
-            const bool yok = yy >= 0 && yy < h;
-#pragma unroll
-            for (int c4 = 0; c4 < 3; c4++) {
-                const int xx = x - 4 + 4 * c4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (yok && xx >= 0 && xx < w) v = *reinterpret_cast<const float4*>(from + yy * w + xx);
-                win[r][4 * c4] = v.x; win[r][4 * c4 + 1] = v.y; win[r][4 * c4 + 2] = v.z; win[r][4 * c4 + 3] = v.w;
-            }
-        }
-        const float4 b1 = *reinterpret_cast<const float4*>(bl + i1 * n + i);
-        const float4 a0 = *reinterpret_cast<const float4*>(ac + (b * 2 + 0) * n + i);
-        const float4 a1 = *reinterpret_cast<const float4*>(ac + (b * 2 + 1) * n + i);
-        const float4 m0 = *reinterpret_cast<const float4*>(mf + (i0 * 3 + 2) * n + i);
-        const float4 m1 = *reinterpret_cast<const float4*>(mf + (i1 * 3 + 2) * n + i);
+        const size_t i = (size_t)q * 4;
+        const float4 b0 = ld(bl + i0 * n + i), b1 = ld(bl + i1 * n + i);
+        const float4 a0 = ld(ac + (b * 2 + 0) * n + i), a1 = ld(ac + (b * 2 + 1) * n + i);
+        const float4 m0 = ld(mf + (i0 * 3 + 2) * n + i), m1 = ld(mf + (i1 * 3 + 2) * n + i);
+        const float4 ky = ld(mask + (i0 * 2 + 0) * n + i), kdc = ld(mask + (i0 * 2 + 1) * n + i);
         float4 l0[3], l1[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            l0[c] = *reinterpret_cast<const float4*>(lf + (i0 * 3 + c) * n + i);
-            l1[c] = *reinterpret_cast<const float4*>(lf + (i1 * 3 + c) * n + i);
+            l0[c] = ld(lf + (i0 * 3 + c) * n + i);
+            l1[c] = ld(lf + (i1 * 3 + c) * n + i);
         }
-        const float b1v[4] = {b1.x, b1.y, b1.z, b1.w}, a0v[4] = {a0.x, a0.y, a0.z, a0.w}, a1v[4] = {a1.x, a1.y, a1.z, a1.w};
+        const float b0v[4] = {b0.x, b0.y, b0.z, b0.w}, b1v[4] = {b1.x, b1.y, b1.z, b1.w};
+        const float a0v[4] = {a0.x, a0.y, a0.z, a0.w}, a1v[4] = {a1.x, a1.y, a1.z, a1.w};
         const float m0v[4] = {m0.x, m0.y, m0.z, m0.w}, m1v[4] = {m1.x, m1.y, m1.z, m1.w};
+        const float kyv[4] = {ky.x, ky.y, ky.z, ky.w}, kdcv[4] = {kdc.x, kdc.y, kdc.z, kdc.w};
         const float l0v[3][4] = {{l0[0].x, l0[0].y, l0[0].z, l0[0].w}, {l0[1].x, l0[1].y, l0[1].z, l0[1].w}, {l0[2].x, l0[2].y, l0[2].z, l0[2].w}};
         const float l1v[3][4] = {{l1[0].x, l1[0].y, l1[0].z, l1[0].w}, {l1[1].x, l1[1].y, l1[1].z, l1[1].w}, {l1[2].x, l1[2].y, l1[2].z, l1[2].w}};
         float res[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int xk = x + k;
-            const int c = 4 + k;   // centre column in the window
-            const float ctr = win[1][c];
-            float mn0 = ctr, mn1 = 2.0f * mn0, mn2 = mn1;
-            const bool up = y >= S, dn = y < h - S;
-            if (xk >= S) {
-                store_min3(win[1][c - S], mn0, mn1, mn2);
-                if (up) store_min3(win[0][c - S], mn0, mn1, mn2);
-                if (dn) store_min3(win[2][c - S], mn0, mn1, mn2);
-            }
-            if (xk < w - S) {
-                store_min3(win[1][c + S], mn0, mn1, mn2);
-                if (up) store_min3(win[0][c + S], mn0, mn1, mn2);
-                if (dn) store_min3(win[2][c + S], mn0, mn1, mn2);
-            }
-            if (up) store_min3(win[0][c], mn0, mn1, mn2);
-            if (dn) store_min3(win[2][c], mn0, mn1, mn2);
-            const float mask = (0.45f * mn0 + 0.3f * mn1) + 0.25f * mn2;
-
-            const float dmk = ctr - b1v[k];
+            const float dmk = b0v[k] - b1v[k];
             const float ac0 = a0v[k];
             float ac1 = a1v[k];
             ac1 += (10.0f * dmk) * dmk;
@@ -1039,7 +1076,7 @@ __global__ void __launch_bounds__(256, 3) k_ba_combine4(const float* __restrict_
             const float dc0 = (e0 * e0) * 29.2353797994f;
             const float dc1 = (e1 * e1) * 0.844626970982f;
             const float dc2 = (e2 * e2) * 0.703646627719f;
-            const float maskval = ba_mask_y(mask), dc_maskval = ba_mask_dc_y(mask);
+            const float maskval = kyv[k], dc_maskval = kdcv[k];
             const float dsum = ((dc0 * xmul) * dc_maskval + dc1 * dc_maskval) + dc2 * dc_maskval;
             const float asum = ((ac0 * xmul) * maskval + ac1 * maskval) + ac2 * maskval;
             res[k] = sqrt_rn_nonneg(dsum + asum);
@@ -1055,6 +1092,27 @@ __global__ void __launch_bounds__(256) k_ba_subsample(const float* __restrict__ 
                                                        size_t on, size_t total, float* __restrict__ out) {
     const size_t pl = blockIdx.y;
     const float* p = in + pl * n;
+    if ((w & 3) == 0) {
+        // two outputs per thread from one 128-bit load per input row (w % 4 == 0: no odd column, ow is even)
+        const unsigned ow2 = (unsigned)ow >> 1, per = (unsigned)(on >> 1);
+        for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
+            const unsigned oy = q / ow2, ox = (q - oy * ow2) * 2;
+            const unsigned y0 = 2 * oy;
+            const bool vy = (int)y0 + 1 < h;
+            const float4 a = *reinterpret_cast<const float4*>(p + (size_t)y0 * w + 2 * ox);
+            float s0 = 0.0f, s1 = 0.0f;
+            s0 += 0.25f * a.x; s0 += 0.25f * a.y;
+            s1 += 0.25f * a.z; s1 += 0.25f * a.w;
+            if (vy) {
+                const float4 b = *reinterpret_cast<const float4*>(p + (size_t)(y0 + 1) * w + 2 * ox);
+                s0 += 0.25f * b.x; s0 += 0.25f * b.y;
+                s1 += 0.25f * b.z; s1 += 0.25f * b.w;
+            }
+            if ((h & 1) && (int)oy == oh - 1) { s0 *= 2.0f; s1 *= 2.0f; }
+            *reinterpret_cast<float2*>(out + pl * on + (size_t)oy * ow + ox) = make_float2(s0, s1);
+        }
+        return;
+    }
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)on; i += gridDim.x * blockDim.x) {
         const size_t t = pl * on + i;
         int oy = (int)(i / (unsigned)ow), ox = (int)(i - (unsigned)oy * (unsigned)ow);
@@ -1085,21 +1143,40 @@ __global__ void __launch_bounds__(256) k_ba_finish(float* __restrict__ diffmap, 
     const float keep = (float)(1.0 - 0.3 * 0.5);
     float mx = 0.0f;
     double s3 = 0, s6 = 0, s12 = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float v = dm[i];
-        if (sb) {
-            int y = (int)(i / w), x = (int)(i - (size_t)y * w);
-            v = v * keep;
-            v = v + 0.5f * sb[(size_t)(y >> 1) * sw + (x >> 1)];
-            dm[i] = v;
-        }
+    auto pool = [&](float v) {
         mx = fmaxf(mx, v);
-        double d = (double)v;
-        double d3 = d * d * d;
+        const double d = (double)v;
+        const double d3 = d * d * d;
         s3 += d3;
-        double d6 = d3 * d3;
+        const double d6 = d3 * d3;
         s6 += d6;
         s12 += d6 * d6;
+    };
+    if ((w & 3) == 0) {
+        // 4 pixels per thread: one 128-bit load / store of the map, one 64-bit load of the two half-resolution values
+        const int w4 = w >> 2, per = (int)(n >> 2);
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
+            float4 v = *reinterpret_cast<const float4*>(dm + (size_t)q * 4);
+            if (sb) {
+                const int y = q / w4, x = (q - y * w4) * 4;
+                const float2 u = *reinterpret_cast<const float2*>(sb + (size_t)(y >> 1) * sw + (x >> 1));
+                v.x = v.x * keep; v.y = v.y * keep; v.z = v.z * keep; v.w = v.w * keep;
+                v.x = v.x + 0.5f * u.x; v.y = v.y + 0.5f * u.x; v.z = v.z + 0.5f * u.y; v.w = v.w + 0.5f * u.y;
+                *reinterpret_cast<float4*>(dm + (size_t)q * 4) = v;
+            }
+            pool(v.x); pool(v.y); pool(v.z); pool(v.w);
+        }
+    } else {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            float v = dm[i];
+            if (sb) {
+                int y = (int)(i / w), x = (int)(i - (size_t)y * w);
+                v = v * keep;
+                v = v + 0.5f * sb[(size_t)(y >> 1) * sw + (x >> 1)];
+                dm[i] = v;
+            }
+            pool(v);
+        }
     }
     mx = warp_max(mx);
     double v3[3] = {s3, s6, s12};
@@ -1174,7 +1251,7 @@ static size_t ba_level_floats_per_pair(size_t n) {
     return 38 * n;
 }
 
-static unsigned ew_blocks(Context& c, size_t total) {
+[[maybe_unused]] static unsigned ew_blocks(Context& c, size_t total) {
     return (unsigned)std::min<size_t>(cdiv(total, 256), (size_t)c.sm_count * 32);
 }
 // 2-D variant: grid.y = units (pairs or pair-channels), grid.x = blocks of 256 threads striding over `per` items of a unit,
@@ -1317,13 +1394,17 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
             CE_LAUNCH_SHARED(c, "k_ba_malta", ((double)B * 48 + (double)R * 16) * n, (double)B * n * 64,
                       k_ba_malta<false><<<grid, MT_THREADS, MT_SMEM, c.stream>>>(L.mdiff, L.hf, L.mf, (int)w, (int)h, n, R, ridx, mp, maps, L.ac));
     }
-    if (w % 4 == 0)
-        CE_LAUNCH_SHARED(c, "k_ba_combine", ((double)B * 32 + (double)R * 20) * n, (double)B * n * 52,
-                  k_ba_combine4<<<ew_grid2(c, n / 4, B), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul,
-                                                                                diffmap));
-    else
-        CE_LAUNCH_SHARED(c, "k_ba_combine", ((double)B * 32 + (double)R * 20) * n, (double)B * n * 52,
-                  k_ba_combine<<<ew_blocks(c, B * n), 256, 0, c.stream>>>(L.bl, L.ac, L.mf, L.lf, (int)w, (int)h, n, B, R, ridx, xmul, diffmap));
+    // the mask factors of the R distinct references go where hf_pre lived (L.tmp is dead after the R3 blur)
+    float* mask = L.tmp;
+    if (w % 4 == 0) {
+        CE_LAUNCH(c, "k_ba_mask", (double)R * n * 12, k_ba_mask4<<<ew_grid2(c, n / 4, R), 256, 0, c.stream>>>(L.bl, (int)w, (int)h, n, mask));
+        CE_LAUNCH_SHARED(c, "k_ba_combine", ((double)B * 32 + (double)R * 28) * n, (double)B * n * 60,
+                  k_ba_combine4<<<ew_grid2(c, n / 4, B), 256, 0, c.stream>>>(L.bl, mask, L.ac, L.mf, L.lf, n, B, R, ridx, xmul, diffmap));
+    } else {
+        CE_LAUNCH(c, "k_ba_mask", (double)R * n * 12, k_ba_mask<<<ew_grid2(c, n, R), 256, 0, c.stream>>>(L.bl, (int)w, (int)h, n, mask));
+        CE_LAUNCH_SHARED(c, "k_ba_combine", ((double)B * 32 + (double)R * 28) * n, (double)B * n * 60,
+                  k_ba_combine<<<ew_grid2(c, n, B), 256, 0, c.stream>>>(L.bl, mask, L.ac, L.mf, L.lf, n, B, R, ridx, xmul, diffmap));
+    }
     CE_CUDA(cudaGetLastError());
     c.arena.release(mark);
 }

@@ -98,6 +98,18 @@ CE_DEVINL float rg_step(RGState& s, float sum) {
 #ifndef HP_SLOTS
 #define HP_SLOTS 2
 #endif
+// Output stage: a warp collects HP_OC finished columns of its 32 rows (lane = row) and writes them out transposed
+// (lane = 16-byte group).  The recurrence runs 4 columns behind the loads, so a chunk finishes columns 64k-4 .. 64k+59;
+// the stage is used as a ring over the ALIGNED block of HP_OC columns (column g at g mod HP_OC) and a block leaves as
+// soon as the group that completes it has been stored: every row segment of a store is then whole 128-byte lines
+// (with the stores starting at 64k-4 each 256-byte row segment touched three lines, and narrower unaligned stages --
+// 32 / 16 columns, 4 / 5 blocks per SM instead of 3 -- were measured slower on the corpus step, 236 / 304 ms against
+// 194: the kernel waits for its stores, not for occupancy).
+#ifndef HP_OC
+#define HP_OC 32
+#endif
+#define HP_OC4 (HP_OC / 4)
+#define HP_OPITCH (HP_OC + 4)    // lane = row writes STS.128 at row pitch OC+4 floats: conflict free per quarter warp
 
 // Which blurs a launch computes.  The reference-side statistics (mu1 = blur(i1), blur(i1^2)) do not depend on the
 // distorted image, so when a sub-batch has shared references they are computed once per distinct reference
@@ -106,8 +118,8 @@ enum { S2_ALL = 0, S2_REF = 1, S2_PAIR = 2 };
 template <int MODE> struct S2Mode {
     static constexpr int NW = MODE == S2_ALL ? 5 : MODE == S2_REF ? 2 : 3;     // products = warps per block
     static constexpr int NIN = MODE == S2_REF ? 1 : 2;                          // image planes staged by the row pass
-    static constexpr int HP_SMEM = (HP_SLOTS * NIN + NW) * HP_ROWS * HP_PITCH * 4;
-    static constexpr int HP_SMEM_TMA = (2 * NIN * (HP_COLS / 32) * 32 * 32 + NW * HP_ROWS * HP_PITCH) * 4;   // HP_SLOTS_TMA = 2
+    static constexpr int HP_SMEM = (HP_SLOTS * NIN * HP_PITCH + NW * HP_OPITCH) * HP_ROWS * 4;
+    static constexpr int HP_SMEM_TMA = (2 * NIN * (HP_COLS / 32) * 32 * 32 + NW * HP_ROWS * HP_OPITCH) * 4;   // HP_SLOTS_TMA = 2
 };
 
 // grid (ceil(h/32), 3*units); block NW warps (product) x 32 lanes (row); unit = pair (S2_ALL, S2_PAIR) or distinct
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float*
     __shared__ __align__(8) unsigned long long s_bar[HP_SLOTS_TMA];
     float* s_in = s_dyn;
     const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
-    float* so = s_dyn + SLOTS * NIN * PLANE + p * (HP_ROWS * HP_PITCH);
+    float* so = s_dyn + SLOTS * NIN * PLANE + p * (HP_ROWS * HP_OPITCH);
     const size_t u = blockIdx.y / 3;
     const int c = blockIdx.y % 3;
     const int row0 = blockIdx.x * HP_ROWS;
@@ -206,6 +218,31 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float*
     RGState st = {0, 0, 0, 0, 0, 0};
     // products of the previous 16 columns: Q0 = c-16..c-13, Q1 = c-12..c-9, Q2 = c-8..c-5, Q3 = c-4..c-1
     float Q0[4] = {0, 0, 0, 0}, Q1[4] = {0, 0, 0, 0}, Q2[4] = {0, 0, 0, 0}, Q3[4] = {0, 0, 0, 0};
+    // this warp writes out aligned block kb (HP_OC columns) of the plane it produced:
+    // lane -> (row lane/OC4 + (32/OC4)*i, 16-B group lane%OC4)
+    auto flush = [&](int kb) {
+        __syncwarp();
+        const int x = kb * HP_OC + 4 * (lane % HP_OC4);
+        if (x < w) {
+#pragma unroll
+            for (int i = 0; i < HP_OC4; i++) {
+                const int rr = (32 / HP_OC4) * i + lane / HP_OC4;
+                const int y = row0 + rr;
+                if (y < h) {
+                    const float4 v = *reinterpret_cast<const float4*>(so + rr * HP_OPITCH + 4 * (lane % HP_OC4));
+                    float* d = op + (size_t)y * w + x;
+                    if (vec) *reinterpret_cast<float4*>(d) = v;
+                    else {
+                        d[0] = v.x;
+                        if (x + 1 < w) d[1] = v.y;
+                        if (x + 2 < w) d[2] = v.z;
+                        if (x + 3 < w) d[3] = v.w;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    };
     for (int k = 0; k < nchunks; k++) {
         if (TMA) {
             mbar_wait(&s_bar[k % SLOTS], (unsigned)(k / SLOTS) & 1u);
@@ -240,33 +277,15 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_hpass(const float*
                 o.y = rg_step(st, L0[3] + g4.y);
                 o.z = rg_step(st, L1[0] + g4.z);
                 o.w = rg_step(st, L1[1] + g4.w);
-                *reinterpret_cast<float4*>(so + lane * HP_PITCH + 4 * m) = o;
+                // columns 64k-4+4m .. +3 -> ring position (4m-4) mod HP_OC
+                *reinterpret_cast<float4*>(so + lane * HP_OPITCH + ((4 * m + HP_OC - 4) & (HP_OC - 1))) = o;
                 NWQ[0] = g4.x; NWQ[1] = g4.y; NWQ[2] = g4.z; NWQ[3] = g4.w;
+                // a group that ends at a multiple of HP_OC columns completed the block before it
+                if (mm == 0 && (m0 % HP_OC4) == 0 && (k > 0 || m0 > 0)) flush((k * HP_COLS + 4 * m0) / HP_OC - 1);
             }
         }
-        __syncwarp();
-        // this warp writes out the plane it produced: lane -> (row lane/C4 + (32/C4)*i, 16-B group lane%C4)
-        const int x = k * HP_COLS - 4 + 4 * (lane % HP_C4);
-        if (x >= 0 && x < w) {
-#pragma unroll
-            for (int i = 0; i < HP_C4; i++) {
-                const int rr = (32 / HP_C4) * i + lane / HP_C4;
-                const int y = row0 + rr;
-                if (y < h) {
-                    const float4 v = *reinterpret_cast<const float4*>(so + rr * HP_PITCH + 4 * (lane % HP_C4));
-                    float* d = op + (size_t)y * w + x;
-                    if (vec) *reinterpret_cast<float4*>(d) = v;
-                    else {
-                        d[0] = v.x;
-                        if (x + 1 < w) d[1] = v.y;
-                        if (x + 2 < w) d[2] = v.z;
-                        if (x + 3 < w) d[3] = v.w;
-                    }
-                }
-            }
-        }
-        __syncwarp();
     }
+    flush(nchunks * (HP_COLS / HP_OC) - 1);   // what the last, incomplete block holds of the image (often nothing)
 }
 
 // Tried in round 2 and dropped (measurements on the 192-pair batch, block version above = 1.39 ms):
