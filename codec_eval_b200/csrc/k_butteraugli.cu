@@ -248,57 +248,85 @@ __global__ void __launch_bounds__(256) k_ba_opsin(const float* __restrict__ lin,
 }
 
 // ---------------------------------------------------------------- wide separable blur (sigma 7.16)
-// horizontal: tile 128 x 8, thread = 4 consecutive outputs of one row
-// TMA: the tile is one bulk tensor copy (map = in as [planes][h][w], box (PITCH, 8, 1)); otherwise per-thread loads.
+// horizontal: tile 128 x 8, thread = 4 consecutive outputs of one row.  A block walks down BH_NT vertically adjacent
+// tiles through a ring of BH_SLOTS buffers with BH_SLOTS - 1 tiles in flight ahead of the one being computed: with one
+// tile per block (round 1) or two buffers the kernel moved 3.9 TB/s and its warps spun on the tile barrier (ncu:
+// 55 executed instructions per pixel against 42 in the loop body) -- too few bytes in flight per SM, not arithmetic.
+// TMA: a tile is one bulk tensor copy (map = in as [planes][h][w], box (PITCH, 8, 1)); otherwise per-thread loads.
+#define BH_NT 16
+#define BH_SLOTS 4
 template <int SLOT, int R, bool TMA>
 __global__ void __launch_bounds__(256) k_ba_blur_h(const float* __restrict__ in, int w, int h, size_t n,
                                                     const float* __restrict__ inv, float* __restrict__ out, int vec,
                                                     const __grid_constant__ CUtensorMap map) {
     constexpr int RUP = (R + 3) & ~3;
     constexpr int PITCH = 128 + 2 * RUP;
-    __shared__ __align__(128) float s[8 * PITCH];
-    __shared__ __align__(8) unsigned long long s_bar;
-    const int x0 = blockIdx.x * 128, y0 = blockIdx.y * 8;
+    constexpr int NS = TMA ? BH_SLOTS : 1;
+    __shared__ __align__(128) float s[NS][8 * PITCH];
+    __shared__ __align__(8) unsigned long long s_bar[NS];
+    const int x0 = blockIdx.x * 128, yb = blockIdx.y * (8 * BH_NT);
+    const int nt = min(BH_NT, (h - yb + 7) / 8);
     const float* p = in + (size_t)blockIdx.z * n;
     float* o = out + (size_t)blockIdx.z * n;
+    auto issue = [&](int t) {   // thread 0: tile t -> slot t % NS
+        mbar_expect_tx(&s_bar[t % NS], 8 * PITCH * 4);
+        tma_load_3d(s[t % NS], &map, x0 - RUP, yb + 8 * t, (int)blockIdx.z, &s_bar[t % NS]);
+    };
     if (TMA) {
         if (threadIdx.x == 0) {
-            mbar_init(&s_bar, 1);
+#pragma unroll
+            for (int i = 0; i < NS; i++) mbar_init(&s_bar[i], 1);
             mbar_fence_init();
-            mbar_expect_tx(&s_bar, 8 * PITCH * 4);
-            tma_load_3d(s, &map, x0 - RUP, y0, (int)blockIdx.z, &s_bar);
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (i < nt) issue(i);
         }
-        __syncthreads();   // barrier initialised before anyone polls it
-        mbar_wait(&s_bar, 0);
-    } else {
-        load_tile<0, PITCH / 4, 8, 256>(s, PITCH, p, w, h, x0 - RUP, y0, vec != 0);
-        __syncthreads();
+        __syncthreads();   // barriers initialised before anyone polls them
     }
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int y = y0 + ty, x = x0 + tx * 4;
-    if (y >= h || x >= w) return;
-    float v[4 + 2 * RUP];
-#pragma unroll
-    for (int q = 0; q < (4 + 2 * RUP) / 4; q++) {
-        float4 f = *reinterpret_cast<const float4*>(&s[ty * PITCH + tx * 4 + q * 4]);
-        v[q * 4] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
-    }
-    const float4 iv = *reinterpret_cast<const float4*>(inv + x);   // zero-padded table
+    const int x = x0 + tx * 4;
+    float4 iv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x < w) iv = *reinterpret_cast<const float4*>(inv + x);   // zero-padded table
     const float ivk[4] = {iv.x, iv.y, iv.z, iv.w};
-    float res[4];
+    for (int t = 0; t < nt; t++) {
+        const float* sb = s[t % NS];
+        if (TMA) {
+            mbar_wait(&s_bar[t % NS], (unsigned)(t / NS) & 1u);
+        } else {
+            __syncthreads();   // the previous tile has been consumed
+            load_tile<0, PITCH / 4, 8, 256>(s[0], PITCH, p, w, h, x0 - RUP, yb + 8 * t, vec != 0);
+            __syncthreads();
+        }
+        const int y = yb + 8 * t + ty;
+        float res[4] = {0.f, 0.f, 0.f, 0.f};
+        if (y < h && x < w) {
+            float v[4 + 2 * RUP];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        float sum = 0.0f;
+            for (int q = 0; q < (4 + 2 * RUP) / 4; q++) {
+                float4 f = *reinterpret_cast<const float4*>(&sb[ty * PITCH + tx * 4 + q * 4]);
+                v[q * 4] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
+            }
 #pragma unroll
-        for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], baw<SLOT>(t), sum);
-        res[k] = sum * ivk[k];
-    }
-    float* d = o + (y * w + x);
-    if (vec) *reinterpret_cast<float4*>(d) = make_float4(res[0], res[1], res[2], res[3]);
-    else {
+            for (int k = 0; k < 4; k++) {
+                float sum = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (x + k < w) d[k] = res[k];
+                for (int tt = 0; tt <= 2 * R; tt++) sum = __fmaf_rn(v[k + (RUP - R) + tt], baw<SLOT>(tt), sum);
+                res[k] = sum * ivk[k];
+            }
+        }
+        if (TMA && t + NS < nt) {   // block-uniform: the slot is refilled once every thread is done reading it
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0) issue(t + NS);
+        }
+        if (y >= h || x >= w) continue;
+        float* d = o + ((size_t)y * w + x);
+        if (vec) *reinterpret_cast<float4*>(d) = make_float4(res[0], res[1], res[2], res[3]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (x + k < w) d[k] = res[k];
+        }
     }
 }
 
@@ -380,6 +408,33 @@ __global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in,
     }
     if (x >= w) return;
     const bool two = x + 1 < w;
+    if ((w & 1) == 0) {
+        // even widths: the lane's two columns leave (and the xyb values arrive) as one 64-bit access, so a half warp
+        // writes a whole 128-byte line per instruction instead of every other word of it
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int y = y0 + g * 4 + k;
+            if (y >= h) break;
+            const size_t idx = base + (size_t)y * w + x;
+            if (EPI == 0) {
+#pragma unroll
+                for (int c = 0; c < NPL; c++) *reinterpret_cast<float2*>(out + idx + (size_t)c * n) = make_float2(res[c][k][0], res[c][k][1]);
+            } else {
+                const float2 xx = *reinterpret_cast<const float2*>(xyb + idx), xy = *reinterpret_cast<const float2*>(xyb + idx + n),
+                             xb = *reinterpret_cast<const float2*>(xyb + idx + 2 * n);
+                const float lx[2] = {res[0][k][0], res[0][k][1]}, ly[2] = {res[NPL > 1 ? 1 : 0][k][0], res[NPL > 1 ? 1 : 0][k][1]},
+                            lb[2] = {res[NPL > 2 ? 2 : 0][k][0], res[NPL > 2 ? 2 : 0][k][1]};
+                *reinterpret_cast<float2*>(mf_pre + idx) = make_float2(xx.x - lx[0], xx.y - lx[1]);
+                *reinterpret_cast<float2*>(mf_pre + idx + n) = make_float2(xy.x - ly[0], xy.y - ly[1]);
+                *reinterpret_cast<float2*>(mf_pre + idx + 2 * n) = make_float2(xb.x - lb[0], xb.y - lb[1]);
+                const float bb0 = __fmaf_rn(-0.362267051518f, ly[0], lb[0]), bb1 = __fmaf_rn(-0.362267051518f, ly[1], lb[1]);
+                *reinterpret_cast<float2*>(out + idx + 2 * n) = make_float2(bb0 * 49.87984651440f, bb1 * 49.87984651440f);
+                *reinterpret_cast<float2*>(out + idx) = make_float2(lx[0] * 33.832837186260f, lx[1] * 33.832837186260f);
+                *reinterpret_cast<float2*>(out + idx + n) = make_float2(ly[0] * 14.458268100570f, ly[1] * 14.458268100570f);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int y = y0 + g * 4 + k;
@@ -414,8 +469,15 @@ __global__ void __launch_bounds__(256) k_ba_blur_v(const float* __restrict__ in,
 //                   out_c = mask input m [img][n] = DiffPrecompute(combine(hf, uhf))
 #define B2_TW 64
 #define B2_TH 32
+#define B2_NT 4      // a block walks down B2_NT vertically adjacent tiles: plane c of tile t is work item t * NPL + c
+#ifndef B2_MINB3
+#define B2_MINB3 3   // minimum blocks / SM asked of ptxas: three-plane (MF) instance; 4 for the others
+#endif
+// Items go through two input buffers: item i + 2 is requested as soon as the horizontal pass of item i has left its
+// buffer, so only the block's very first load is exposed (with one tile per block the first plane of EVERY tile was:
+// ncu had 24 % of the HF kernel's stall samples in the wait for it, and all of the one-plane mask blur's loads).
 template <int SLOT, int R, int NPL, int EPI, bool TMA>
-__global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in, int w, int h, size_t n,
+__global__ void __launch_bounds__(256, (NPL == 3 ? B2_MINB3 : 4)) k_ba_blur2d(const float* __restrict__ in, int w, int h, size_t n,
                                                     const float* __restrict__ inv_x, const float* __restrict__ inv_y,
                                                     float* __restrict__ out_a, float* __restrict__ out_b,
                                                     float* __restrict__ out_c, const __grid_constant__ CUtensorMap map) {
@@ -423,19 +485,28 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
     constexpr int PITCH = B2_TW + 2 * RUP;
     constexpr int ROWS = B2_TH + 2 * R;
     constexpr int TILE = (ROWS * PITCH + 31) & ~31;   // 128-byte multiple so both buffers are valid TMA destinations
-    __shared__ __align__(128) float s_in2[2][TILE];   // plane c+1 is staged (TMA / cp.async) while plane c is computed
+    __shared__ __align__(128) float s_in2[2][TILE];   // item i+1 is staged (TMA / cp.async) while item i is computed
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ __align__(16) float s_h[ROWS * B2_TW];
-    const int x0 = blockIdx.x * B2_TW, y0 = blockIdx.y * B2_TH;
+    const int x0 = blockIdx.x * B2_TW;
+    const int tiles_y = (h + B2_TH - 1) / B2_TH;
+    const int t_begin = blockIdx.y * B2_NT, nt = min(B2_NT, tiles_y - t_begin);
+    const int nitems = nt * NPL;
     const size_t img = blockIdx.z;
     const bool vec = (w & 3) == 0;
     // vertical pass: thread = 4 rows (g*4 ..) of the two adjacent columns 2*cp, 2*cp+1, held as packed fp32x2 pairs
     const int cp = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int x = x0 + 2 * cp;
     float res[NPL][4][2], ctr[NPL][4][2];
-    auto tma_issue = [&](int c) {   // thread 0: plane c -> buffer c & 1 (map = in as [planes][h][w], box (PITCH, ROWS, 1))
-        mbar_expect_tx(&s_bar[c & 1], ROWS * PITCH * 4);
-        tma_load_3d(s_in2[c & 1], &map, x0 - RUP, y0 - R, (int)(img * NPL + c), &s_bar[c & 1]);
+    auto tma_issue = [&](int i) {   // thread 0: item i -> buffer i & 1 (map = in as [planes][h][w], box (PITCH, ROWS, 1))
+        const int t = i / NPL, c = i - t * NPL;
+        mbar_expect_tx(&s_bar[i & 1], ROWS * PITCH * 4);
+        tma_load_3d(s_in2[i & 1], &map, x0 - RUP, (t_begin + t) * B2_TH - R, (int)(img * NPL + c), &s_bar[i & 1]);
+    };
+    auto async_issue = [&](int i) {   // all threads: item i -> buffer i & 1 by cp.async
+        const int t = i / NPL, c = i - t * NPL;
+        load_tile_async<PITCH / 4, ROWS, 256>(s_in2[i & 1], PITCH, in + (img * NPL + c) * n, w, h, x0 - RUP, (t_begin + t) * B2_TH - R, vec);
+        cp_async_commit();
     };
     if (TMA) {
         if (threadIdx.x == 0) {
@@ -443,124 +514,147 @@ __global__ void __launch_bounds__(256) k_ba_blur2d(const float* __restrict__ in,
             mbar_init(&s_bar[1], 1);
             mbar_fence_init();
             tma_issue(0);
-            if (NPL > 1) tma_issue(1);
+            if (nitems > 1) tma_issue(1);
         }
         __syncthreads();
     } else {
-        load_tile_async<PITCH / 4, ROWS, 256>(s_in2[0], PITCH, in + (img * NPL) * n, w, h, x0 - RUP, y0 - R, vec);
-        cp_async_commit();
+        async_issue(0);
     }
+    for (int t = 0; t < nt; t++) {
+        const int y0 = (t_begin + t) * B2_TH;
 #pragma unroll
-    for (int c = 0; c < NPL; c++) {
-        if (TMA) {
-            mbar_wait(&s_bar[c & 1], (unsigned)(c >> 1) & 1u);
-        } else if (c + 1 < NPL) {
-            load_tile_async<PITCH / 4, ROWS, 256>(s_in2[(c + 1) & 1], PITCH, in + (img * NPL + c + 1) * n, w, h, x0 - RUP, y0 - R, vec);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();   // plane c staged; the previous plane's vertical pass is done with s_h
-        const float* s_in = s_in2[c & 1];
-        for (int e = threadIdx.x; e < ROWS * (B2_TW / 4); e += 256) {
-            const int r = e >> 4, q4 = e & 15;
-            float v[4 + 2 * RUP];
-#pragma unroll
-            for (int q = 0; q < (4 + 2 * RUP) / 4; q++) {
-                float4 f = *reinterpret_cast<const float4*>(&s_in[r * PITCH + q4 * 4 + q * 4]);
-                v[q * 4] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
+        for (int c = 0; c < NPL; c++) {
+            const int i = t * NPL + c;
+            if (TMA) {
+                mbar_wait(&s_bar[i & 1], (unsigned)(i >> 1) & 1u);
+            } else if (i + 1 < nitems) {
+                async_issue(i + 1);   // buffer (i+1) & 1 was released by the second barrier of item i-1
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
             }
-            const float4 iv = *reinterpret_cast<const float4*>(inv_x + min(x0 + q4 * 4, (w + 3) & ~3));   // zero-padded table
-            const float ivk[4] = {iv.x, iv.y, iv.z, iv.w};
-            float o4[4];
+            __syncthreads();   // item i staged; the previous item's vertical pass is done with s_h
+            const float* s_in = s_in2[i & 1];
+            for (int e = threadIdx.x; e < ROWS * (B2_TW / 4); e += 256) {
+                const int r = e >> 4, q4 = e & 15;
+                float v[4 + 2 * RUP];
+#pragma unroll
+                for (int q = 0; q < (4 + 2 * RUP) / 4; q++) {
+                    float4 f = *reinterpret_cast<const float4*>(&s_in[r * PITCH + q4 * 4 + q * 4]);
+                    v[q * 4] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
+                }
+                const float4 iv = *reinterpret_cast<const float4*>(inv_x + min(x0 + q4 * 4, (w + 3) & ~3));   // zero-padded table
+                const float ivk[4] = {iv.x, iv.y, iv.z, iv.w};
+                float o4[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int tt = 0; tt <= 2 * R; tt++) sum = __fmaf_rn(v[k + (RUP - R) + tt], baw<SLOT>(tt), sum);
+                    o4[k] = sum * ivk[k];
+                }
+                *reinterpret_cast<float4*>(&s_h[r * B2_TW + q4 * 4]) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            }
+            if (EPI != 0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float2 tc = *reinterpret_cast<const float2*>(&s_in[(g * 4 + k + R) * PITCH + 2 * cp + RUP]);
+                    ctr[c][k][0] = tc.x; ctr[c][k][1] = tc.y;
+                }
+            }
+            if (TMA && i + 2 < nitems) fence_proxy_async();   // the ctr loads above may still be in flight
+            __syncthreads();
+            if (TMA && i + 2 < nitems && threadIdx.x == 0) tma_issue(i + 2);   // everyone is done with buffer i & 1
+            f32x2 v[4 + 2 * R];
+#pragma unroll
+            for (int q = 0; q < 4 + 2 * R; q++) v[q] = *reinterpret_cast<const f32x2*>(&s_h[(g * 4 + q) * B2_TW + 2 * cp]);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                float sum = 0.0f;
+                const int y = y0 + g * 4 + k;
+                f32x2 sum = 0ULL;
 #pragma unroll
-                for (int t = 0; t <= 2 * R; t++) sum = __fmaf_rn(v[k + (RUP - R) + t], baw<SLOT>(t), sum);
-                o4[k] = sum * ivk[k];
-            }
-            *reinterpret_cast<float4*>(&s_h[r * B2_TW + q4 * 4]) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        }
-        if (EPI != 0) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float2 t = *reinterpret_cast<const float2*>(&s_in[(g * 4 + k + R) * PITCH + 2 * cp + RUP]);
-                ctr[c][k][0] = t.x; ctr[c][k][1] = t.y;
+                for (int tt = 0; tt <= 2 * R; tt++) sum = fma2(v[k + tt], baw2<SLOT>(tt), sum);
+                const float iy = y < h ? inv_y[y] : 0.0f;
+                float lo, hi;
+                unpk2(sum, lo, hi);
+                res[c][k][0] = lo * iy;
+                res[c][k][1] = hi * iy;
             }
         }
-        if (TMA && c + 2 < NPL) fence_proxy_async();   // the ctr loads above may still be in flight
-        __syncthreads();
-        if (TMA && c + 2 < NPL && threadIdx.x == 0) tma_issue(c + 2);   // everyone is done with buffer c & 1
-        f32x2 v[4 + 2 * R];
-#pragma unroll
-        for (int q = 0; q < 4 + 2 * R; q++) v[q] = *reinterpret_cast<const f32x2*>(&s_h[(g * 4 + q) * B2_TW + 2 * cp]);
+        // epilogue of tile t from registers.  Even widths: the lane's two columns leave as one 64-bit store (a warp then
+        // writes whole 128-byte lines instead of every other word of them)
+        if (x >= w) continue;
+        const bool two = x + 1 < w, pair = (w & 1) == 0;
+        auto put = [&](float* d, float v0, float v1) {
+            if (pair) *reinterpret_cast<float2*>(d) = make_float2(v0, v1);
+            else {
+                d[0] = v0;
+                if (two) d[1] = v1;
+            }
+        };
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int y = y0 + g * 4 + k;
-            f32x2 sum = 0ULL;
+            if (y >= h) break;
+            const size_t i = (size_t)y * w + x;
+            if (EPI == 0) {
 #pragma unroll
-            for (int t = 0; t <= 2 * R; t++) sum = fma2(v[k + t], baw2<SLOT>(t), sum);
-            const float iy = y < h ? inv_y[y] : 0.0f;
-            float lo, hi;
-            unpk2(sum, lo, hi);
-            res[c][k][0] = lo * iy;
-            res[c][k][1] = hi * iy;
+                for (int c = 0; c < NPL; c++) put(out_a + (img * NPL + c) * n + i, res[c][k][0], res[c][k][1]);
+            } else if (EPI == 2) {
+                float m0[2], m1[2], h0[2], h1[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const float bx = res[0][k][j], by = res[NPL > 1 ? 1 : 0][k][j];
+                    const float hfx = ctr[0][k][j] - bx, hfy = ctr[NPL > 1 ? 1 : 0][k][j] - by;
+                    m0[j] = ba_remove_range(bx, 0.29f);
+                    m1[j] = ba_amplify_range(by, 0.1f);
+                    const float scaler = __fmaf_rn(46.0f / __fmaf_rn(hfy, hfy, 46.0f), (float)(1.0 - 0.653020556257), 0.653020556257f);
+                    h0[j] = scaler * hfx;
+                    h1[j] = hfy;
+                }
+                float* M = out_a + img * 3 * n + i;
+                put(M, m0[0], m0[1]);
+                put(M + n, m1[0], m1[1]);
+                put(M + 2 * n, res[NPL > 2 ? 2 : 0][k][0], res[NPL > 2 ? 2 : 0][k][1]);
+                float* H = out_b + img * 2 * n + i;
+                put(H, h0[0], h0[1]);
+                put(H + n, h1[0], h1[1]);
+            } else {
+                float hx[2], ux[2], hy[2], uy[2], mk[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    {
+                        const float hb = res[0][k][j];
+                        ux[j] = ba_remove_range(ctr[0][k][j] - hb, 0.04f);
+                        hx[j] = ba_remove_range(hb, 1.5f);
+                    }
+                    {
+                        float hb = ba_max_clamp(res[NPL > 1 ? 1 : 0][k][j], 28.4691806922f);
+                        float u = ctr[NPL > 1 ? 1 : 0][k][j] - hb;
+                        u = ba_max_clamp(u, 5.19175294647f);
+                        uy[j] = u * 2.69313763794f;
+                        hb = hb * 2.155f;
+                        hy[j] = ba_amplify_range(hb, 0.132f);
+                    }
+                    // mask input: DiffPrecompute(sqrt(((uhf_x+hf_x)*2.5)^2 + (uhf_y*0.4+hf_y*0.4)^2))
+                    const float kMul = 6.19424080439f, kBias = 12.61050594197f;
+                    const float bias = kMul * kBias;
+                    const float xd = (ux[j] + hx[j]) * 2.5f;
+                    const float yd = uy[j] * 0.4f + hy[j] * 0.4f;
+                    const float vv = sqrt_rn_nonneg(xd * xd + yd * yd);
+                    mk[j] = sqrt_rn_nonneg(kMul * fabsf(vv) + bias) - sqrtf(bias);
+                }
+                float* H = out_a + img * 2 * n + i;
+                float* U = out_b + img * 2 * n + i;
+                put(H, hx[0], hx[1]);
+                put(H + n, hy[0], hy[1]);
+                put(U, ux[0], ux[1]);
+                put(U + n, uy[0], uy[1]);
+                put(out_c + img * n + i, mk[0], mk[1]);
+            }
         }
     }
-    if (x >= w) return;
-    const bool two = x + 1 < w;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int y = y0 + g * 4 + k;
-        if (y >= h) break;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-        if (j == 1 && !two) break;
-        const size_t i = (size_t)y * w + x + j;
-        if (EPI == 0) {
-#pragma unroll
-            for (int c = 0; c < NPL; c++) out_a[(img * NPL + c) * n + i] = res[c][k][j];
-        } else if (EPI == 2) {
-            const float bx = res[0][k][j], by = res[NPL > 1 ? 1 : 0][k][j];
-            const float hfx = ctr[0][k][j] - bx, hfy = ctr[NPL > 1 ? 1 : 0][k][j] - by;
-            float* M = out_a + img * 3 * n + i;
-            M[0] = ba_remove_range(bx, 0.29f);
-            M[n] = ba_amplify_range(by, 0.1f);
-            M[2 * n] = res[NPL > 2 ? 2 : 0][k][j];
-            const float scaler = __fmaf_rn(46.0f / __fmaf_rn(hfy, hfy, 46.0f), (float)(1.0 - 0.653020556257), 0.653020556257f);
-            float* H = out_b + img * 2 * n + i;
-            H[0] = scaler * hfx;
-            H[n] = hfy;
-        } else {
-            float* H = out_a + img * 2 * n + i;
-            float* U = out_b + img * 2 * n + i;
-            float hx, ux, hy, uy;
-            {
-                const float hb = res[0][k][j];
-                ux = ba_remove_range(ctr[0][k][j] - hb, 0.04f);
-                hx = ba_remove_range(hb, 1.5f);
-            }
-            {
-                float hb = ba_max_clamp(res[NPL > 1 ? 1 : 0][k][j], 28.4691806922f);
-                float u = ctr[NPL > 1 ? 1 : 0][k][j] - hb;
-                u = ba_max_clamp(u, 5.19175294647f);
-                uy = u * 2.69313763794f;
-                hb = hb * 2.155f;
-                hy = ba_amplify_range(hb, 0.132f);
-            }
-            H[0] = hx; H[n] = hy; U[0] = ux; U[n] = uy;
-            // mask input: DiffPrecompute(sqrt(((uhf_x+hf_x)*2.5)^2 + (uhf_y*0.4+hf_y*0.4)^2))
-            const float kMul = 6.19424080439f, kBias = 12.61050594197f;
-            const float bias = kMul * kBias;
-            const float xd = (ux + hx) * 2.5f;
-            const float yd = uy * 0.4f + hy * 0.4f;
-            const float vv = sqrt_rn_nonneg(xd * xd + yd * yd);
-            out_c[img * n + i] = sqrt_rn_nonneg(kMul * fabsf(vv) + bias) - sqrtf(bias);
-        }
-        }
-    }
+    if (!TMA) cp_async_wait<0>();
 }
 
 struct BlurTables {
@@ -1304,7 +1398,7 @@ static void ba_psycho_level(Context& c, const float* lin, size_t NI, size_t w, s
     }
     if (dbg_opsin) CE_CUDA(cudaMemcpyAsync(dbg_opsin, L.xyb, 3 * n * 4, cudaMemcpyDeviceToDevice, c.stream));
     {
-        dim3 gh(cdiv(w, 128), cdiv(h, 8), (unsigned)(NI * 3));
+        dim3 gh(cdiv(w, 128), cdiv(h, 8 * BH_NT), (unsigned)(NI * 3));
         CUtensorMap mh, mv;
         memset(&mh, 0, sizeof(mh));
         memset(&mv, 0, sizeof(mv));
@@ -1323,7 +1417,7 @@ static void ba_psycho_level(Context& c, const float* lin, size_t NI, size_t w, s
             CE_LAUNCH(c, "k_ba_blur_v<R16>+lf", (double)NI * n * 48,
                       k_ba_blur_v<0, 16, 3, 1, false><<<gv, 256, 0, c.stream>>>(L.tmp, (int)w, (int)h, n, L.tables.inv_y[0], L.lf, L.xyb, L.mf_pre, mv));
     }
-    dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), (unsigned)NI);
+    dim3 g2(cdiv(w, B2_TW), cdiv(cdiv(h, B2_TH), B2_NT), (unsigned)NI);
     {
         CUtensorMap m7, m3;
         memset(&m7, 0, sizeof(m7));
@@ -1359,7 +1453,7 @@ static void ba_diffmap_level(Context& c, const float* lin, size_t R, const int* 
     ba_alloc_level(c, NI, B, w, h, L);
     ba_psycho_level(c, lin, NI, w, h, intensity, L, nullptr);
     {
-        dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), (unsigned)NI);
+        dim3 g2(cdiv(w, B2_TW), cdiv(cdiv(h, B2_TH), B2_NT), (unsigned)NI);
         CUtensorMap m6;
         memset(&m6, 0, sizeof(m6));
         if (tma_enabled(3) && tma_plane_map(&m6, L.m, w, h, NI, B2_TW + 16, B2_TH + 12, 1))
@@ -1481,7 +1575,7 @@ void butteraugli_debug_blur(Context& c, const float* in, size_t w, size_t h, flo
     BaLevelBufs L;
     ba_alloc_level(c, 2, 1, w, h, L);
     const int vec = (w % 4 == 0) ? 1 : 0;
-    dim3 g2(cdiv(w, B2_TW), cdiv(h, B2_TH), 1);
+    dim3 g2(cdiv(w, B2_TW), cdiv(cdiv(h, B2_TH), B2_NT), 1);
     if (fabsf(sigma - 1.2f) < 1e-6f) {
         dim3 grid(cdiv(w, OP_TW), cdiv(h, OP_TH), 1);
         CUtensorMap m5;
@@ -1491,7 +1585,7 @@ void butteraugli_debug_blur(Context& c, const float* in, size_t w, size_t h, flo
         else
             CE_LAUNCH(c, "k_ba_blur5", (double)n * 8, k_ba_opsin<false, false><<<grid, 256, 0, c.stream>>>(in, (int)w, (int)h, n, 0.0f, out, vec, m5));
     } else if (fabsf(sigma - kSigmas[0]) < 1e-5f) {
-        dim3 gh(cdiv(w, 128), cdiv(h, 8), 1);
+        dim3 gh(cdiv(w, 128), cdiv(h, 8 * BH_NT), 1);
         dim3 gv(cdiv(w, 32), cdiv(h, 64), 1);
         CUtensorMap mh, mv;
         memset(&mh, 0, sizeof(mh));
