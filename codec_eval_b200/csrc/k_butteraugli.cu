@@ -843,7 +843,9 @@ __global__ void __launch_bounds__(256) k_ba_malta_diff(const float* __restrict__
 // pixels; round 1's 4 x 1 layout needed 27 for 4 pixels and was bound by shared-memory bandwidth: 81 LDS.128 = 324
 // shared-memory cycles per warp and band set against 234 cycles of FP32 issue) and evaluates the 16 oriented line sums
 // of each pixel from there.
-#define MT_NT 4
+#ifndef MT_NT
+#define MT_NT 8
+#endif
 #define MT_THREADS 128
 #define MT_BAND_FLOATS (MT_ROWS * MT_P)
 #define MT_BUF_FLOATS (3 * MT_BAND_FLOATS + 4 * MT_TH * MT_TW)

@@ -10,7 +10,10 @@ namespace ce {
 // sRGB8 interleaved -> 3 linear fp32 planes (shared by SSIMULACRA2 / DSSIM /
 // Butteraugli).  Reference: src/metrics/dssim.rs:77-85 (per byte powf); here a
 // 256-entry table holding exactly those fp32 values.
-// One thread = 16 pixels = 48 B in (3 x LDG.128), 3 x 4 x STG.128 out.
+// A warp converts 512 consecutive pixels in four rounds of 128: lane l takes pixels 4l .. 4l+3 of the round, i.e. three
+// 32-bit loads at a 12-byte lane stride (the warp reads 384 contiguous bytes, through L1) and one 128-bit store per
+// plane, so that every store instruction of the warp writes 512 contiguous bytes.  (Round 1 gave a thread 16 consecutive
+// pixels: its four stores per plane were 64 bytes apart across lanes, 16 lines per instruction instead of 4.)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_srgb8_to_linear_v16(const uint8_t* __restrict__ rgb, const int* __restrict__ src_index,
                                                               const float* __restrict__ lut, size_t n_groups,
@@ -19,27 +22,30 @@ __global__ void __launch_bounds__(256) k_srgb8_to_linear_v16(const uint8_t* __re
     __shared__ float s_lut[256];
     s_lut[threadIdx.x] = lut[threadIdx.x];
     __syncthreads();
-    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < n_groups; g += (size_t)gridDim.x * blockDim.x) {
-        const size_t img = g / groups_per_img;
-        const size_t gi = g - img * groups_per_img;
-        const size_t simg = src_index ? (size_t)src_index[img] : img;   // output image `img` reads source image simg
-        const uint4* src = reinterpret_cast<const uint4*>(rgb + (simg * groups_per_img + gi) * 48);
-        uint4 a = ldg_stream_u4(src), b = ldg_stream_u4(src + 1), c = ldg_stream_u4(src + 2);
-        uint32_t wds[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-        float ch[3][16];
+    const size_t total_px = n_groups * 16;
+    const int lane = threadIdx.x & 31;
+    (void)groups_per_img;
+    for (size_t wbase = (blockIdx.x * (size_t)blockDim.x + threadIdx.x - lane) * 16; wbase < total_px;
+         wbase += (size_t)gridDim.x * blockDim.x * 16) {
+        size_t img = wbase / npix;
+        size_t i = wbase - img * npix + (size_t)lane * 4;
 #pragma unroll
-        for (int k = 0; k < 48; k++) {
-            uint32_t byte = (wds[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-            ch[k % 3][k / 3] = s_lut[byte];
-        }
-        size_t p0 = gi * 16;
-        float* base = planes + img * 3 * npix + p0;
+        for (int q = 0; q < 4; q++, i += 128) {
+            while (i >= npix) { i -= npix; img++; }   // npix % 16 == 0: the 4 pixels of a lane never straddle images
+            if (img * npix + i >= total_px) break;
+            const size_t simg = src_index ? (size_t)src_index[img] : img;   // output image `img` reads source image simg
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(rgb + (simg * npix + i) * 3);
+            const uint32_t wds[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+            float ch[3][4];
 #pragma unroll
-        for (int cc = 0; cc < 3; cc++) {
-            float4* dst = reinterpret_cast<float4*>(base + (size_t)cc * npix);
+            for (int k = 0; k < 12; k++) {
+                const uint32_t byte = (wds[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                ch[k % 3][k / 3] = s_lut[byte];
+            }
+            float* base = planes + img * 3 * npix + i;
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                dst[q] = make_float4(ch[cc][q * 4], ch[cc][q * 4 + 1], ch[cc][q * 4 + 2], ch[cc][q * 4 + 3]);
+            for (int cc = 0; cc < 3; cc++)
+                *reinterpret_cast<float4*>(base + (size_t)cc * npix) = make_float4(ch[cc][0], ch[cc][1], ch[cc][2], ch[cc][3]);
         }
     }
 }
