@@ -474,11 +474,11 @@ def main():
     if prof:
         name, v = max(prof.items(), key=lambda kv: kv[1]["ms"])
         ach = v["bytes"] / (v["ms"] / 1e3) / 1e9
-        # what ncu says binds the kernels that are not HBM bound (profiles/r2_final_*_summary.txt)
-        binding = {"k_ba_malta": "FP32 pipe, not HBM: ncu FMA pipe 70 % busy, 81 % issue-active (16 line sums x 3 bands per pixel)",
-                   "k_ds_stats<pair>": "FP32 issue, not HBM: ncu 85 % issue-active, FMA pipe 67 % (un-fused 3x3 chains, dssim-core order)",
-                   "k_s2_vpass<pair>": "FP32 issue, not HBM: ncu 81 % issue-active (3 recurrences + SSIM / edge terms per pixel)",
-                   "k_s2_hpass<pair>": "latency of the serial recurrence, not HBM: ncu 48 % issue-active at 9 warps / SM"}
+        # what ncu says binds the kernels that are not HBM bound (profiles/r2b_*_summary.txt)
+        binding = {"k_ba_malta": "FP32 pipe, not HBM: ncu FMA pipe 68 % busy, 79 % issue-active (16 line sums x 3 bands per pixel)",
+                   "k_ds_stats<pair>": "FP32 issue, not HBM: ncu 85 % issue-active, FMA pipe 66 % (un-fused 3x3 chains, dssim-core order)",
+                   "k_s2_vpass<pair>": "FP32 issue, not HBM: ncu 80 % issue-active (3 recurrences + SSIM / edge terms per pixel)",
+                   "k_s2_hpass<pair>": "its own DRAM traffic: ncu 5.2 TB/s = 80 % of the measured peak (row-pass planes out), 67 % issue-active"}
         tr = traffic_table.get("cfg5", {}).get(name)
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "frac_per_pair": v["bytes_per_pair"] / (v["ms"] / 1e3) / 1e9 / peak,

@@ -30,7 +30,7 @@ PASSES = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 NAMES = {"k_ds_stream<0>": "k_ds_stats<ref>", "k_ds_stream<1>": "k_ds_stats<pair>",
          "k_ds_stream<0, 1>": "k_ds_stats<ref>", "k_ds_stream<0, 0>": "k_ds_stats<ref> edge", "k_ds_stream<1, 1>": "k_ds_stats<pair>",
          "k_ds_stream<1, 0>": "k_ds_stats<pair> edge", "k_ds_blur2<1>": "k_ds_blur2",
-         "k_ds_blur2<0>": "k_ds_blur2", "k_ba_combine4": "k_ba_combine", "k_ba_malta<1>": "k_ba_malta", "k_ba_malta<0>": "k_ba_malta",
+         "k_ds_blur2<0>": "k_ds_blur2", "k_ba_combine4": "k_ba_combine", "k_ba_mask4": "k_ba_mask", "k_ba_malta<1>": "k_ba_malta", "k_ba_malta<0>": "k_ba_malta",
          "k_ba_malta_diff<1>": "k_ba_malta_diff", "k_ba_malta_diff<0>": "k_ba_malta_diff", "k_ba_opsin<1, 1>": "k_ba_opsin",
          "k_ba_opsin<1, 0>": "k_ba_opsin"}
 for t in ("0", "1"):
