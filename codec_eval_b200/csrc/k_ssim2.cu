@@ -374,8 +374,10 @@ __global__ void __launch_bounds__(S2Mode<MODE>::NW * 32) k_s2_vpass(const float*
     auto issue = [&](int t) {   // called for t = 0, 1, 2, ... in order
         if (TMA) {
             // one thread: arm the slot's barrier with the byte count, then one bulk tensor copy per source tensor
-            // (rows / columns outside the image arrive as zeros)
-            if (threadIdx.x == 0 && t < nbatch) {
+            // (rows / columns outside the image arrive as zeros).  The ~60 instructions of the issue go to the LAST warp:
+            // in pair mode it evaluates one map row per batch where the other two evaluate two, so the three warps
+            // reach the batch barrier together (on warp 0 the issue made it the slowest by a third).
+            if (threadIdx.x == NT - 32 && t < nbatch) {
                 float* slot = s_ld + (t & (VP_SLOTS - 1)) * SLOT_FLOATS;
                 unsigned long long* bar = &s_bar[t & (VP_SLOTS - 1)];
                 const int jn = t * VP_BATCH;
