@@ -668,94 +668,8 @@ struct BlurTables {
 #define MT_P (MT_TW + 8)
 #define MT_ROWS (MT_TH + 8)
 #define MT_WIN_ROWS 10   // a thread's register window: its 2 output rows + 4 rows of halo above and below
-#define D(dy, dx) win[(dy) + 4 + J][(dx) + 4 + K]
-// The 16 line sums of a pixel share sub-sums (the centre triples of the four principal directions, the pairs
-// next to the centre of the "knight" lines); they are formed once per pixel.  Mathematically the upstream sums;
-// the association differs, i.e. ~1e-7 relative per sum.
-template <int K, int J>
-CE_DEVINL float malta_hf(const float (&win)[MT_WIN_ROWS][12]) {  // pixel (row J, column K) of the thread's 2 x 4; window rows -4..5, cols -4..7
-    const float c = D(0,0);
-    const float V3 = (D(-1,0) + c) + D(1,0), H3 = (D(0,-1) + c) + D(0,1);
-    const float D3 = (D(-1,-1) + c) + D(1,1), A3 = (D(-1,1) + c) + D(1,-1);
-    const float H2 = c + D(0,1), V2 = c + D(1,0);
-    const float R12 = D(-1,2) + D(-1,3), R13 = D(1,2) + D(1,3);
-    const float B14 = D(2,1) + D(3,1), B15 = D(2,-1) + D(3,-1);
-    float acc = 0.0f, t;
-    t = ((D(0,-4) + D(0,-3)) + (D(0,-2) + H3)) + ((D(0,2) + D(0,3)) + D(0,4));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-4,0) + D(-3,0)) + (D(-2,0) + V3)) + ((D(2,0) + D(3,0)) + D(4,0));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-3,-3) + D(-2,-2)) + D3) + (D(2,2) + D(3,3));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-3,3) + D(-2,2)) + A3) + (D(2,-2) + D(3,-3));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-4,1) + D(-3,1)) + (D(-2,1) + V3)) + (B15 + D(4,-1));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-4,-1) + D(-3,-1)) + (D(-2,-1) + V3)) + (B14 + D(4,1));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-1,-4) + D(-1,-3)) + (D(-1,-2) + H3)) + (R13 + D(1,4));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(1,-4) + D(1,-3)) + (D(1,-2) + H3)) + (R12 + D(-1,4));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-3,-2) + D(-2,-1)) + D3) + (D(2,1) + D(3,2));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-3,2) + D(-2,1)) + A3) + (D(2,-1) + D(3,-2));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-2,-3) + D(-1,-2)) + D3) + (D(1,2) + D(2,3));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-2,3) + D(-1,2)) + A3) + (D(1,-2) + D(2,-3));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(2,-4) + D(2,-3)) + (D(1,-2) + D(1,-1))) + (H2 + R12);
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-2,-4) + D(-2,-3)) + (D(-1,-2) + D(-1,-1))) + (H2 + R13);
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-4,-2) + D(-3,-2)) + (D(-2,-1) + D(-1,-1))) + (V2 + B14);
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-4,2) + D(-3,2)) + (D(-2,1) + D(-1,1))) + (V2 + B15);
-    acc = __fmaf_rn(t, t, acc);
-    return acc;
-}
-template <int K, int J>
-CE_DEVINL float malta_lf(const float (&win)[MT_WIN_ROWS][12]) {
-    const float c = D(0,0);
-    const float Ia = (c + D(-2,-1)) + D(2,1), Ib = (c + D(-2,1)) + D(2,-1);
-    const float Ic = (c + D(-1,-2)) + D(1,2), Id = (c + D(-1,2)) + D(1,-2);
-    float acc = 0.0f, t;
-    t = ((D(0,-4) + D(0,-2)) + c) + (D(0,2) + D(0,4));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-4,0) + D(-2,0)) + c) + (D(2,0) + D(4,0));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-3,-3) + D(-2,-2)) + c) + (D(2,2) + D(3,3));
-    acc = __fmaf_rn(t, t, acc);
-    t = ((D(-3,3) + D(-2,2)) + c) + (D(2,-2) + D(3,-3));
-    acc = __fmaf_rn(t, t, acc);
-    t = Ib + (D(-4,1) + D(4,-1));
-    acc = __fmaf_rn(t, t, acc);
-    t = Ia + (D(-4,-1) + D(4,1));
-    acc = __fmaf_rn(t, t, acc);
-    t = Ic + (D(-1,-4) + D(1,4));
-    acc = __fmaf_rn(t, t, acc);
-    t = Id + (D(1,-4) + D(-1,4));
-    acc = __fmaf_rn(t, t, acc);
-    t = Ia + (D(-3,-2) + D(3,2));
-    acc = __fmaf_rn(t, t, acc);
-    t = Ib + (D(-3,2) + D(3,-2));
-    acc = __fmaf_rn(t, t, acc);
-    t = Ic + (D(-2,-3) + D(2,3));
-    acc = __fmaf_rn(t, t, acc);
-    t = Id + (D(-2,3) + D(2,-3));
-    acc = __fmaf_rn(t, t, acc);
-    t = Id + (D(2,-4) + D(-2,4));
-    acc = __fmaf_rn(t, t, acc);
-    t = Ic + (D(-2,-4) + D(2,4));
-    acc = __fmaf_rn(t, t, acc);
-    t = Ia + (D(-4,-2) + D(4,2));
-    acc = __fmaf_rn(t, t, acc);
-    t = Ib + (D(-4,2) + D(4,-2));
-    acc = __fmaf_rn(t, t, acc);
-    return acc;
-}
-#undef D
+// The 16 line sums of a pixel share sub-sums with one another and with the sums of the thread's other pixels; they
+// are generated (tools/gen_malta.py).  Mathematically the upstream sums; the association differs, i.e. ~1e-7 relative.
 #include "malta_sums.inc"
 
 
@@ -939,15 +853,6 @@ __global__ void __launch_bounds__(MT_THREADS, 3) k_ba_malta(const float* __restr
                     win[r][4 * q] = f.x; win[r][4 * q + 1] = f.y; win[r][4 * q + 2] = f.z; win[r][4 * q + 3] = f.w;
                 }
             }
-#ifdef CE_MALTA_PER_PIXEL
-            if (bd == 0) {
-                acc[0][0] += malta_hf<0, 0>(win); acc[0][1] += malta_hf<1, 0>(win); acc[0][2] += malta_hf<2, 0>(win); acc[0][3] += malta_hf<3, 0>(win);
-                acc[1][0] += malta_hf<0, 1>(win); acc[1][1] += malta_hf<1, 1>(win); acc[1][2] += malta_hf<2, 1>(win); acc[1][3] += malta_hf<3, 1>(win);
-            } else {
-                acc[0][0] += malta_lf<0, 0>(win); acc[0][1] += malta_lf<1, 0>(win); acc[0][2] += malta_lf<2, 0>(win); acc[0][3] += malta_lf<3, 0>(win);
-                acc[1][0] += malta_lf<0, 1>(win); acc[1][1] += malta_lf<1, 1>(win); acc[1][2] += malta_lf<2, 1>(win); acc[1][3] += malta_lf<3, 1>(win);
-            }
-#else
             float accb[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};   // a band's squares sum from 0, as upstream
             if (bd == 0) malta_hf8(win, accb);
             else malta_lf8(win, accb);
@@ -955,7 +860,6 @@ __global__ void __launch_bounds__(MT_THREADS, 3) k_ba_malta(const float* __restr
             for (int j = 0; j < 2; j++)
 #pragma unroll
                 for (int k = 0; k < 4; k++) acc[j][k] += accb[j][k];
-#endif
         }
         float4 pw[2][4];   // hf(ref), hf(dist), mf(ref), mf(dist) of the thread's two rows
 #pragma unroll
