@@ -119,3 +119,57 @@ def test_both_arms_describe_the_same_config():
         for s in shards:                                       # a reference group never straddles two ranks
             assert len(s) % 8 == 0 and len({int(ref_ids[i]) for i in s}) == len(s) // 8
     assert len({len(s) for s in bench.corpus_layout(8)[1]}) == 2       # 1250 groups over 8 ranks: 157 / 156 -> ragged
+
+
+def test_traffic_table_matches_the_benched_kernels():
+    """`roofline.traffic` is looked up by kernel name in profiles/ncu_traffic.json (made by tools/launch_table.py from the
+    ncu launch list): every kernel of the newest committed bench line must be in it, with the launch count the launch
+    list implies for the full corpus, and the step-level figures must be the ones the line carries."""
+    import glob
+
+    t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    newest = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2d_bench.json")) or glob.glob(os.path.join(ROOT, "profiles", "r2*_bench.json")))[-1]
+    d = json.loads(open(newest).read().strip().splitlines()[-1])
+    assert d["roofline"]["traffic_source"] == t["_source"]
+    assert abs(d["roofline"]["step_dram_frac"] - t["_step_dram_frac_cfg5"]) < 1e-12
+    for k, v in d["kernels"].items():
+        assert k in t["cfg5"], k
+        # the bench table counts launches over its profiled steps (2): 39 sub-batches x launches per sub-batch
+        per_sub = t["cfg5"][k]["launches_per_pass"] / 4
+        assert v["launches"] == 2 * 39 * per_sub, (k, v["launches"], per_sub)
+    top = d["roofline"]["kernel"]
+    assert d["roofline"]["traffic"] == t["cfg5"][top]["bytes_per_launch"]
+    # DRAM traffic of the dominant kernel within 1.5x of its algorithmic bytes (no wasted re-reads)
+    assert 0.8 < d["roofline"]["traffic"] / d["roofline"]["algorithmic_bytes_per_launch"] < 1.5
+
+
+def test_committed_round2_lines_carry_the_corpus_contract():
+    """The round-2 lines: BASELINE's 1/2/4/8 config strong-scaled, per-metric / cfg1-cfg4 / parity nested inside `roofline`
+    (so the driver's record keeps them), both byte accountings, the library stamp, the reference arm on the same config."""
+    lines = (("r2d_bench.json", 1), ("r2c_bench.json", 1), ("r2b_bench.json", 1), ("r2b_bench_2gpu.json", 2), ("r2d_bench_4gpu.json", 4))
+    for name, n in lines:
+        d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        assert d["n_gpus"] == n and d["scaling"] == "strong" and d["metric"] == "mpix_pairs_per_sec_all_metrics"
+        assert d["config"]["pairs"] == 10000 and "cfg5" in d["config"]["workload"] and d["dtype"] == "f32"
+        assert d["steps"] >= 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and "src:" in d["lib"] and d["status_ok"]
+        assert abs(d["value"] - 10000 * 1024 * 1024 / 1e6 / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-6
+        e = d["e2e"]
+        assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] == 10000 * (1 + 1 / 8) * 3 * 1024 * 1024
+        assert e["results_identical_to_resident"] is True and e["pageable"]["value"] > 0
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["frac_per_pair"] >= r["frac"]
+        assert set(r["per_metric"]) == {"psnr", "ssimulacra2", "dssim", "butteraugli"}
+        assert 0.3 < r["step_dram_frac"] < 1.0 and r["step_dram_gb"] > 0
+        c = d["clocks"]
+        assert c["sm_mhz"] > 0 and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+        if n == 1:
+            p = r["parity"]
+            assert p["ok"] and p["checked"] >= 8 and p["sse_exact"] and p["max_abs_ssim2"] < p["tol"]["ssimulacra2_abs"]
+            assert p["max_rel_dssim"] < p["tol"]["dssim_rel"] and p["max_rel_ba"] < p["tol"]["butteraugli_rel"]
+            assert all(k in r for k in ("cfg1", "cfg2", "cfg3", "cfg4")) and r["cfg4"]["mpix_pairs_per_sec"] > 0
+            assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    for name in ("r2d_reference.json", "r2c_reference.json"):
+        ref = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        ours = json.loads(open(os.path.join(ROOT, "profiles", name.replace("_reference", "_bench"))).read().strip().splitlines()[-1])
+        assert ref["impl"] == "reference" and ref["config"] == ours["config"] and ref["metric"] == ours["metric"]
+        assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["gpu_launches"] == 0 and ref["value"] == ref["cpu_baseline"]["value"]
